@@ -1,0 +1,131 @@
+"""Pin the CPU oracle (oracle/qms_oracle.py) against vectors produced by the unmodified reference
+(tests/golden/make_golden.py) and against the reference's own golden vectors.  Bit-exact."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle.qms_oracle import OracleLibrary, m_key
+from tests.golden.cases import CASES, PEPTIDE_SEQUENCE_KATS, QUICK_START_EXPECT, QUICK_START_PEAKS
+from tests.helpers import GOLDEN, assert_results_equal, load_case, lp_tuple, results_to_rows
+
+import sys
+sys.setrecursionlimit(20000)
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request):
+    blob, peaks, offsets = load_case(request.param)
+    lib = OracleLibrary(**CASES[request.param]["lib"])
+    return request.param, blob, peaks, offsets, lib
+
+
+def test_library_matches_reference_dump(case):
+    name, blob, _, _, lib = case
+    ref = blob["library"]
+    assert sorted(lib.keys()) == sorted(ref["formulas"])      # order = set() iteration order (hash seed)
+    lps = [lp_tuple(x) for x in ref["labled_percentiles"]]
+    assert lib.labled_percentiles == lps
+    assert lib.lookup["molecule to formula"] == ref["molecule_to_formula"]
+    assert {k: sorted(v) for k, v in lib.lookup["molecule fixed label variations"].items()} == \
+        ref["fixed_label_variations"]
+    for formula in ref["formulas"]:
+        assert dict(lib[formula]["cc"]) == ref["cc"][formula]
+        for lp, want in zip(lps, ref["env"][formula]):
+            env = lib[formula]["env"][lp]
+            for field in ("mass", "abun", "relabun", "c_peak_pos", "n_c_peaks"):
+                assert env[field] == want[field], (formula, lp, field)
+            for z in lib.charges:
+                assert env[z]["mz"] == want["z"][str(z)]["mz"]
+                wins = [None if s is None else [min(s), max(s), len(s)] for s in env[z]["tmzs"]]
+                assert wins == want["z"][str(z)]["win"]
+                assert len(env[z]["atmzs"]) == want["z"][str(z)]["n_atmzs"]
+    index = [[lo, hi, z, lps.index(lp), f] for lo, hi, z, lp, f in lib.formulas_sorted_by_mz]
+    assert index == [[lo, hi, z, lp, ref["formulas"][f]] for lo, hi, z, lp, f in ref["index"]]
+    assert lib.match_set_mz_range == ref["match_set_mz_range"]
+    assert [[m["ids"], m["mz_range"], len(m["tmzs"])] for m in lib.match_sets.values()] == ref["match_sets"]
+    for el, by_label in ref["trees"].items():
+        for label, levels in by_label.items():
+            for n, want in levels.items():
+                node = lib.element_trees[el][label][int(n)]
+                if want is None:
+                    assert node["minPos"] is None
+                    continue
+                lo, hi, abun, mass = want
+                assert (node["minPos"], node["maxPos"]) == (lo, hi)
+                span = range(min(lo, hi), max(lo, hi) + 1)
+                assert [node["env"][p]["abun"] for p in span] == abun
+                assert [node["env"][p]["mass"] for p in span] == mass
+
+
+@pytest.mark.parametrize("mode", ["numpy", "list"])
+def test_match_all_matches_reference(case, mode):
+    name, blob, peaks, offsets, lib = case
+    res = {}
+    for s in range(len(offsets) - 1):
+        spec = peaks[offsets[s]:offsets[s + 1]]
+        if mode == "list":
+            spec = [(float(a), float(b)) for a, b in spec]
+        lib.match_all(spec, "run", s, s * 0.2, res)
+    assert_results_equal(results_to_rows(res), blob["results_" + mode])
+
+
+def test_reference_peptide_sequence_vectors(golden_dir):
+    """tests/peptide_sequence_test.py:12-37 of the reference."""
+    for molecule, formula, abun, (lo, hi) in PEPTIDE_SEQUENCE_KATS:
+        lib = OracleLibrary([molecule], [2], unimod_files=[golden_dir / "usermod_silac_tmt.xml"])
+        env = lib[formula]["env"][(("N", "0.000"),)]
+        assert env["abun"] == abun
+        first = next(s for s in env[2]["tmzs"] if s is not None)
+        assert first == set(range(lo, hi + 1))
+
+
+def test_quick_start_known_answer():
+    """docs/source/quick_start.rst:119-136: key, scaling factor exact; score to 2e-12 (the docs
+    value was produced by an older Python: sum() is compensated since 3.12)."""
+    lib = OracleLibrary(["DDSPDLPK"], [2])
+    for spec in (QUICK_START_PEAKS, np.array(QUICK_START_PEAKS)):
+        res = lib.match_all(spec, "BSA_test", 1165, 29.10)
+        assert list(res.keys()) == [m_key(*QUICK_START_EXPECT["key"])]
+        (hit,) = res[m_key(*QUICK_START_EXPECT["key"])]
+        assert hit.scaling_factor == QUICK_START_EXPECT["scaling_factor"]
+        assert abs(hit.score - QUICK_START_EXPECT["score"]) < 2e-12
+        for got, want in zip(hit.peaks, QUICK_START_EXPECT["peaks"]):
+            assert got[0] == want[0] and got[1] == want[1] and got[4] == want[4]
+            assert abs(got[2] - want[2]) < 1e-12 and abs(got[3] - want[3]) < 1e-9
+
+
+def test_score_matches_known_answers():
+    kat = json.loads((GOLDEN / "kat.json").read_text())
+    lib = OracleLibrary(["ELVISLIVES"], [2], build=False)
+    for peaks, xi, score, scaling in kat["score_matches"]:
+        got = lib.score_matches([tuple(p) for p in peaks], xi)
+        assert (float(got[0]), float(got[1])) == (score, scaling)
+    for key, spec_id, score, scaling, peaks in kat["bsa_pickle_matches"]:
+        got = lib.score_matches([tuple(p) for p in peaks], kat["bsa_pickle_xi"])
+        assert (float(got[0]), float(got[1])) == (score, scaling)
+
+
+def test_bsa_pickle_library_values():
+    """tests/data/test_BSA_pyqms_results.pkl: cmz / ri / ci of the 16 real matches are reproduced by a
+    rebuilt library (fixed label CAM with 14N, charges 1-5): ri, ci exact, cmz to 1e-12 relative."""
+    kat = json.loads((GOLDEN / "kat.json").read_text())
+    lib = OracleLibrary(["SHCIAEVEK"], [1, 2, 3, 4, 5], metabolic_labels={"15N": [0]},
+                        fixed_labels={"C": ["C(2)H(3)14N(1)O(1)"]})
+    for key, spec_id, score, scaling, peaks in kat["bsa_pickle_matches"]:
+        env = lib[key[1]]["env"][lp_tuple(key[3])]
+        rows = [(env["relabun"][n], env[key[2]]["mz"][n], env["abun"][n])
+                for n, p in enumerate(env["c_peak_pos"]) if p is not None]
+        assert len(rows) == len(peaks)
+        for (ri, cmz, ci), p in zip(rows, peaks):
+            assert ri == p[2] and ci == p[4]
+            assert abs(cmz - p[3]) <= 1e-12 * p[3]    # element order of the real parser differs: few ulp
+
+
+def test_list_vs_numpy_slicing_quirk():
+    """list input slices by +-2 elements, numpy input by +-2 Da."""
+    lib = OracleLibrary(["DDSPDLPK"], [2])
+    spec = [(100.0 + i, 1.0) for i in range(5)] + list(QUICK_START_PEAKS[19:26])
+    a = lib.slice_list(spec, ((443.7, 0), (445.3, 0)))
+    b = lib.slice_list(np.array(spec), ((443.7, 0), (445.3, 0)))
+    assert len(a) == 9 and len(b) == 7
