@@ -1,0 +1,214 @@
+/*
+ * qms_b200.h -- C ABI of libqms_b200.so: the two data-parallel hot paths of pyQms as sm_100a CUDA.
+ *
+ * The reference (pyQms v0.6.5, pure Python) has no FFI; the boundary it offers is the method
+ * surface of pyqms.IsotopologueLibrary.  Each entry point below names the reference code it
+ * replaces (file:line relative to the reference repository; IL = pyqms/isotopologue_library.py).
+ * The Python host class pyqms_b200.IsotopologueLibrary binds these with ctypes
+ * (pyqms_b200/_capi.py); INTEGRATION.md shows the stub a pyQms maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 (QMS_OK) or a negative
+ * QMS_E_* code and leaves a message in qms_last_error(ctx).  A context owns one device, one
+ * CUDA stream and all device buffers; it is not thread-safe (one context per GPU / per thread).
+ * "host-or-device" pointers are resolved with cudaPointerGetAttributes, so a torch tensor's
+ * data_ptr() can be passed wherever a host array can.  There is no CPU fallback anywhere.
+ */
+#ifndef QMS_B200_H
+#define QMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMS_OK 0
+#define QMS_E_CUDA (-1)       /* a CUDA runtime call failed (message has the call and the error) */
+#define QMS_E_ARG (-2)        /* invalid argument / call order                                   */
+#define QMS_E_CAPACITY (-3)   /* caller buffer too small; required sizes are reported            */
+#define QMS_E_PARAM (-4)      /* parameter combination outside the supported domain              */
+#define QMS_E_LIMIT (-5)      /* an internal hard limit was hit (message says which)             */
+#define QMS_E_INPUT (-6)      /* input violates a documented precondition (e.g. unsorted m/z)    */
+
+typedef struct qms_ctx qms_ctx;
+
+/* Numeric subset of pyqms.params (pyqms/params.py:29-74) that the kernels read. */
+typedef struct qms_params {
+    double element_min_abundance;       /* ELEMENT_MIN_ABUNDANCE            IL:1312, 1773       */
+    double min_rel_peak_intensity;      /* MIN_REL_PEAK_INTENSITY_FOR_MATCHING  IL:759, 2445    */
+    double intensity_transformation;    /* INTENSITY_TRANSFORMATION_FACTOR  IL:746              */
+    double lower_mz_limit;              /* LOWER_MZ_LIMIT                   IL:834              */
+    double upper_mz_limit;              /* UPPER_MZ_LIMIT                   IL:835              */
+    double rel_mz_range;                /* REL_MZ_RANGE                     IL:2456, 2545       */
+    double rel_i_range;                 /* REL_I_RANGE                      IL:2457             */
+    double internal_precision;          /* INTERNAL_PRECISION               IL:2547, 2582       */
+    double machine_offset_ppm;          /* MACHINE_OFFSET_IN_PPM            IL:791-795          */
+    double m_score_threshold;           /* M_SCORE_THRESHOLD                IL:1860             */
+    double required_peak_overlap;       /* REQUIRED_PERCENTILE_PEAK_OVERLAP IL:1975             */
+    double proton;                      /* knowledge_base.PROTON            IL:785              */
+    int32_t min_matched_isotopologues;  /* MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES IL:1844,1868,1973 */
+    int32_t max_molecules_per_bin;      /* MAX_MOLECULES_PER_MATCH_BIN      IL:874 (list-mode slicing only) */
+} qms_params;
+
+/* Counters for roofline accounting; all cumulative since qms_reset_counters. */
+typedef struct qms_counters {
+    int64_t spectra;            /* spectra passed through qms_match_batch                        */
+    int64_t peaks;              /* spectrum peaks streamed by the probe kernel                   */
+    int64_t live_peaks;         /* peaks whose 1/P-Da bucket is covered by >= 1 library window   */
+    int64_t incidences;         /* (peak bucket, library window) incidences gated                */
+    int64_t candidates;         /* (spectrum, entry) pairs that passed both overlap gates        */
+    int64_t candidate_windows;  /* sum of c-peak windows over those pairs                        */
+    int64_t combinations;       /* candidate combinations scored (IL:2010)                       */
+    int64_t hits;               /* matches emitted                                               */
+    int64_t hit_windows;        /* sum of c-peak windows over the emitted matches                */
+    int64_t kernel_launches;    /* kernels of this library launched                              */
+    double ms_probe;            /* device ms in spectrum_probe_gate (CUDA events on ctx stream)  */
+    double ms_score;            /* device ms in assemble_score                                   */
+    double ms_compact;          /* device ms in sort + compaction of hits                        */
+    double ms_h2d;              /* device ms copying spectra host->device                        */
+    double ms_d2h;              /* device ms copying hits device->host                           */
+    double ms_trees;            /* device ms in the element-tree kernels                         */
+    double ms_envelopes;        /* device ms in envelope_convolve                                */
+    double ms_index;            /* device ms in mz_windows + index/probe-table build             */
+    int64_t envelopes;          /* envelopes built by this context                               */
+    int64_t envelope_flops;     /* FP64 operations of the convolutions (2 mul + 2 add per pair and array) */
+} qms_counters;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int qms_ctx_create(int device, qms_ctx** out);
+void qms_ctx_destroy(qms_ctx* ctx);
+const char* qms_last_error(qms_ctx* ctx);            /* ctx may be NULL: error of a failed create */
+int qms_set_params(qms_ctx* ctx, const qms_params* p);
+void* qms_stream(qms_ctx* ctx);                      /* cudaStream_t, e.g. for torch.cuda.ExternalStream */
+int qms_synchronize(qms_ctx* ctx);
+int qms_get_counters(qms_ctx* ctx, qms_counters* out);
+int qms_reset_counters(qms_ctx* ctx);
+int qms_device_bytes(qms_ctx* ctx, int64_t* out);    /* device memory currently owned by the context */
+
+/* ---- P1 prologue: enriched isotope tables ----------------------------------------------------
+ * Replaces _recalc_isotopic_distribution IL:2109-2165: the isotope whose rounded mass equals
+ * enriched_isotope gets abundance target_percentile, the others share (natural - target) in
+ * proportion to their abundance.  mass/abun: the template element's natural table in mass order
+ * (host); out_abun: n_iso doubles (host). */
+int qms_recalc_distribution(qms_ctx* ctx, int32_t n_iso, const double* mass, const double* abun,
+                            int32_t enriched_isotope, double target_percentile, double* out_abun);
+
+/* ---- P1a: element trees -------------------------------------------------------------------
+ * Replaces IL:1078-1214 (_create_element_trees), IL:1216-1324 (_calc_distributions__two_isotopes)
+ * and IL:1679-1792 (_increase_element_envelope).
+ * A *pool* is one (element, label percentile) isotope table: isotopes [iso_off[p], iso_off[p+1])
+ * sorted by mass, each (mass, abundance, position q) -- q is the knowledge-base enumeration index
+ * (IL:1019-1022).  Levels (atom counts) 1..max_level[p] are built; for 2-isotope pools levels
+ * below two_iso_min (IL:1230, library-wide minimum count) other than level 1 do not exist.
+ * Host inputs only. */
+int qms_build_element_trees(qms_ctx* ctx, int32_t n_pools, const int32_t* iso_off,
+                            const double* iso_mass, const double* iso_abun, const int32_t* iso_q,
+                            const int32_t* max_level, int32_t two_iso_min);
+
+/* Read back one level of one pool (API parity: lib.element_trees).  abun/mass receive the slice
+ * [minPos, maxPos]; cap is the capacity of both arrays; *n_out its length (0 if the level has no
+ * entry above the threshold or does not exist). */
+int qms_export_tree_level(qms_ctx* ctx, int32_t pool, int32_t level, int32_t* min_pos,
+                          int32_t* max_pos, double* abun, double* mass, int32_t cap, int32_t* n_out);
+
+/* ---- P1b: isotope envelopes -------------------------------------------------------------------
+ * Replaces the combination loop IL:518-775 incl. _create_combinations IL:1028-1076.
+ * Envelope e = one (formula, label-percentile tuple); its terms [term_off[e], term_off[e+1]) are
+ * (pool, level) pairs in the reference's element order (unlabeled elements in composition order,
+ * then the labelled elements of the tuple, IL:589-646).  qms_set_envelope_terms uploads the
+ * descriptors of ALL envelopes and sizes the global layout; qms_build_envelopes computes the
+ * shard [e_begin, e_end) (one warp per envelope).  Host inputs only. */
+int qms_set_envelope_terms(qms_ctx* ctx, int64_t n_env, const int64_t* term_off,
+                           const int32_t* term_pool, const int32_t* term_level);
+int qms_build_envelopes(qms_ctx* ctx, int64_t e_begin, int64_t e_end);
+
+/* Shard exchange for the multi-GPU build (NCCL all-gather is done by the host on these buffers,
+ * SURVEY.md section 8e).  The layout is identical on every rank: peak slot range of envelope e is
+ * [slot_off[e], slot_off[e+1]).  qms_envelope_layout returns n_slots and copies slot_off
+ * (n_env+1 int64, host) if slot_off != NULL.  qms_envelope_buffers returns the DEVICE pointers of
+ * the per-slot arrays (mass f64, relabun f64, abun i32, pos i32, c_flag u8) and per-envelope
+ * arrays (len i32, n_c i32) so the host can wrap them as tensors and gather in place. */
+int qms_envelope_layout(qms_ctx* ctx, int64_t* n_env, int64_t* n_slots, int64_t* slot_off);
+int qms_envelope_buffers(qms_ctx* ctx, void** mass, void** relabun, void** abun, void** pos,
+                         void** c_flag, void** len, void** n_c);
+
+/* ---- P1c: m/z windows + sorted index ------------------------------------------------------
+ * Replaces IL:777-811 + _transform_mz_to_set IL:2533-2552 (per-charge m/z, integer ppm windows),
+ * the admission test IL:817-844, the tuple sort IL:867 and the match bins IL:869-939.
+ * env_rank[e] = rank of (label tuple, formula) under Python tuple ordering (host strings), used
+ * to break ties of (lower_mz, upper_mz, charge) exactly like the reference's sort. */
+int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t* charges, const int64_t* env_rank);
+
+typedef struct qms_index_info {
+    int64_t n_entries;      /* admitted (envelope, charge) entries = len(formulas_sorted_by_mz) */
+    int64_t n_windows;      /* total c-peak windows over all entries                           */
+    int32_t t_min, t_max;   /* integer m/z grid covered by any window                          */
+    int32_t max_width;      /* widest window in grid cells                                     */
+    double mz_min, mz_max;  /* match_set_mz_range (IL:923-939)                                 */
+} qms_index_info;
+int qms_index_info_get(qms_ctx* ctx, qms_index_info* out);
+
+/* Host copies for the Python views (all caller-allocated, sizes from the calls above):
+ * per slot: mass, relabun, abun, pos(-1 = dropped slot), c_flag; per envelope: len, n_c;
+ * per charge plane z (0..n_charges-1): mz, lo, hi of every slot. */
+int qms_export_envelopes(qms_ctx* ctx, double* mass, double* relabun, int32_t* abun, int32_t* pos,
+                         uint8_t* c_flag, int32_t* len, int32_t* n_c);
+int qms_export_charge_plane(qms_ctx* ctx, int32_t z_index, double* mz, int32_t* lo, int32_t* hi);
+/* per entry: envelope id, charge index, lower/upper mz, window offset (n_entries+1). */
+int qms_export_index(qms_ctx* ctx, int64_t* env, int32_t* z_index, double* lower_mz, double* upper_mz,
+                     int64_t* win_off);
+/* per window (entry-major): lo, hi, cmz, ri, ci. */
+int qms_export_windows(qms_ctx* ctx, int32_t* lo, int32_t* hi, double* cmz, double* ri, int32_t* ci);
+
+/* _transform_mz_to_set IL:2533-2552 and the bucket transform of _transform_spectrum IL:2582/2589 for
+ * n caller-supplied m/z values (host arrays): lo/hi = integer ppm window edges, tmz = int(round(mz*P)).
+ * Any output may be NULL. */
+int qms_transform_mz(qms_ctx* ctx, int64_t n, const double* mz, int32_t* lo, int32_t* hi, int32_t* tmz);
+
+/* ---- P2: spectrum matching -------------------------------------------------------------------
+ * Replaces match_all IL:1794-1883 (incl. _slice_list IL:2500-2531, _transform_spectrum
+ * IL:2554-2603), match_isotopologue IL:1885-2040 and score_matches IL:2441-2498 for a batch of
+ * spectra.  peaks: (n_peaks, 2) float64 rows (m/z, intensity), the integer m/z bucket
+ * int(round(mz*INTERNAL_PRECISION)) non-decreasing inside each spectrum, i.e. sorted by m/z
+ * (QMS_E_INPUT otherwise); offsets: n_spectra+1 int64 row offsets; both host-or-device.
+ * input_kind: 0 = numpy-array semantics, 1 = list-of-tuples semantics.
+ * mz_score_percentile = results.params["MZ_SCORE_PERCENTILE"] (IL:1855).
+ * Hits are ordered by (spectrum, index entry) like the reference's loops.  Outputs are
+ * host-or-device caller buffers with capacities cap_hits / cap_windows; on overflow the call
+ * returns QMS_E_CAPACITY with the required sizes in n_hits / n_hit_windows and writes nothing.
+ *   hit_spec[h], hit_entry[h], hit_score[h], hit_scaling[h], hit_win_off[h] (cap_hits+1 entries)
+ *   per hit window w in [hit_win_off[h], hit_win_off[h+1]): hit_mmz[w], hit_mi[w] (NaN = None,
+ *   IL:1994-2000) and hit_peak[w] = row of the matched peak in `peaks` (-1 = None).
+ * Any output pointer may be NULL to skip it. */
+typedef struct qms_hits {
+    int64_t cap_hits, cap_windows;
+    int32_t* hit_spec;
+    int32_t* hit_entry;
+    double* hit_score;
+    double* hit_scaling;
+    int64_t* hit_win_off;
+    double* hit_mmz;
+    double* hit_mi;
+    int64_t* hit_peak;
+} qms_hits;
+int qms_match_batch(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra,
+                    int32_t input_kind, double mz_score_percentile, qms_hits* out, int64_t* n_hits,
+                    int64_t* n_hit_windows);
+
+/* match_isotopologue IL:1885-2040 for ONE index entry against ONE spectrum: same kernels, restricted
+ * to `entry`, with the overlap gates of IL:1973-1976 but WITHOUT the score / matched-peak thresholds of
+ * match_all (IL:1860-1870), i.e. the best (score, scaling, peaks) or no hit. */
+int qms_match_entry(qms_ctx* ctx, const double* peaks, int64_t n_peaks, int32_t input_kind, int32_t entry,
+                    double mz_score_percentile, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows);
+
+/* score_matches (IL:2441-2498) for caller-supplied peak tuples, on the device: n rows of
+ * (mmz, mi, ri, cmz, ci) with NaN mmz = None.  One launch of the same scoring routine the
+ * matcher uses; exists for unit parity tests (tests/score_matches_tests.py). */
+int qms_score_matches(qms_ctx* ctx, int32_t n, const double* mmz, const double* mi, const double* ri,
+                      const double* cmz, const double* ci, double mz_score_percentile, double* score,
+                      double* scaling);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMS_B200_H */

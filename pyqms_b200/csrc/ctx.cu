@@ -1,0 +1,159 @@
+// Context, error handling and device-memory bookkeeping of libqms_b200.so.
+#include <stdarg.h>
+
+#include "qms_internal.cuh"
+
+static thread_local std::string g_create_error;
+
+int qms_fail(qms_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+bool qms_is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int qms_reserve_bytes(qms_ctx* ctx, void** p, size_t* cap_elems, size_t elems, size_t elem_size, bool keep) {
+    if (elems <= *cap_elems && *p) return QMS_OK;
+    size_t want = elems;
+    if (*cap_elems && !keep) want = elems + elems / 4;  // scratch buffers grow geometrically
+    if (want == 0) want = 1;
+    void* fresh = nullptr;
+    cudaError_t e = cudaMalloc(&fresh, want * elem_size);
+    if (e != cudaSuccess)
+        return qms_fail(ctx, QMS_E_CUDA, "cudaMalloc(%zu bytes) failed: %s", want * elem_size, cudaGetErrorString(e));
+    if (*p) {
+        if (keep && *cap_elems) {
+            e = cudaMemcpyAsync(fresh, *p, *cap_elems * elem_size, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) {
+                cudaFree(fresh);
+                return qms_fail(ctx, QMS_E_CUDA, "device copy on grow failed: %s", cudaGetErrorString(e));
+            }
+        } else {
+            cudaStreamSynchronize(ctx->stream);
+        }
+        cudaFree(*p);
+        ctx->dev_bytes -= (int64_t)(*cap_elems * elem_size);
+    }
+    *p = fresh;
+    *cap_elems = want;
+    ctx->dev_bytes += (int64_t)(want * elem_size);
+    return QMS_OK;
+}
+
+extern "C" {
+
+int qms_ctx_create(int device, qms_ctx** out) {
+    if (!out) return qms_fail(nullptr, QMS_E_ARG, "qms_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return qms_fail(nullptr, QMS_E_CUDA, "no CUDA device available (%s); libqms_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return qms_fail(nullptr, QMS_E_ARG, "device %d out of range [0,%d)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return qms_fail(nullptr, QMS_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    qms_ctx* ctx = new qms_ctx();
+    ctx->device = device;
+    memset(&ctx->cnt, 0, sizeof(ctx->cnt));
+    memset(&ctx->prm, 0, sizeof(ctx->prm));
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        qms_fail(nullptr, QMS_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        delete ctx;
+        return QMS_E_CUDA;
+    }
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaHostAlloc((void**)&ctx->h_pinned, 64 * sizeof(unsigned long long), cudaHostAllocDefault);
+    *out = ctx;
+    return QMS_OK;
+}
+
+void qms_ctx_destroy(qms_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+#define REL(b) qms_release(ctx, ctx->b)
+    REL(iso_off); REL(iso_q); REL(max_level); REL(lvl_base); REL(lvl_min); REL(lvl_max); REL(lvl_f); REL(lvl_l);
+    REL(iso_mass); REL(iso_abun); REL(lvl_off); REL(tree_abun); REL(tree_mass);
+    REL(term_off); REL(slot_off); REL(term_pool); REL(term_level); REL(env_mass); REL(env_relabun);
+    REL(env_abun); REL(env_pos); REL(env_len); REL(env_nc); REL(env_flops);
+    REL(charges); REL(pl_mz); REL(pl_lo); REL(pl_hi); REL(env_cflag);
+    REL(ent_env); REL(ent_win_off); REL(ent_z); REL(ent_lower); REL(ent_upper); REL(bin_upper);
+    REL(win_lo); REL(win_hi); REL(win_ci); REL(win_cmz); REL(win_ri); REL(probe); REL(cell_start); REL(cover);
+    REL(d_peaks); REL(d_offsets); REL(pair_keys); REL(pair_keys_alt); REL(cub_tmp); REL(dev_counters);
+    REL(pair_score); REL(pair_scaling); REL(pair_flag); REL(pair_win_off); REL(pair_best);
+    REL(blk_hits); REL(blk_wins);
+    REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak);
+#undef REL
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* qms_last_error(qms_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int qms_set_params(qms_ctx* ctx, const qms_params* p) {
+    if (!ctx || !p) return qms_fail(ctx, QMS_E_ARG, "qms_set_params: NULL argument");
+    if (!(p->internal_precision > 0) || !(p->rel_mz_range >= 0))
+        return qms_fail(ctx, QMS_E_PARAM, "INTERNAL_PRECISION must be > 0 and REL_MZ_RANGE >= 0");
+    if (!(p->upper_mz_limit * p->internal_precision < 2.0e9))
+        return qms_fail(ctx, QMS_E_PARAM, "UPPER_MZ_LIMIT*INTERNAL_PRECISION must stay below 2e9 (int32 m/z grid)");
+    // numpy-input semantics re-slice by +-2 Da per match bin (IL:2525-2530); that slicing is a no-op
+    // for the windows of the bin's own entries as long as a window is narrower than 2 Da.
+    if (!(p->upper_mz_limit * p->rel_mz_range + 1.0 / p->internal_precision < 2.0))
+        return qms_fail(ctx, QMS_E_PARAM, "UPPER_MZ_LIMIT*REL_MZ_RANGE + 1/INTERNAL_PRECISION must be < 2 Da");
+    if (!(p->intensity_transformation > 0 && p->intensity_transformation <= 2.0e9))
+        return qms_fail(ctx, QMS_E_PARAM, "INTENSITY_TRANSFORMATION_FACTOR must be in (0, 2e9] (int32 abundances)");
+    if (p->max_molecules_per_bin < 1) return qms_fail(ctx, QMS_E_PARAM, "MAX_MOLECULES_PER_MATCH_BIN must be >= 1");
+    ctx->prm = *p;
+    ctx->have_params = true;
+    return QMS_OK;
+}
+
+void* qms_stream(qms_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int qms_synchronize(qms_ctx* ctx) {
+    if (!ctx) return QMS_E_ARG;
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return QMS_OK;
+}
+
+int qms_get_counters(qms_ctx* ctx, qms_counters* out) {
+    if (!ctx || !out) return QMS_E_ARG;
+    *out = ctx->cnt;
+    return QMS_OK;
+}
+
+int qms_reset_counters(qms_ctx* ctx) {
+    if (!ctx) return QMS_E_ARG;
+    memset(&ctx->cnt, 0, sizeof(ctx->cnt));
+    return QMS_OK;
+}
+
+int qms_device_bytes(qms_ctx* ctx, int64_t* out) {
+    if (!ctx || !out) return QMS_E_ARG;
+    *out = ctx->dev_bytes;
+    return QMS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,803 @@
+// P2 -- spectrum matching.  Replaces match_all IL:1794-1883 (+ _slice_list IL:2500-2531,
+// _transform_spectrum IL:2554-2603), match_isotopologue IL:1885-2040 and score_matches IL:2441-2498.
+//
+// The reference walks every match bin for every spectrum, re-hashes the spectrum per bin and
+// intersects Python sets.  Here the work is driven by the spectrum peaks instead:
+//
+//  K5 spectrum_probe_gate   flat, coalesced stream over all peaks of the batch (one LDG.128 per
+//      (m/z, intensity) row).  tmz = rint(mz*P); a two-level cover bitmap rejects peaks whose 1/P-Da
+//      bucket no library window contains (the HBM-bound regime of small libraries).  A live bucket
+//      looks up the lo-sorted window list through the direct-address cell table; for every
+//      (bucket, window) incidence the owning index entry is gated exactly like IL:1968-1976:
+//      |distinct spectrum buckets inside the entry's windows| >= MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES
+//      and / n_c_peaks >= REQUIRED_PERCENTILE_PEAK_OVERLAP.  Each (spectrum, entry) pair is gated
+//      once, at its canonical incidence = lowest window, lowest bucket.  Survivors are appended
+//      to a pair list.
+//  K6 assemble_score        one thread per surviving pair (sorted by spectrum, entry): per c-peak
+//      candidate buckets (first peak of a bucket only, IL:2014), odometer over all candidate
+//      combinations (IL:2004-2031), sequential FP64 mScore per combination, best under the
+//      reference's (score, scaling, peaks) tuple order, thresholds IL:1860-1870.
+//  K7 compact_hits          order-preserving warp-ballot stream compaction of the passing pairs
+//      into the hit arrays.
+#include <cub/cub.cuh>
+
+#include "qms_internal.cuh"
+
+#define QMS_DBL_EPS 2.220446049250313e-16
+
+enum { C_PEAKS = 0, C_LIVE, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_PAIR_WINDOWS, C_N };
+
+struct MatchView {
+    const double2* peaks;
+    const int64_t* offsets;
+    int64_t n_spectra;
+    const ProbeRec* probe;
+    const int32_t* cell_start;
+    const uint32_t* cover;
+    const uint32_t* cover2;
+    int32_t t_min, t_max, max_width;
+    const int64_t* ent_win_off;
+    const int32_t* win_lo;
+    const int32_t* win_hi;
+    const double* win_cmz;
+    const double* win_ri;
+    const int32_t* win_ci;
+    const double* ent_lower;
+    const double* bin_upper;
+    int per_bin;
+    int input_kind;
+    int only_entry;        // >= 0: match_isotopologue mode (one entry, no score thresholds)
+    double precision, mz_min, mz_max;
+    int min_match;
+    double req_overlap, min_rel, rel_mz, rel_i, xi, score_thr;
+};
+
+__device__ __forceinline__ int32_t tmz_at(const double2* __restrict__ peaks, int64_t i, double precision) {
+    return qms_tmz(__ldg(&peaks[i].x), precision);
+}
+
+// first index in [a,b) whose bucket is >= t
+__device__ __forceinline__ int64_t lower_bound_t(const double2* __restrict__ peaks, int64_t a, int64_t b, int32_t t, double precision) {
+    while (a < b) {
+        const int64_t mid = a + ((b - a) >> 1);
+        if (tmz_at(peaks, mid, precision) < t)
+            a = mid + 1;
+        else
+            b = mid;
+    }
+    return a;
+}
+
+// bisect.bisect_right of the tuple (mz, inten) in a list of (mz, intensity) tuples (IL:2511-2516)
+__device__ __forceinline__ int64_t bisect_right_tuple(const double2* __restrict__ peaks, int64_t a, int64_t b, double mz, double inten) {
+    while (a < b) {
+        const int64_t mid = a + ((b - a) >> 1);
+        const double2 v = __ldg(&peaks[mid]);
+        const bool greater = v.x > mz || (v.x == mz && v.y > inten);  // element > key
+        if (greater)
+            b = mid;
+        else
+            a = mid + 1;
+    }
+    return a;
+}
+
+// Peak rows an index entry may see in this spectrum.  numpy input: the +-2 Da slices of
+// IL:2525-2530 never cut a window of the bin's own entries (checked in qms_set_params), so the
+// whole spectrum.  list input: +-2 ELEMENTS around the global range, then around the entry's
+// match bin (IL:1831-1839, 2511-2523, 2570) -- SURVEY.md Q12.
+__device__ __forceinline__ void entry_clamp(const MatchView& v, int64_t b, int64_t e, int32_t entry, int64_t& ca, int64_t& cb) {
+    ca = b;
+    cb = e;
+    if (v.input_kind == 0) return;
+    int64_t ga = bisect_right_tuple(v.peaks, b, e, v.mz_min, 0.0) - 2;
+    int64_t gb = bisect_right_tuple(v.peaks, b, e, v.mz_max, 0.0) + 2;
+    if (ga < b) ga = b;
+    if (gb > e) gb = e;
+    if (gb < ga) gb = ga;
+    const int64_t bin = entry / v.per_bin;
+    const double bin_lo = __ldg(&v.ent_lower[bin * v.per_bin]);
+    const double bin_hi = __ldg(&v.bin_upper[bin]);
+    int64_t la = bisect_right_tuple(v.peaks, ga, gb, bin_lo, 0.001) - 2;
+    int64_t lb = bisect_right_tuple(v.peaks, ga, gb, bin_hi, 0.001) + 2;
+    ca = la < ga ? ga : la;
+    cb = lb > gb ? gb : lb;
+    if (cb < ca) cb = ca;
+}
+
+__device__ __forceinline__ int64_t spectrum_of(const int64_t* __restrict__ offsets, int64_t n_spectra, int64_t i) {
+    int64_t a = 0, b = n_spectra;  // last s with offsets[s] <= i
+    while (b - a > 1) {
+        const int64_t mid = a + ((b - a) >> 1);
+        if (__ldg(&offsets[mid]) <= i)
+            a = mid;
+        else
+            b = mid;
+    }
+    return a;
+}
+
+// Gate one (bucket t at peak row i, window k of entry x) incidence.  Returns true if this is the
+// pair's canonical incidence and the pair passes both overlap gates.
+__device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64_t i, int32_t t, int32_t x, int32_t k) {
+    int64_t ca, cb;
+    entry_clamp(v, sb, se, x, ca, cb);
+    if (i < ca || i >= cb) return false;
+    if (i > ca && tmz_at(v.peaks, i - 1, v.precision) == t) return false;  // not the first row of its bucket (IL:2014)
+    const int64_t w0 = __ldg(&v.ent_win_off[x]);
+    const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
+    int cnt = 0;
+    int32_t covered_to = INT32_MIN;  // union of the windows seen so far ends here (Q10: distinct buckets)
+    for (int m = 0; m < nc; ++m) {
+        const int32_t lo = __ldg(&v.win_lo[w0 + m]);
+        const int32_t hi = __ldg(&v.win_hi[w0 + m]);
+        const int32_t ulo = lo > covered_to ? lo : (covered_to == INT32_MAX ? covered_to : covered_to + 1);
+        if (ulo <= hi) {
+            int64_t j = lower_bound_t(v.peaks, ca, cb, ulo, v.precision);
+            while (j < cb) {
+                const int32_t tj = tmz_at(v.peaks, j, v.precision);
+                if (tj > hi) break;
+                if (cnt == 0 && !(m == k && j == i)) return false;  // an earlier incidence owns this pair
+                ++cnt;
+                do {
+                    ++j;
+                } while (j < cb && tmz_at(v.peaks, j, v.precision) == tj);
+            }
+        }
+        if (cnt == 0 && m >= k) return false;  // cannot happen for a true incidence; defensive
+        if (hi > covered_to) covered_to = hi;
+    }
+    if (cnt < v.min_match) return false;                              // IL:1973
+    if ((double)cnt / (double)nc < v.req_overlap) return false;      // IL:1975
+    return true;
+}
+
+#define PROBE_THREADS 256
+#define PROBE_UNROLL 4
+
+__global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_gate_kernel(MatchView v, int64_t p_begin, int64_t p_end,
+                                                                             unsigned long long* __restrict__ pair_keys,
+                                                                             unsigned long long pair_cap,
+                                                                             unsigned long long* __restrict__ counters) {
+    unsigned long long n_live = 0, n_inc = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)PROBE_THREADS * PROBE_UNROLL;
+    for (int64_t base = p_begin + (int64_t)blockIdx.x * tile; base < p_end; base += (int64_t)gridDim.x * tile) {
+        double2 row[PROBE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PROBE_UNROLL; ++u) {
+            const int64_t i = base + (int64_t)u * PROBE_THREADS + threadIdx.x;
+            row[u] = i < p_end ? __ldg(&v.peaks[i]) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < PROBE_UNROLL; ++u) {
+            const int64_t i = base + (int64_t)u * PROBE_THREADS + threadIdx.x;
+            const bool valid = i < p_end;
+            // m/z of the previous row: neighbour lane, lane 0 reloads (sortedness + bucket dedupe)
+            double prev = __shfl_up_sync(0xffffffffu, row[u].x, 1);
+            if (lane == 0 && valid && i > p_begin) prev = __ldg(&v.peaks[i - 1].x);
+            if (!valid) continue;
+            const double mz = row[u].x;
+            const int32_t t = qms_tmz(mz, v.precision);
+            const bool descends = i > p_begin && t < qms_tmz(prev, v.precision);
+            bool live = false;
+            if (t >= v.t_min && t <= v.t_max) {
+                const uint32_t c = (uint32_t)(t - v.t_min);
+                if ((__ldg(&v.cover2[c >> 10]) >> ((c >> 5) & 31)) & 1u) live = (__ldg(&v.cover[c >> 5]) >> (c & 31)) & 1u;
+            }
+            if (!live && !descends) continue;
+            const int64_t s = spectrum_of(v.offsets, v.n_spectra, i);
+            const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
+            if (descends && i > sb) atomicAdd(&counters[C_UNSORTED], 1ull);  // m/z buckets not ascending inside a spectrum
+            if (!live) continue;
+            ++n_live;
+            // numpy input: only the first row of a bucket is ever used (Q9); list input decides per bin
+            if (v.input_kind == 0 && i > sb && qms_tmz(prev, v.precision) == t) continue;
+            int32_t c_lo = t - v.max_width + 1;
+            if (c_lo < v.t_min) c_lo = v.t_min;
+            const int32_t j0 = __ldg(&v.cell_start[c_lo - v.t_min]);
+            const int32_t j1 = __ldg(&v.cell_start[t + 1 - v.t_min]);
+            for (int32_t j = j0; j < j1; ++j) {
+                const int4 raw = __ldg(reinterpret_cast<const int4*>(&v.probe[j]));  // lo, hi, entry, k
+                if (raw.y < t) continue;
+                if (v.only_entry >= 0 && raw.z != v.only_entry) continue;
+                ++n_inc;
+                if (gate_incidence(v, sb, se, i, t, raw.z, raw.w)) {
+                    const unsigned long long slot = atomicAdd(&counters[C_PAIRS], 1ull);
+                    if (slot < pair_cap) pair_keys[slot] = ((unsigned long long)s << 32) | (unsigned long long)(uint32_t)raw.z;
+                }
+            }
+        }
+    }
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        n_live += __shfl_xor_sync(0xffffffffu, n_live, sft);
+        n_inc += __shfl_xor_sync(0xffffffffu, n_inc, sft);
+    }
+    if (lane == 0) {
+        if (n_live) atomicAdd(&counters[C_LIVE], n_live);
+        if (n_inc) atomicAdd(&counters[C_INCID], n_inc);
+    }
+}
+
+// ---- scoring (IL:2441-2498), sequential FP64, no FMA ------------------------------------------------
+struct ScoreAcc {
+    double measured, calculated, ri_sum;
+};
+
+template <class Rows>  // Rows: n(), matched(m), mmz(m), mi(m), ri(m), cmz(m), ci(m)
+__device__ void score_rows(const Rows& r, double min_rel, double rel_mz, double rel_i, double xi, double& score, double& scaling) {
+    double measured = 0.0, calculated = 0.0, ri_sum = 0.0;
+    const int n = r.n();
+    for (int m = 0; m < n; ++m) {
+        const double ri = r.ri(m);
+        if (ri < min_rel) continue;
+        if (r.matched(m)) {
+            calculated = __dadd_rn(calculated, __dmul_rn(r.ci(m), ri));
+            measured = __dadd_rn(measured, __dmul_rn(r.mi(m), ri));
+        }
+        ri_sum = __dadd_rn(ri_sum, ri);
+    }
+    scaling = __ddiv_rn(measured, calculated);
+    double mz_score = 0.0, i_score = 0.0;
+    for (int m = 0; m < n; ++m) {
+        const double ri = r.ri(m);
+        if (ri < min_rel || !r.matched(m)) continue;
+        const double si = __dmul_rn(r.ci(m), scaling);
+        const double cmz = r.cmz(m);
+        if (cmz > QMS_DBL_EPS) {
+            const double err = __ddiv_rn(fabs(__dsub_rn(r.mmz(m), cmz)), cmz);
+            const double local = err > rel_mz ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, rel_mz));
+            mz_score = __dadd_rn(mz_score, __dmul_rn(local, ri));
+        }
+        if (si > QMS_DBL_EPS) {
+            const double err = __ddiv_rn(fabs(__dsub_rn(r.mi(m), si)), si);
+            const double span = __dsub_rn(__dadd_rn(1.0, rel_i), ri);
+            const double local = err > span ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, span));
+            i_score = __dadd_rn(i_score, __dmul_rn(local, ri));
+        }
+    }
+    mz_score = __ddiv_rn(mz_score, ri_sum);
+    i_score = __ddiv_rn(i_score, ri_sum);
+    score = __dadd_rn(__dmul_rn(mz_score, xi), __dmul_rn(i_score, __dsub_rn(1.0, xi)));
+}
+
+struct PairRows {  // rows of one (spectrum, entry) pair under the current candidate choice
+    const MatchView* v;
+    int64_t w0;
+    int nc;
+    const int64_t* cur;  // absolute peak row per window, -1 = None
+    __device__ int n() const { return nc; }
+    __device__ bool matched(int m) const { return cur[m] >= 0; }
+    __device__ double mmz(int m) const { return __ldg(&v->peaks[cur[m]].x); }
+    __device__ double mi(int m) const { return __ldg(&v->peaks[cur[m]].y); }
+    __device__ double ri(int m) const { return __ldg(&v->win_ri[w0 + m]); }
+    __device__ double cmz(int m) const { return __ldg(&v->win_cmz[w0 + m]); }
+    __device__ double ci(int m) const { return (double)__ldg(&v->win_ci[w0 + m]); }
+};
+
+__global__ void pair_windows_kernel(int64_t n_pairs, const unsigned long long* __restrict__ keys,
+                                    const int64_t* __restrict__ ent_win_off, int64_t* __restrict__ pair_nc) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int32_t x = (int32_t)(keys[p] & 0xffffffffull);
+    pair_nc[p] = ent_win_off[x + 1] - ent_win_off[x];
+}
+
+// next first-of-bucket row after row j (bucket tj) that still lies inside [.., hi]; -1 if none
+__device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, int64_t cb, int32_t hi) {
+    const int32_t tj = tmz_at(v.peaks, j, v.precision);
+    do {
+        ++j;
+    } while (j < cb && tmz_at(v.peaks, j, v.precision) == tj);
+    if (j >= cb || tmz_at(v.peaks, j, v.precision) > hi) return -1;
+    return j;
+}
+
+__global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys,
+                                                             const int64_t* __restrict__ pair_win_off, int64_t* __restrict__ scr_first,
+                                                             int64_t* __restrict__ scr_cur, int64_t* __restrict__ pair_best,
+                                                             double* __restrict__ pair_score, double* __restrict__ pair_scaling,
+                                                             int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const int64_t s = (int64_t)(keys[p] >> 32);
+    const int32_t x = (int32_t)(keys[p] & 0xffffffffull);
+    const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
+    int64_t ca, cb;
+    entry_clamp(v, sb, se, x, ca, cb);
+    const int64_t w0 = __ldg(&v.ent_win_off[x]);
+    const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
+    int64_t* first = scr_first + pair_win_off[p];
+    int64_t* cur = scr_cur + pair_win_off[p];
+    int64_t* best = pair_best + pair_win_off[p];
+    int n_matched = 0;
+    for (int m = 0; m < nc; ++m) {  // candidates of window m = distinct buckets in [lo, hi] (IL:2001-2002)
+        const int32_t lo = __ldg(&v.win_lo[w0 + m]);
+        const int32_t hi = __ldg(&v.win_hi[w0 + m]);
+        int64_t j = lower_bound_t(v.peaks, ca, cb, lo, v.precision);
+        if (j >= cb || tmz_at(v.peaks, j, v.precision) > hi) j = -1;
+        first[m] = cur[m] = best[m] = j;
+        n_matched += j >= 0;
+    }
+    PairRows rows{&v, w0, nc, cur};
+    double best_score = 0.0, best_scaling = 0.0;
+    bool have = false;
+    unsigned long long combos = 0;
+    while (n_matched > 0) {
+        double score, scaling;
+        score_rows(rows, v.min_rel, v.rel_mz, v.rel_i, v.xi, score, scaling);
+        ++combos;
+        // max under Python tuple order (score, scaling_factor, peaks) -- IL:2022-2034
+        bool better = !have;
+        if (have) {
+            if (score > best_score)
+                better = true;
+            else if (score == best_score) {
+                if (scaling > best_scaling)
+                    better = true;
+                else if (scaling == best_scaling) {
+                    for (int m = 0; m < nc; ++m) {
+                        if (cur[m] < 0 || cur[m] == best[m]) continue;
+                        const double2 a = __ldg(&v.peaks[cur[m]]), b = __ldg(&v.peaks[best[m]]);
+                        if (a.x != b.x) {
+                            better = a.x > b.x;
+                            break;
+                        }
+                        if (a.y != b.y) {
+                            better = a.y > b.y;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        if (better) {
+            have = true;
+            best_score = score;
+            best_scaling = scaling;
+            for (int m = 0; m < nc; ++m) best[m] = cur[m];
+        }
+        int m = nc - 1;  // odometer over the candidate lists, last window fastest
+        while (m >= 0) {
+            if (cur[m] >= 0) {
+                const int64_t nx = next_bucket(v, cur[m], cb, __ldg(&v.win_hi[w0 + m]));
+                if (nx >= 0) {
+                    cur[m] = nx;
+                    break;
+                }
+                cur[m] = first[m];
+            }
+            --m;
+        }
+        if (m < 0) break;
+    }
+    bool pass = have;
+    if (v.only_entry < 0) {
+        if (best_score < v.score_thr) pass = false;          // IL:1860
+        if (n_matched < v.min_match) pass = false;           // IL:1862-1870
+    }
+    pair_score[p] = best_score;
+    pair_scaling[p] = best_scaling;
+    pair_flag[p] = pass ? 1 : 0;
+    atomicAdd(&counters[C_COMBOS], combos);
+}
+
+// ---- K7: order-preserving warp-ballot compaction -----------------------------------------------------
+#define CMP_THREADS 256
+
+__global__ void __launch_bounds__(CMP_THREADS) compact_count_kernel(int64_t n_pairs, const int32_t* __restrict__ pair_flag,
+                                                                    const int64_t* __restrict__ pair_win_off,
+                                                                    int64_t* __restrict__ blk_hits, int64_t* __restrict__ blk_wins) {
+    __shared__ int64_t s_h[CMP_THREADS / 32], s_w[CMP_THREADS / 32];
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool flag = p < n_pairs && pair_flag[p];
+    int64_t wins = flag ? pair_win_off[p + 1] - pair_win_off[p] : 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, flag);
+    for (int s = 16; s > 0; s >>= 1) wins += __shfl_xor_sync(0xffffffffu, wins, s);
+    if ((threadIdx.x & 31) == 0) {
+        s_h[threadIdx.x >> 5] = __popc(mask);
+        s_w[threadIdx.x >> 5] = wins;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t h = 0, w = 0;
+        for (int i = 0; i < CMP_THREADS / 32; ++i) {
+            h += s_h[i];
+            w += s_w[i];
+        }
+        blk_hits[blockIdx.x] = h;
+        blk_wins[blockIdx.x] = w;
+    }
+}
+
+// single warp: exclusive scan of the per-block totals; totals to out[0], out[1]
+__global__ void compact_scan_kernel(int64_t n_blocks, int64_t* __restrict__ blk_hits, int64_t* __restrict__ blk_wins,
+                                    unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x;
+    const int64_t chunk = (n_blocks + 31) / 32;
+    const int64_t a = lane * chunk, b = a + chunk < n_blocks ? a + chunk : n_blocks;
+    int64_t h = 0, w = 0;
+    for (int64_t i = a; i < b; ++i) {
+        h += blk_hits[i];
+        w += blk_wins[i];
+    }
+    int64_t hp = h, wp = w;  // inclusive prefix over lanes
+    for (int s = 1; s < 32; s <<= 1) {
+        const int64_t oh = __shfl_up_sync(0xffffffffu, hp, s), ow = __shfl_up_sync(0xffffffffu, wp, s);
+        if (lane >= s) {
+            hp += oh;
+            wp += ow;
+        }
+    }
+    int64_t hb = hp - h, wb = wp - w;
+    for (int64_t i = a; i < b; ++i) {
+        const int64_t th = blk_hits[i], tw = blk_wins[i];
+        blk_hits[i] = hb;
+        blk_wins[i] = wb;
+        hb += th;
+        wb += tw;
+    }
+    if (lane == 31) {
+        out[0] = (unsigned long long)hp;
+        out[1] = (unsigned long long)wp;
+    }
+}
+
+__global__ void __launch_bounds__(CMP_THREADS) compact_emit_kernel(
+    MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys, const int32_t* __restrict__ pair_flag,
+    const int64_t* __restrict__ pair_win_off, const int64_t* __restrict__ pair_best, const double* __restrict__ pair_score,
+    const double* __restrict__ pair_scaling, const int64_t* __restrict__ blk_hits, const int64_t* __restrict__ blk_wins,
+    int32_t* __restrict__ o_spec, int32_t* __restrict__ o_entry, double* __restrict__ o_score, double* __restrict__ o_scaling,
+    int64_t* __restrict__ o_win_off, double* __restrict__ o_mmz, double* __restrict__ o_mi, int64_t* __restrict__ o_peak,
+    int64_t peak_base) {
+    __shared__ int64_t s_h[CMP_THREADS / 32], s_w[CMP_THREADS / 32];
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool flag = p < n_pairs && pair_flag[p];
+    const int64_t nc = flag ? pair_win_off[p + 1] - pair_win_off[p] : 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, flag);
+    int64_t wpre = nc;  // inclusive prefix of windows inside the warp
+    for (int s = 1; s < 32; s <<= 1) {
+        const int64_t o = __shfl_up_sync(0xffffffffu, wpre, s);
+        if (lane >= s) wpre += o;
+    }
+    if (lane == 31) {
+        s_h[warp] = __popc(mask);
+        s_w[warp] = wpre;
+    }
+    __syncthreads();
+    int64_t hbase = blk_hits[blockIdx.x], wbase = blk_wins[blockIdx.x];
+    for (int i = 0; i < warp; ++i) {
+        hbase += s_h[i];
+        wbase += s_w[i];
+    }
+    if (!flag) return;
+    const int64_t h = hbase + __popc(mask & ((1u << lane) - 1u));
+    const int64_t w = wbase + wpre - nc;
+    o_spec[h] = (int32_t)(keys[p] >> 32);
+    o_entry[h] = (int32_t)(keys[p] & 0xffffffffull);
+    o_score[h] = pair_score[p];
+    o_scaling[h] = pair_scaling[p];
+    o_win_off[h] = w;
+    const int64_t* best = pair_best + pair_win_off[p];
+    for (int64_t m = 0; m < nc; ++m) {
+        const int64_t row = best[m];
+        o_peak[w + m] = row < 0 ? -1 : row - peak_base;
+        o_mmz[w + m] = row < 0 ? __longlong_as_double(0x7ff8000000000000ll) : __ldg(&v.peaks[row].x);
+        o_mi[w + m] = row < 0 ? __longlong_as_double(0x7ff8000000000000ll) : __ldg(&v.peaks[row].y);
+    }
+}
+
+// host-or-device output copy
+template <class T>
+static int copy_out(qms_ctx* ctx, T* dst, const T* src, size_t n) {
+    if (!dst || !n) return QMS_OK;
+    const cudaMemcpyKind kind = qms_is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    QMS_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(T), kind, ctx->stream));
+    return QMS_OK;
+}
+
+static float elapsed(qms_ctx* ctx, int a, int b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
+    return ms;
+}
+
+static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra, int32_t input_kind,
+                      double mz_score_percentile, int32_t only_entry, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
+    if (!ctx || !offsets || n_spectra < 0 || !n_hits || !n_hit_windows)
+        return qms_fail(ctx, QMS_E_ARG, "qms_match_batch: bad arguments");
+    if (!ctx->have_index) return qms_fail(ctx, QMS_E_ARG, "library index not built (qms_finalize_index)");
+    if (input_kind != 0 && input_kind != 1) return qms_fail(ctx, QMS_E_ARG, "input_kind must be 0 (numpy) or 1 (list)");
+    if (n_spectra >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 spectra per batch");
+    QMS_CUDA(ctx, cudaSetDevice(ctx->device));
+    *n_hits = 0;
+    *n_hit_windows = 0;
+    const qms_params& P = ctx->prm;
+    // ---- inputs -> device ----
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    const bool off_dev = qms_is_device_ptr(offsets);
+    int64_t p_begin = 0, p_end = 0;
+    const int64_t* d_off = offsets;
+    if (off_dev) {
+        int64_t ends[2] = {0, 0};
+        QMS_CUDA(ctx, cudaMemcpyAsync(&ends[0], offsets, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        QMS_CUDA(ctx, cudaMemcpyAsync(&ends[1], offsets + n_spectra, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        p_begin = ends[0];
+        p_end = ends[1];
+    } else {
+        p_begin = offsets[0];
+        p_end = offsets[n_spectra];
+        QMS_TRY(qms_upload(ctx, ctx->d_offsets, offsets, (size_t)n_spectra + 1));
+        d_off = ctx->d_offsets.p;
+    }
+    if (p_begin < 0 || p_end < p_begin) return qms_fail(ctx, QMS_E_ARG, "offsets must be non-decreasing and non-negative");
+    const int64_t n_peaks = p_end - p_begin;
+    if (n_peaks > 0 && !peaks) return qms_fail(ctx, QMS_E_ARG, "peaks is NULL");
+    const double2* d_peaks = reinterpret_cast<const double2*>(peaks);
+    // the device copy mirrors the caller's row numbering, so reported peak rows need no rebasing
+    if (n_peaks > 0 && !qms_is_device_ptr(peaks)) {
+        QMS_TRY(qms_reserve(ctx, ctx->d_peaks, (size_t)p_end * 2));
+        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->d_peaks.p + 2 * p_begin, peaks + 2 * p_begin, (size_t)n_peaks * 2 * sizeof(double),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        d_peaks = reinterpret_cast<const double2*>(ctx->d_peaks.p);
+    }
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->cnt.spectra += n_spectra;
+    ctx->cnt.peaks += n_peaks;
+    if (n_peaks == 0 || n_spectra == 0 || ctx->n_windows == 0) {
+        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->cnt.ms_h2d += elapsed(ctx, 0, 1);
+        if (out && out->hit_win_off && out->cap_hits >= 0) {
+            const int64_t zero = 0;
+            if (qms_is_device_ptr(out->hit_win_off))
+                cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t), cudaMemcpyHostToDevice);
+            else
+                out->hit_win_off[0] = 0;
+        }
+        return QMS_OK;
+    }
+    const int64_t span = (int64_t)ctx->t_max - ctx->t_min + 1;
+    const int64_t cover_words = (span + 31) / 32;
+    static_assert(sizeof(ProbeRec) == 16, "ProbeRec must be 16 bytes");
+    MatchView v;
+    v.peaks = d_peaks;
+    v.offsets = d_off;
+    v.n_spectra = n_spectra;
+    v.probe = ctx->probe.p;
+    v.cell_start = ctx->cell_start.p;
+    v.cover = ctx->cover.p;
+    v.cover2 = ctx->cover.p + cover_words + 1;  // coarse bitmap sits behind the fine one (qms_finalize_index)
+    v.t_min = ctx->t_min;
+    v.t_max = ctx->t_max;
+    v.max_width = ctx->max_width;
+    v.ent_win_off = ctx->ent_win_off.p;
+    v.win_lo = ctx->win_lo.p;
+    v.win_hi = ctx->win_hi.p;
+    v.win_cmz = ctx->win_cmz.p;
+    v.win_ri = ctx->win_ri.p;
+    v.win_ci = ctx->win_ci.p;
+    v.ent_lower = ctx->ent_lower.p;
+    v.bin_upper = ctx->bin_upper.p;
+    v.per_bin = P.max_molecules_per_bin;
+    v.input_kind = input_kind;
+    v.only_entry = only_entry;
+    v.precision = P.internal_precision;
+    v.mz_min = ctx->mz_min;
+    v.mz_max = ctx->mz_max;
+    v.min_match = P.min_matched_isotopologues;
+    v.req_overlap = P.required_peak_overlap;
+    v.min_rel = P.min_rel_peak_intensity;
+    v.rel_mz = P.rel_mz_range;
+    v.rel_i = P.rel_i_range;
+    v.xi = mz_score_percentile;
+    v.score_thr = P.m_score_threshold;
+
+    // ---- K5 ----
+    QMS_TRY(qms_reserve(ctx, ctx->dev_counters, 64));
+    size_t pair_cap = ctx->pair_keys.cap;
+    if (pair_cap < 65536) {
+        QMS_TRY(qms_reserve(ctx, ctx->pair_keys, 65536));
+        pair_cap = ctx->pair_keys.cap;
+    }
+    const int64_t tile = (int64_t)PROBE_THREADS * PROBE_UNROLL;
+    int64_t blocks = (n_peaks + tile - 1) / tile;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    unsigned long long n_pairs = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        QMS_CUDA(ctx, cudaMemsetAsync(ctx->dev_counters.p, 0, 64 * sizeof(unsigned long long), ctx->stream));
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+        spectrum_probe_gate_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, ctx->pair_keys.p,
+                                                                                       (unsigned long long)pair_cap, ctx->dev_counters.p);
+        QMS_CUDA(ctx, cudaGetLastError());
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+        ctx->cnt.kernel_launches++;
+        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->cnt.ms_probe += elapsed(ctx, 2, 3);
+        if (ctx->h_pinned[C_UNSORTED])
+            return qms_fail(ctx, QMS_E_INPUT, "m/z values are not ascending inside %llu spectrum position(s)",
+                            (unsigned long long)ctx->h_pinned[C_UNSORTED]);
+        n_pairs = ctx->h_pinned[C_PAIRS];
+        if (n_pairs <= pair_cap) break;
+        if (attempt == 1) return qms_fail(ctx, QMS_E_LIMIT, "pair list overflow after regrow");
+        QMS_TRY(qms_reserve(ctx, ctx->pair_keys, (size_t)n_pairs + 1024));
+        pair_cap = ctx->pair_keys.cap;
+    }
+    ctx->cnt.ms_h2d += elapsed(ctx, 0, 1);
+    ctx->cnt.live_peaks += (int64_t)ctx->h_pinned[C_LIVE];
+    ctx->cnt.incidences += (int64_t)ctx->h_pinned[C_INCID];
+    ctx->cnt.candidates += (int64_t)n_pairs;
+    if (n_pairs == 0) {
+        if (out && out->hit_win_off) {
+            const int64_t zero = 0;
+            QMS_CUDA(ctx, cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t),
+                                     qms_is_device_ptr(out->hit_win_off) ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+        }
+        return QMS_OK;
+    }
+    // ---- sort pairs by (spectrum, entry) ----
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_keys_alt, (size_t)n_pairs + 1));
+    {
+        size_t bytes = 0;
+        QMS_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, (int64_t)n_pairs, 0, 64,
+                                                     ctx->stream));
+        QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
+        QMS_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, (int64_t)n_pairs, 0,
+                                                     64, ctx->stream));
+        ctx->cnt.kernel_launches += 3;
+    }
+    const unsigned long long* keys = ctx->pair_keys_alt.p;
+    // ---- per-pair window offsets ----
+    TmpBuf<int64_t> pair_nc(ctx);
+    QMS_TRY(qms_reserve(ctx, pair_nc.b, (size_t)n_pairs + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_win_off, (size_t)n_pairs + 1));
+    QMS_CUDA(ctx, cudaMemsetAsync(pair_nc.b.p, 0, ((size_t)n_pairs + 1) * sizeof(int64_t), ctx->stream));
+    pair_windows_kernel<<<qms_blocks((int64_t)n_pairs, 256), 256, 0, ctx->stream>>>((int64_t)n_pairs, keys, ctx->ent_win_off.p,
+                                                                                   pair_nc.b.p);
+    {
+        size_t bytes = 0;
+        QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, bytes, pair_nc.b.p, ctx->pair_win_off.p, (int64_t)n_pairs + 1, ctx->stream));
+        QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
+        QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, bytes, pair_nc.b.p, ctx->pair_win_off.p, (int64_t)n_pairs + 1,
+                                                    ctx->stream));
+        ctx->cnt.kernel_launches += 3;
+    }
+    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 32, ctx->pair_win_off.p + n_pairs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t pair_windows = (int64_t)ctx->h_pinned[32];
+    ctx->cnt.candidate_windows += pair_windows;
+    ctx->cnt.ms_compact += elapsed(ctx, 2, 3);
+    // ---- K6 ----
+    TmpBuf<int64_t> scr_first(ctx), scr_cur(ctx);
+    QMS_TRY(qms_reserve(ctx, scr_first.b, (size_t)pair_windows + 1));
+    QMS_TRY(qms_reserve(ctx, scr_cur.b, (size_t)pair_windows + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_best, (size_t)pair_windows + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_score, (size_t)n_pairs));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)n_pairs));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)n_pairs));
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    assemble_score_kernel<<<qms_blocks((int64_t)n_pairs, 128), 128, 0, ctx->stream>>>(
+        v, (int64_t)n_pairs, keys, ctx->pair_win_off.p, scr_first.b.p, scr_cur.b.p, ctx->pair_best.p, ctx->pair_score.p,
+        ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
+    QMS_CUDA(ctx, cudaGetLastError());
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->cnt.kernel_launches++;
+    // ---- K7 ----
+    const int64_t cblocks = qms_blocks((int64_t)n_pairs, CMP_THREADS);
+    QMS_TRY(qms_reserve(ctx, ctx->blk_hits, (size_t)cblocks + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->blk_wins, (size_t)cblocks + 1));
+    compact_count_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>((int64_t)n_pairs, ctx->pair_flag.p, ctx->pair_win_off.p,
+                                                                            ctx->blk_hits.p, ctx->blk_wins.p);
+    compact_scan_kernel<<<1, 32, 0, ctx->stream>>>(cblocks, ctx->blk_hits.p, ctx->blk_wins.p, ctx->dev_counters.p + 40);
+    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 40, ctx->dev_counters.p + 40, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + C_COMBOS, ctx->dev_counters.p + C_COMBOS, sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->cnt.kernel_launches += 2;
+    ctx->cnt.ms_score += elapsed(ctx, 2, 3);
+    ctx->cnt.combinations += (int64_t)ctx->h_pinned[C_COMBOS];
+    const int64_t nh = (int64_t)ctx->h_pinned[40], nw = (int64_t)ctx->h_pinned[41];
+    *n_hits = nh;
+    *n_hit_windows = nw;
+    if (out && (nh > out->cap_hits || nw > out->cap_windows))
+        return qms_fail(ctx, QMS_E_CAPACITY, "hit buffers too small: need %lld hits / %lld windows, have %lld / %lld", (long long)nh,
+                        (long long)nw, (long long)out->cap_hits, (long long)out->cap_windows);
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    QMS_TRY(qms_reserve(ctx, ctx->o_spec, (size_t)nh + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->o_entry, (size_t)nh + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->o_score, (size_t)nh + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->o_scaling, (size_t)nh + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->o_win_off, (size_t)nh + 2));
+    QMS_TRY(qms_reserve(ctx, ctx->o_mmz, (size_t)nw + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->o_mi, (size_t)nw + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->o_peak, (size_t)nw + 1));
+    compact_emit_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(
+        v, (int64_t)n_pairs, keys, ctx->pair_flag.p, ctx->pair_win_off.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p,
+        ctx->blk_hits.p, ctx->blk_wins.p, ctx->o_spec.p, ctx->o_entry.p, ctx->o_score.p, ctx->o_scaling.p, ctx->o_win_off.p,
+        ctx->o_mmz.p, ctx->o_mi.p, ctx->o_peak.p, 0);
+    QMS_CUDA(ctx, cudaGetLastError());
+    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->o_win_off.p + nh, &ctx->h_pinned[41], sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->cnt.kernel_launches++;
+    if (out) {
+        QMS_TRY(copy_out(ctx, out->hit_spec, ctx->o_spec.p, (size_t)nh));
+        QMS_TRY(copy_out(ctx, out->hit_entry, ctx->o_entry.p, (size_t)nh));
+        QMS_TRY(copy_out(ctx, out->hit_score, ctx->o_score.p, (size_t)nh));
+        QMS_TRY(copy_out(ctx, out->hit_scaling, ctx->o_scaling.p, (size_t)nh));
+        QMS_TRY(copy_out(ctx, out->hit_win_off, ctx->o_win_off.p, (size_t)nh + 1));
+        QMS_TRY(copy_out(ctx, out->hit_mmz, ctx->o_mmz.p, (size_t)nw));
+        QMS_TRY(copy_out(ctx, out->hit_mi, ctx->o_mi.p, (size_t)nw));
+        QMS_TRY(copy_out(ctx, out->hit_peak, ctx->o_peak.p, (size_t)nw));
+    }
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->cnt.ms_compact += elapsed(ctx, 2, 3);
+    ctx->cnt.ms_d2h += elapsed(ctx, 3, 4);
+    ctx->cnt.hits += nh;
+    ctx->cnt.hit_windows += nw;
+    return QMS_OK;
+}
+
+extern "C" int qms_match_batch(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra,
+                               int32_t input_kind, double mz_score_percentile, qms_hits* out, int64_t* n_hits,
+                               int64_t* n_hit_windows) {
+    return match_impl(ctx, peaks, offsets, n_spectra, input_kind, mz_score_percentile, -1, out, n_hits, n_hit_windows);
+}
+
+extern "C" int qms_match_entry(qms_ctx* ctx, const double* peaks, int64_t n_peaks, int32_t input_kind, int32_t entry,
+                               double mz_score_percentile, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
+    if (!ctx || !ctx->have_index) return qms_fail(ctx, QMS_E_ARG, "library index not built (qms_finalize_index)");
+    if (entry < 0 || entry >= ctx->n_entries) return qms_fail(ctx, QMS_E_ARG, "entry %d outside [0,%lld)", entry, (long long)ctx->n_entries);
+    const int64_t offsets[2] = {0, n_peaks};
+    return match_impl(ctx, peaks, offsets, 1, input_kind, mz_score_percentile, entry, out, n_hits, n_hit_windows);
+}
+
+// ---- score_matches for caller-supplied rows (unit parity with tests/score_matches_tests.py) -------------
+struct PlainRows {
+    int n_;
+    const double *mmz_, *mi_, *ri_, *cmz_, *ci_;
+    __device__ int n() const { return n_; }
+    __device__ bool matched(int m) const { return mmz_[m] == mmz_[m]; }  // NaN = None
+    __device__ double mmz(int m) const { return mmz_[m]; }
+    __device__ double mi(int m) const { return mi_[m]; }
+    __device__ double ri(int m) const { return ri_[m]; }
+    __device__ double cmz(int m) const { return cmz_[m]; }
+    __device__ double ci(int m) const { return ci_[m]; }
+};
+
+__global__ void score_rows_kernel(PlainRows rows, double min_rel, double rel_mz, double rel_i, double xi, double* out) {
+    double score, scaling;
+    score_rows(rows, min_rel, rel_mz, rel_i, xi, score, scaling);
+    out[0] = score;
+    out[1] = scaling;
+}
+
+extern "C" int qms_score_matches(qms_ctx* ctx, int32_t n, const double* mmz, const double* mi, const double* ri, const double* cmz,
+                                 const double* ci, double mz_score_percentile, double* score, double* scaling) {
+    if (!ctx || n < 0 || !score || !scaling) return qms_fail(ctx, QMS_E_ARG, "qms_score_matches: bad arguments");
+    if (!ctx->have_params) return qms_fail(ctx, QMS_E_ARG, "qms_set_params must be called first");
+    QMS_CUDA(ctx, cudaSetDevice(ctx->device));
+    TmpBuf<double> buf(ctx);
+    QMS_TRY(qms_reserve(ctx, buf.b, (size_t)5 * n + 2));
+    const double* src[5] = {mmz, mi, ri, cmz, ci};
+    for (int a = 0; a < 5; ++a)
+        if (n) QMS_CUDA(ctx, cudaMemcpyAsync(buf.b.p + (size_t)a * n, src[a], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PlainRows rows{n, buf.b.p, buf.b.p + n, buf.b.p + 2 * n, buf.b.p + 3 * n, buf.b.p + 4 * n};
+    score_rows_kernel<<<1, 1, 0, ctx->stream>>>(rows, ctx->prm.min_rel_peak_intensity, ctx->prm.rel_mz_range, ctx->prm.rel_i_range,
+                                               mz_score_percentile, buf.b.p + 5 * n);
+    QMS_CUDA(ctx, cudaGetLastError());
+    ctx->cnt.kernel_launches++;
+    double res[2];
+    QMS_CUDA(ctx, cudaMemcpyAsync(res, buf.b.p + 5 * n, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *score = res[0];
+    *scaling = res[1];
+    return QMS_OK;
+}

@@ -1,0 +1,173 @@
+// Internal declarations shared by the translation units of libqms_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/qms_b200.h"
+
+#define QMS_WARP 32
+
+// ---- error plumbing -------------------------------------------------------------------------
+int qms_fail(qms_ctx* ctx, int code, const char* fmt, ...);
+
+#define QMS_CUDA(ctx, call)                                                                       \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return qms_fail((ctx), QMS_E_CUDA, "%s failed: %s (%s:%d)", #call,                    \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+    } while (0)
+
+#define QMS_TRY(expr)                                                                             \
+    do {                                                                                          \
+        int r__ = (expr);                                                                         \
+        if (r__ != QMS_OK) return r__;                                                            \
+    } while (0)
+
+// ---- device buffer owned by a context ----------------------------------------------------------
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+};
+
+struct ProbeRec {  // one c-peak window in the lo-sorted probe list (16 B, one LDG.128 per record)
+    int32_t lo;
+    int32_t hi;
+    int32_t entry;
+    int32_t k;  // ordinal of the window inside its entry
+};
+
+struct qms_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    qms_params prm;
+    bool have_params = false;
+    qms_counters cnt;
+    int64_t dev_bytes = 0;
+    cudaEvent_t ev[8];
+    int sm_count = 148;
+
+    // ---- element trees (P1a) ----
+    int32_t n_pools = 0;
+    int32_t two_iso_min = 0;
+    std::vector<int32_t> h_iso_off, h_max_level, h_lvl_base;      // per pool
+    std::vector<int32_t> h_lvl_min, h_lvl_max;                    // per (pool, level) after build
+    std::vector<int64_t> h_lvl_off;
+    DBuf<int32_t> iso_off, iso_q, max_level, lvl_base, lvl_min, lvl_max, lvl_f, lvl_l;
+    DBuf<double> iso_mass, iso_abun;
+    DBuf<int64_t> lvl_off;
+    DBuf<double> tree_abun, tree_mass;
+    int64_t tree_slots = 0;
+    bool have_trees = false;
+
+    // ---- envelopes (P1b) ----
+    int64_t n_env = 0, n_terms = 0, n_slots = 0;
+    int32_t max_slots_per_env = 0, max_slice = 0;
+    std::vector<int64_t> h_slot_off;
+    DBuf<int64_t> term_off, slot_off;
+    DBuf<int32_t> term_pool, term_level;
+    DBuf<double> env_mass, env_relabun;
+    DBuf<int32_t> env_abun, env_pos, env_len, env_nc;
+    DBuf<unsigned long long> env_flops;
+    bool have_terms = false;
+
+    // ---- charge planes + index (P1c) ----
+    int32_t n_charges = 0;
+    std::vector<int32_t> h_charges;
+    DBuf<int32_t> charges;
+    DBuf<double> pl_mz;           // [n_charges][n_slots]
+    DBuf<int32_t> pl_lo, pl_hi;   // [n_charges][n_slots]
+    DBuf<uint8_t> env_cflag;      // per slot
+    int64_t n_entries = 0, n_windows = 0;
+    DBuf<int64_t> ent_env, ent_win_off;
+    DBuf<int32_t> ent_z;          // charge index
+    DBuf<double> ent_lower, ent_upper, bin_upper;
+    DBuf<int32_t> win_lo, win_hi, win_ci;
+    DBuf<double> win_cmz, win_ri;
+    DBuf<ProbeRec> probe;         // windows sorted by lo
+    DBuf<int32_t> cell_start;     // S[c - t_min] = first probe index with lo >= c ; size span+2
+    DBuf<uint32_t> cover;         // 1 bit per grid cell: covered by >= 1 window
+    int32_t t_min = 0, t_max = -1, max_width = 0;
+    double mz_min = 0, mz_max = 0;
+    bool have_index = false;
+
+    // ---- matching scratch (P2) ----
+    DBuf<double> d_peaks;
+    DBuf<int64_t> d_offsets;
+    DBuf<unsigned long long> pair_keys, pair_keys_alt;
+    DBuf<uint8_t> cub_tmp;
+    DBuf<unsigned long long> dev_counters;   // see match.cu
+    DBuf<double> pair_score, pair_scaling;
+    DBuf<int32_t> pair_flag;
+    DBuf<int64_t> pair_win_off, pair_best;
+    DBuf<int64_t> blk_hits, blk_wins;
+    DBuf<int32_t> o_spec, o_entry;
+    DBuf<double> o_score, o_scaling, o_mmz, o_mi;
+    DBuf<int64_t> o_win_off, o_peak;
+    unsigned long long* h_pinned = nullptr;  // small pinned mailbox for counters
+};
+
+// allocation helpers (ctx.cu)
+int qms_reserve_bytes(qms_ctx* ctx, void** p, size_t* cap_elems, size_t elems, size_t elem_size, bool keep);
+template <class T>
+inline int qms_reserve(qms_ctx* ctx, DBuf<T>& b, size_t elems, bool keep = false) {
+    return qms_reserve_bytes(ctx, (void**)&b.p, &b.cap, elems, sizeof(T), keep);
+}
+template <class T>
+inline void qms_release(qms_ctx* ctx, DBuf<T>& b) {
+    if (b.p) {
+        cudaFree(b.p);
+        ctx->dev_bytes -= (int64_t)(b.cap * sizeof(T));
+    }
+    b.p = nullptr;
+    b.cap = 0;
+}
+template <class T>
+struct TmpBuf {  // scratch device buffer released on scope exit
+    qms_ctx* ctx;
+    DBuf<T> b;
+    explicit TmpBuf(qms_ctx* c) : ctx(c) {}
+    ~TmpBuf() { qms_release(ctx, b); }
+    TmpBuf(const TmpBuf&) = delete;
+    TmpBuf& operator=(const TmpBuf&) = delete;
+};
+template <class T>
+inline int qms_upload(qms_ctx* ctx, DBuf<T>& b, const T* host, size_t n) {
+    QMS_TRY(qms_reserve(ctx, b, n ? n : 1));
+    if (n) QMS_CUDA(ctx, cudaMemcpyAsync(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return QMS_OK;
+}
+template <class T>
+inline int qms_download(qms_ctx* ctx, T* host, const T* dev, size_t n) {
+    if (n && host) QMS_CUDA(ctx, cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return QMS_OK;
+}
+bool qms_is_device_ptr(const void* p);
+
+static inline int qms_blocks(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ---- arithmetic that must follow the reference's rounding (no FMA contraction: the library is
+// compiled with -fmad=false; intrinsics used where the order matters for a threshold) ----------
+__device__ __forceinline__ double qms_mz_of_mass(double mass, int z, double proton, double offset_ppm) {
+    // IL:784-795   mz = (mass + z*PROTON) / float(abs(z));  mz = mz + mz*1e-6*OFFSET
+    double mz = __ddiv_rn(__dadd_rn(mass, __dmul_rn((double)z, proton)), (double)(z < 0 ? -z : z));
+    if (offset_ppm != 0.0) mz = __dadd_rn(mz, __dmul_rn(__dmul_rn(mz, 1e-6), offset_ppm));
+    return mz;
+}
+__device__ __forceinline__ void qms_window(double mz, double rel, double precision, int32_t& lo, int32_t& hi) {
+    // IL:2545-2551   int(round((mz - mz*r)*P)), int(round((mz + mz*r)*P)); round = half-to-even
+    double err = __dmul_rn(mz, rel);
+    lo = __double2int_rn(__dmul_rn(__dsub_rn(mz, err), precision));
+    hi = __double2int_rn(__dmul_rn(__dadd_rn(mz, err), precision));
+}
+__device__ __forceinline__ int32_t qms_tmz(double mz, double precision) {
+    // IL:2582 / 2589   int(round(mz * P))  (np.round and round() are both half-to-even)
+    return __double2int_rn(__dmul_rn(mz, precision));
+}

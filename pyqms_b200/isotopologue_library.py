@@ -1,0 +1,812 @@
+"""``IsotopologueLibrary`` -- drop-in for ``pyqms.IsotopologueLibrary`` with both hot paths on the GPU.
+
+Host side of the B200-native build.  The constructor signature, the ``params`` dict, the dict layout
+``lib[formula] = {"cc", "env": {lp_tuple: {...}}}``, ``match_all(mz_i_list, file_name, spec_id, spec_rt,
+results)`` and the ``Results`` / ``match`` structures follow the reference
+(pyqms/isotopologue_library.py, "IL" below).  What runs where:
+
+* host (this file): string work only -- molecule parsing, fixed-label expansion (IL:1375-1677), label
+  percentile tuples (IL:958-995), the per-envelope (element pool, atom count) descriptors (IL:546-646),
+  Python tie-break ranks for the index sort, and lazy dict/list views over arrays exported from the GPU.
+* device (libqms_b200.so through ctypes, include/qms_b200.h): enriched isotope tables, element trees,
+  envelope convolution, per-charge m/z + ppm windows, index sort + probe tables, spectrum probe,
+  candidate assembly, mScore and hit compaction.  There is no CPU fallback.
+"""
+import copy
+import ctypes as C
+import operator
+import re
+import sys
+
+import numpy as np
+
+from . import knowledge_base
+from .params import params as _default_params
+from ._capi import QMS_E_INPUT, Context, QmsError, QmsHits, QmsIndexInfo, QmsParams, ptr
+from .chemistry import ChemicalComposition
+from .results import Results
+
+_ISOTOPE_ELEMENT = re.compile(r"(?P<isotope>[0-9]*)(?P<element>[A-Z][a-z]*)")
+_ISOTOPE_ELEMENT_COUNT = re.compile(r"(?P<isotope>[0-9]*)(?P<element>[A-Z][a-z]*)\((?P<count>[-]*[0-9]*)\)")
+_NAN = float("nan")
+
+
+def _cartesian(ranges):
+    """All index combinations of [(token, n), ...], first token slowest (IL:1028-1076)."""
+    if not ranges:
+        return []
+    combos = [[]]
+    for token, n in ranges:
+        combos = [c + [(token, i)] for c in combos for i in range(n)]
+    return combos
+
+
+class _LazyEnvelopes(dict):
+    """``lib[formula]["env"]``: label tuple -> envelope dict, materialised from device exports on access."""
+
+    def __init__(self, library, formula, label_tuples):
+        super().__init__((lp, None) for lp in label_tuples)
+        self._library = library
+        self._formula = formula
+
+    def __getitem__(self, lp):
+        value = dict.__getitem__(self, lp)
+        if value is None:
+            value = self._library._materialise_envelope(self._formula, lp)
+            dict.__setitem__(self, lp, value)
+        return value
+
+    def get(self, lp, default=None):
+        return self[lp] if lp in self else default
+
+    def values(self):
+        return [self[lp] for lp in self.keys()]
+
+    def items(self):
+        return [(lp, self[lp]) for lp in self.keys()]
+
+
+class IsotopologueLibrary(dict):
+    """Isotopologue library built and matched on one B200.
+
+    Arguments as in the reference (IL:212-224): ``molecules``, ``charges``, ``metabolic_labels``,
+    ``fixed_labels``, ``params``, ``trivial_names``, ``verbose``, ``evidences``, ``unimod_files``,
+    ``add_default_files``.  Extra, keyword-only: ``device`` (CUDA ordinal, default ``LOCAL_RANK`` or 0)
+    and ``distributed`` (shard the envelope build over the ranks of ``torch.distributed`` and all-gather
+    the shards with NCCL; default: on when a process group with more than one rank is initialised).
+    """
+
+    def __init__(self, molecules=None, charges=None, metabolic_labels=None, fixed_labels=None, params=None,
+                 trivial_names=None, verbose=True, evidences=None, unimod_files=None, add_default_files=True, *,
+                 device=None, distributed=None, _plan_only=False):
+        super().__init__()
+        assert molecules is not None, "require list of molecules"
+        assert charges is not None, "require list of charges"
+        self.params = copy.deepcopy(_default_params)
+        if params is not None:
+            self.params.update(params)
+        self._fmt = self.params["PERCENTILE_FORMAT_STRING"].format
+        self.zero_labeled_percentile = self._fmt(0)
+        if metabolic_labels is None or metabolic_labels == {}:
+            metabolic_labels = {"15N": [0.0]}
+        self.build_isotoplogues = True
+        self.verbose = verbose
+        self.metabolic_labels = metabolic_labels
+        self.fixed_labels = {} if fixed_labels is None else fixed_labels
+        self.charges = charges
+        self.lookup = {"molecule to formula": {}, "formula to molecule": {}, "molecule to annotations": {},
+                       "molecule fixed label variations": {}, "formula to trivial name": {}}
+        self.break_points = {}
+        self.skipped_molecules = set()
+        if trivial_names is not None:
+            self.lookup["molecule to trivial name"] = trivial_names
+        self.unimod_files = unimod_files
+        self.lookup["formula to evidences"] = {} if evidences is None else evidences
+        self.regex = {"<isotope><element>(<count>)": _ISOTOPE_ELEMENT_COUNT, "<isotope><element>": _ISOTOPE_ELEMENT}
+        self.aa_compositions = {}
+        self.isotopic_distributions = {}
+        self.labled_percentiles = []
+        self.metabolically_labeled_elements = set()
+        # _plan_only: host tables only (CPU unit tests of the string/planning layer); nothing can be built or matched
+        self._ctx = None if _plan_only else Context(device)   # raises without the CUDA library / a GPU: no fallback
+        self._push_params()
+        self._views = {}
+
+        self._cache_kb()
+        if self.verbose:
+            print("> Metabolic labels        >", self.metabolic_labels)
+            print("> Fixed labels            >", self.fixed_labels)
+            print("> Charges                 >", self.charges)
+            print("> Machine ppm offset      > {MACHINE_OFFSET_IN_PPM}".format(**self.params))
+        self._extend_isotopic_distributions_with_metabolic_labels()
+        self._build_label_percentile_tuples()
+        if self.verbose:
+            print("> Label percentile tuples >", self.labled_percentiles)
+        if len(self.fixed_labels) != 0:
+            self._extend_kb_with_fixed_labels()
+            molecules = self._extend_molecules_with_fixed_labels(molecules)
+            self._push_params()              # enrichment levels may have been added (IL:1469-1471)
+        self._register_molecules(molecules, trivial_names, add_default_files)
+        self._plan_device_tables()
+        if _plan_only:
+            return
+        self._build_on_device(distributed)
+        if self.verbose:
+            if self._n_entries == 0:
+                print("> No molecules have been added into the library ")
+                print("  maybe molecules are out of mz limit range ?")
+                print("  Current mz limits in params are: [ {LOWER_MZ_LIMIT} .. {UPPER_MZ_LIMIT}]".format(**self.params))
+                raise SystemExit(1)          # IL:941-949
+            print("> Created {0} match sets, total mz range [{1:10.5f} .. {2:10.5f}]".format(
+                self._n_bins(), *self.match_set_mz_range))
+
+    # ------------------------------------------------------------------ parameters -> device
+    def _push_params(self):
+        if self._ctx is None:
+            return
+        P = self.params
+        q = QmsParams(
+            element_min_abundance=P["ELEMENT_MIN_ABUNDANCE"], min_rel_peak_intensity=P["MIN_REL_PEAK_INTENSITY_FOR_MATCHING"],
+            intensity_transformation=P["INTENSITY_TRANSFORMATION_FACTOR"], lower_mz_limit=P["LOWER_MZ_LIMIT"],
+            upper_mz_limit=P["UPPER_MZ_LIMIT"], rel_mz_range=P["REL_MZ_RANGE"], rel_i_range=P["REL_I_RANGE"],
+            internal_precision=P["INTERNAL_PRECISION"], machine_offset_ppm=P["MACHINE_OFFSET_IN_PPM"],
+            m_score_threshold=P["M_SCORE_THRESHOLD"], required_peak_overlap=P["REQUIRED_PERCENTILE_PEAK_OVERLAP"],
+            proton=knowledge_base.PROTON, min_matched_isotopologues=int(P["MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES"]),
+            max_molecules_per_bin=int(P["MAX_MOLECULES_PER_MATCH_BIN"]))
+        self._ctx.call("qms_set_params", C.byref(q))
+
+    # ------------------------------------------------------------------ knowledge base (IL:997-1026)
+    def _cache_kb(self):
+        for aa, formula in knowledge_base.aa_compositions.items():
+            self.aa_compositions[aa] = ChemicalComposition(formula="+" + formula, unimod_file_list=self.unimod_files)
+        for aa, formula in self.params.get("AMINO_ACIDS", {}).items():
+            self.aa_compositions[aa] = ChemicalComposition(formula="+" + formula, unimod_file_list=self.unimod_files)
+        for element, table in knowledge_base.isotopic_distributions.items():
+            rows = sorted((mass, abundance, pos) for pos, (mass, abundance) in enumerate(table))
+            self.isotopic_distributions[element] = {self.zero_labeled_percentile: rows}
+
+    def _recalc_isotopic_distribution(self, element=None, target_percentile=None, enriched_isotope=None):
+        """Enriched isotope table of ``element`` (IL:2109-2165), computed by ``qms_recalc_distribution``."""
+        natural = self.isotopic_distributions[element][self.zero_labeled_percentile]
+        if self._ctx is None:               # plan-only: the planner needs the isotope count, not the values
+            return [(row[0], _NAN, row[2]) for row in natural]
+        mass = np.array([row[0] for row in natural], dtype=np.float64)
+        abun = np.array([row[1] for row in natural], dtype=np.float64)
+        out = np.empty_like(abun)
+        self._ctx.call("qms_recalc_distribution", len(natural), ptr(mass), ptr(abun), int(enriched_isotope),
+                       float(target_percentile), ptr(out))
+        return [(row[0], float(a), row[2]) for row, a in zip(natural, out)]
+
+    def _extend_isotopic_distributions_with_metabolic_labels(self):
+        """One isotope pool per (labelled element, percentile > 0) -- IL:1326-1373."""
+        for isotope_element, percentiles in self.metabolic_labels.items():
+            for percentile in percentiles:
+                if percentile <= sys.float_info.epsilon:
+                    continue
+                found = _ISOTOPE_ELEMENT.match(isotope_element)
+                element = found.group("element")
+                self.isotopic_distributions[element][self._fmt(percentile)] = self._recalc_isotopic_distribution(
+                    element=element, target_percentile=percentile,
+                    enriched_isotope=int(round(float(found.group("isotope")))))
+                self.metabolically_labeled_elements.add(element)
+        if not self.metabolically_labeled_elements:
+            self.metabolically_labeled_elements.add("N")
+
+    def _build_label_percentile_tuples(self):
+        """Cartesian product of the label percentile lists (IL:958-995)."""
+        for combo in self._create_combinations([(k, len(v)) for k, v in self.metabolic_labels.items()]):
+            chosen = {}
+            for name, index in combo:
+                chosen[_ISOTOPE_ELEMENT.match(name).group("element")] = self._fmt(self.metabolic_labels[name][index])
+            self.labled_percentiles.append(tuple(sorted(chosen.items())))
+
+    def _create_combinations(self, input_list, all_combos=None, current_combo=None, pos=0):
+        """Position combinations of ``[(token, length), ...]`` (IL:1028-1076)."""
+        return _cartesian(list(input_list))
+
+    # ------------------------------------------------------------------ fixed labels (IL:1375-1677)
+    def _extend_kb_with_fixed_labels(self, synthetic_abundance=0.994):
+        levels = self.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"]
+        for amino_acid, definitions in self.fixed_labels.items():
+            for index, unimod_string in enumerate(definitions):
+                if amino_acid not in self.aa_compositions:
+                    print("Error in _extend_kb_with_fixed_labels: unknown amino acid", amino_acid)
+                    raise SystemExit(1)
+                composition = copy.deepcopy(self.aa_compositions[amino_acid])
+                for isotope, element, count in _ISOTOPE_ELEMENT_COUNT.findall(unimod_string):
+                    if isotope == "":
+                        key = element
+                    else:
+                        most_abundant = max(self.isotopic_distributions[element][self.zero_labeled_percentile],
+                                            key=operator.itemgetter(1))
+                        natural_name = str(round(most_abundant[0])).split(".")[0]
+                        # a label naming the natural isotope (14N in carbamidomethyl) is "not enriched" (Q6)
+                        percentile = 0.0 if isotope == natural_name else synthetic_abundance
+                        key = isotope + element
+                        if key in levels:
+                            percentile = levels[key]
+                        else:
+                            if self.verbose:
+                                print(">Enrichment levels of {0} was not specified in params."
+                                      "Falling back to {1} and inserting temporarily into self.params".format(key, percentile))
+                            levels[key] = percentile
+                    composition[key] += int(count)
+                    if isotope != "":
+                        self.isotopic_distributions.setdefault(key, {})[self._fmt(percentile)] = \
+                            self._recalc_isotopic_distribution(element=element, target_percentile=percentile,
+                                                               enriched_isotope=isotope)
+                for symbol in [s for s, n in composition.items() if n == 0]:
+                    del composition[symbol]
+                self.aa_compositions["{0}{1}".format(amino_acid, index)] = composition
+
+    def _extend_molecules_with_fixed_labels(self, molecules):
+        locked = self.params["SILAC_AAS_LOCKED_IN_EXPERIMENT"]
+        if locked is not None:
+            assert len(locked) != 1, 'only one aa in self.params["SILAC_AAS_LOCKED_IN_EXPERIMENT"]  ?'
+            assert len({len(self.fixed_labels[aa]) for aa in locked}) == 1, \
+                "Length of fixed_labels for aas that ought to be locked into same experiment dont show same number of labels ..."
+        expanded = set()
+        for full_molecule in molecules:
+            cut = len(full_molecule)
+            for position, letter in enumerate(full_molecule):
+                if letter not in self.aa_compositions:
+                    cut = position
+                    break
+            sequence, addon = full_molecule[:cut], full_molecule[cut:]
+            sites = []
+            for amino_acid in self.fixed_labels:
+                for hit in re.finditer(amino_acid, sequence):
+                    sites.append(("{0}{1}".format(hit.start(), amino_acid), len(self.fixed_labels[amino_acid])))
+            if not sites:
+                expanded.add(sequence + addon)
+                continue
+            for combination in self._create_combinations(sorted(sites, reverse=True)):
+                exchange = sorted(((int(token[:-1]), token[-1], state) for token, state in combination), reverse=True)
+                labelled = sequence
+                states = set()
+                for position, amino_acid, state in exchange:
+                    labelled = "{0}{1}{2}{3}".format(labelled[:position], amino_acid, state, labelled[position + 1:])
+                    if locked is not None and amino_acid in locked:
+                        states.add(state)
+                keep = True
+                if locked is not None:
+                    keep = False
+                    if len(states) == 1:
+                        present = {int(state) for aa, state in re.findall(r"([A-Z]{1})([0-9]+)", labelled) if aa in locked}
+                        keep = present == states
+                if keep:
+                    expanded.add(labelled + addon)
+                    self.lookup["molecule fixed label variations"].setdefault(full_molecule, set()).add(labelled + addon)
+        return expanded
+
+    # ------------------------------------------------------------------ molecules -> formulas (IL:312-497)
+    def _register_molecules(self, molecules, trivial_names, add_default_files):
+        self._highest_element_count = {}
+        self._range_for_elements_with_two_isotopes = [None, None]
+        factory = ChemicalComposition(aa_compositions=self.aa_compositions,
+                                      isotopic_distributions=self.isotopic_distributions,
+                                      unimod_file_list=self.unimod_files, add_default_files=add_default_files)
+        levels = self.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"]
+        two_iso = self._range_for_elements_with_two_isotopes
+        for molecule in dict.fromkeys(molecules):          # the reference iterates set(molecules): order-free
+            if molecule.count("#") > 1:
+                raise ValueError(f"{molecule} contains too many '#' {molecule.count('#') + 1} only one allowed")
+            factory.use(deprecated_format=molecule)
+            composition = factory.generate_cc_dict()
+            formula = factory.hill_notation_unimod()
+            if trivial_names is not None:
+                name = trivial_names.get(molecule, None)
+                if name is not None:
+                    self.lookup["formula to trivial name"].setdefault(formula, []).append(name)
+                else:
+                    print("No trivial name for molecule", molecule)
+            self.lookup["molecule to formula"][molecule] = formula
+            self.lookup["formula to molecule"].setdefault(formula, []).append(molecule)
+            if formula not in self:
+                self[formula] = {"env": _LazyEnvelopes(self, formula, self.labled_percentiles), "cc": composition}
+            for element in composition:
+                if element in self.isotopic_distributions:
+                    continue
+                # isotope-labelled element introduced by a modification (e.g. 13C of a SILAC/TMT unimod), IL:378-436
+                found = _ISOTOPE_ELEMENT.match(element)
+                try:
+                    enriched = int(round(float(found.group("isotope"))))
+                except Exception:
+                    print("Failed on", element)
+                    print("Maybe element is not in pyqms.knowledge_base.py ?")
+                    raise SystemExit(1)
+                template = found.group("element")
+                target = levels.get("{0}{1}".format(enriched, template)) or 0.994
+                if self.verbose:
+                    print("> Extending isotopic distribution that are within the modifications for "
+                          "element {0}{1}, enrichment levels set to {2}".format(enriched, template, target))
+                self.isotopic_distributions[element] = {self.zero_labeled_percentile: self._recalc_isotopic_distribution(
+                    element=template, target_percentile=target, enriched_isotope=enriched)}
+            highest = self._highest_element_count
+            for element, count in composition.items():
+                if element not in highest:
+                    highest[element] = 0
+                if highest[element] < count:
+                    highest[element] = count
+                for table in self.isotopic_distributions[element].values():
+                    if len(table) == 2:
+                        if two_iso[0] is None or count < two_iso[0]:
+                            two_iso[0] = count
+                        if two_iso[1] is None or count > two_iso[1]:
+                            two_iso[1] = count
+                        break                               # one 2-isotope label of the element is enough (IL:448-460)
+        # fold the isotope-labelled counts into their template element (IL:467-497)
+        for element in list(self._highest_element_count):
+            if element.isalpha():
+                continue
+            template = _ISOTOPE_ELEMENT.match(element).group("element")
+            self._highest_element_count.setdefault(template, 0)
+            self._highest_element_count[template] += self._highest_element_count.get(element, 0)
+            for table in self.isotopic_distributions[template].values():
+                if len(table) == 2 and self._highest_element_count[template] > two_iso[1]:
+                    two_iso[1] = self._highest_element_count[template]
+
+    # ------------------------------------------------------------------ host tables for the device build
+    def _plan_device_tables(self):
+        """Pools (one per element x label) and per-envelope (pool, atom count) term lists (IL:546-646)."""
+        self._pool_ids = {}             # (element, label) -> pool
+        self._pools = []                # [(element, label)]
+        iso_off, iso_mass, iso_abun, iso_q, max_level = [0], [], [], [], []
+        self._default_label = {}
+        for element, count in self._highest_element_count.items():
+            assert element in self.isotopic_distributions, \
+                "Isotopic distribution and abundance of {0} not in knowledge base".format(element)
+            labels = self.isotopic_distributions[element]
+            self._default_label[element] = sorted(labels, reverse=True)[0]      # first key of element_trees[element]
+            for label, table in labels.items():
+                self._pool_ids[(element, label)] = len(self._pools)
+                self._pools.append((element, label))
+                for _mass, _abundance, q in table:
+                    # the reference reads the isotope of a step by its POSITION (IL:1733-1746); for mass-sorted
+                    # knowledge-base tables that is the row itself
+                    iso_mass.append(table[q][0] if len(table) > 2 else _mass)
+                    iso_abun.append(table[q][1] if len(table) > 2 else _abundance)
+                    iso_q.append(q)
+                iso_off.append(len(iso_q))
+                max_level.append(count)
+        self._pool_tables = (np.array(iso_off, dtype=np.int32), np.array(iso_mass, dtype=np.float64),
+                             np.array(iso_abun, dtype=np.float64), np.array(iso_q, dtype=np.int32),
+                             np.array(max_level, dtype=np.int32))
+        levels = self.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"]
+        labelled = self.metabolically_labeled_elements
+        n_lp = len(self.labled_percentiles)
+        self._formulas = list(self.keys())
+        self._formula_index = {f: i for i, f in enumerate(self._formulas)}
+        self._lp_index = {lp: i for i, lp in enumerate(self.labled_percentiles)}
+        term_off, term_pool, term_level = [0], [], []
+        pool_ids, default_label = self._pool_ids, self._default_label
+        for formula in self._formulas:
+            composition = self[formula]["cc"]
+            for lp in self.labled_percentiles:
+                merged = {}
+                for element, count in composition.items():
+                    target = element
+                    if element in levels:
+                        bare = element[-1]
+                        for lp_element, lp_label in lp:
+                            if lp_element == bare and lp_label == self._fmt(levels[element]):
+                                target = bare               # fixed-label isotope folds into the labelled pool (Q6)
+                    merged[target] = merged.get(target, 0) + count
+                for element, level in merged.items():
+                    if element in labelled:
+                        continue
+                    term_pool.append(pool_ids[(element, default_label[element])])
+                    term_level.append(level)
+                for element, label in lp:
+                    level = merged.get(element, 0)
+                    if level == 0:
+                        continue
+                    term_pool.append(pool_ids[(element, label)])
+                    term_level.append(level)
+                term_off.append(len(term_pool))
+        self._n_env = len(self._formulas) * n_lp
+        self._terms = (np.array(term_off, dtype=np.int64), np.array(term_pool, dtype=np.int32),
+                       np.array(term_level, dtype=np.int32))
+
+    # ------------------------------------------------------------------ device build
+    def _build_on_device(self, distributed):
+        import time
+        self.break_points["Building isotopologues"] = time.time()
+        ctx = self._ctx
+        iso_off, iso_mass, iso_abun, iso_q, max_level = self._pool_tables
+        two_iso_min = self._range_for_elements_with_two_isotopes[0] or 1
+        ctx.call("qms_build_element_trees", len(self._pools), ptr(iso_off), ptr(iso_mass), ptr(iso_abun), ptr(iso_q),
+                 ptr(max_level), int(two_iso_min))
+        term_off, term_pool, term_level = self._terms
+        ctx.call("qms_set_envelope_terms", self._n_env, ptr(term_off), ptr(term_pool), ptr(term_level))
+        from . import distributed as dist_mod
+        world = dist_mod.world_size() if distributed is not False else 1
+        if distributed is None:
+            distributed = world > 1
+        if distributed and world > 1:
+            begin, end = dist_mod.shard_range(self._n_env, dist_mod.rank(), world)
+            ctx.call("qms_build_envelopes", begin, end)
+            dist_mod.allgather_envelopes(ctx, self._n_env, world)
+        else:
+            ctx.call("qms_build_envelopes", 0, self._n_env)
+        # ranks of (label tuple, formula) under Python ordering: tie-break of the index sort (IL:836-867)
+        n_lp = len(self.labled_percentiles)
+        order = sorted(range(self._n_env), key=lambda e: (self.labled_percentiles[e % n_lp], self._formulas[e // n_lp]))
+        rank = np.empty(self._n_env, dtype=np.int64)
+        rank[np.array(order, dtype=np.int64)] = np.arange(self._n_env, dtype=np.int64)
+        charges = np.array(self.charges, dtype=np.int32)
+        ctx.call("qms_finalize_index", len(charges), ptr(charges), ptr(rank))
+        info = QmsIndexInfo()
+        ctx.call("qms_index_info_get", C.byref(info))
+        self._n_entries, self._n_windows = info.n_entries, info.n_windows
+        self.match_set_mz_range = [info.mz_min, info.mz_max] if info.n_entries else [None, None]
+        # entry table + entry-major windows: needed on the host to label every hit
+        n, w = self._n_entries, self._n_windows
+        self._ent_env = np.empty(n, dtype=np.int64)
+        self._ent_z = np.empty(n, dtype=np.int32)
+        self._ent_lower = np.empty(n, dtype=np.float64)
+        self._ent_upper = np.empty(n, dtype=np.float64)
+        self._ent_win_off = np.zeros(n + 1, dtype=np.int64)
+        ctx.call("qms_export_index", ptr(self._ent_env), ptr(self._ent_z), ptr(self._ent_lower), ptr(self._ent_upper),
+                 ptr(self._ent_win_off))
+        self._win_lo = np.empty(w, dtype=np.int32)
+        self._win_hi = np.empty(w, dtype=np.int32)
+        self._win_cmz = np.empty(w, dtype=np.float64)
+        self._win_ri = np.empty(w, dtype=np.float64)
+        self._win_ci = np.empty(w, dtype=np.int32)
+        ctx.call("qms_export_windows", ptr(self._win_lo), ptr(self._win_hi), ptr(self._win_cmz), ptr(self._win_ri),
+                 ptr(self._win_ci))
+        self._entry_static = {}
+        if self.verbose:
+            print("\n> Execution time {0:.2f} seconds".format(time.time() - self.break_points["Building isotopologues"]))
+
+    # ------------------------------------------------------------------ lazy host views
+    def _n_bins(self):
+        step = self.params["MAX_MOLECULES_PER_MATCH_BIN"]
+        return (self._n_entries + step - 1) // step
+
+    def _export_envelopes(self):
+        if "env" not in self._views:
+            ctx = self._ctx
+            n_env, n_slots = C.c_int64(), C.c_int64()
+            ctx.call("qms_envelope_layout", C.byref(n_env), C.byref(n_slots), None)
+            slot_off = np.zeros(n_env.value + 1, dtype=np.int64)
+            ctx.call("qms_envelope_layout", C.byref(n_env), C.byref(n_slots), ptr(slot_off))
+            s = n_slots.value
+            view = {"slot_off": slot_off, "mass": np.empty(s), "relabun": np.empty(s), "abun": np.empty(s, dtype=np.int32),
+                    "pos": np.empty(s, dtype=np.int32), "c_flag": np.empty(s, dtype=np.uint8),
+                    "len": np.empty(n_env.value, dtype=np.int32), "n_c": np.empty(n_env.value, dtype=np.int32), "planes": {}}
+            ctx.call("qms_export_envelopes", ptr(view["mass"]), ptr(view["relabun"]), ptr(view["abun"]), ptr(view["pos"]),
+                     ptr(view["c_flag"]), ptr(view["len"]), ptr(view["n_c"]))
+            self._views["env"] = view
+        return self._views["env"]
+
+    def _charge_plane(self, z_index):
+        view = self._export_envelopes()
+        if z_index not in view["planes"]:
+            s = len(view["mass"])
+            mz, lo, hi = np.empty(s), np.empty(s, dtype=np.int32), np.empty(s, dtype=np.int32)
+            self._ctx.call("qms_export_charge_plane", z_index, ptr(mz), ptr(lo), ptr(hi))
+            view["planes"][z_index] = (mz, lo, hi)
+        return view["planes"][z_index]
+
+    def _materialise_envelope(self, formula, lp):
+        """Reference layout of ``lib[formula]["env"][lp]`` (IL:703-811) from the exported device arrays."""
+        view = self._export_envelopes()
+        e = self._formula_index[formula] * len(self.labled_percentiles) + self._lp_index[lp]
+        a, n = int(view["slot_off"][e]), int(view["len"][e])
+        sl = slice(a, a + n)
+        c_flag = view["c_flag"][sl].astype(bool)
+        env = {"isot": [], "mass": view["mass"][sl].tolist(), "abun": view["abun"][sl].tolist(),
+               "relabun": view["relabun"][sl].tolist(),
+               "c_peak_pos": [int(p) if c else None for p, c in zip(view["pos"][sl], c_flag)],
+               "n_c_peaks": float(view["n_c"][e]) if view["n_c"][e] else 0}
+        for z_index, charge in enumerate(self.charges):
+            mz, lo, hi = self._charge_plane(z_index)
+            tmzs = [set(range(int(l), int(h) + 1)) if c else None for l, h, c in zip(lo[sl], hi[sl], c_flag)]
+            env[charge] = {"mz": mz[sl].tolist(), "tmzs": tmzs, "atmzs": set().union(*[t for t in tmzs if t is not None])}
+        return env
+
+    def _entry_tuple(self, index):
+        n_lp = len(self.labled_percentiles)
+        e = int(self._ent_env[index])
+        return (float(self._ent_lower[index]), float(self._ent_upper[index]), self.charges[int(self._ent_z[index])],
+                self.labled_percentiles[e % n_lp], self._formulas[e // n_lp])
+
+    @property
+    def formulas_sorted_by_mz(self):
+        """[(lower_mz, upper_mz, charge, label tuple, formula)] in index order (IL:836-867)."""
+        if "index" not in self._views:
+            self._views["index"] = [self._entry_tuple(i) for i in range(self._n_entries)]
+        return self._views["index"]
+
+    @property
+    def match_sets(self):
+        """Bins of MAX_MOLECULES_PER_MATCH_BIN entries with their window union and m/z range (IL:869-916)."""
+        if "bins" not in self._views:
+            step = self.params["MAX_MOLECULES_PER_MATCH_BIN"]
+            bins = {}
+            for number, start in enumerate(range(0, self._n_entries, step)):
+                stop = min(start + step, self._n_entries)
+                union = set()
+                for w in range(int(self._ent_win_off[start]), int(self._ent_win_off[stop])):
+                    union.update(range(int(self._win_lo[w]), int(self._win_hi[w]) + 1))
+                bins[number] = {"ids": [start, stop], "tmzs": union,
+                                "mz_range": [float(self._ent_lower[start:stop].min()), float(self._ent_upper[start:stop].max())]}
+            self._views["bins"] = bins
+        return self._views["bins"]
+
+    @property
+    def element_trees(self):
+        """{element: {label: {n: {"env": {pos: {"mass","abun"}}, "minPos", "maxPos"}}}} (IL:1086-1106); only the
+        pruned slice [minPos, maxPos] of each level is held on the device and materialised here."""
+        if "trees" not in self._views:
+            trees = {}
+            cap = 1 << 16
+            abun, mass = np.empty(cap), np.empty(cap)
+            lo, hi, n = C.c_int32(), C.c_int32(), C.c_int32()
+            for (element, label), pool in self._pool_ids.items():
+                levels = trees.setdefault(element, {}).setdefault(label, {})
+                for level in range(1, int(self._pool_tables[4][pool]) + 1):
+                    self._ctx.call("qms_export_tree_level", pool, level, C.byref(lo), C.byref(hi), ptr(abun), ptr(mass), cap,
+                                   C.byref(n))
+                    if n.value == 0:
+                        continue
+                    levels[level] = {"minPos": lo.value, "maxPos": hi.value,
+                                     "env": {lo.value + j: {"mass": float(mass[j]), "abun": float(abun[j])}
+                                             for j in range(n.value)}}
+            self._views["trees"] = trees
+        return self._views["trees"]
+
+    # ------------------------------------------------------------------ matching (P2)
+    def _new_results(self):
+        return Results(aa_compositions=self.aa_compositions, charges=self.charges, fixed_labels=self.fixed_labels,
+                       isotopic_distributions=self.isotopic_distributions, lookup=self.lookup,
+                       metabolic_labels=self.metabolic_labels, params=self.params)
+
+    def _run_matcher(self, peaks, offsets, input_kind, xi, only_entry=None):
+        """One ``qms_match_batch`` / ``qms_match_entry`` call with host buffers; returns packed hit arrays."""
+        ctx = self._ctx
+        n_spec = len(offsets) - 1
+        cap_h, cap_w = max(1024, 4 * n_spec), max(8192, 32 * n_spec)
+        while True:
+            out = {"spec": np.empty(cap_h, dtype=np.int32), "entry": np.empty(cap_h, dtype=np.int32),
+                   "score": np.empty(cap_h), "scaling": np.empty(cap_h), "win_off": np.zeros(cap_h + 1, dtype=np.int64),
+                   "mmz": np.empty(cap_w), "mi": np.empty(cap_w), "peak": np.empty(cap_w, dtype=np.int64)}
+            hits = QmsHits(cap_h, cap_w, *[out[k].ctypes.data for k in ("spec", "entry", "score", "scaling", "win_off",
+                                                                        "mmz", "mi", "peak")])
+            nh, nw = C.c_int64(), C.c_int64()
+            if only_entry is None:
+                rc = ctx.lib.qms_match_batch(ctx.handle, ptr(peaks), ptr(offsets), n_spec, input_kind, float(xi),
+                                             C.byref(hits), C.byref(nh), C.byref(nw))
+            else:
+                rc = ctx.lib.qms_match_entry(ctx.handle, ptr(peaks), len(peaks), input_kind, int(only_entry), float(xi),
+                                             C.byref(hits), C.byref(nh), C.byref(nw))
+            if rc == -3:                                    # QMS_E_CAPACITY: sizes reported, retry once
+                cap_h, cap_w = nh.value, nw.value
+                continue
+            ctx.check(rc)
+            out["n_hits"], out["n_windows"] = nh.value, nw.value
+            return out
+
+    @staticmethod
+    def _as_peak_array(mz_i_list):
+        """(n,2) float64 C-contiguous array + input kind (0 numpy semantics, 1 list semantics; Q12)."""
+        is_numpy = getattr(mz_i_list, "tolist", False) is not False
+        array = np.ascontiguousarray(mz_i_list, dtype=np.float64)
+        if array.size == 0:
+            array = array.reshape(0, 2)
+        return array, 0 if is_numpy else 1
+
+    def _sorted_or_reordered(self, array, kind):
+        """The device wants ascending m/z buckets; an unsorted numpy spectrum is reordered by (bucket, row),
+        which keeps 'first row of a bucket' (IL:2592-2600) what it was.  Returns (array, row map or None)."""
+        mz = array[:, 0]
+        if len(mz) < 2 or bool(np.all(mz[1:] >= mz[:-1])):
+            return array, None
+        if kind == 1:
+            raise ValueError("list input must be sorted by m/z (the reference bisects it, IL:2511)")
+        order = np.argsort(np.round(mz * self.params["INTERNAL_PRECISION"]), kind="stable")
+        return np.ascontiguousarray(array[order]), order
+
+    def _emit(self, out, results, file_name, spec_ids, spec_rts, sources, row_maps):
+        """Packed hits -> ``results.add`` in (spectrum, entry) order (IL:1872-1882)."""
+        win_off = out["win_off"]
+        statics = self._entry_static
+        for h in range(out["n_hits"]):
+            s, x = int(out["spec"][h]), int(out["entry"][h])
+            static = statics.get(x)
+            if static is None:
+                lo, hi, charge, lp, formula = self._entry_tuple(x)
+                a, b = int(self._ent_win_off[x]), int(self._ent_win_off[x + 1])
+                static = statics[x] = (formula, charge, lp, self._win_ri[a:b].tolist(), self._win_cmz[a:b].tolist(),
+                                       self._win_ci[a:b].tolist())
+            formula, charge, lp, ri, cmz, ci = static
+            source, row_map, base = sources[s]
+            peaks = []
+            for m, w in enumerate(range(int(win_off[h]), int(win_off[h + 1]))):
+                row = int(out["peak"][w])
+                if row < 0:
+                    peaks.append((None, None, ri[m], cmz[m], ci[m]))
+                else:
+                    row -= base
+                    if row_map is not None:
+                        row = int(row_map[row])
+                    item = source[row]
+                    peaks.append((item[0], item[1], ri[m], cmz[m], ci[m]))
+            score, scaling = out["score"][h], out["scaling"][h]
+            if not isinstance(source, np.ndarray):
+                score, scaling = float(score), float(scaling)
+            results.add((file_name, formula, charge, lp), (spec_ids[s], spec_rts[s], score, scaling, tuple(peaks)))
+        return results
+
+    def match_all(self, mz_i_list=None, file_name=None, spec_id=None, spec_rt=None, results=None):
+        """Match every library entry against one spectrum (IL:1794-1883); returns/updates ``results``."""
+        if results is None:
+            results = self._new_results()
+        if self._n_entries == 0:
+            return results
+        array, kind = self._as_peak_array(mz_i_list)
+        array, row_map = self._sorted_or_reordered(array, kind)
+        offsets = np.array([0, len(array)], dtype=np.int64)
+        out = self._run_matcher(array, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
+        return self._emit(out, results, file_name, [spec_id], [spec_rt], [(mz_i_list, row_map, 0)], None)
+
+    def match_many(self, spectra, file_name=None, spec_ids=None, spec_rts=None, results=None, offsets=None):
+        """Batched ``match_all``: one device pass over many spectra (additive API).
+
+        ``spectra``: list of (n,2) arrays / lists of (mz, i) tuples, or one packed (N,2) array together with
+        ``offsets`` (n_spectra+1 row offsets).  Hits are added to ``results`` in the order a ``match_all`` loop
+        over the spectra would add them."""
+        if results is None:
+            results = self._new_results()
+        if offsets is None:
+            arrays, kinds, sources = [], set(), []
+            base = 0
+            for spectrum in spectra:
+                array, kind = self._as_peak_array(spectrum)
+                array, row_map = self._sorted_or_reordered(array, kind)
+                kinds.add(kind)
+                arrays.append(array)
+                sources.append((spectrum, row_map, base))
+                base += len(array)
+            if len(kinds) > 1:
+                raise ValueError("match_many needs all spectra as numpy arrays or all as lists")
+            kind = kinds.pop() if kinds else 0
+            peaks = np.concatenate(arrays) if arrays else np.zeros((0, 2))
+            offsets = np.zeros(len(arrays) + 1, dtype=np.int64)
+            np.cumsum([len(a) for a in arrays], out=offsets[1:])
+        else:
+            peaks = np.ascontiguousarray(spectra, dtype=np.float64)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            kind = 0
+            sources = [(peaks, None, 0)] * (len(offsets) - 1)
+        n_spec = len(offsets) - 1
+        spec_ids = list(range(n_spec)) if spec_ids is None else spec_ids
+        spec_rts = [None] * n_spec if spec_rts is None else spec_rts
+        if self._n_entries == 0 or n_spec == 0:
+            return results
+        out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
+        return self._emit(out, results, file_name, spec_ids, spec_rts, sources, None)
+
+    def match_packed(self, peaks, offsets, mz_score_percentile=None, input_kind=0):
+        """Device pass without Python object creation: returns the packed hit arrays of ``qms_match_batch``
+        (dict with spec, entry, score, scaling, win_off, mmz, mi, peak, n_hits, n_windows)."""
+        xi = self.params["MZ_SCORE_PERCENTILE"] if mz_score_percentile is None else mz_score_percentile
+        return self._run_matcher(np.ascontiguousarray(peaks, dtype=np.float64), np.ascontiguousarray(offsets, dtype=np.int64),
+                                 input_kind, xi)
+
+    def match_isotopologue(self, index=None, formula=None, charge=None, label_percentile=None, spec_tmz_set=None,
+                           spec_tmz_lookup=None, mz_i_list=None, mz_score_percentile=None):
+        """Best match of one library entry (IL:1885-2040): (score, scaling_factor, peaks) or None."""
+        if index is None:
+            assert formula is not None, "require formula information for match"
+            assert charge is not None, "require charge information for match"
+            assert label_percentile is not None, "require tuple list"
+            e = self._formula_index[formula] * len(self.labled_percentiles) + self._lp_index[label_percentile]
+            z_index = list(self.charges).index(charge)
+            found = np.flatnonzero((self._ent_env == e) & (self._ent_z == z_index))
+            if len(found) == 0:
+                raise KeyError("entry is not in the m/z range of the library index")
+            index = int(found[0])
+        if mz_i_list is not None:
+            assert spec_tmz_set is None, "both a transformed spec and mz_i_list were given ... which one to use ?"
+            source = mz_i_list
+        else:
+            source = [spec_tmz_lookup[t][0] for t in sorted(spec_tmz_set)]   # first peak of every bucket (IL:2014)
+        array, kind = self._as_peak_array(source)
+        if mz_i_list is None:
+            kind = 0
+        array, row_map = self._sorted_or_reordered(array, kind)
+        xi = self.params["MZ_SCORE_PERCENTILE"] if mz_score_percentile is None else mz_score_percentile
+        out = self._run_matcher(array, np.array([0, len(array)], dtype=np.int64), kind, xi, only_entry=index)
+        if out["n_hits"] == 0:
+            return None
+        collected = self._emit(out, _Collector(), None, [None], [None], [(source, row_map, 0)], None)
+        return collected.rows[0]
+
+    def score_matches(self, matched_peaks, mz_score_percentile):
+        """mScore and scaling factor of one list of (mmz, mi, ri, cmz, ci) tuples (IL:2441-2498), on the device."""
+        rows = list(matched_peaks)
+        cols = [np.array([_NAN if r[j] is None else float(r[j]) for r in rows], dtype=np.float64) for j in range(5)]
+        score, scaling = C.c_double(), C.c_double()
+        self._ctx.call("qms_score_matches", len(rows), ptr(cols[0]), ptr(cols[1]), ptr(cols[2]), ptr(cols[3]), ptr(cols[4]),
+                       float(mz_score_percentile), C.byref(score), C.byref(scaling))
+        return score.value, scaling.value
+
+    # ------------------------------------------------------------------ reference helpers kept for API parity
+    def _transform_values(self, mz_values):
+        mz = np.ascontiguousarray(mz_values, dtype=np.float64)
+        lo, hi, tmz = (np.empty(len(mz), dtype=np.int32) for _ in range(3))
+        self._ctx.call("qms_transform_mz", len(mz), ptr(mz), ptr(lo), ptr(hi), ptr(tmz))
+        return lo, hi, tmz
+
+    def _transform_mz_to_set(self, mz):
+        """Integer ppm window of one m/z as a set (IL:2533-2552); edges computed by ``qms_transform_mz``."""
+        lo, hi, _ = self._transform_values([mz])
+        return set(range(int(lo[0]), int(hi[0]) + 1))
+
+    def _slice_list(self, source_list, borders, tolerance=2):
+        """+-2 elements (list) / +-2 Da (numpy) slice around ``borders`` (IL:2500-2531)."""
+        import bisect
+        lower, upper = list(borders[0]), list(borders[1])
+        if getattr(source_list, "tolist", False) is False:
+            try:
+                start, stop = bisect.bisect(source_list, lower) - tolerance, bisect.bisect(source_list, upper) + tolerance
+            except TypeError:
+                start = bisect.bisect(source_list, tuple(lower)) - tolerance
+                stop = bisect.bisect(source_list, tuple(upper)) + tolerance
+            return source_list[max(start, 0):min(stop, len(source_list))]
+        keep = (lower[0] - tolerance < source_list[:, 0]) * (source_list[:, 0] < upper[0] + tolerance)
+        return source_list[np.where(keep)]
+
+    def _transform_spectrum(self, mz_i_list, mz_range=None):
+        """(set of integer m/z buckets, bucket -> [(mz, i), ...]) of a spectrum (IL:2554-2603)."""
+        target = mz_i_list if mz_range is None else self._slice_list(mz_i_list, [(x, 0.001) for x in mz_range])
+        is_numpy = getattr(target, "tolist", False) is not False
+        mz = target[:, 0] if is_numpy else [p[0] for p in target]
+        _, _, tmz = self._transform_values(mz)
+        lookup = {}
+        for row, bucket in enumerate(tmz if is_numpy else tmz.tolist()):
+            lookup.setdefault(bucket, []).append((target[row][0], target[row][1]))
+        return set(tmz if is_numpy else tmz.tolist()), lookup
+
+    def print_overview(self, formula, charge=None):
+        """Isotope pattern table of one formula/molecule (IL:2042-2103)."""
+        if formula not in self:
+            formula = self.lookup["molecule to formula"][formula]
+        if charge is None:
+            charge = self.charges[0]
+        print("\n\n{0: ^30}\n\n".format("Overview"))
+        print("> Chemical formula", formula)
+        names = self.lookup["formula to trivial name"].get(formula, None)
+        if names is not None:
+            print("> Trivial name{0} {1}".format("" if len(names) == 1 else "s", names))
+        for lp in sorted(self[formula]["env"]):
+            env = self[formula]["env"][lp]
+            print("> Label percentile", lp)
+            print("> Isotope pattern                                                Abundance\n pos      Mass\t\t\t"
+                  "m/z [MH]{0:+1}               transformed    rel.".format(charge))
+            for n in range(len(env["abun"])):
+                print("{0: >3}\t{1:16.10f}\t{2:16.10f}\t{3:10.0f}\t{4:12.11f}\t{5}".format(
+                    n, env["mass"][n], env[charge]["mz"][n], env["abun"][n], env["relabun"][n], env["c_peak_pos"][n]))
+
+    # ------------------------------------------------------------------ introspection for benchmarks/tests
+    def device_counters(self):
+        return self._ctx.counters()
+
+    def entry_peaks(self):
+        """Per index entry: (theoretical c-peak m/z array, integer abundance array) -- workload generators."""
+        off = self._ent_win_off
+        return ([self._win_cmz[off[i]:off[i + 1]] for i in range(self._n_entries)],
+                [self._win_ci[off[i]:off[i + 1]].astype(np.float64) for i in range(self._n_entries)])
+
+
+class _Collector:
+    """Minimal ``results`` stand-in used by match_isotopologue."""
+
+    def __init__(self):
+        self.rows = []
+
+    def add(self, key, value):
+        self.rows.append((value[2], value[3], value[4]))

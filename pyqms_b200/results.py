@@ -1,0 +1,77 @@
+"""Result container of ``match_all`` -- the boundary type of the matching path.
+
+Mirrors the core of the reference's ``pyqms.Results`` (pyqms/results.py:40-57, 81-203): a ``dict``
+keyed by ``m_key(file_name, formula, charge, label_percentiles)`` whose values hold the list of
+``match(spec_id, rt, score, scaling_factor, peaks)`` tuples plus the running maximum score.
+Reporting (csv/xlsx/mzTab writers, RT-window curation, plots; results.py:205-2064) is out of scope
+of this build and works on top of this structure unchanged.
+"""
+from collections import namedtuple
+
+m_key = namedtuple("m_key", ["file_name", "formula", "charge", "label_percentiles"])
+match = namedtuple("match", ["spec_id", "rt", "score", "scaling_factor", "peaks"])
+combined = namedtuple("combined", ["file_name", "formula", "charge", "label_percentiles", "spec_id", "rt",
+                                   "score", "scaling_factor", "peaks"])
+
+
+class Results(dict):
+    def __init__(self, lookup=None, params=None, fixed_labels=None, metabolic_labels=None, aa_compositions=None,
+                 isotopic_distributions=None, charges=None, verbose=False):
+        super().__init__()
+        self.params = params
+        self.lookup = lookup if lookup is not None else {}
+        self.fixed_labels = fixed_labels
+        self.metabolic_labels = metabolic_labels
+        self.aa_compositions = aa_compositions
+        self.charges = charges
+        self.isotopic_distribution = isotopic_distributions
+        self.verbose = verbose
+        self.index = {"files": set(), "charges": set(), "formulas": set(), "label_percentiles": set()}
+        self._match_class = match
+        self._m_key_class = m_key
+        self._combined_class = combined
+        self._silac_pairs = None
+
+    def add(self, key, value):
+        """Append one match (results.py:144-203); returns the formatted key."""
+        key = self._m_key_class(*key)
+        slot = self.get(key)
+        if slot is None:
+            slot = self[key] = {"data": [], "max_score": -1, "max_score_index": -1, "len_data": 0}
+        entry = self._match_class(*value)
+        if slot["max_score"] < entry.score:
+            slot["max_score"] = entry.score
+            slot["max_score_index"] = len(slot["data"])
+        slot["len_data"] += 1
+        slot["data"].append(entry)
+        index = self.index
+        index["files"].add(key.file_name)
+        index["charges"].add(key.charge)
+        index["formulas"].add(key.formula)
+        index["label_percentiles"].add(key.label_percentiles)
+        return key
+
+    def extract_results(self, molecules=None, charges=None, file_names=None, label_percentiles=None, formulas=None):
+        """Yield (key, i, match) for every stored match that passes the given filters (results.py:305-341)."""
+        wanted_formulas = set(formulas or [])
+        for molecule in molecules or []:
+            wanted_formulas.add(self.lookup.get("molecule to formula", {}).get(molecule, molecule))
+        for key, slot in self.items():
+            if wanted_formulas and key.formula not in wanted_formulas:
+                continue
+            if charges is not None and key.charge not in charges:
+                continue
+            if file_names is not None and key.file_name not in file_names:
+                continue
+            if label_percentiles is not None and key.label_percentiles not in label_percentiles:
+                continue
+            for i, entry in enumerate(slot["data"]):
+                yield key, i, entry
+
+    def max_score(self, **filters):
+        """(key, index, match) of the best-scoring match under the filters, or (None, None, None)."""
+        best = (None, None, None)
+        for key, i, entry in self.extract_results(**filters):
+            if best[2] is None or entry.score > best[2].score:
+                best = (key, i, entry)
+        return best

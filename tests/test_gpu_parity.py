@@ -1,0 +1,230 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI via the host class) against
+ (1) vectors produced by the unmodified reference (tests/golden/*.json.gz),
+ (2) the CPU oracle on fresh seeded inputs,
+ (3) the reference's own golden vectors / the docs' known answer.
+Bar: hit sets, keys, key order, matched peaks, integer abundances, c-peak positions and integer
+m/z windows bit-exact; isotope abundances <= 1e-9 relative; mScore / scaling <= 1e-6 absolute (relative
+for the scaling factor, which is an amount)."""
+import json
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests.golden.cases import CASES, PEPTIDE_SEQUENCE_KATS, QUICK_START_EXPECT, QUICK_START_PEAKS  # noqa: E402
+from tests.helpers import GOLDEN, assert_results_equal, load_case, lp_tuple, results_to_rows  # noqa: E402
+
+REL_ABUN = 1e-9
+REL_MASS = 1e-12
+SCORE_TOL = 1e-6
+
+
+def rel_close(a, b, tol):
+    return abs(a - b) <= tol * max(abs(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def pyqms():
+    import pyqms_b200
+    return pyqms_b200
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, pyqms):
+    blob, peaks, offsets = load_case(request.param)
+    lib = pyqms.IsotopologueLibrary(verbose=False, **CASES[request.param]["lib"])
+    return request.param, blob, peaks, offsets, lib
+
+
+def test_library_matches_reference_dump(case):
+    name, blob, _, _, lib = case
+    ref = blob["library"]
+    assert sorted(lib.keys()) == sorted(ref["formulas"])
+    lps = [lp_tuple(x) for x in ref["labled_percentiles"]]
+    assert lib.labled_percentiles == lps
+    assert lib.lookup["molecule to formula"] == ref["molecule_to_formula"]
+    assert {k: sorted(v) for k, v in lib.lookup["molecule fixed label variations"].items()} == ref["fixed_label_variations"]
+    for formula in ref["formulas"]:
+        assert dict(lib[formula]["cc"]) == ref["cc"][formula]
+        for lp, want in zip(lps, ref["env"][formula]):
+            env = lib[formula]["env"][lp]
+            assert env["abun"] == want["abun"], (formula, lp)                  # integers: exact
+            assert env["c_peak_pos"] == want["c_peak_pos"], (formula, lp)
+            assert env["n_c_peaks"] == want["n_c_peaks"]
+            assert len(env["mass"]) == len(want["mass"])
+            for a, b in zip(env["mass"], want["mass"]):
+                assert rel_close(a, b, REL_MASS), (formula, lp, a, b)
+            for a, b in zip(env["relabun"], want["relabun"]):
+                assert rel_close(a, b, REL_ABUN), (formula, lp, a, b)
+            for z in lib.charges:
+                wz = want["z"][str(z)]
+                for a, b in zip(env[z]["mz"], wz["mz"]):
+                    assert rel_close(a, b, REL_MASS)
+                wins = [None if s is None else [min(s), max(s), len(s)] for s in env[z]["tmzs"]]
+                assert wins == wz["win"], (formula, lp, z)                       # integer windows: exact
+                assert len(env[z]["atmzs"]) == wz["n_atmzs"]
+    got = lib.formulas_sorted_by_mz
+    assert len(got) == len(ref["index"])
+    for (lo, hi, z, lp, formula), (wlo, whi, wz, wlp, wf) in zip(got, ref["index"]):
+        assert (z, lp, formula) == (wz, lps[wlp], ref["formulas"][wf])           # index order: exact
+        assert rel_close(lo, wlo, REL_MASS) and rel_close(hi, whi, REL_MASS)
+    if ref["index"]:
+        assert rel_close(lib.match_set_mz_range[0], ref["match_set_mz_range"][0], REL_MASS)
+        assert rel_close(lib.match_set_mz_range[1], ref["match_set_mz_range"][1], REL_MASS)
+    sets = lib.match_sets
+    assert [[m["ids"], len(m["tmzs"])] for m in sets.values()] == [[ids, n] for ids, _, n in ref["match_sets"]]
+
+
+def test_element_trees_match_reference(case):
+    name, blob, _, _, lib = case
+    trees = lib.element_trees
+    for el, by_label in blob["library"]["trees"].items():
+        for label, levels in by_label.items():
+            for n, want in levels.items():
+                if want is None:
+                    assert int(n) not in trees[el][label]
+                    continue
+                lo, hi, abun, mass = want
+                if int(n) > max(trees[el][label]):
+                    continue        # the reference builds one level more than it can use for >2-isotope elements (Q5)
+                node = trees[el][label][int(n)]
+                assert (node["minPos"], node["maxPos"]) == (lo, hi), (el, label, n)
+                for j, p in enumerate(range(min(lo, hi), max(lo, hi) + 1)):
+                    assert rel_close(node["env"][p]["abun"], abun[j], REL_ABUN), (el, label, n, p)
+                    assert rel_close(node["env"][p]["mass"], mass[j], REL_MASS), (el, label, n, p)
+
+
+@pytest.mark.parametrize("mode", ["numpy", "list"])
+def test_match_all_matches_reference(case, mode):
+    name, blob, peaks, offsets, lib = case
+    res = None
+    for s in range(len(offsets) - 1):
+        spec = peaks[offsets[s]:offsets[s + 1]]
+        if mode == "list":
+            spec = [(float(a), float(b)) for a, b in spec]
+        res = lib.match_all(mz_i_list=spec, file_name="run", spec_id=s, spec_rt=s * 0.2, results=res)
+    assert_results_equal(results_to_rows(res), blob["results_" + mode], score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+
+
+def test_match_many_equals_match_all_loop(case):
+    name, blob, peaks, offsets, lib = case
+    n = len(offsets) - 1
+    res = lib.match_many(peaks, file_name="run", spec_ids=list(range(n)), spec_rts=[s * 0.2 for s in range(n)], offsets=offsets)
+    assert_results_equal(results_to_rows(res), blob["results_numpy"], score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+    as_lists = [[(float(a), float(b)) for a, b in peaks[offsets[s]:offsets[s + 1]]] for s in range(n)]
+    res = lib.match_many(as_lists, file_name="run", spec_ids=list(range(n)), spec_rts=[s * 0.2 for s in range(n)])
+    assert_results_equal(results_to_rows(res), blob["results_list"], score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+
+
+def test_reference_peptide_sequence_vectors(pyqms, golden_dir):
+    for molecule, formula, abun, (lo, hi) in PEPTIDE_SEQUENCE_KATS:
+        lib = pyqms.IsotopologueLibrary(molecules=[molecule], charges=[2], verbose=False,
+                                        unimod_files=[golden_dir / "usermod_silac_tmt.xml"])
+        assert formula in lib
+        env = lib[formula]["env"][(("N", "0.000"),)]
+        assert env["abun"] == abun
+        first = next(s for s in env[2]["tmzs"] if s is not None)
+        assert first == set(range(lo, hi + 1))
+
+
+def test_quick_start_known_answer(pyqms):
+    lib = pyqms.IsotopologueLibrary(molecules=["DDSPDLPK"], charges=[2], metabolic_labels=None, fixed_labels=None, verbose=False)
+    for spec in (QUICK_START_PEAKS, np.array(QUICK_START_PEAKS)):
+        res = lib.match_all(mz_i_list=spec, file_name="BSA_test", spec_id=1165, spec_rt=29.10, results=None)
+        assert [tuple(k) for k in res.keys()] == [QUICK_START_EXPECT["key"]]
+        slot = res[list(res.keys())[0]]
+        assert slot["len_data"] == 1 and slot["max_score_index"] == 0
+        hit = slot["data"][0]
+        assert hit.spec_id == 1165 and hit.rt == 29.10
+        assert abs(hit.score - QUICK_START_EXPECT["score"]) < SCORE_TOL
+        assert abs(hit.scaling_factor - QUICK_START_EXPECT["scaling_factor"]) < 1e-9 * QUICK_START_EXPECT["scaling_factor"]
+        for got, want in zip(hit.peaks, QUICK_START_EXPECT["peaks"]):
+            assert got[0] == want[0] and got[1] == want[1] and got[4] == want[4]
+            assert rel_close(got[2], want[2], REL_ABUN) and rel_close(got[3], want[3], REL_MASS)
+
+
+def test_score_matches_known_answers(pyqms):
+    kat = json.loads((GOLDEN / "kat.json").read_text())
+    lib = pyqms.IsotopologueLibrary(molecules=["ELVISLIVES"], charges=[2], verbose=False, params={"MZ_SCORE_PERCENTILE": 0.5})
+    for peaks, xi, score, scaling in kat["score_matches"][:80] + kat["score_matches"][-40:]:
+        got = lib.score_matches([tuple(p) for p in peaks], xi)
+        assert got == (score, scaling), (peaks, xi)                # same operation order: bit-exact
+    for key, spec_id, score, scaling, peaks in kat["bsa_pickle_matches"]:
+        got = lib.score_matches([tuple(p) for p in peaks], kat["bsa_pickle_xi"])
+        assert got == (score, scaling)
+
+
+def test_private_helpers(pyqms):
+    """tests/transform_mz_to_set_test.py, transform_spectrum_test.py, slice_list_test.py of the reference."""
+    lib = pyqms.IsotopologueLibrary(molecules=["PEPTIDE"], charges=[2], verbose=False, params={"REL_MZ_RANGE": 10e-6})
+    assert len(lib._transform_mz_to_set(1000.001)) == 21
+    lib2 = pyqms.IsotopologueLibrary(molecules=["PEPTIDE"], charges=[2], verbose=False,
+                                     params={"REL_MZ_RANGE": 5e-6, "INTERNAL_PRECISION": 10000})
+    assert len(lib2._transform_mz_to_set(1000.001)) == 101
+    keys, lookup = lib2._transform_spectrum([(1000.0009, 1.0), (1000.00091, 2.0), (1200.5, 3.0)])
+    assert keys == {10000009, 12005000}
+    assert lookup[10000009] == [(1000.0009, 1.0), (1000.00091, 2.0)]
+    data = [(float(i), float(i)) for i in range(20)]
+    assert lib._slice_list(data, ((5, 0), (10, 0))) == data[4:13]
+    assert len(lib._slice_list(np.array(data), ((5, 0), (10, 0)))) == 8
+
+
+def test_match_isotopologue(pyqms):
+    lib = pyqms.IsotopologueLibrary(molecules=["DDSPDLPK"], charges=[2], verbose=False)
+    best = lib.match_isotopologue(index=0, mz_i_list=QUICK_START_PEAKS, mz_score_percentile=0.4)
+    assert best is not None and abs(best[0] - QUICK_START_EXPECT["score"]) < SCORE_TOL
+    assert [(p[0], p[1]) for p in best[2]] == [(p[0], p[1]) for p in QUICK_START_EXPECT["peaks"]]
+    assert lib.match_isotopologue(index=0, mz_i_list=QUICK_START_PEAKS[:10], mz_score_percentile=0.4) is None
+    keys, lookup = lib._transform_spectrum(QUICK_START_PEAKS)
+    again = lib.match_isotopologue(formula="C(37)H(59)N(9)O(16)", charge=2, label_percentile=(("N", "0.000"),),
+                                   spec_tmz_set=keys, spec_tmz_lookup=lookup, mz_score_percentile=0.4)
+    assert again is not None and abs(again[0] - best[0]) < 1e-12
+
+
+def test_edge_cases(pyqms):
+    lib = pyqms.IsotopologueLibrary(molecules=["DDSPDLPK", "LVTDLTK"], charges=[1, 2], verbose=False)
+    assert len(lib.match_all(mz_i_list=[], file_name="f", spec_id=0, spec_rt=0.0)) == 0
+    assert len(lib.match_all(mz_i_list=np.zeros((0, 2)), file_name="f", spec_id=0, spec_rt=0.0)) == 0
+    assert len(lib.match_all(mz_i_list=[(443.7112, 1000.0)], file_name="f", spec_id=0, spec_rt=0.0)) == 0
+    assert len(lib.match_all(mz_i_list=np.array([[100.0, 1.0], [2500.0, 2.0]]), file_name="f", spec_id=0, spec_rt=0.0)) == 0
+    # unsorted numpy input: same hits as the sorted spectrum (reference semantics, IL:2592-2600)
+    spec = np.array(QUICK_START_PEAKS)
+    want = results_to_rows(lib.match_all(mz_i_list=spec, file_name="f", spec_id=1, spec_rt=1.0))
+    shuffled = spec[np.random.default_rng(3).permutation(len(spec))]
+    got = results_to_rows(lib.match_all(mz_i_list=shuffled, file_name="f", spec_id=1, spec_rt=1.0))
+    assert_results_equal(got, want)
+    with pytest.raises(ValueError):
+        lib.match_all(mz_i_list=[tuple(r) for r in shuffled], file_name="f", spec_id=1, spec_rt=1.0)
+    # ragged batch with empty spectra in the middle
+    parts = [spec, np.zeros((0, 2)), spec[:5], np.zeros((0, 2)), spec]
+    res = lib.match_many(parts, file_name="f", spec_ids=list(range(5)), spec_rts=[0.0] * 5)
+    rows = results_to_rows(res)
+    assert [r[0] for r in rows[0][1]] == [0, 4]
+    # library with nothing in range: no hits, no crash
+    empty = pyqms.IsotopologueLibrary(molecules=["+H2O"], charges=[1], verbose=False)
+    assert empty.formulas_sorted_by_mz == [] and len(empty.match_all(mz_i_list=spec, file_name="f", spec_id=0, spec_rt=0)) == 0
+    with pytest.raises(SystemExit):
+        pyqms.IsotopologueLibrary(molecules=["KLEINERTEST"], charges=[2], fixed_labels={"X": ["C(-6) 13C(6)"]}, verbose=False)
+
+
+def test_oracle_differential_random(pyqms):
+    """Fresh seeded inputs (not in the fixtures): CUDA path vs the CPU oracle."""
+    sys.setrecursionlimit(20000)
+    from oracle.qms_oracle import OracleLibrary
+    from pyqms_b200.synthetic import random_tryptic_peptides, synth_run
+    from tests.golden.spectra import entry_peaks
+    kwargs = dict(molecules=random_tryptic_peptides(60, seed=77), charges=[2, 3, 4], metabolic_labels={"15N": [0, 0.6, 0.99]},
+                  fixed_labels={"C": ["C(2)H(3)14N(1)O(1)"]})
+    ora = OracleLibrary(**kwargs)
+    lib = pyqms.IsotopologueLibrary(verbose=False, **kwargs)
+    assert [(z, lp, f) for _, _, z, lp, f in lib.formulas_sorted_by_mz] == [(z, lp, f) for _, _, z, lp, f in ora.formulas_sorted_by_mz]
+    mzs, cis = entry_peaks(ora)
+    peaks, offsets = synth_run(mzs, cis, n_spectra=25, seed=4242, mean_peaks=400, elution_sigma=1.5, entry_fraction=0.3)
+    want = {}
+    for s in range(len(offsets) - 1):
+        ora.match_all(peaks[offsets[s]:offsets[s + 1]], "r", s, float(s), want)
+    got = lib.match_many(peaks, file_name="r", spec_ids=list(range(25)), spec_rts=[float(s) for s in range(25)], offsets=offsets)
+    assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+    assert sum(len(v) for v in want.values()) > 50
