@@ -40,6 +40,12 @@ __global__ void envelope_convolve_kernel(int64_t e_begin, int64_t e_end, const i
 
     int len = 1;
     int zero_pos = 0;
+    // The first and the last position are reached by exactly one combination (every element at its
+    // minPos / maxPos); their mass is the plain sum of the slice-edge masses in element order, which is
+    // what the reference's mass*abun/total collapses to (IL:731-737).  Keeping it free of the abundance
+    // round trip makes equal formulas under different label percentiles tie exactly on lower_mz, so the
+    // index sort falls through to upper_mz like the reference's tuple sort.
+    double edge_lo = 0.0, edge_hi = 0.0;
     unsigned long long pairs = 0;
     if (lane == 0) {
         a_prev[0] = 1.0;  // abun = 1, mass = 0 (IL:662-663)
@@ -57,6 +63,8 @@ __global__ void envelope_convolve_kernel(int64_t e_begin, int64_t e_end, const i
             s_mass[j] = tree_mass[off + j];
         }
         __syncwarp();
+        edge_lo = __dadd_rn(edge_lo, s_mass[0]);
+        edge_hi = __dadd_rn(edge_hi, s_mass[r - 1]);
         const int new_len = len + r - 1;
         for (int p = lane; p < new_len; p += 32) {
             double acc_a = 0.0, acc_w = 0.0;
@@ -98,7 +106,7 @@ __global__ void envelope_convolve_kernel(int64_t e_begin, int64_t e_end, const i
             const int64_t o = out0 + kept + __popc(mask & ((1u << lane) - 1u));
             rel = __ddiv_rn(total, top);
             c_peak = rel >= min_rel;
-            env_mass[o] = __ddiv_rn(w_prev[p], total);
+            env_mass[o] = p == 0 ? edge_lo : (p == len - 1 ? edge_hi : __ddiv_rn(w_prev[p], total));
             env_relabun[o] = rel;
             env_abun[o] = __double2int_rn(__dmul_rn(total, factor));
             env_pos[o] = zero_pos + p;

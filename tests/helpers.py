@@ -33,10 +33,22 @@ def results_to_rows(res):
     return out
 
 
-def assert_results_equal(got, want, score_tol=0.0, cmz_rel=0.0, ri_rel=0.0):
-    """Hit sets, keys, key order and matched (mmz, mi) exact; score/scaling within score_tol;
-    cmz / ri within the relative tolerances (0 = bit-exact)."""
-    assert [g[0] for g in got] == [w[0] for w in want], "key sets / first-hit order differ"
+def _key_sort(key):
+    return (key[0], key[1], key[2], str(key[3]))
+
+
+def assert_results_equal(got, want, score_tol=0.0, cmz_rel=0.0, ri_rel=0.0, key_order=True):
+    """Hit sets, keys and matched (mmz, mi) exact; score/scaling within score_tol; cmz / ri within the
+    relative tolerances (0 = bit-exact).  key_order: also require the keys' first-hit order to be equal.
+    (Entries whose lower m/z differ only in the last ulp have no defined mutual order -- the reference's
+    own order among them changes with the Python version, SURVEY.md Q7/Q14 -- so callers comparing against
+    the reference on libraries with label-percentile grids pass key_order=False.)"""
+    if key_order:
+        assert [g[0] for g in got] == [w[0] for w in want], "key sets / first-hit order differ"
+    else:
+        got = sorted(got, key=lambda r: _key_sort(r[0]))
+        want = sorted(want, key=lambda r: _key_sort(r[0]))
+        assert [g[0] for g in got] == [w[0] for w in want], "key sets differ"
     for (key, grows), (_, wrows) in zip(got, want):
         assert len(grows) == len(wrows), (key, len(grows), len(wrows))
         for g, w in zip(grows, wrows):
@@ -49,3 +61,21 @@ def assert_results_equal(got, want, score_tol=0.0, cmz_rel=0.0, ri_rel=0.0):
                 assert abs(gp[2] - wp[2]) <= ri_rel * abs(wp[2]), (key, gp, wp)
                 assert abs(gp[3] - wp[3]) <= cmz_rel * abs(wp[3]), (key, gp, wp)
                 assert gp[4] == wp[4], (key, gp, wp)
+
+
+def assert_index_order_equal(got, want, rel=1e-12):
+    """got / want: [(lower_mz, upper_mz, z, lp, formula)].  Equal as sequences, except that runs of entries
+    whose lower m/z agree to `rel` may be permuted (their order is decided by last-ulp noise)."""
+    assert len(got) == len(want)
+    i = 0
+    n_exact = 0
+    while i < len(want):
+        j = i + 1
+        while j < len(want) and abs(want[j][0] - want[i][0]) <= rel * want[i][0]:
+            j += 1
+        a = sorted((z, str(lp), f) for _, _, z, lp, f in got[i:j])
+        b = sorted((z, str(lp), f) for _, _, z, lp, f in want[i:j])
+        assert a == b, (i, j, got[i:j], want[i:j])
+        n_exact += [g[2:] for g in got[i:j]] == [w[2:] for w in want[i:j]]
+        i = j
+    return n_exact
