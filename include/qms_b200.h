@@ -62,7 +62,8 @@ typedef struct qms_counters {
     int64_t hits;               /* matches emitted                                               */
     int64_t hit_windows;        /* sum of c-peak windows over the emitted matches                */
     int64_t kernel_launches;    /* kernels of this library launched                              */
-    double ms_probe;            /* device ms in spectrum_probe_gate (CUDA events on ctx stream)  */
+    double ms_probe;            /* device ms in spectrum_probe_kernel (CUDA events on ctx stream) */
+    double ms_gate;             /* device ms in gate_rows_kernel                                 */
     double ms_score;            /* device ms in assemble_score                                   */
     double ms_compact;          /* device ms in sort + compaction of hits                        */
     double ms_h2d;              /* device ms copying spectra host->device                        */

@@ -30,7 +30,7 @@ class QmsCounters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "spectra", "peaks", "live_peaks", "incidences", "candidates", "candidate_windows", "combinations", "hits",
         "hit_windows", "kernel_launches")] + [(n, C.c_double) for n in (
-            "ms_probe", "ms_score", "ms_compact", "ms_h2d", "ms_d2h", "ms_trees", "ms_envelopes", "ms_index")] + [
+            "ms_probe", "ms_gate", "ms_score", "ms_compact", "ms_h2d", "ms_d2h", "ms_trees", "ms_envelopes", "ms_index")] + [
         ("envelopes", C.c_int64), ("envelope_flops", C.c_int64)]
 
     def as_dict(self):

@@ -4,11 +4,13 @@
 // The reference walks every match bin for every spectrum, re-hashes the spectrum per bin and
 // intersects Python sets.  Here the work is driven by the spectrum peaks instead:
 //
-//  K5 spectrum_probe_gate   flat, coalesced stream over all peaks of the batch (one LDG.128 per
-//      (m/z, intensity) row).  tmz = rint(mz*P); a two-level cover bitmap rejects peaks whose 1/P-Da
-//      bucket no library window contains (the HBM-bound regime of small libraries).  A live bucket
-//      looks up the lo-sorted window list through the direct-address cell table; for every
-//      (bucket, window) incidence the owning index entry is gated exactly like IL:1968-1976:
+//  K5a spectrum_probe     flat, coalesced stream over all peaks of the batch (one LDG.128 per
+//      (m/z, intensity) row).  tmz = rint(mz*P); a two-level cover bitmap rejects rows whose 1/P-Da
+//      bucket no library window contains (the HBM-bound regime of small libraries); surviving rows are
+//      compacted (warp ballot + shared-memory cursor) into per-block segments.
+//  K5b gate_rows            one thread per surviving row: spectrum lookup, bucket dedupe, the lo-sorted
+//      window list through the direct-address cell table; for every (bucket, window) incidence the
+//      owning index entry is gated exactly like IL:1968-1976:
 //      |distinct spectrum buckets inside the entry's windows| >= MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES
 //      and / n_c_peaks >= REQUIRED_PERCENTILE_PEAK_OVERLAP.  Each (spectrum, entry) pair is gated
 //      once, at its canonical incidence = lowest window, lowest bucket.  Survivors are appended
@@ -154,13 +156,22 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
 
 #define PROBE_THREADS 256
 #define PROBE_UNROLL 4
+#define ROW_CHECK_ONLY 0x80000000u   // row listed only because its bucket is below its predecessor's
 
-__global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_gate_kernel(MatchView v, int64_t p_begin, int64_t p_end,
-                                                                             unsigned long long* __restrict__ pair_keys,
-                                                                             unsigned long long pair_cap,
-                                                                             unsigned long long* __restrict__ counters) {
-    unsigned long long n_live = 0, n_inc = 0;
+// K5a: the streaming half.  Every (m/z, intensity) row is read once with one LDG.128, coalesced (a warp
+// covers 512 contiguous bytes per load, PROBE_UNROLL independent loads in flight per thread).  A row
+// survives if its bucket is covered by a library window (two-level bitmap, the coarse level is a few KB
+// and stays in L1) or if its bucket descends against the previous row (sortedness is verified by K5b,
+// which knows the spectrum boundaries).  Survivors are appended to the block's own segment of
+// `live_rows` through a shared-memory cursor (warp-aggregated), so the stream issues no global atomics.
+__global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_kernel(MatchView v, int64_t p_begin, int64_t p_end,
+                                                                        int64_t seg_cap, uint32_t* __restrict__ live_rows,
+                                                                        uint32_t* __restrict__ live_count) {
+    __shared__ uint32_t s_cursor;
+    if (threadIdx.x == 0) s_cursor = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
+    uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
     const int64_t tile = (int64_t)PROBE_THREADS * PROBE_UNROLL;
     for (int64_t base = p_begin + (int64_t)blockIdx.x * tile; base < p_end; base += (int64_t)gridDim.x * tile) {
         double2 row[PROBE_UNROLL];
@@ -173,39 +184,65 @@ __global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_gate_kernel(Matc
         for (int u = 0; u < PROBE_UNROLL; ++u) {
             const int64_t i = base + (int64_t)u * PROBE_THREADS + threadIdx.x;
             const bool valid = i < p_end;
-            // m/z of the previous row: neighbour lane, lane 0 reloads (sortedness + bucket dedupe)
-            double prev = __shfl_up_sync(0xffffffffu, row[u].x, 1);
-            if (lane == 0 && valid && i > p_begin) prev = __ldg(&v.peaks[i - 1].x);
-            if (!valid) continue;
-            const double mz = row[u].x;
-            const int32_t t = qms_tmz(mz, v.precision);
-            const bool descends = i > p_begin && t < qms_tmz(prev, v.precision);
+            const int32_t t = qms_tmz(row[u].x, v.precision);
+            int32_t t_prev = __shfl_up_sync(0xffffffffu, t, 1);
+            if (lane == 0) t_prev = (valid && i > p_begin) ? tmz_at(v.peaks, i - 1, v.precision) : t;
             bool live = false;
-            if (t >= v.t_min && t <= v.t_max) {
+            if (valid && t >= v.t_min && t <= v.t_max) {
                 const uint32_t c = (uint32_t)(t - v.t_min);
                 if ((__ldg(&v.cover2[c >> 10]) >> ((c >> 5) & 31)) & 1u) live = (__ldg(&v.cover[c >> 5]) >> (c & 31)) & 1u;
             }
-            if (!live && !descends) continue;
-            const int64_t s = spectrum_of(v.offsets, v.n_spectra, i);
-            const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
-            if (descends && i > sb) atomicAdd(&counters[C_UNSORTED], 1ull);  // m/z buckets not ascending inside a spectrum
-            if (!live) continue;
-            ++n_live;
-            // numpy input: only the first row of a bucket is ever used (Q9); list input decides per bin
-            if (v.input_kind == 0 && i > sb && qms_tmz(prev, v.precision) == t) continue;
-            int32_t c_lo = t - v.max_width + 1;
-            if (c_lo < v.t_min) c_lo = v.t_min;
-            const int32_t j0 = __ldg(&v.cell_start[c_lo - v.t_min]);
-            const int32_t j1 = __ldg(&v.cell_start[t + 1 - v.t_min]);
-            for (int32_t j = j0; j < j1; ++j) {
-                const int4 raw = __ldg(reinterpret_cast<const int4*>(&v.probe[j]));  // lo, hi, entry, k
-                if (raw.y < t) continue;
-                if (v.only_entry >= 0 && raw.z != v.only_entry) continue;
-                ++n_inc;
-                if (gate_incidence(v, sb, se, i, t, raw.z, raw.w)) {
-                    const unsigned long long slot = atomicAdd(&counters[C_PAIRS], 1ull);
-                    if (slot < pair_cap) pair_keys[slot] = ((unsigned long long)s << 32) | (unsigned long long)(uint32_t)raw.z;
-                }
+            const bool descends = valid && t < t_prev;
+            const bool push = live || descends;
+            const unsigned mask = __ballot_sync(0xffffffffu, push);
+            if (mask) {
+                uint32_t warp_base = 0;
+                if (lane == 0) warp_base = atomicAdd(&s_cursor, (uint32_t)__popc(mask));
+                warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+                if (push)
+                    segment[warp_base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(i - p_begin) | (live ? 0u : ROW_CHECK_ONLY);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) live_count[blockIdx.x] = s_cursor;
+}
+
+// K5b: the gating half, one thread per surviving row (all lanes of a warp are in the slow path together).
+// Spectrum lookup, bucket dedupe (Q9), window lookup through the cell table, entry gating (IL:1968-1976).
+__global__ void __launch_bounds__(PROBE_THREADS) gate_rows_kernel(MatchView v, int64_t p_begin, int64_t seg_cap,
+                                                                   const uint32_t* __restrict__ live_rows,
+                                                                   const uint32_t* __restrict__ live_count,
+                                                                   unsigned long long* __restrict__ pair_keys,
+                                                                   unsigned long long pair_cap,
+                                                                   unsigned long long* __restrict__ counters) {
+    unsigned long long n_live = 0, n_inc = 0;
+    const uint32_t n_rows = live_count[blockIdx.x];
+    const uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
+    for (uint32_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        const uint32_t word = segment[r];
+        const int64_t i = p_begin + (int64_t)(word & ~ROW_CHECK_ONLY);
+        const int64_t s = spectrum_of(v.offsets, v.n_spectra, i);
+        const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
+        const int32_t t = tmz_at(v.peaks, i, v.precision);
+        const int32_t t_prev = i > sb ? tmz_at(v.peaks, i - 1, v.precision) : INT32_MIN;
+        if (t < t_prev) atomicAdd(&counters[C_UNSORTED], 1ull);  // buckets not ascending inside a spectrum
+        if (word & ROW_CHECK_ONLY) continue;
+        ++n_live;
+        // numpy input: only the first row of a bucket is ever used (Q9); list input decides per bin
+        if (v.input_kind == 0 && t_prev == t) continue;
+        int32_t c_lo = t - v.max_width + 1;
+        if (c_lo < v.t_min) c_lo = v.t_min;
+        const int32_t j0 = __ldg(&v.cell_start[c_lo - v.t_min]);
+        const int32_t j1 = __ldg(&v.cell_start[t + 1 - v.t_min]);
+        for (int32_t j = j0; j < j1; ++j) {
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(&v.probe[j]));  // lo, hi, entry, k
+            if (raw.y < t) continue;
+            if (v.only_entry >= 0 && raw.z != v.only_entry) continue;
+            ++n_inc;
+            if (gate_incidence(v, sb, se, i, t, raw.z, raw.w)) {
+                const unsigned long long slot = atomicAdd(&counters[C_PAIRS], 1ull);
+                if (slot < pair_cap) pair_keys[slot] = ((unsigned long long)s << 32) | (unsigned long long)(uint32_t)raw.z;
             }
         }
     }
@@ -213,7 +250,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_gate_kernel(Matc
         n_live += __shfl_xor_sync(0xffffffffu, n_live, sft);
         n_inc += __shfl_xor_sync(0xffffffffu, n_inc, sft);
     }
-    if (lane == 0) {
+    if ((threadIdx.x & 31) == 0) {
         if (n_live) atomicAdd(&counters[C_LIVE], n_live);
         if (n_inc) atomicAdd(&counters[C_INCID], n_inc);
     }
@@ -594,7 +631,8 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     v.xi = mz_score_percentile;
     v.score_thr = P.m_score_threshold;
 
-    // ---- K5 ----
+    // ---- K5a + K5b ----
+    if (n_peaks >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 peaks per batch (split the run)");
     QMS_TRY(qms_reserve(ctx, ctx->dev_counters, 64));
     size_t pair_cap = ctx->pair_keys.cap;
     if (pair_cap < 65536) {
@@ -603,21 +641,31 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     }
     const int64_t tile = (int64_t)PROBE_THREADS * PROBE_UNROLL;
     int64_t blocks = (n_peaks + tile - 1) / tile;
-    const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * 8;   // 8 resident CTAs of 256 threads per SM
     if (blocks > max_blocks) blocks = max_blocks;
+    const int64_t tiles_total = (n_peaks + tile - 1) / tile;
+    const int64_t seg_cap = ((tiles_total + blocks - 1) / blocks) * tile;   // every row of a block could survive
+    QMS_TRY(qms_reserve(ctx, ctx->live_rows, (size_t)(seg_cap * blocks)));
+    QMS_TRY(qms_reserve(ctx, ctx->live_count, (size_t)blocks));
     unsigned long long n_pairs = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         QMS_CUDA(ctx, cudaMemsetAsync(ctx->dev_counters.p, 0, 64 * sizeof(unsigned long long), ctx->stream));
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-        spectrum_probe_gate_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, ctx->pair_keys.p,
-                                                                                       (unsigned long long)pair_cap, ctx->dev_counters.p);
+        spectrum_probe_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p,
+                                                                                  ctx->live_count.p);
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-        ctx->cnt.kernel_launches++;
+        gate_rows_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p,
+                                                                             ctx->pair_keys.p, (unsigned long long)pair_cap,
+                                                                             ctx->dev_counters.p);
+        QMS_CUDA(ctx, cudaGetLastError());
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+        ctx->cnt.kernel_launches += 2;
         QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                       ctx->stream));
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->cnt.ms_probe += elapsed(ctx, 2, 3);
+        ctx->cnt.ms_gate += elapsed(ctx, 3, 5);
         if (ctx->h_pinned[C_UNSORTED])
             return qms_fail(ctx, QMS_E_INPUT, "m/z values are not ascending inside %llu spectrum position(s)",
                             (unsigned long long)ctx->h_pinned[C_UNSORTED]);
