@@ -263,7 +263,13 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
         QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, bytes, ent_nc.b.p, ctx->ent_win_off.p, n_entries + 1, ctx->stream));
         TmpBuf<double> d_top(ctx);
+        TmpBuf<int64_t> d_max_nc(ctx);
         QMS_TRY(qms_reserve(ctx, d_top.b, 1));
+        QMS_TRY(qms_reserve(ctx, d_max_nc.b, 1));
+        bytes = 0;
+        QMS_CUDA(ctx, cub::DeviceReduce::Max(nullptr, bytes, ent_nc.b.p, d_max_nc.b.p, n_entries, ctx->stream));
+        QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
+        QMS_CUDA(ctx, cub::DeviceReduce::Max(ctx->cub_tmp.p, bytes, ent_nc.b.p, d_max_nc.b.p, n_entries, ctx->stream));
         bytes = 0;
         QMS_CUDA(ctx, cub::DeviceReduce::Max(nullptr, bytes, ctx->ent_upper.p, d_top.b.p, n_entries, ctx->stream));
         QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
@@ -273,7 +279,10 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->ent_win_off.p + n_entries, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         QMS_CUDA(ctx, cudaMemcpyAsync(&range[0], ctx->ent_lower.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         QMS_CUDA(ctx, cudaMemcpyAsync(&range[1], d_top.b.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        int64_t h_max_nc = 0;
+        QMS_CUDA(ctx, cudaMemcpyAsync(&h_max_nc, d_max_nc.b.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->max_nc = (int32_t)h_max_nc;
         ctx->n_windows = (int64_t)ctx->h_pinned[0];
         ctx->mz_min = range[0];   // entries are sorted by lower m/z (IL:923-931)
         ctx->mz_max = range[1];   // IL:932-939

@@ -119,39 +119,86 @@ __device__ __forceinline__ int64_t spectrum_of(const int64_t* __restrict__ offse
     return a;
 }
 
+// first index j in [from, end) whose bucket is >= t, searching forward exponentially from `from`
+// (consecutive windows of an entry are ~1/z Da apart, i.e. a handful of rows: 1-3 probes instead of log2(P))
+__device__ __forceinline__ int64_t gallop_forward(const double2* __restrict__ peaks, int64_t from, int64_t end, int32_t t, double precision) {
+    if (from >= end || tmz_at(peaks, from, precision) >= t) return from < end ? from : end;
+    int64_t step = 1, lo = from;  // bucket(lo) < t
+    while (lo + step < end && tmz_at(peaks, lo + step, precision) < t) {
+        lo += step;
+        step <<= 1;
+    }
+    int64_t hi = lo + step < end ? lo + step : end;  // bucket(hi) >= t or hi == end
+    return lower_bound_t(peaks, lo + 1, hi, t, precision);
+}
+
+// last index j in [begin, from] whose bucket is <= t, searching backward from `from`; begin-1 if none
+__device__ __forceinline__ int64_t gallop_backward(const double2* __restrict__ peaks, int64_t begin, int64_t from, int32_t t, double precision) {
+    if (from < begin) return begin - 1;
+    if (tmz_at(peaks, from, precision) <= t) return from;
+    int64_t step = 1, hi = from;  // bucket(hi) > t
+    while (hi - step >= begin && tmz_at(peaks, hi - step, precision) > t) {
+        hi -= step;
+        step <<= 1;
+    }
+    const int64_t lo = hi - step >= begin ? hi - step : begin - 1;  // bucket(lo) <= t or lo == begin-1
+    // first index in (lo, hi) whose bucket is > t, minus one
+    int64_t a = lo + 1, b = hi;
+    while (a < b) {
+        const int64_t mid = a + ((b - a) >> 1);
+        if (tmz_at(peaks, mid, precision) <= t)
+            a = mid + 1;
+        else
+            b = mid;
+    }
+    return a - 1;
+}
+
 // Gate one (bucket t at peak row i, window k of entry x) incidence.  Returns true if this is the
-// pair's canonical incidence and the pair passes both overlap gates.
+// pair's canonical incidence (lowest window, lowest bucket) and the pair passes both overlap gates.
 __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64_t i, int32_t t, int32_t x, int32_t k) {
     int64_t ca, cb;
     entry_clamp(v, sb, se, x, ca, cb);
     if (i < ca || i >= cb) return false;
-    if (i > ca && tmz_at(v.peaks, i - 1, v.precision) == t) return false;  // not the first row of its bucket (IL:2014)
+    const int32_t t_before = i > ca ? tmz_at(v.peaks, i - 1, v.precision) : INT32_MIN;
+    if (t_before == t) return false;                      // not the first row of its bucket (IL:2014)
     const int64_t w0 = __ldg(&v.ent_win_off[x]);
     const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
+    if (t_before >= __ldg(&v.win_lo[w0 + k])) return false;   // an earlier bucket of window k owns the pair
+    // windows below k must hold no bucket at all (else an earlier incidence owns the pair); a window that
+    // overlaps window k and contains t counts as holding one
+    int64_t pos = i;
+    for (int m = k - 1; m >= 0; --m) {
+        const int64_t j = gallop_backward(v.peaks, ca, pos, __ldg(&v.win_hi[w0 + m]), v.precision);
+        if (j < ca) break;
+        if (tmz_at(v.peaks, j, v.precision) >= __ldg(&v.win_lo[w0 + m])) return false;
+        pos = j;
+    }
+    // distinct buckets inside the union of the windows (Q10), walking forward from row i
     int cnt = 0;
-    int32_t covered_to = INT32_MIN;  // union of the windows seen so far ends here (Q10: distinct buckets)
-    for (int m = 0; m < nc; ++m) {
+    int32_t covered_to = INT32_MIN;
+    pos = i;
+    for (int m = k; m < nc; ++m) {
         const int32_t lo = __ldg(&v.win_lo[w0 + m]);
         const int32_t hi = __ldg(&v.win_hi[w0 + m]);
         const int32_t ulo = lo > covered_to ? lo : (covered_to == INT32_MAX ? covered_to : covered_to + 1);
         if (ulo <= hi) {
-            int64_t j = lower_bound_t(v.peaks, ca, cb, ulo, v.precision);
+            int64_t j = gallop_forward(v.peaks, pos, cb, ulo, v.precision);
+            pos = j;
             while (j < cb) {
                 const int32_t tj = tmz_at(v.peaks, j, v.precision);
                 if (tj > hi) break;
-                if (cnt == 0 && !(m == k && j == i)) return false;  // an earlier incidence owns this pair
                 ++cnt;
+                if (cnt >= v.min_match && !((double)cnt / (double)nc < v.req_overlap)) return true;   // IL:1973-1976
                 do {
                     ++j;
                 } while (j < cb && tmz_at(v.peaks, j, v.precision) == tj);
+                pos = j;
             }
         }
-        if (cnt == 0 && m >= k) return false;  // cannot happen for a true incidence; defensive
         if (hi > covered_to) covered_to = hi;
     }
-    if (cnt < v.min_match) return false;                              // IL:1973
-    if ((double)cnt / (double)nc < v.req_overlap) return false;      // IL:1975
-    return true;
+    return false;
 }
 
 #define PROBE_THREADS 256
@@ -210,10 +257,20 @@ __global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_kernel(MatchView
 
 // K5b: the gating half, one thread per surviving row (all lanes of a warp are in the slow path together).
 // Spectrum lookup, bucket dedupe (Q9), window lookup through the cell table, entry gating (IL:1968-1976).
+__global__ void tile_spectrum_kernel(int64_t n_tiles, int64_t p_begin, int64_t tile, const int64_t* __restrict__ offsets,
+                                     int64_t n_spectra, int32_t* __restrict__ tile_spec) {
+    // spectrum holding the first row of every probe tile: bounds the per-row lookup of K5b to 1-2 steps
+    const int64_t tidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tidx > n_tiles) return;
+    tile_spec[tidx] = tidx == n_tiles ? (int32_t)(n_spectra - 1) : (int32_t)spectrum_of(offsets, n_spectra, p_begin + tidx * tile);
+}
+
 __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_kernel(MatchView v, int64_t p_begin, int64_t seg_cap,
                                                                    const uint32_t* __restrict__ live_rows,
                                                                    const uint32_t* __restrict__ live_count,
+                                                                   const int32_t* __restrict__ tile_spec, int shift, int entry_bits,
                                                                    unsigned long long* __restrict__ pair_keys,
+                                                                   unsigned long long* __restrict__ pair_vals,
                                                                    unsigned long long pair_cap,
                                                                    unsigned long long* __restrict__ counters) {
     unsigned long long n_live = 0, n_inc = 0;
@@ -222,7 +279,18 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_kernel(MatchView v, i
     for (uint32_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
         const uint32_t word = segment[r];
         const int64_t i = p_begin + (int64_t)(word & ~ROW_CHECK_ONLY);
-        const int64_t s = spectrum_of(v.offsets, v.n_spectra, i);
+        const int64_t tile_id = (int64_t)(word & ~ROW_CHECK_ONLY) >> shift;
+        int64_t s = __ldg(&tile_spec[tile_id]);
+        {   // last spectrum in [s, s_hi] whose first row is <= i
+            int64_t s_hi = __ldg(&tile_spec[tile_id + 1]) + 1;
+            while (s_hi - s > 1) {
+                const int64_t mid = s + ((s_hi - s) >> 1);
+                if (__ldg(&v.offsets[mid]) <= i)
+                    s = mid;
+                else
+                    s_hi = mid;
+            }
+        }
         const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
         const int32_t t = tmz_at(v.peaks, i, v.precision);
         const int32_t t_prev = i > sb ? tmz_at(v.peaks, i - 1, v.precision) : INT32_MIN;
@@ -242,7 +310,10 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_kernel(MatchView v, i
             ++n_inc;
             if (gate_incidence(v, sb, se, i, t, raw.z, raw.w)) {
                 const unsigned long long slot = atomicAdd(&counters[C_PAIRS], 1ull);
-                if (slot < pair_cap) pair_keys[slot] = ((unsigned long long)s << 32) | (unsigned long long)(uint32_t)raw.z;
+                if (slot < pair_cap) {
+                    pair_keys[slot] = ((unsigned long long)s << entry_bits) | (unsigned long long)(uint32_t)raw.z;
+                    pair_vals[slot] = ((unsigned long long)(word & ~ROW_CHECK_ONLY) << 16) | (unsigned long long)(raw.w & 0xffff);
+                }
             }
         }
     }
@@ -312,11 +383,11 @@ struct PairRows {  // rows of one (spectrum, entry) pair under the current candi
     __device__ double ci(int m) const { return (double)__ldg(&v->win_ci[w0 + m]); }
 };
 
-__global__ void pair_windows_kernel(int64_t n_pairs, const unsigned long long* __restrict__ keys,
+__global__ void pair_windows_kernel(int64_t n_pairs, const unsigned long long* __restrict__ keys, int entry_bits,
                                     const int64_t* __restrict__ ent_win_off, int64_t* __restrict__ pair_nc) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
-    const int32_t x = (int32_t)(keys[p] & 0xffffffffull);
+    const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
     pair_nc[p] = ent_win_off[x + 1] - ent_win_off[x];
 }
 
@@ -331,28 +402,40 @@ __device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, in
 }
 
 __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys,
+                                                             const unsigned long long* __restrict__ vals, int entry_bits,
+                                                             int64_t p_begin, int max_nc,
                                                              const int64_t* __restrict__ pair_win_off, int64_t* __restrict__ scr_first,
                                                              int64_t* __restrict__ scr_cur, int64_t* __restrict__ pair_best,
                                                              double* __restrict__ pair_score, double* __restrict__ pair_scaling,
                                                              int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
-    const int64_t s = (int64_t)(keys[p] >> 32);
-    const int32_t x = (int32_t)(keys[p] & 0xffffffffull);
+    const int64_t s = (int64_t)(keys[p] >> entry_bits);
+    const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
+    const int64_t row0 = p_begin + (int64_t)(vals[p] >> 16);   // canonical incidence: first bucket of the
+    const int k0 = (int)(vals[p] & 0xffffull);                 // lowest window that holds any (from K5b)
     const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
     int64_t ca, cb;
     entry_clamp(v, sb, se, x, ca, cb);
     const int64_t w0 = __ldg(&v.ent_win_off[x]);
     const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
-    int64_t* first = scr_first + pair_win_off[p];
-    int64_t* cur = scr_cur + pair_win_off[p];
+    int64_t* first = scr_first + p * max_nc;
+    int64_t* cur = scr_cur + p * max_nc;
     int64_t* best = pair_best + pair_win_off[p];
     int n_matched = 0;
+    int64_t pos = row0;             // = first row whose bucket is >= lo of window k0
+    int32_t prev_lo = INT32_MIN;
     for (int m = 0; m < nc; ++m) {  // candidates of window m = distinct buckets in [lo, hi] (IL:2001-2002)
-        const int32_t lo = __ldg(&v.win_lo[w0 + m]);
-        const int32_t hi = __ldg(&v.win_hi[w0 + m]);
-        int64_t j = lower_bound_t(v.peaks, ca, cb, lo, v.precision);
-        if (j >= cb || tmz_at(v.peaks, j, v.precision) > hi) j = -1;
+        int64_t j = -1;
+        if (m >= k0) {              // windows below k0 hold no bucket (gate_incidence)
+            const int32_t lo = __ldg(&v.win_lo[w0 + m]);
+            const int32_t hi = __ldg(&v.win_hi[w0 + m]);
+            if (lo < prev_lo) pos = ca;   // window edges normally ascend with the isotope position
+            j = gallop_forward(v.peaks, pos, cb, lo, v.precision);
+            pos = j;
+            prev_lo = lo;
+            if (j >= cb || tmz_at(v.peaks, j, v.precision) > hi) j = -1;
+        }
         first[m] = cur[m] = best[m] = j;
         n_matched += j >= 0;
     }
@@ -486,7 +569,7 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_emit_kernel(
     const double* __restrict__ pair_scaling, const int64_t* __restrict__ blk_hits, const int64_t* __restrict__ blk_wins,
     int32_t* __restrict__ o_spec, int32_t* __restrict__ o_entry, double* __restrict__ o_score, double* __restrict__ o_scaling,
     int64_t* __restrict__ o_win_off, double* __restrict__ o_mmz, double* __restrict__ o_mi, int64_t* __restrict__ o_peak,
-    int64_t peak_base) {
+    int64_t peak_base, int entry_bits) {
     __shared__ int64_t s_h[CMP_THREADS / 32], s_w[CMP_THREADS / 32];
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -511,8 +594,8 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_emit_kernel(
     if (!flag) return;
     const int64_t h = hbase + __popc(mask & ((1u << lane) - 1u));
     const int64_t w = wbase + wpre - nc;
-    o_spec[h] = (int32_t)(keys[p] >> 32);
-    o_entry[h] = (int32_t)(keys[p] & 0xffffffffull);
+    o_spec[h] = (int32_t)(keys[p] >> entry_bits);
+    o_entry[h] = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
     o_score[h] = pair_score[p];
     o_scaling[h] = pair_scaling[p];
     o_win_off[h] = w;
@@ -634,19 +717,26 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     // ---- K5a + K5b ----
     if (n_peaks >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 peaks per batch (split the run)");
     QMS_TRY(qms_reserve(ctx, ctx->dev_counters, 64));
-    size_t pair_cap = ctx->pair_keys.cap;
+    size_t pair_cap = ctx->pair_keys.cap < ctx->pair_vals.cap ? ctx->pair_keys.cap : ctx->pair_vals.cap;
     if (pair_cap < 65536) {
         QMS_TRY(qms_reserve(ctx, ctx->pair_keys, 65536));
-        pair_cap = ctx->pair_keys.cap;
+        QMS_TRY(qms_reserve(ctx, ctx->pair_vals, 65536));
+        pair_cap = ctx->pair_keys.cap < ctx->pair_vals.cap ? ctx->pair_keys.cap : ctx->pair_vals.cap;
     }
+    int entry_bits = 1, spec_bits = 1;
+    while ((1ll << entry_bits) < ctx->n_entries) ++entry_bits;
+    while ((1ll << spec_bits) < n_spectra) ++spec_bits;
+    const int tile_shift = 10;
+    static_assert(PROBE_THREADS * PROBE_UNROLL == 1 << 10, "tile_shift must match the probe tile");
     const int64_t tile = (int64_t)PROBE_THREADS * PROBE_UNROLL;
-    int64_t blocks = (n_peaks + tile - 1) / tile;
+    const int64_t tiles_total = (n_peaks + tile - 1) / tile;
+    int64_t blocks = tiles_total;
     const int64_t max_blocks = (int64_t)ctx->sm_count * 8;   // 8 resident CTAs of 256 threads per SM
     if (blocks > max_blocks) blocks = max_blocks;
-    const int64_t tiles_total = (n_peaks + tile - 1) / tile;
     const int64_t seg_cap = ((tiles_total + blocks - 1) / blocks) * tile;   // every row of a block could survive
     QMS_TRY(qms_reserve(ctx, ctx->live_rows, (size_t)(seg_cap * blocks)));
     QMS_TRY(qms_reserve(ctx, ctx->live_count, (size_t)blocks));
+    QMS_TRY(qms_reserve(ctx, ctx->tile_spec, (size_t)tiles_total + 2));
     unsigned long long n_pairs = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         QMS_CUDA(ctx, cudaMemsetAsync(ctx->dev_counters.p, 0, 64 * sizeof(unsigned long long), ctx->stream));
@@ -655,12 +745,15 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
                                                                                   ctx->live_count.p);
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+        tile_spectrum_kernel<<<qms_blocks(tiles_total + 1, 256), 256, 0, ctx->stream>>>(tiles_total, p_begin, tile, d_off, n_spectra,
+                                                                                      ctx->tile_spec.p);
         gate_rows_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p,
-                                                                             ctx->pair_keys.p, (unsigned long long)pair_cap,
+                                                                             ctx->tile_spec.p, tile_shift, entry_bits, ctx->pair_keys.p,
+                                                                             ctx->pair_vals.p, (unsigned long long)pair_cap,
                                                                              ctx->dev_counters.p);
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
-        ctx->cnt.kernel_launches += 2;
+        ctx->cnt.kernel_launches += 3;
         QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                       ctx->stream));
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -673,7 +766,8 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         if (n_pairs <= pair_cap) break;
         if (attempt == 1) return qms_fail(ctx, QMS_E_LIMIT, "pair list overflow after regrow");
         QMS_TRY(qms_reserve(ctx, ctx->pair_keys, (size_t)n_pairs + 1024));
-        pair_cap = ctx->pair_keys.cap;
+        QMS_TRY(qms_reserve(ctx, ctx->pair_vals, (size_t)n_pairs + 1024));
+        pair_cap = ctx->pair_keys.cap < ctx->pair_vals.cap ? ctx->pair_keys.cap : ctx->pair_vals.cap;
     }
     ctx->cnt.ms_h2d += elapsed(ctx, 0, 1);
     ctx->cnt.live_peaks += (int64_t)ctx->h_pinned[C_LIVE];
@@ -687,54 +781,51 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         }
         return QMS_OK;
     }
-    // ---- sort pairs by (spectrum, entry) ----
+    // ---- sort pairs by (spectrum, entry): only the populated key bits are radix-sorted ----
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     QMS_TRY(qms_reserve(ctx, ctx->pair_keys_alt, (size_t)n_pairs + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_vals_alt, (size_t)n_pairs + 1));
     {
         size_t bytes = 0;
-        QMS_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, (int64_t)n_pairs, 0, 64,
-                                                     ctx->stream));
+        QMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, ctx->pair_vals.p,
+                                                      ctx->pair_vals_alt.p, (int64_t)n_pairs, 0, entry_bits + spec_bits, ctx->stream));
         QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
-        QMS_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, (int64_t)n_pairs, 0,
-                                                     64, ctx->stream));
+        QMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, ctx->pair_vals.p,
+                                                      ctx->pair_vals_alt.p, (int64_t)n_pairs, 0, entry_bits + spec_bits, ctx->stream));
         ctx->cnt.kernel_launches += 3;
     }
     const unsigned long long* keys = ctx->pair_keys_alt.p;
-    // ---- per-pair window offsets ----
-    TmpBuf<int64_t> pair_nc(ctx);
-    QMS_TRY(qms_reserve(ctx, pair_nc.b, (size_t)n_pairs + 1));
+    const unsigned long long* vals = ctx->pair_vals_alt.p;
+    // ---- per-pair window offsets (output layout); scratch is bounded by max_nc, so no host round trip ----
+    const int max_nc = ctx->max_nc > 0 ? ctx->max_nc : 1;
+    QMS_TRY(qms_reserve(ctx, ctx->pair_nc, (size_t)n_pairs + 1));
     QMS_TRY(qms_reserve(ctx, ctx->pair_win_off, (size_t)n_pairs + 1));
-    QMS_CUDA(ctx, cudaMemsetAsync(pair_nc.b.p, 0, ((size_t)n_pairs + 1) * sizeof(int64_t), ctx->stream));
-    pair_windows_kernel<<<qms_blocks((int64_t)n_pairs, 256), 256, 0, ctx->stream>>>((int64_t)n_pairs, keys, ctx->ent_win_off.p,
-                                                                                   pair_nc.b.p);
+    QMS_CUDA(ctx, cudaMemsetAsync(ctx->pair_nc.p + n_pairs, 0, sizeof(int64_t), ctx->stream));
+    pair_windows_kernel<<<qms_blocks((int64_t)n_pairs, 256), 256, 0, ctx->stream>>>((int64_t)n_pairs, keys, entry_bits,
+                                                                                   ctx->ent_win_off.p, ctx->pair_nc.p);
     {
         size_t bytes = 0;
-        QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, bytes, pair_nc.b.p, ctx->pair_win_off.p, (int64_t)n_pairs + 1, ctx->stream));
+        QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, bytes, ctx->pair_nc.p, ctx->pair_win_off.p, (int64_t)n_pairs + 1, ctx->stream));
         QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
-        QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, bytes, pair_nc.b.p, ctx->pair_win_off.p, (int64_t)n_pairs + 1,
+        QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, bytes, ctx->pair_nc.p, ctx->pair_win_off.p, (int64_t)n_pairs + 1,
                                                     ctx->stream));
         ctx->cnt.kernel_launches += 3;
     }
     QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 32, ctx->pair_win_off.p + n_pairs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int64_t pair_windows = (int64_t)ctx->h_pinned[32];
-    ctx->cnt.candidate_windows += pair_windows;
-    ctx->cnt.ms_compact += elapsed(ctx, 2, 3);
     // ---- K6 ----
-    TmpBuf<int64_t> scr_first(ctx), scr_cur(ctx);
-    QMS_TRY(qms_reserve(ctx, scr_first.b, (size_t)pair_windows + 1));
-    QMS_TRY(qms_reserve(ctx, scr_cur.b, (size_t)pair_windows + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_best, (size_t)pair_windows + 1));
+    const size_t scratch = (size_t)n_pairs * (size_t)max_nc + 1;
+    QMS_TRY(qms_reserve(ctx, ctx->scr_first, scratch));
+    QMS_TRY(qms_reserve(ctx, ctx->scr_cur, scratch));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_best, scratch));
     QMS_TRY(qms_reserve(ctx, ctx->pair_score, (size_t)n_pairs));
     QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)n_pairs));
     QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)n_pairs));
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     assemble_score_kernel<<<qms_blocks((int64_t)n_pairs, 128), 128, 0, ctx->stream>>>(
-        v, (int64_t)n_pairs, keys, ctx->pair_win_off.p, scr_first.b.p, scr_cur.b.p, ctx->pair_best.p, ctx->pair_score.p,
-        ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
+        v, (int64_t)n_pairs, keys, vals, entry_bits, p_begin, max_nc, ctx->pair_win_off.p, ctx->scr_first.p, ctx->scr_cur.p,
+        ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
     QMS_CUDA(ctx, cudaGetLastError());
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->cnt.kernel_launches++;
     // ---- K7 ----
     const int64_t cblocks = qms_blocks((int64_t)n_pairs, CMP_THREADS);
@@ -749,7 +840,9 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
                                   cudaMemcpyDeviceToHost, ctx->stream));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->cnt.kernel_launches += 2;
-    ctx->cnt.ms_score += elapsed(ctx, 2, 3);
+    ctx->cnt.ms_compact += elapsed(ctx, 2, 3);
+    ctx->cnt.ms_score += elapsed(ctx, 3, 5);
+    ctx->cnt.candidate_windows += (int64_t)ctx->h_pinned[32];
     ctx->cnt.combinations += (int64_t)ctx->h_pinned[C_COMBOS];
     const int64_t nh = (int64_t)ctx->h_pinned[40], nw = (int64_t)ctx->h_pinned[41];
     *n_hits = nh;
@@ -769,7 +862,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     compact_emit_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(
         v, (int64_t)n_pairs, keys, ctx->pair_flag.p, ctx->pair_win_off.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p,
         ctx->blk_hits.p, ctx->blk_wins.p, ctx->o_spec.p, ctx->o_entry.p, ctx->o_score.p, ctx->o_scaling.p, ctx->o_win_off.p,
-        ctx->o_mmz.p, ctx->o_mi.p, ctx->o_peak.p, 0);
+        ctx->o_mmz.p, ctx->o_mi.p, ctx->o_peak.p, 0, entry_bits);
     QMS_CUDA(ctx, cudaGetLastError());
     QMS_CUDA(ctx, cudaMemcpyAsync(ctx->o_win_off.p + nh, &ctx->h_pinned[41], sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));

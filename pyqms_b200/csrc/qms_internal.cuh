@@ -101,7 +101,10 @@ struct qms_ctx {
     // ---- matching scratch (P2) ----
     DBuf<double> d_peaks;
     DBuf<int64_t> d_offsets;
-    DBuf<unsigned long long> pair_keys, pair_keys_alt;
+    DBuf<unsigned long long> pair_keys, pair_keys_alt, pair_vals, pair_vals_alt;
+    DBuf<int64_t> pair_nc, scr_first, scr_cur;
+    DBuf<int32_t> tile_spec;
+    int32_t max_nc = 0;            // most c-peak windows of any index entry
     DBuf<uint8_t> cub_tmp;
     DBuf<unsigned long long> dev_counters;   // see match.cu
     DBuf<double> pair_score, pair_scaling;

@@ -56,14 +56,37 @@ def _device_tensor(ptr_value, n_elems, dtype, device):
     return torch.as_tensor(w, device="cuda:%d" % device)
 
 
+def allgather_ranges(full, ranges):
+    """In-place assembly of a 1-D tensor whose slice ``ranges[r]`` was filled by rank r.
+
+    Shard sizes differ by construction, so each rank pads its slice to the widest shard, the padded
+    pieces are all-gathered (NCCL on GPU tensors, gloo on CPU tensors) and every foreign piece is copied to
+    its global offset.  Returns the number of bytes this rank received."""
+    import torch
+    import torch.distributed as dist
+    me, world = dist.get_rank(), dist.get_world_size()
+    widest = max(e - b for b, e in ranges)
+    if widest == 0:
+        return 0
+    mine = torch.zeros(widest, dtype=full.dtype, device=full.device)
+    b, e = ranges[me]
+    mine[: e - b] = full[b:e]
+    pieces = [torch.empty(widest, dtype=full.dtype, device=full.device) for _ in range(world)]
+    dist.all_gather(pieces, mine)
+    received = 0
+    for r, (rb, re) in enumerate(ranges):
+        if r != me and re > rb:
+            full[rb:re] = pieces[r][: re - rb]
+            received += (re - rb) * full.element_size()
+    return received
+
+
 def allgather_envelopes(ctx, n_env, world):
     """Assemble the envelope shards of all ranks in place (NCCL all-gather over NVLink).
 
-    Every rank has written its shard [begin_r, end_r) into the shared layout; per array, shard sizes
-    differ, so each is padded to the largest shard, gathered with ``all_gather_into_tensor`` and the
-    pieces are copied to their global offsets on the device."""
+    Every rank has written its shard [begin_r, end_r) of envelopes into the shared slot layout; the per-slot
+    arrays (mass, relabun, abun, pos, c_flag) and per-envelope arrays (len, n_c) are gathered one by one."""
     import torch
-    import torch.distributed as dist
     n_e, n_s = C.c_int64(), C.c_int64()
     ctx.call("qms_envelope_layout", C.byref(n_e), C.byref(n_s), None)
     slot_off = np.zeros(n_e.value + 1, dtype=np.int64)
@@ -73,27 +96,16 @@ def allgather_envelopes(ctx, n_env, world):
     ctx.call("qms_synchronize")
     env_ranges = [shard_range(n_env, r, world) for r in range(world)]
     slot_ranges = [(int(slot_off[b]), int(slot_off[e])) for b, e in env_ranges]
-    me = dist.get_rank()
     specs = [(ptrs[0], np.float64, n_s.value, slot_ranges), (ptrs[1], np.float64, n_s.value, slot_ranges),
              (ptrs[2], np.int32, n_s.value, slot_ranges), (ptrs[3], np.int32, n_s.value, slot_ranges),
              (ptrs[4], np.uint8, n_s.value, slot_ranges), (ptrs[5], np.int32, n_e.value, env_ranges),
              (ptrs[6], np.int32, n_e.value, env_ranges)]
+    received = 0
     for pointer, dtype, total, ranges in specs:
-        if total == 0:
-            continue
-        full = _device_tensor(pointer.value, total, dtype, ctx.device)
-        widest = max(e - b for b, e in ranges)
-        if widest == 0:
-            continue
-        mine = torch.zeros(widest, dtype=full.dtype, device=full.device)
-        b, e = ranges[me]
-        mine[: e - b] = full[b:e]
-        gathered = torch.empty(widest * world, dtype=full.dtype, device=full.device)
-        dist.all_gather_into_tensor(gathered, mine)
-        for r, (rb, re) in enumerate(ranges):
-            if r != me and re > rb:
-                full[rb:re] = gathered[r * widest: r * widest + (re - rb)]
+        if total:
+            received += allgather_ranges(_device_tensor(pointer.value, total, dtype, ctx.device), ranges)
     torch.cuda.synchronize(ctx.device)
+    return received
 
 
 def gather_packed_hits(out, spectrum_begin, world):

@@ -1,0 +1,68 @@
+"""N>1 host path on CPU: world_size-2 gloo processes exercise shard assembly and hit gathering."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from pyqms_b200 import distributed as qd
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    assert qd.world_size() == world and qd.rank() == rank
+    # --- envelope shard assembly: ragged slot ranges, several dtypes
+    rng = np.random.default_rng(5)
+    n_env = 11
+    lens = rng.integers(1, 9, size=n_env)
+    slot_off = np.concatenate([[0], np.cumsum(lens)])
+    truth = {np.float64: rng.normal(size=slot_off[-1]), np.int32: rng.integers(0, 1 << 20, size=slot_off[-1]).astype(np.int32),
+             np.uint8: rng.integers(0, 2, size=slot_off[-1]).astype(np.uint8)}
+    env_ranges = [qd.shard_range(n_env, r, world) for r in range(world)]
+    slot_ranges = [(int(slot_off[b]), int(slot_off[e])) for b, e in env_ranges]
+    for dtype, full_truth in truth.items():
+        mine = np.zeros_like(full_truth)
+        b, e = slot_ranges[rank]
+        mine[b:e] = full_truth[b:e]                     # this rank computed only its shard
+        t = torch.from_numpy(mine)
+        qd.allgather_ranges(t, slot_ranges)
+        assert np.array_equal(t.numpy(), full_truth), dtype
+    # --- hits of spectrum shards come back in spectrum order on rank 0
+    n_spec = 9
+    begin, end = qd.shard_range(n_spec, rank, world)
+    nh = 2 * (end - begin)
+    local = {"spec": np.repeat(np.arange(end - begin, dtype=np.int32), 2), "entry": np.tile(np.array([3, 7], dtype=np.int32), end - begin),
+             "score": np.linspace(0.5, 0.9, nh), "scaling": np.ones(nh), "win_off": np.arange(0, 3 * nh + 1, 3, dtype=np.int64),
+             "mmz": np.arange(3 * nh, dtype=np.float64) + 1000 * rank, "mi": np.ones(3 * nh), "n_hits": nh, "n_windows": 3 * nh}
+    merged = qd.gather_packed_hits(local, begin, world)
+    if rank == 0:
+        assert merged["n_hits"] == 2 * n_spec and merged["n_windows"] == 6 * n_spec
+        assert list(merged["spec"]) == [s for s in range(n_spec) for _ in range(2)]
+        assert list(merged["win_off"]) == list(range(0, 6 * n_spec + 1, 3))
+        assert merged["mmz"][6 * (qd.shard_range(n_spec, 1, world)[0])] == 1000.0
+    else:
+        assert merged is None
+    dist.barrier()
+    dist.destroy_process_group()
+    Path(out_dir, "ok%d" % rank).write_text("ok")
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

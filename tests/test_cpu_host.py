@@ -1,0 +1,133 @@
+"""CPU-only checks (-m "not gpu"): the C-ABI library loads and exports every declared symbol, the host
+planning layer (string work) matches the reference's golden dumps, sharding helpers, synthetic generators."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests.golden.cases import CASES
+from tests.helpers import load_case, lp_tuple
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "qms_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qms_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyqms_b200 import _capi
+    lib = ctypes.CDLL(str(_capi.LIB_PATH))          # built by __graft_entry__.build() / make -C pyqms_b200/csrc
+    names = declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), name
+    assert sorted(_capi.EXPORTS) == names           # the ctypes table binds exactly the declared ABI
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import pyqms_b200
+    from pyqms_b200._capi import QmsError
+    with pytest.raises(QmsError, match="no CPU fallback"):
+        pyqms_b200.IsotopologueLibrary(molecules=["PEPTIDE"], charges=[2], verbose=False)
+
+
+def test_product_never_imports_the_oracle():
+    for path in (ROOT / "pyqms_b200").rglob("*.py"):
+        assert "oracle" not in path.read_text(), path
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_host_planning_matches_reference(name):
+    """Formulas, compositions, label tuples, fixed-label expansion, pools and envelope terms (no device)."""
+    import pyqms_b200
+    blob, _, _ = load_case(name)
+    ref = blob["library"]
+    lib = pyqms_b200.IsotopologueLibrary(verbose=False, _plan_only=True, **CASES[name]["lib"])
+    assert sorted(lib.keys()) == sorted(ref["formulas"])
+    assert lib.labled_percentiles == [lp_tuple(x) for x in ref["labled_percentiles"]]
+    assert lib.lookup["molecule to formula"] == ref["molecule_to_formula"]
+    assert {k: sorted(v) for k, v in lib.lookup["molecule fixed label variations"].items()} == ref["fixed_label_variations"]
+    for formula in ref["formulas"]:
+        assert dict(lib[formula]["cc"]) == ref["cc"][formula]
+    assert lib.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"] == ref["fixed_label_levels"]
+    # every element tree the reference built has a pool, with the reference's isotope table layout
+    for element, by_label in ref["isotopic_distributions"].items():
+        for label, table in by_label.items():
+            pool = lib._pool_ids[(element, label)]
+            off = lib._pool_tables[0]
+            assert off[pool + 1] - off[pool] == len(table)
+            assert list(lib._pool_tables[3][off[pool]:off[pool + 1]]) == [row[2] for row in table]
+    term_off = lib._terms[0]
+    assert len(term_off) == len(ref["formulas"]) * len(ref["labled_percentiles"]) + 1
+    # envelope terms: (pool, level) in the reference's element order -> levels must exist in its trees
+    for e in range(len(term_off) - 1):
+        for t in range(term_off[e], term_off[e + 1]):
+            element, label = lib._pools[lib._terms[1][t]]
+            assert str(lib._terms[2][t]) in ref["trees"][element][label], (element, label, lib._terms[2][t])
+
+
+def test_chemistry_parser():
+    from pyqms_b200.chemistry import ChemicalComposition, parse_formula
+    assert parse_formula("C(2)H(3)14N(1)O(1)") == {"C": 2, "H": 3, "14N": 1, "O": 1}
+    assert parse_formula("+H2O") == {"H": 2, "O": 1}
+    assert parse_formula("C(-6) 13C(6) N(-4) 15N(4)") == {"C": -6, "13C": 6, "N": -4, "15N": 4}
+    import pyqms_b200
+    aa = {k: ChemicalComposition(formula="+" + v) for k, v in pyqms_b200.knowledge_base.aa_compositions.items()}
+    cc = ChemicalComposition(aa_compositions=aa)
+    cc.use(deprecated_format="PEPTIDE")
+    assert cc.hill_notation_unimod() == "C(34)H(53)N(7)O(15)"          # IL docstring, IL:100-104
+    cc.use(deprecated_format="TESTPEPTIDE#Oxidation:1")
+    assert cc.hill_notation_unimod() == "C(50)H(79)N(11)O(25)"          # tests/peptide_sequence_test.py:24
+    cc.use(deprecated_format="PEPTIDE+PO3")
+    assert cc["P"] == 1 and cc["O"] == 18
+    with pytest.raises(KeyError):
+        cc.use(deprecated_format="PEPTIDE#NoSuchModification:1")
+    assert cc["Zz"] == 0
+
+
+def test_results_container():
+    import pyqms_b200
+    res = pyqms_b200.Results(params=pyqms_b200.params)
+    key = ("f.mzML", "C(2)H(4)", 2, (("N", "0.000"),))
+    res.add(key, (1, 0.1, 0.6, 2.0, ((1.0, 2.0, 1.0, 1.0, 5),)))
+    k = res.add(key, (2, 0.2, 0.9, 3.0, ((None, None, 1.0, 1.0, 5),)))
+    assert isinstance(k, pyqms_b200.m_key) and k.charge == 2
+    slot = res[k]
+    assert slot["len_data"] == 2 and slot["max_score"] == 0.9 and slot["max_score_index"] == 1
+    assert isinstance(slot["data"][0], pyqms_b200.match) and slot["data"][1].spec_id == 2
+    assert res.index["formulas"] == {"C(2)H(4)"} and res.index["charges"] == {2}
+    assert res.max_score()[2].score == 0.9
+    assert len(list(res.extract_results(charges=[3]))) == 0
+
+
+def test_shard_ranges_cover_exactly():
+    from pyqms_b200.distributed import shard_range
+    for n in (0, 1, 7, 8, 9, 1000003):
+        for world in (1, 2, 3, 8):
+            parts = [shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert max(e - b for b, e in parts) - min(e - b for b, e in parts) <= 1
+
+
+def test_synthetic_generators_are_deterministic():
+    from pyqms_b200.synthetic import averagine_formulas, random_tryptic_peptides, synth_run
+    a, b = random_tryptic_peptides(50, seed=1), random_tryptic_peptides(50, seed=1)
+    assert a == b and len(set(a)) == 50 and all(p[-1] in "KR" and 7 <= len(p) <= 30 for p in a)
+    assert averagine_formulas(5, seed=2) == averagine_formulas(5, seed=2)
+    mz = [np.array([500.0, 500.5]), np.array([700.0, 700.33, 700.66])]
+    ci = [np.array([60000.0, 20000.0]), np.array([50000.0, 30000.0, 9000.0])]
+    p1, o1 = synth_run(mz, ci, n_spectra=10, seed=3, mean_peaks=50, min_peaks=10, elution_sigma=2.0)
+    p2, o2 = synth_run(mz, ci, n_spectra=10, seed=3, mean_peaks=50, min_peaks=10, elution_sigma=2.0)
+    assert np.array_equal(p1, p2) and np.array_equal(o1, o2) and o1[-1] == len(p1)
+    for s in range(10):
+        seg = p1[o1[s]:o1[s + 1], 0]
+        assert np.all(seg[1:] >= seg[:-1])
