@@ -96,6 +96,16 @@ def allgather_envelopes(ctx, n_env, world):
     ctx.call("qms_synchronize")
     env_ranges = [shard_range(n_env, r, world) for r in range(world)]
     slot_ranges = [(int(slot_off[b]), int(slot_off[e])) for b, e in env_ranges]
+    # every rank must hold the same layout, or the collectives below would wait for each other forever
+    import torch.distributed as dist
+    digest = torch.tensor([n_e.value, n_s.value, int(np.bitwise_xor.reduce(slot_off * np.arange(1, len(slot_off) + 1)))],
+                          dtype=torch.int64, device="cuda:%d" % ctx.device)
+    lo, hi = digest.clone(), digest.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if not bool(torch.equal(lo, hi)):
+        raise RuntimeError("ranks disagree on the envelope layout (different molecule lists / parameters per rank?): %s vs %s"
+                           % (lo.tolist(), hi.tolist()))
     specs = [(ptrs[0], np.float64, n_s.value, slot_ranges), (ptrs[1], np.float64, n_s.value, slot_ranges),
              (ptrs[2], np.int32, n_s.value, slot_ranges), (ptrs[3], np.int32, n_s.value, slot_ranges),
              (ptrs[4], np.uint8, n_s.value, slot_ranges), (ptrs[5], np.int32, n_e.value, env_ranges),

@@ -288,7 +288,9 @@ class IsotopologueLibrary(dict):
                                       unimod_file_list=self.unimod_files, add_default_files=add_default_files)
         levels = self.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"]
         two_iso = self._range_for_elements_with_two_isotopes
-        for molecule in dict.fromkeys(molecules):          # the reference iterates set(molecules): order-free
+        # the reference iterates set(molecules) (hash order); sorted() makes the envelope order identical in
+        # every process, which the sharded multi-GPU build relies on
+        for molecule in sorted(set(molecules)):
             if molecule.count("#") > 1:
                 raise ValueError(f"{molecule} contains too many '#' {molecule.count('#') + 1} only one allowed")
             factory.use(deprecated_format=molecule)

@@ -28,7 +28,9 @@ def _worker(rank, world, port, out_dir):
     from pyqms_b200 import distributed as qd
     from pyqms_b200.synthetic import BSA_MOLECULES, CAM_FIXED_LABEL, random_tryptic_peptides, synth_run
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=120))
     kwargs = dict(molecules=BSA_MOLECULES + random_tryptic_peptides(300, seed=9), charges=[1, 2, 3], fixed_labels=CAM_FIXED_LABEL,
                   metabolic_labels={"15N": [0, 0.5, 0.99]}, verbose=False, device=rank)
     sharded = pyqms_b200.IsotopologueLibrary(distributed=True, **kwargs)
