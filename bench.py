@@ -348,6 +348,11 @@ def run_ours(args):
 
 
 def main():
+    # exactly one line may reach stdout (the JSON line): libraries that print to fd 1 (NCCL's version banner)
+    # are diverted to stderr for the whole run, the JSON line is written to the saved descriptor
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
