@@ -1,0 +1,114 @@
+"""Full-size parity through size-independent properties (BASELINE.json configs at their named shape, or a
+bounded version for the proteome): ordering, idempotence, batch-split invariance, sub-library independence,
+and exact agreement with the CPU oracle on a random sample of spectra."""
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from pyqms_b200.synthetic import (BSA_MOLECULES, CAM_FIXED_LABEL, averagine_formulas, random_tryptic_peptides,  # noqa: E402
+                                  synth_run)
+from tests.helpers import assert_results_equal, results_to_rows  # noqa: E402
+
+
+def packed_rows(out, lo=None, hi=None):
+    nh = out["n_hits"]
+    rows = []
+    for h in range(nh):
+        s = int(out["spec"][h])
+        if lo is not None and not (lo <= s < hi):
+            continue
+        a, b = int(out["win_off"][h]), int(out["win_off"][h + 1])
+        rows.append((s, int(out["entry"][h]), float(out["score"][h]), float(out["scaling"][h]),
+                     tuple(np.nan_to_num(out["mmz"][a:b], nan=-1.0)), tuple(np.nan_to_num(out["mi"][a:b], nan=-1.0))))
+    return rows
+
+
+def test_bsa_full_run_properties():
+    """configs[1]: BSA 14N+15N z1-4 vs the 30 000-spectrum run of bench.py."""
+    import pyqms_b200
+    from oracle.qms_oracle import OracleLibrary
+    kw = dict(molecules=BSA_MOLECULES, charges=[1, 2, 3, 4], metabolic_labels={"15N": [0, 0.99]}, fixed_labels=CAM_FIXED_LABEL)
+    lib = pyqms_b200.IsotopologueLibrary(verbose=False, **kw)
+    mz, ci = lib.entry_peaks()
+    peaks, offsets = synth_run(mz, ci, n_spectra=30000, seed=20260101)
+    out = lib.match_packed(peaks, offsets)
+    nh = out["n_hits"]
+    assert nh > 5000
+    key = out["spec"][:nh].astype(np.int64) << 32 | out["entry"][:nh]
+    assert np.all(key[1:] > key[:-1])                                   # (spectrum, entry) strictly ascending
+    assert np.all(out["score"][:nh] >= lib.params["M_SCORE_THRESHOLD"])
+    again = lib.match_packed(peaks, offsets)
+    assert packed_rows(out) == packed_rows(again)                       # idempotent
+    cut = 17321                                                         # batch split invariance
+    first = lib.match_packed(peaks[:offsets[cut]], offsets[:cut + 1])
+    second = lib.match_packed(peaks[offsets[cut]:], offsets[cut:] - offsets[cut])
+    shifted = [(r[0] + cut,) + r[1:] for r in packed_rows(second)]
+    assert packed_rows(first) + shifted == packed_rows(out)
+    # exact agreement with the oracle on 300 random spectra (hit sets, matched peaks; score 1e-6)
+    ora = OracleLibrary(**kw)
+    sample = sorted(np.random.default_rng(1).choice(30000, size=300, replace=False).tolist())
+    want = {}
+    for s in sample:
+        ora.match_all(peaks[offsets[s]:offsets[s + 1]], "run", s, s * 0.2, want)
+    got = lib.match_many([peaks[offsets[s]:offsets[s + 1]] for s in sample], file_name="run", spec_ids=sample,
+                         spec_rts=[s * 0.2 for s in sample])
+    assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=1e-6, cmz_rel=1e-12, ri_rel=1e-9)
+    assert sum(len(v) for v in want.values()) > 50
+
+
+def test_proteome_sublibrary_independence():
+    """configs[3] shape, bounded: 20 000 tryptic peptides z1-5 CAM vs 1 500 spectra.  Matching of an entry does
+    not depend on the other entries (numpy input), so the hits of a 300-peptide sub-library computed by the CPU
+    oracle must equal the full-library GPU hits restricted to those formulas."""
+    import pyqms_b200
+    from oracle.qms_oracle import OracleLibrary
+    peptides = random_tryptic_peptides(20000, seed=20260104)
+    lib = pyqms_b200.IsotopologueLibrary(molecules=peptides, charges=[1, 2, 3, 4, 5], fixed_labels=CAM_FIXED_LABEL, verbose=False)
+    assert lib._n_entries > 60000
+    mz, ci = lib.entry_peaks()
+    peaks, offsets = synth_run(mz, ci, n_spectra=1500, seed=20260104, entry_fraction=0.02, elution_sigma=3.0)
+    subset = peptides[::67][:300]
+    ora = OracleLibrary(molecules=subset, charges=[1, 2, 3, 4, 5], fixed_labels=CAM_FIXED_LABEL)
+    sample = list(range(0, 1500, 10))
+    want = {}
+    for s in sample:
+        ora.match_all(peaks[offsets[s]:offsets[s + 1]], "run", s, float(s), want)
+    got = lib.match_many([peaks[offsets[s]:offsets[s + 1]] for s in sample], file_name="run", spec_ids=sample,
+                         spec_rts=[float(s) for s in sample])
+    formulas = set(ora.keys())
+    got_rows = [r for r in results_to_rows(got) if r[0][1] in formulas]
+    assert_results_equal(got_rows, results_to_rows(want), score_tol=1e-6, cmz_rel=1e-12, ri_rel=1e-9, key_order=False)
+    assert sum(len(v) for v in want.values()) > 20
+    # dense-library regime sanity: every spectrum row is live, hits stay ordered
+    out = lib.match_packed(peaks, offsets)
+    nh = out["n_hits"]
+    key = out["spec"][:nh].astype(np.int64) << 32 | out["entry"][:nh]
+    assert np.all(key[1:] > key[:-1])
+
+
+def test_envelope_sweep_against_oracle():
+    """configs[4] shape, bounded: averagine formulas 100 Da - 12 kDa, FP64 abundance parity 1e-9 vs the oracle."""
+    sys.setrecursionlimit(20000)
+    import pyqms_b200
+    from oracle.qms_oracle import OracleLibrary
+    formulas = averagine_formulas(60, seed=20260105, min_mass=100.0, max_mass=12000.0)
+    kw = dict(molecules=formulas, charges=[1, 4, 9], params={"UPPER_MZ_LIMIT": 20000, "LOWER_MZ_LIMIT": 10})
+    lib = pyqms_b200.IsotopologueLibrary(verbose=False, **kw)
+    ora = OracleLibrary(**kw)
+    assert sorted(lib.keys()) == sorted(ora.keys())
+    lp = (("N", "0.000"),)
+    worst = 0.0
+    for formula in ora.keys():
+        a, b = lib[formula]["env"][lp], ora[formula]["env"][lp]
+        assert a["abun"] == b["abun"] and a["c_peak_pos"] == b["c_peak_pos"] and a["n_c_peaks"] == b["n_c_peaks"], formula
+        for x, y in zip(a["relabun"], b["relabun"]):
+            worst = max(worst, abs(x - y) / y)
+        for z in (1, 4, 9):
+            assert [None if s is None else (min(s), max(s)) for s in a[z]["tmzs"]] == \
+                [None if s is None else (min(s), max(s)) for s in b[z]["tmzs"]], (formula, z)
+            for x, y in zip(a[z]["mz"], b[z]["mz"]):
+                assert abs(x - y) <= 1e-12 * y
+    assert worst < 1e-9
