@@ -273,13 +273,19 @@ def run_ours(args):
     pin_peaks = torch.from_numpy(peaks).pin_memory()
     pin_offsets = torch.from_numpy(offsets).pin_memory()
     h_peaks, h_offsets = pin_peaks.numpy(), pin_offsets.numpy()
-    out = lib.match_packed(h_peaks, h_offsets)
-    for _ in range(max(1, args.warmup - 1)):
-        out = lib.match_packed(h_peaks, h_offsets)
+    spec_ids = list(range(n_spec))
+
+    def e2e_step():
+        # the call a user makes for a whole run: host (N,2) array in, pyqms Results out (hits stay packed until read)
+        res = lib.match_many(h_peaks, file_name="run", spec_ids=spec_ids, spec_rts=spec_ids, offsets=h_offsets)
+        return res.packed_batches()[-1]
+
+    for _ in range(max(1, args.warmup)):
+        out = e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = lib.match_packed(h_peaks, h_offsets)
+        out = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -287,7 +293,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n_spec * args.steps / float(t.item())
     h2d = int(peaks.nbytes + offsets.nbytes)
-    d2h = int(out["n_hits"] * (4 + 4 + 8 + 8 + 8) + 8 + out["n_windows"] * (8 + 8 + 8))
+    d2h = int(out["n_hits"] * (4 + 4 + 8 + 8 + 8) + 8 + out["n_windows"] * 8)   # spec, entry, score, scaling, win_off + peak rows
 
     # ---- roofline of the dominant kernel (spectrum_probe_gate): SURVEY.md 8d algorithmic bytes
     launches_per_step = counters["kernel_launches"] / max(steps_counted, 1)
@@ -311,6 +317,34 @@ def run_ours(args):
             roofline["traffic"] = json.loads(traffic_file.read_text()).get(args.workload)
         except Exception:
             pass
+
+    # ---- second half of the metric: isotopologue envelopes built per second (BASELINE.json configs[4] shape, bounded)
+    build_metric = None
+    if rank == 0 and not args.no_build_metric:
+        from pyqms_b200.synthetic import averagine_formulas
+        formulas = averagine_formulas(args.build_formulas, seed=20260105)
+        t0 = time.perf_counter()
+        sweep = pyqms_b200.IsotopologueLibrary(molecules=formulas, charges=[1], verbose=False, device=local, distributed=False,
+                                               params={"UPPER_MZ_LIMIT": 60000, "LOWER_MZ_LIMIT": 50})
+        wall = time.perf_counter() - t0
+        c = sweep.device_counters()
+        build_metric = {"metric": "isotopologue envelopes built/sec", "workload": "%d averagine formulas 100 Da - 50 kDa, natural abundance" % args.build_formulas,
+                        "envelopes": int(c["envelopes"]), "value_device": c["envelopes"] / (c["ms_envelopes"] * 1e-3),
+                        "value_e2e_host_strings_to_index": c["envelopes"] / wall, "unit": "envelopes/s", "ms_envelope_kernel": c["ms_envelopes"],
+                        "ms_trees": c["ms_trees"], "ms_index": c["ms_index"], "fp64_gflops": c["envelope_flops"] / (c["ms_envelopes"] * 1e-3) / 1e9,
+                        "wall_s": wall}
+        if not args.no_cpu_baseline:
+            from oracle.qms_oracle import OracleLibrary
+            sys.setrecursionlimit(20000)
+            # the reference's build is O(N^2) big-int work in the largest atom count (552 s for one 50 kDa formula,
+            # SURVEY.md section 6): the CPU sample is bounded to formulas below ~3 kDa (<= 130 carbons)
+            small = [f for f in formulas[:20000] if int(f[2:].split("H")[0]) <= 130][:args.build_cpu_formulas]
+            t0 = time.perf_counter()
+            ora = OracleLibrary(molecules=small, charges=[1], params={"UPPER_MZ_LIMIT": 60000, "LOWER_MZ_LIMIT": 50})
+            secs = time.perf_counter() - t0
+            build_metric["cpu_baseline"] = {"value": len(ora) / secs, "unit": "envelopes/s", "cores": 1, "kind": "port",
+                                            "sample": "first %d formulas <= 130 C (~3 kDa) of the same sweep (%.1f s)" % (len(small), secs)}
+        del sweep
 
     line = None
     if rank == 0:
@@ -337,6 +371,7 @@ def run_ours(args):
                               "ms_index": build_counters["ms_index"],
                               "envelopes_per_s_device": (build_counters["envelopes"] / (build_counters["ms_envelopes"] * 1e-3)
                                                          if build_counters["ms_envelopes"] > 0 else None)},
+            "build": build_metric,
             "counters_per_step": {k: counters[k] / max(steps_counted, 1) for k in
                                   ("peaks", "live_peaks", "incidences", "candidates", "combinations", "hits")},
         }
@@ -363,6 +398,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU oracle time for cpu_baseline")
     ap.add_argument("--ref-spectra-per-core", type=int, default=250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-build-metric", action="store_true")
+    ap.add_argument("--build-formulas", type=int, default=100000)
+    ap.add_argument("--build-cpu-formulas", type=int, default=2000)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -176,7 +176,9 @@ int qms_transform_mz(qms_ctx* ctx, int64_t n, const double* mz, int32_t* lo, int
  * mz_score_percentile = results.params["MZ_SCORE_PERCENTILE"] (IL:1855).
  * Hits are ordered by (spectrum, index entry) like the reference's loops.  Outputs are
  * host-or-device caller buffers with capacities cap_hits / cap_windows; on overflow the call
- * returns QMS_E_CAPACITY with the required sizes in n_hits / n_hit_windows and writes nothing.
+ * returns QMS_E_CAPACITY with the required sizes in n_hits / n_hit_windows, writes nothing, and keeps
+ * the hits on the device: qms_fetch_hits copies them out without matching again.  Passing out = NULL
+ * is the size query of that two-call pattern.
  *   hit_spec[h], hit_entry[h], hit_score[h], hit_scaling[h], hit_win_off[h] (cap_hits+1 entries)
  *   per hit window w in [hit_win_off[h], hit_win_off[h+1]): hit_mmz[w], hit_mi[w] (NaN = None,
  *   IL:1994-2000) and hit_peak[w] = row of the matched peak in `peaks` (-1 = None).
@@ -195,6 +197,9 @@ typedef struct qms_hits {
 int qms_match_batch(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra,
                     int32_t input_kind, double mz_score_percentile, qms_hits* out, int64_t* n_hits,
                     int64_t* n_hit_windows);
+
+/* Copy the hits of the last qms_match_batch / qms_match_entry call into caller buffers (same layout). */
+int qms_fetch_hits(qms_ctx* ctx, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows);
 
 /* match_isotopologue IL:1885-2040 for ONE index entry against ONE spectrum: same kernels, restricted
  * to `entry`, with the overlap gates of IL:1973-1976 but WITHOUT the score / matched-peak thresholds of

@@ -75,6 +75,7 @@ EXPORTS = {  # name -> (restype, argtypes); must list every symbol of include/qm
     "qms_export_windows": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "qms_match_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double,
                                   C.POINTER(QmsHits), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "qms_fetch_hits": (C.c_int, [C.c_void_p, C.POINTER(QmsHits), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "qms_match_entry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double,
                                   C.POINTER(QmsHits), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "qms_transform_mz": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,5 +1,8 @@
 // Context, error handling and device-memory bookkeeping of libqms_b200.so.
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <chrono>
 
 #include "qms_internal.cuh"
 
@@ -16,6 +19,21 @@ int qms_fail(qms_ctx* ctx, int code, const char* fmt, ...) {
     else
         g_create_error = buf;
     return code;
+}
+
+void qms_trace(qms_ctx* ctx, const char* label) {
+    static int on = -1;
+    static std::chrono::steady_clock::time_point last;
+    if (on < 0) {
+        const char* e = getenv("QMS_TRACE");
+        on = (e && e[0] && e[0] != '0') ? 1 : 0;
+        last = std::chrono::steady_clock::now();
+    }
+    if (!on) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[qms trace] %-40s %9.3f ms\n", label, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
 }
 
 bool qms_is_device_ptr(const void* p) {

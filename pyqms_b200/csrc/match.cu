@@ -21,6 +21,8 @@
 //      reference's (score, scaling, peaks) tuple order, thresholds IL:1860-1870.
 //  K7 compact_hits          order-preserving warp-ballot stream compaction of the passing pairs
 //      into the hit arrays.
+#include <stdlib.h>
+
 #include <cub/cub.cuh>
 
 #include "qms_internal.cuh"
@@ -211,6 +213,14 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
 // and stays in L1) or if its bucket descends against the previous row (sortedness is verified by K5b,
 // which knows the spectrum boundaries).  Survivors are appended to the block's own segment of
 // `live_rows` through a shared-memory cursor (warp-aggregated), so the stream issues no global atomics.
+__device__ __forceinline__ double2 load_row_streaming(const double2* p) {
+    // read-once stream: evict-first so the cover bitmaps and the cell table keep their L1/L2 lines
+    double2 r;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+template <int UNROLL, bool STREAMING>
 __global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_kernel(MatchView v, int64_t p_begin, int64_t p_end,
                                                                         int64_t seg_cap, uint32_t* __restrict__ live_rows,
                                                                         uint32_t* __restrict__ live_count) {
@@ -219,16 +229,16 @@ __global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_kernel(MatchView
     __syncthreads();
     const int lane = threadIdx.x & 31;
     uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
-    const int64_t tile = (int64_t)PROBE_THREADS * PROBE_UNROLL;
+    const int64_t tile = (int64_t)PROBE_THREADS * UNROLL;
     for (int64_t base = p_begin + (int64_t)blockIdx.x * tile; base < p_end; base += (int64_t)gridDim.x * tile) {
-        double2 row[PROBE_UNROLL];
+        double2 row[UNROLL];
 #pragma unroll
-        for (int u = 0; u < PROBE_UNROLL; ++u) {
+        for (int u = 0; u < UNROLL; ++u) {
             const int64_t i = base + (int64_t)u * PROBE_THREADS + threadIdx.x;
-            row[u] = i < p_end ? __ldg(&v.peaks[i]) : make_double2(0.0, 0.0);
+            row[u] = i < p_end ? (STREAMING ? load_row_streaming(&v.peaks[i]) : __ldg(&v.peaks[i])) : make_double2(0.0, 0.0);
         }
 #pragma unroll
-        for (int u = 0; u < PROBE_UNROLL; ++u) {
+        for (int u = 0; u < UNROLL; ++u) {
             const int64_t i = base + (int64_t)u * PROBE_THREADS + threadIdx.x;
             const bool valid = i < p_end;
             const int32_t t = qms_tmz(row[u].x, v.precision);
@@ -633,6 +643,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     QMS_CUDA(ctx, cudaSetDevice(ctx->device));
     *n_hits = 0;
     *n_hit_windows = 0;
+    ctx->last_hits = ctx->last_windows = 0;
     const qms_params& P = ctx->prm;
     // ---- inputs -> device ----
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -726,12 +737,22 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     int entry_bits = 1, spec_bits = 1;
     while ((1ll << entry_bits) < ctx->n_entries) ++entry_bits;
     while ((1ll << spec_bits) < n_spectra) ++spec_bits;
-    const int tile_shift = 10;
-    static_assert(PROBE_THREADS * PROBE_UNROLL == 1 << 10, "tile_shift must match the probe tile");
-    const int64_t tile = (int64_t)PROBE_THREADS * PROBE_UNROLL;
+    static int variant = -1;   // QMS_PROBE_VARIANT: tuning switch for profiling runs (default = best measured)
+    if (variant < 0) {
+        const char* e = getenv("QMS_PROBE_VARIANT");
+        variant = e ? atoi(e) : 0;
+    }
+    const int unroll = (variant == 2 || variant == 3) ? 8 : 4;
+    const int tile_shift = unroll == 8 ? 11 : 10;
+    const int64_t tile = (int64_t)PROBE_THREADS * unroll;
     const int64_t tiles_total = (n_peaks + tile - 1) / tile;
     int64_t blocks = tiles_total;
-    const int64_t max_blocks = (int64_t)ctx->sm_count * 8;   // 8 resident CTAs of 256 threads per SM
+    static int ctas_per_sm = -1;
+    if (ctas_per_sm < 0) {
+        const char* e = getenv("QMS_PROBE_CTAS");
+        ctas_per_sm = e ? atoi(e) : 16;
+    }
+    const int64_t max_blocks = (int64_t)ctx->sm_count * ctas_per_sm;   // CTAs of 256 threads per SM: 8 are resident, 16 measured best (tail balance)
     if (blocks > max_blocks) blocks = max_blocks;
     const int64_t seg_cap = ((tiles_total + blocks - 1) / blocks) * tile;   // every row of a block could survive
     QMS_TRY(qms_reserve(ctx, ctx->live_rows, (size_t)(seg_cap * blocks)));
@@ -741,8 +762,12 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     for (int attempt = 0; attempt < 2; ++attempt) {
         QMS_CUDA(ctx, cudaMemsetAsync(ctx->dev_counters.p, 0, 64 * sizeof(unsigned long long), ctx->stream));
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-        spectrum_probe_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p,
-                                                                                  ctx->live_count.p);
+        switch (variant) {
+            case 1: spectrum_probe_kernel<4, true><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
+            case 2: spectrum_probe_kernel<8, false><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
+            case 3: spectrum_probe_kernel<8, true><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
+            default: spectrum_probe_kernel<4, false><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
+        }
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
         tile_spectrum_kernel<<<qms_blocks(tiles_total + 1, 256), 256, 0, ctx->stream>>>(tiles_total, p_begin, tile, d_off, n_spectra,
@@ -847,9 +872,6 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     const int64_t nh = (int64_t)ctx->h_pinned[40], nw = (int64_t)ctx->h_pinned[41];
     *n_hits = nh;
     *n_hit_windows = nw;
-    if (out && (nh > out->cap_hits || nw > out->cap_windows))
-        return qms_fail(ctx, QMS_E_CAPACITY, "hit buffers too small: need %lld hits / %lld windows, have %lld / %lld", (long long)nh,
-                        (long long)nw, (long long)out->cap_hits, (long long)out->cap_windows);
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     QMS_TRY(qms_reserve(ctx, ctx->o_spec, (size_t)nh + 1));
     QMS_TRY(qms_reserve(ctx, ctx->o_entry, (size_t)nh + 1));
@@ -867,7 +889,10 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     QMS_CUDA(ctx, cudaMemcpyAsync(ctx->o_win_off.p + nh, &ctx->h_pinned[41], sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->cnt.kernel_launches++;
-    if (out) {
+    ctx->last_hits = nh;            // retained in the o_* buffers for qms_fetch_hits
+    ctx->last_windows = nw;
+    const bool fits = out && nh <= out->cap_hits && nw <= out->cap_windows;
+    if (fits) {
         QMS_TRY(copy_out(ctx, out->hit_spec, ctx->o_spec.p, (size_t)nh));
         QMS_TRY(copy_out(ctx, out->hit_entry, ctx->o_entry.p, (size_t)nh));
         QMS_TRY(copy_out(ctx, out->hit_score, ctx->o_score.p, (size_t)nh));
@@ -883,6 +908,40 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     ctx->cnt.ms_d2h += elapsed(ctx, 3, 4);
     ctx->cnt.hits += nh;
     ctx->cnt.hit_windows += nw;
+    if (out && !fits)
+        return qms_fail(ctx, QMS_E_CAPACITY,
+                        "hit buffers too small: need %lld hits / %lld windows, have %lld / %lld (results retained: qms_fetch_hits)",
+                        (long long)nh, (long long)nw, (long long)out->cap_hits, (long long)out->cap_windows);
+    return QMS_OK;
+}
+
+extern "C" int qms_fetch_hits(qms_ctx* ctx, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
+    if (!ctx || !out) return qms_fail(ctx, QMS_E_ARG, "qms_fetch_hits: bad arguments");
+    QMS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nh = ctx->last_hits, nw = ctx->last_windows;
+    if (n_hits) *n_hits = nh;
+    if (n_hit_windows) *n_hit_windows = nw;
+    if (nh > out->cap_hits || nw > out->cap_windows)
+        return qms_fail(ctx, QMS_E_CAPACITY, "hit buffers too small: need %lld hits / %lld windows", (long long)nh, (long long)nw);
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (nh == 0) {
+        const int64_t zero = 0;
+        if (out->hit_win_off)
+            QMS_CUDA(ctx, cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t),
+                                     qms_is_device_ptr(out->hit_win_off) ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+        return QMS_OK;
+    }
+    QMS_TRY(copy_out(ctx, out->hit_spec, ctx->o_spec.p, (size_t)nh));
+    QMS_TRY(copy_out(ctx, out->hit_entry, ctx->o_entry.p, (size_t)nh));
+    QMS_TRY(copy_out(ctx, out->hit_score, ctx->o_score.p, (size_t)nh));
+    QMS_TRY(copy_out(ctx, out->hit_scaling, ctx->o_scaling.p, (size_t)nh));
+    QMS_TRY(copy_out(ctx, out->hit_win_off, ctx->o_win_off.p, (size_t)nh + 1));
+    QMS_TRY(copy_out(ctx, out->hit_mmz, ctx->o_mmz.p, (size_t)nw));
+    QMS_TRY(copy_out(ctx, out->hit_mi, ctx->o_mi.p, (size_t)nw));
+    QMS_TRY(copy_out(ctx, out->hit_peak, ctx->o_peak.p, (size_t)nw));
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->cnt.ms_d2h += elapsed(ctx, 3, 4);
     return QMS_OK;
 }
 

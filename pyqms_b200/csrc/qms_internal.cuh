@@ -12,6 +12,9 @@
 
 #define QMS_WARP 32
 
+// ---- host-side phase tracing (QMS_TRACE=1): wall ms since the previous mark, to stderr ----
+void qms_trace(qms_ctx* ctx, const char* label);
+
 // ---- error plumbing -------------------------------------------------------------------------
 int qms_fail(qms_ctx* ctx, int code, const char* fmt, ...);
 
@@ -105,6 +108,7 @@ struct qms_ctx {
     DBuf<int64_t> pair_nc, scr_first, scr_cur;
     DBuf<int32_t> tile_spec;
     int32_t max_nc = 0;            // most c-peak windows of any index entry
+    int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
     DBuf<uint8_t> cub_tmp;
     DBuf<unsigned long long> dev_counters;   // see match.cu
     DBuf<double> pair_score, pair_scaling;

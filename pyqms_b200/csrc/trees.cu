@@ -328,6 +328,7 @@ extern "C" int qms_build_element_trees(qms_ctx* ctx, int32_t n_pools, const int3
         return qms_fail(ctx, QMS_E_LIMIT, "multi-isotope element chain needs %zu B shared memory (> 200 KiB): atom count too large",
                         chain_smem);
     const int n_lvl = ctx->h_lvl_base[n_pools];
+    qms_trace(ctx, "trees: enter");
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     QMS_TRY(qms_upload(ctx, ctx->iso_off, iso_off, (size_t)n_pools + 1));
     QMS_TRY(qms_upload(ctx, ctx->iso_mass, iso_mass, (size_t)n_iso));
@@ -345,6 +346,7 @@ extern "C" int qms_build_element_trees(qms_ctx* ctx, int32_t n_pools, const int3
     QMS_CUDA(ctx, cudaMemsetAsync(ctx->lvl_l.p, 0xFF, n_lvl * sizeof(int32_t), ctx->stream));
 
     const int threads = 128;
+    qms_trace(ctx, "trees: uploads + memsets");
     if (two_top >= two_iso_min) {
         dim3 grid(qms_blocks(two_top - two_iso_min + 1, threads), n_pools);
         two_iso_bounds_kernel<<<grid, threads, 0, ctx->stream>>>(n_pools, ctx->iso_off.p, ctx->iso_abun.p, ctx->max_level.p,
@@ -379,6 +381,7 @@ extern "C" int qms_build_element_trees(qms_ctx* ctx, int32_t n_pools, const int3
         }
     }
     ctx->tree_slots = total;
+    qms_trace(ctx, "trees: bounds kernels + host offsets");
     QMS_TRY(qms_upload(ctx, ctx->lvl_off, ctx->h_lvl_off.data(), (size_t)n_lvl));
     QMS_TRY(qms_reserve(ctx, ctx->tree_abun, (size_t)total + 1));
     QMS_TRY(qms_reserve(ctx, ctx->tree_mass, (size_t)total + 1));
@@ -410,6 +413,7 @@ extern "C" int qms_build_element_trees(qms_ctx* ctx, int32_t n_pools, const int3
         qms_release(ctx, d_multi);
     }
     QMS_CUDA(ctx, cudaGetLastError());
+    qms_trace(ctx, "trees: fill + chain kernels");
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     QMS_TRY(qms_download(ctx, ctx->h_lvl_min.data(), ctx->lvl_min.p, n_lvl));
     QMS_TRY(qms_download(ctx, ctx->h_lvl_max.data(), ctx->lvl_max.p, n_lvl));

@@ -566,30 +566,28 @@ class IsotopologueLibrary(dict):
                        isotopic_distributions=self.isotopic_distributions, lookup=self.lookup,
                        metabolic_labels=self.metabolic_labels, params=self.params)
 
-    def _run_matcher(self, peaks, offsets, input_kind, xi, only_entry=None):
-        """One ``qms_match_batch`` / ``qms_match_entry`` call with host buffers; returns packed hit arrays."""
+    def _run_matcher(self, peaks, offsets, input_kind, xi, only_entry=None, values=True):
+        """One ``qms_match_batch`` / ``qms_match_entry`` pass with host buffers, then ``qms_fetch_hits`` into
+        exactly sized arrays (size query + fetch: the spectra are matched once).  ``values=False`` skips the
+        copies of the matched (m/z, intensity) values when the caller indexes its own spectra by ``peak`` row."""
         ctx = self._ctx
         n_spec = len(offsets) - 1
-        cap_h, cap_w = max(1024, 4 * n_spec), max(8192, 32 * n_spec)
-        while True:
-            out = {"spec": np.empty(cap_h, dtype=np.int32), "entry": np.empty(cap_h, dtype=np.int32),
-                   "score": np.empty(cap_h), "scaling": np.empty(cap_h), "win_off": np.zeros(cap_h + 1, dtype=np.int64),
-                   "mmz": np.empty(cap_w), "mi": np.empty(cap_w), "peak": np.empty(cap_w, dtype=np.int64)}
-            hits = QmsHits(cap_h, cap_w, *[out[k].ctypes.data for k in ("spec", "entry", "score", "scaling", "win_off",
-                                                                        "mmz", "mi", "peak")])
-            nh, nw = C.c_int64(), C.c_int64()
-            if only_entry is None:
-                rc = ctx.lib.qms_match_batch(ctx.handle, ptr(peaks), ptr(offsets), n_spec, input_kind, float(xi),
-                                             C.byref(hits), C.byref(nh), C.byref(nw))
-            else:
-                rc = ctx.lib.qms_match_entry(ctx.handle, ptr(peaks), len(peaks), input_kind, int(only_entry), float(xi),
-                                             C.byref(hits), C.byref(nh), C.byref(nw))
-            if rc == -3:                                    # QMS_E_CAPACITY: sizes reported, retry once
-                cap_h, cap_w = nh.value, nw.value
-                continue
-            ctx.check(rc)
-            out["n_hits"], out["n_windows"] = nh.value, nw.value
-            return out
+        nh, nw = C.c_int64(), C.c_int64()
+        if only_entry is None:
+            ctx.check(ctx.lib.qms_match_batch(ctx.handle, ptr(peaks), ptr(offsets), n_spec, input_kind, float(xi), None,
+                                              C.byref(nh), C.byref(nw)))
+        else:
+            ctx.check(ctx.lib.qms_match_entry(ctx.handle, ptr(peaks), len(peaks), input_kind, int(only_entry), float(xi), None,
+                                              C.byref(nh), C.byref(nw)))
+        h, w = nh.value, nw.value
+        out = {"spec": np.empty(h, dtype=np.int32), "entry": np.empty(h, dtype=np.int32), "score": np.empty(h),
+               "scaling": np.empty(h), "win_off": np.zeros(h + 1, dtype=np.int64), "peak": np.empty(w, dtype=np.int64),
+               "mmz": np.empty(w) if values else None, "mi": np.empty(w) if values else None}
+        hits = QmsHits(h, w, *[None if out[k] is None else out[k].ctypes.data
+                               for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
+        ctx.check(ctx.lib.qms_fetch_hits(ctx.handle, C.byref(hits), C.byref(nh), C.byref(nw)))
+        out["n_hits"], out["n_windows"] = h, w
+        return out
 
     @staticmethod
     def _as_peak_array(mz_i_list):
@@ -651,15 +649,17 @@ class IsotopologueLibrary(dict):
         array, kind = self._as_peak_array(mz_i_list)
         array, row_map = self._sorted_or_reordered(array, kind)
         offsets = np.array([0, len(array)], dtype=np.int64)
-        out = self._run_matcher(array, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
+        out = self._run_matcher(array, offsets, kind, results.params["MZ_SCORE_PERCENTILE"], values=False)
         return self._emit(out, results, file_name, [spec_id], [spec_rt], [(mz_i_list, row_map, 0)], None)
 
-    def match_many(self, spectra, file_name=None, spec_ids=None, spec_rts=None, results=None, offsets=None):
+    def match_many(self, spectra, file_name=None, spec_ids=None, spec_rts=None, results=None, offsets=None, lazy=True):
         """Batched ``match_all``: one device pass over many spectra (additive API).
 
         ``spectra``: list of (n,2) arrays / lists of (mz, i) tuples, or one packed (N,2) array together with
         ``offsets`` (n_spectra+1 row offsets).  Hits are added to ``results`` in the order a ``match_all`` loop
-        over the spectra would add them."""
+        over the spectra would add them; with ``lazy`` (default) the ``match`` tuples are only built when
+        ``results`` is first read (``Results.defer``), the packed arrays are available at once through
+        ``results.packed_batches()``."""
         if results is None:
             results = self._new_results()
         if offsets is None:
@@ -688,7 +688,10 @@ class IsotopologueLibrary(dict):
         spec_rts = [None] * n_spec if spec_rts is None else spec_rts
         if self._n_entries == 0 or n_spec == 0:
             return results
-        out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
+        out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"], values=False)
+        if lazy and hasattr(results, "defer"):
+            results.defer(out, lambda target: self._emit(out, target, file_name, spec_ids, spec_rts, sources, None))
+            return results
         return self._emit(out, results, file_name, spec_ids, spec_rts, sources, None)
 
     def match_packed(self, peaks, offsets, mz_score_percentile=None, input_kind=0):

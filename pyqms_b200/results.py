@@ -15,6 +15,13 @@ combined = namedtuple("combined", ["file_name", "formula", "charge", "label_perc
 
 
 class Results(dict):
+    """dict {m_key: {"data": [match, ...], "max_score", "max_score_index", "len_data"}}.
+
+    Batched matching (``IsotopologueLibrary.match_many``) hands over *packed* hit arrays and a thunk that
+    turns them into ``match`` tuples; the thunk runs on the first dict access (any read, ``add``, pickling),
+    so a whole run can be matched at device speed and the Python objects are only built if somebody looks
+    (SURVEY.md section 8f, N1).  ``packed_batches`` exposes the arrays without materialising anything."""
+
     def __init__(self, lookup=None, params=None, fixed_labels=None, metabolic_labels=None, aa_compositions=None,
                  isotopic_distributions=None, charges=None, verbose=False):
         super().__init__()
@@ -31,13 +38,74 @@ class Results(dict):
         self._m_key_class = m_key
         self._combined_class = combined
         self._silac_pairs = None
+        self._pending = []          # [(packed hit dict, thunk)] not yet turned into match tuples
+        self._packed = []           # every packed batch ever handed over (kept for array consumers)
+
+    # ---- deferred materialisation of packed batches -------------------------------------------------
+    def defer(self, packed, thunk):
+        """Register a packed batch; ``thunk(self)`` must ``add`` its hits in (spectrum, entry) order."""
+        self._pending.append(thunk)
+        self._packed.append(packed)
+
+    def packed_batches(self):
+        """The packed hit arrays of every batched call so far (see ``IsotopologueLibrary.match_packed``)."""
+        return list(self._packed)
+
+    def _flush(self):
+        if self._pending:
+            pending, self._pending = self._pending, []
+            for thunk in pending:
+                thunk(self)
+
+    def __getitem__(self, key):
+        self._flush()
+        return dict.__getitem__(self, key)
+
+    def __iter__(self):
+        self._flush()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._flush()
+        return dict.__len__(self)
+
+    def __contains__(self, key):
+        self._flush()
+        return dict.__contains__(self, key)
+
+    def keys(self):
+        self._flush()
+        return dict.keys(self)
+
+    def values(self):
+        self._flush()
+        return dict.values(self)
+
+    def items(self):
+        self._flush()
+        return dict.items(self)
+
+    def get(self, key, default=None):
+        self._flush()
+        return dict.get(self, key, default)
+
+    def __reduce_ex__(self, protocol):
+        self._flush()
+        self._packed = []           # arrays are redundant once materialised; keep pickles reference-sized
+        return dict.__reduce_ex__(self, protocol)
+
+    def __repr__(self):
+        self._flush()
+        return dict.__repr__(self)
 
     def add(self, key, value):
         """Append one match (results.py:144-203); returns the formatted key."""
+        self._flush()
         key = self._m_key_class(*key)
-        slot = self.get(key)
+        slot = dict.get(self, key)
         if slot is None:
-            slot = self[key] = {"data": [], "max_score": -1, "max_score_index": -1, "len_data": 0}
+            slot = {"data": [], "max_score": -1, "max_score_index": -1, "len_data": 0}
+            dict.__setitem__(self, key, slot)
         entry = self._match_class(*value)
         if slot["max_score"] < entry.score:
             slot["max_score"] = entry.score
@@ -53,6 +121,7 @@ class Results(dict):
 
     def extract_results(self, molecules=None, charges=None, file_names=None, label_percentiles=None, formulas=None):
         """Yield (key, i, match) for every stored match that passes the given filters (results.py:305-341)."""
+        self._flush()
         wanted_formulas = set(formulas or [])
         for molecule in molecules or []:
             wanted_formulas.add(self.lookup.get("molecule to formula", {}).get(molecule, molecule))
