@@ -156,8 +156,26 @@ __device__ __forceinline__ int64_t gallop_backward(const double2* __restrict__ p
     return a - 1;
 }
 
+// Is bucket t inside any window of the entry?  Windows normally ascend with the isotope position
+// (monotone = true: advance a cursor), otherwise all windows are scanned.
+__device__ __forceinline__ bool in_any_window(const int32_t* __restrict__ wlo, const int32_t* __restrict__ whi, int nc, int32_t t,
+                                              bool monotone, int& cursor) {
+    if (monotone) {
+        while (cursor < nc && __ldg(&whi[cursor]) < t) ++cursor;
+        return cursor < nc && __ldg(&wlo[cursor]) <= t;
+    }
+    for (int m = 0; m < nc; ++m)
+        if (__ldg(&wlo[m]) <= t && t <= __ldg(&whi[m])) return true;
+    return false;
+}
+
 // Gate one (bucket t at peak row i, window k of entry x) incidence.  Returns true if this is the
-// pair's canonical incidence (lowest window, lowest bucket) and the pair passes both overlap gates.
+// pair's canonical incidence (first bucket inside the union of the entry's windows, lowest window
+// holding it) and the pair passes both overlap gates (IL:1968-1976).
+//
+// An entry's windows span a few Da while a spectrum holds ~0.5 rows per Da, so instead of searching
+// the spectrum once per window the rows next to row i are walked (adjacent 16-byte rows, same cache
+// lines) and each is tested against the entry's window list (two short contiguous int arrays).
 __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64_t i, int32_t t, int32_t x, int32_t k) {
     int64_t ca, cb;
     entry_clamp(v, sb, se, x, ca, cb);
@@ -166,39 +184,46 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
     if (t_before == t) return false;                      // not the first row of its bucket (IL:2014)
     const int64_t w0 = __ldg(&v.ent_win_off[x]);
     const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
-    if (t_before >= __ldg(&v.win_lo[w0 + k])) return false;   // an earlier bucket of window k owns the pair
-    // windows below k must hold no bucket at all (else an earlier incidence owns the pair); a window that
-    // overlaps window k and contains t counts as holding one
-    int64_t pos = i;
-    for (int m = k - 1; m >= 0; --m) {
-        const int64_t j = gallop_backward(v.peaks, ca, pos, __ldg(&v.win_hi[w0 + m]), v.precision);
-        if (j < ca) break;
-        if (tmz_at(v.peaks, j, v.precision) >= __ldg(&v.win_lo[w0 + m])) return false;
-        pos = j;
+    const int32_t* wlo = v.win_lo + w0;
+    const int32_t* whi = v.win_hi + w0;
+    int32_t lo_min = INT32_MAX, hi_max = INT32_MIN, prev_lo = INT32_MIN, prev_hi = INT32_MIN;
+    bool monotone = true;
+    for (int m = 0; m < nc; ++m) {
+        const int32_t lo = __ldg(&wlo[m]), hi = __ldg(&whi[m]);
+        if (m < k && lo <= t && t <= hi) return false;    // a lower window also holds t: that incidence owns the pair
+        monotone = monotone && lo >= prev_lo && hi >= prev_hi;
+        prev_lo = lo;
+        prev_hi = hi;
+        lo_min = lo < lo_min ? lo : lo_min;
+        hi_max = hi > hi_max ? hi : hi_max;
+    }
+    // no earlier bucket may lie inside the union of the windows
+    {
+        int32_t last = t;
+        for (int64_t j = i - 1; j >= ca; --j) {
+            const int32_t tj = tmz_at(v.peaks, j, v.precision);
+            if (tj < lo_min) break;
+            if (tj == last) continue;
+            last = tj;
+            int cursor = 0;
+            if (in_any_window(wlo, whi, nc, tj, monotone, cursor)) return false;
+        }
     }
     // distinct buckets inside the union of the windows (Q10), walking forward from row i
-    int cnt = 0;
-    int32_t covered_to = INT32_MIN;
-    pos = i;
-    for (int m = k; m < nc; ++m) {
-        const int32_t lo = __ldg(&v.win_lo[w0 + m]);
-        const int32_t hi = __ldg(&v.win_hi[w0 + m]);
-        const int32_t ulo = lo > covered_to ? lo : (covered_to == INT32_MAX ? covered_to : covered_to + 1);
-        if (ulo <= hi) {
-            int64_t j = gallop_forward(v.peaks, pos, cb, ulo, v.precision);
-            pos = j;
-            while (j < cb) {
-                const int32_t tj = tmz_at(v.peaks, j, v.precision);
-                if (tj > hi) break;
-                ++cnt;
-                if (cnt >= v.min_match && !((double)cnt / (double)nc < v.req_overlap)) return true;   // IL:1973-1976
-                do {
-                    ++j;
-                } while (j < cb && tmz_at(v.peaks, j, v.precision) == tj);
-                pos = j;
-            }
+    int cnt = 1;
+    if (cnt >= v.min_match && !((double)cnt / (double)nc < v.req_overlap)) return true;
+    int32_t last = t;
+    int cursor = k;
+    if (!monotone) cursor = 0;
+    for (int64_t j = i + 1; j < cb; ++j) {
+        const int32_t tj = tmz_at(v.peaks, j, v.precision);
+        if (tj > hi_max) break;
+        if (tj == last) continue;
+        last = tj;
+        if (in_any_window(wlo, whi, nc, tj, monotone, cursor)) {
+            ++cnt;
+            if (cnt >= v.min_match && !((double)cnt / (double)nc < v.req_overlap)) return true;   // IL:1973-1976
         }
-        if (hi > covered_to) covered_to = hi;
     }
     return false;
 }
@@ -411,11 +436,14 @@ __device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, in
     return j;
 }
 
+#define K6_LOCAL 24
+
 __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys,
                                                              const unsigned long long* __restrict__ vals, int entry_bits,
                                                              int64_t p_begin, int max_nc,
                                                              const int64_t* __restrict__ pair_win_off, int64_t* __restrict__ scr_first,
-                                                             int64_t* __restrict__ scr_cur, int64_t* __restrict__ pair_best,
+                                                             int64_t* __restrict__ scr_cur, int64_t* __restrict__ scr_best,
+                                                             int64_t* __restrict__ pair_best,
                                                              double* __restrict__ pair_score, double* __restrict__ pair_scaling,
                                                              int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -423,31 +451,43 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
     const int64_t s = (int64_t)(keys[p] >> entry_bits);
     const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
     const int64_t row0 = p_begin + (int64_t)(vals[p] >> 16);   // canonical incidence: first bucket of the
-    const int k0 = (int)(vals[p] & 0xffffull);                 // lowest window that holds any (from K5b)
+                                                               // union of the entry's windows (from K5b)
     const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
     int64_t ca, cb;
     entry_clamp(v, sb, se, x, ca, cb);
     const int64_t w0 = __ldg(&v.ent_win_off[x]);
     const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
-    int64_t* first = scr_first + p * max_nc;
-    int64_t* cur = scr_cur + p * max_nc;
-    int64_t* best = pair_best + pair_win_off[p];
-    int n_matched = 0;
-    int64_t pos = row0;             // = first row whose bucket is >= lo of window k0
-    int32_t prev_lo = INT32_MIN;
-    for (int m = 0; m < nc; ++m) {  // candidates of window m = distinct buckets in [lo, hi] (IL:2001-2002)
-        int64_t j = -1;
-        if (m >= k0) {              // windows below k0 hold no bucket (gate_incidence)
-            const int32_t lo = __ldg(&v.win_lo[w0 + m]);
-            const int32_t hi = __ldg(&v.win_hi[w0 + m]);
-            if (lo < prev_lo) pos = ca;   // window edges normally ascend with the isotope position
-            j = gallop_forward(v.peaks, pos, cb, lo, v.precision);
-            pos = j;
-            prev_lo = lo;
-            if (j >= cb || tmz_at(v.peaks, j, v.precision) > hi) j = -1;
+    // per-window candidate cursors: thread-local for the usual short entries (coalesced local memory),
+    // global scratch only for entries with more than K6_LOCAL windows
+    int64_t l_first[K6_LOCAL], l_cur[K6_LOCAL], l_best[K6_LOCAL];
+    int64_t* first = nc <= K6_LOCAL ? l_first : scr_first + p * max_nc;
+    int64_t* cur = nc <= K6_LOCAL ? l_cur : scr_cur + p * max_nc;
+    int64_t* best = nc <= K6_LOCAL ? l_best : scr_best + p * max_nc;
+    const int32_t* wlo = v.win_lo + w0;
+    const int32_t* whi = v.win_hi + w0;
+    int32_t hi_max = INT32_MIN;
+    for (int m = 0; m < nc; ++m) {
+        first[m] = -1;
+        const int32_t hi = __ldg(&whi[m]);
+        hi_max = hi > hi_max ? hi : hi_max;
+    }
+    // candidates of window m = distinct buckets in [lo, hi] (IL:2001-2002): walk the rows from the canonical
+    // row (no bucket of any window lies before it) and record the first row of every window
+    {
+        int32_t last = INT32_MIN;
+        for (int64_t j = row0; j < cb; ++j) {
+            const int32_t tj = tmz_at(v.peaks, j, v.precision);
+            if (tj > hi_max) break;
+            if (tj == last) continue;
+            last = tj;
+            for (int m = 0; m < nc; ++m)
+                if (first[m] < 0 && __ldg(&wlo[m]) <= tj && tj <= __ldg(&whi[m])) first[m] = j;
         }
-        first[m] = cur[m] = best[m] = j;
-        n_matched += j >= 0;
+    }
+    int n_matched = 0;
+    for (int m = 0; m < nc; ++m) {
+        cur[m] = best[m] = first[m];
+        n_matched += first[m] >= 0;
     }
     PairRows rows{&v, w0, nc, cur};
     double best_score = 0.0, best_scaling = 0.0;
@@ -505,6 +545,10 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
     if (v.only_entry < 0) {
         if (best_score < v.score_thr) pass = false;          // IL:1860
         if (n_matched < v.min_match) pass = false;           // IL:1862-1870
+    }
+    {
+        int64_t* out_best = pair_best + pair_win_off[p];
+        for (int m = 0; m < nc; ++m) out_best[m] = best[m];
     }
     pair_score[p] = best_score;
     pair_scaling[p] = best_scaling;
@@ -839,16 +883,17 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 32, ctx->pair_win_off.p + n_pairs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     // ---- K6 ----
-    const size_t scratch = (size_t)n_pairs * (size_t)max_nc + 1;
+    const size_t scratch = max_nc > K6_LOCAL ? (size_t)n_pairs * (size_t)max_nc + 1 : 1;
     QMS_TRY(qms_reserve(ctx, ctx->scr_first, scratch));
     QMS_TRY(qms_reserve(ctx, ctx->scr_cur, scratch));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_best, scratch));
+    QMS_TRY(qms_reserve(ctx, ctx->scr_best, scratch));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_best, (size_t)n_pairs * (size_t)max_nc + 1));
     QMS_TRY(qms_reserve(ctx, ctx->pair_score, (size_t)n_pairs));
     QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)n_pairs));
     QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)n_pairs));
     assemble_score_kernel<<<qms_blocks((int64_t)n_pairs, 128), 128, 0, ctx->stream>>>(
         v, (int64_t)n_pairs, keys, vals, entry_bits, p_begin, max_nc, ctx->pair_win_off.p, ctx->scr_first.p, ctx->scr_cur.p,
-        ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
+        ctx->scr_best.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
     QMS_CUDA(ctx, cudaGetLastError());
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->cnt.kernel_launches++;

@@ -105,7 +105,7 @@ struct qms_ctx {
     DBuf<double> d_peaks;
     DBuf<int64_t> d_offsets;
     DBuf<unsigned long long> pair_keys, pair_keys_alt, pair_vals, pair_vals_alt;
-    DBuf<int64_t> pair_nc, scr_first, scr_cur;
+    DBuf<int64_t> pair_nc, scr_first, scr_cur, scr_best;
     DBuf<int32_t> tile_spec;
     int32_t max_nc = 0;            // most c-peak windows of any index entry
     int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
