@@ -400,17 +400,16 @@ extern "C" int qms_build_element_trees(qms_ctx* ctx, int32_t n_pools, const int3
         ctx->cnt.kernel_launches++;
     }
     if (!multi.empty()) {
-        DBuf<int32_t> d_multi;
-        QMS_TRY(qms_upload(ctx, d_multi, multi.data(), multi.size()));
+        TmpBuf<int32_t> d_multi(ctx);
+        QMS_TRY(qms_upload(ctx, d_multi.b, multi.data(), multi.size()));
         if (chain_smem > 48 * 1024)
             QMS_CUDA(ctx, cudaFuncSetAttribute(multi_iso_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem));
         multi_iso_chain_kernel<<<(int)multi.size(), 256, chain_smem, ctx->stream>>>(
-            d_multi.p, ctx->iso_off.p, ctx->iso_mass.p, ctx->iso_abun.p, ctx->iso_q.p, ctx->max_level.p, ctx->lvl_base.p, thr,
+            d_multi.b.p, ctx->iso_off.p, ctx->iso_mass.p, ctx->iso_abun.p, ctx->iso_q.p, ctx->max_level.p, ctx->lvl_base.p, thr,
             ctx->lvl_min.p, ctx->lvl_max.p, ctx->lvl_off.p, ctx->tree_abun.p, ctx->tree_mass.p);
         ctx->cnt.kernel_launches++;
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        qms_release(ctx, d_multi);
     }
     QMS_CUDA(ctx, cudaGetLastError());
     qms_trace(ctx, "trees: fill + chain kernels");
