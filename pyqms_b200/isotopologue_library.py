@@ -78,7 +78,7 @@ class IsotopologueLibrary(dict):
 
     def __init__(self, molecules=None, charges=None, metabolic_labels=None, fixed_labels=None, params=None,
                  trivial_names=None, verbose=True, evidences=None, unimod_files=None, add_default_files=True, *,
-                 device=None, distributed=None, _plan_only=False):
+                 device=None, distributed=None, defer_matching=True, _plan_only=False):
         super().__init__()
         assert molecules is not None, "require list of molecules"
         assert charges is not None, "require list of charges"
@@ -90,6 +90,7 @@ class IsotopologueLibrary(dict):
         if metabolic_labels is None or metabolic_labels == {}:
             metabolic_labels = {"15N": [0.0]}
         self.build_isotoplogues = True
+        self.defer_matching = defer_matching
         self.verbose = verbose
         self.metabolic_labels = metabolic_labels
         self.fixed_labels = {} if fixed_labels is None else fixed_labels
@@ -609,10 +610,13 @@ class IsotopologueLibrary(dict):
         order = np.argsort(np.round(mz * self.params["INTERNAL_PRECISION"]), kind="stable")
         return np.ascontiguousarray(array[order]), order
 
-    def _emit(self, out, results, file_name, spec_ids, spec_rts, sources, row_maps):
-        """Packed hits -> ``results.add`` in (spectrum, entry) order (IL:1872-1882)."""
-        win_off = out["win_off"]
+    def _emit(self, out, results, file_names, spec_ids, spec_rts, python_floats):
+        """Packed hits -> ``results.add`` in (spectrum, entry) order (IL:1872-1882).  The matched (m/z,
+        intensity) come back from the device: numpy scalars for numpy input, Python floats for list input,
+        like the objects the reference hands back (IL:2014-2017, 2594-2600)."""
+        win_off, mmz, mi = out["win_off"], out["mmz"], out["mi"]
         statics = self._entry_static
+        one_name = not isinstance(file_names, list)
         for h in range(out["n_hits"]):
             s, x = int(out["spec"][h]), int(out["entry"][h])
             static = statics.get(x)
@@ -622,35 +626,62 @@ class IsotopologueLibrary(dict):
                 static = statics[x] = (formula, charge, lp, self._win_ri[a:b].tolist(), self._win_cmz[a:b].tolist(),
                                        self._win_ci[a:b].tolist())
             formula, charge, lp, ri, cmz, ci = static
-            source, row_map, base = sources[s]
-            peaks = []
-            for m, w in enumerate(range(int(win_off[h]), int(win_off[h + 1]))):
-                row = int(out["peak"][w])
-                if row < 0:
-                    peaks.append((None, None, ri[m], cmz[m], ci[m]))
-                else:
-                    row -= base
-                    if row_map is not None:
-                        row = int(row_map[row])
-                    item = source[row]
-                    peaks.append((item[0], item[1], ri[m], cmz[m], ci[m]))
-            score, scaling = out["score"][h], out["scaling"][h]
-            if not isinstance(source, np.ndarray):
-                score, scaling = float(score), float(scaling)
-            results.add((file_name, formula, charge, lp), (spec_ids[s], spec_rts[s], score, scaling, tuple(peaks)))
+            a, b = int(win_off[h]), int(win_off[h + 1])
+            if python_floats:
+                pairs = zip(mmz[a:b].tolist(), mi[a:b].tolist())
+                score, scaling = float(out["score"][h]), float(out["scaling"][h])
+            else:
+                pairs = zip(mmz[a:b], mi[a:b])
+                score, scaling = out["score"][h], out["scaling"][h]
+            peaks = tuple((None, None, ri[m], cmz[m], ci[m]) if x_mz != x_mz else (x_mz, x_i, ri[m], cmz[m], ci[m])
+                          for m, (x_mz, x_i) in enumerate(pairs))
+            results.add((file_names if one_name else file_names[s], formula, charge, lp),
+                        (spec_ids[s], spec_rts[s], score, scaling, peaks))
         return results
 
+    # spectra handed to match_all are queued on the Results object and matched in one device pass when the
+    # results are first read (or when the queue is full): a per-spectrum loop then runs at batch speed
+    QUEUE_MAX_SPECTRA = 4096
+    QUEUE_MAX_PEAKS = 8 << 20
+
+    def _match_queue(self, queue, results):
+        """Device pass over the spectra queued by match_all (called by ``Results._flush``), oldest first."""
+        start = 0
+        while start < len(queue):
+            kind = queue[start][1]
+            stop = start
+            while stop < len(queue) and queue[stop][1] == kind:
+                stop += 1
+            run = queue[start:stop]
+            arrays = [item[0] for item in run]
+            offsets = np.zeros(len(run) + 1, dtype=np.int64)
+            np.cumsum([len(a) for a in arrays], out=offsets[1:])
+            peaks = np.concatenate(arrays) if len(arrays) > 1 else arrays[0]
+            out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
+            self._emit(out, results, [item[2] for item in run], [item[3] for item in run], [item[4] for item in run], kind == 1)
+            start = stop
+
     def match_all(self, mz_i_list=None, file_name=None, spec_id=None, spec_rt=None, results=None):
-        """Match every library entry against one spectrum (IL:1794-1883); returns/updates ``results``."""
+        """Match every library entry against one spectrum (IL:1794-1883); returns/updates ``results``.
+
+        With ``defer_matching`` (default) and a pyqms_b200 ``Results`` the spectrum is copied into the result
+        object's queue and matched with the next device pass (first read of ``results``, a full queue, or
+        ``results.flush()``); hits appear in exactly the order of an eager loop."""
         if results is None:
             results = self._new_results()
         if self._n_entries == 0:
             return results
         array, kind = self._as_peak_array(mz_i_list)
-        array, row_map = self._sorted_or_reordered(array, kind)
+        array, _ = self._sorted_or_reordered(array, kind)
+        if self.defer_matching and hasattr(results, "enqueue"):
+            if array is mz_i_list or array.base is not None or not array.flags["OWNDATA"]:
+                array = array.copy()                       # the caller may reuse its buffer
+            results.enqueue(self, (array, kind, file_name, spec_id, spec_rt), len(array),
+                            self.QUEUE_MAX_SPECTRA, self.QUEUE_MAX_PEAKS)
+            return results
         offsets = np.array([0, len(array)], dtype=np.int64)
-        out = self._run_matcher(array, offsets, kind, results.params["MZ_SCORE_PERCENTILE"], values=False)
-        return self._emit(out, results, file_name, [spec_id], [spec_rt], [(mz_i_list, row_map, 0)], None)
+        out = self._run_matcher(array, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
+        return self._emit(out, results, file_name, [spec_id], [spec_rt], kind == 1)
 
     def match_many(self, spectra, file_name=None, spec_ids=None, spec_rts=None, results=None, offsets=None, lazy=True):
         """Batched ``match_all``: one device pass over many spectra (additive API).
@@ -663,15 +694,12 @@ class IsotopologueLibrary(dict):
         if results is None:
             results = self._new_results()
         if offsets is None:
-            arrays, kinds, sources = [], set(), []
-            base = 0
+            arrays, kinds = [], set()
             for spectrum in spectra:
                 array, kind = self._as_peak_array(spectrum)
-                array, row_map = self._sorted_or_reordered(array, kind)
+                array, _ = self._sorted_or_reordered(array, kind)
                 kinds.add(kind)
                 arrays.append(array)
-                sources.append((spectrum, row_map, base))
-                base += len(array)
             if len(kinds) > 1:
                 raise ValueError("match_many needs all spectra as numpy arrays or all as lists")
             kind = kinds.pop() if kinds else 0
@@ -682,17 +710,18 @@ class IsotopologueLibrary(dict):
             peaks = np.ascontiguousarray(spectra, dtype=np.float64)
             offsets = np.ascontiguousarray(offsets, dtype=np.int64)
             kind = 0
-            sources = [(peaks, None, 0)] * (len(offsets) - 1)
         n_spec = len(offsets) - 1
         spec_ids = list(range(n_spec)) if spec_ids is None else spec_ids
         spec_rts = [None] * n_spec if spec_rts is None else spec_rts
         if self._n_entries == 0 or n_spec == 0:
             return results
-        out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"], values=False)
+        if hasattr(results, "flush_queue"):
+            results.flush_queue()                          # spectra queued by earlier match_all calls come first
+        out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
         if lazy and hasattr(results, "defer"):
-            results.defer(out, lambda target: self._emit(out, target, file_name, spec_ids, spec_rts, sources, None))
+            results.defer(out, lambda target: self._emit(out, target, file_name, spec_ids, spec_rts, kind == 1))
             return results
-        return self._emit(out, results, file_name, spec_ids, spec_rts, sources, None)
+        return self._emit(out, results, file_name, spec_ids, spec_rts, kind == 1)
 
     def match_packed(self, peaks, offsets, mz_score_percentile=None, input_kind=0):
         """Device pass without Python object creation: returns the packed hit arrays of ``qms_match_batch``
@@ -727,7 +756,7 @@ class IsotopologueLibrary(dict):
         out = self._run_matcher(array, np.array([0, len(array)], dtype=np.int64), kind, xi, only_entry=index)
         if out["n_hits"] == 0:
             return None
-        collected = self._emit(out, _Collector(), None, [None], [None], [(source, row_map, 0)], None)
+        collected = self._emit(out, _Collector(), None, [None], [None], kind == 1 or mz_i_list is None)
         return collected.rows[0]
 
     def score_matches(self, matched_peaks, mz_score_percentile):

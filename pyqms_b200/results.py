@@ -14,6 +14,22 @@ combined = namedtuple("combined", ["file_name", "formula", "charge", "label_perc
                                    "score", "scaling_factor", "peaks"])
 
 
+class _FlushingIndex(dict):
+    """``Results.index`` that brings the owning container up to date before it is read."""
+
+    def __init__(self, owner, content):
+        super().__init__(content)
+        self._owner = owner
+
+    def __getitem__(self, key):
+        if self._owner._queue or self._owner._pending:
+            self._owner._flush()
+        return dict.__getitem__(self, key)
+
+    def __reduce__(self):
+        return (dict, (dict(self),))          # pickles hold a plain dict, like the reference's Results.index
+
+
 class Results(dict):
     """dict {m_key: {"data": [match, ...], "max_score", "max_score_index", "len_data"}}.
 
@@ -38,8 +54,13 @@ class Results(dict):
         self._m_key_class = m_key
         self._combined_class = combined
         self._silac_pairs = None
-        self._pending = []          # [(packed hit dict, thunk)] not yet turned into match tuples
+        self._pending = []          # thunks of packed batches not yet turned into match tuples
         self._packed = []           # every packed batch ever handed over (kept for array consumers)
+        self._queue = []            # spectra handed to match_all and not yet matched
+        self._queue_peaks = 0
+        self._queue_library = None
+        self._busy = False
+        self.index = _FlushingIndex(self, self.index)
 
     # ---- deferred materialisation of packed batches -------------------------------------------------
     def defer(self, packed, thunk):
@@ -51,11 +72,40 @@ class Results(dict):
         """The packed hit arrays of every batched call so far (see ``IsotopologueLibrary.match_packed``)."""
         return list(self._packed)
 
+    def enqueue(self, library, item, n_peaks, max_spectra, max_peaks):
+        """Queue one spectrum of a ``match_all`` loop; a full queue is matched at once (bounded memory)."""
+        if self._queue_library is not None and self._queue_library is not library:
+            self.flush_queue()
+        self._queue_library = library
+        self._queue.append(item)
+        self._queue_peaks += n_peaks
+        if len(self._queue) >= max_spectra or self._queue_peaks >= max_peaks:
+            self.flush_queue()
+
+    def flush_queue(self):
+        """Match the queued spectra now (one device pass) and add their hits (after any older packed batch)."""
+        self._flush()
+
+    def flush(self):
+        """Bring the container up to date: queued spectra are matched, packed batches materialised."""
+        self._flush()
+
     def _flush(self):
-        if self._pending:
-            pending, self._pending = self._pending, []
-            for thunk in pending:
-                thunk(self)
+        if self._busy or not (self._pending or self._queue):
+            return
+        self._busy = True           # add() re-enters _flush while a thunk or the queue is being emitted
+        try:
+            while self._pending or self._queue:
+                if self._pending:   # packed batches are always older than the queue (match_many flushes it first)
+                    pending, self._pending = self._pending, []
+                    for thunk in pending:
+                        thunk(self)
+                else:
+                    queue, library = self._queue, self._queue_library
+                    self._queue, self._queue_peaks = [], 0
+                    library._match_queue(queue, self)
+        finally:
+            self._busy = False
 
     def __getitem__(self, key):
         self._flush()
@@ -92,6 +142,7 @@ class Results(dict):
     def __reduce_ex__(self, protocol):
         self._flush()
         self._packed = []           # arrays are redundant once materialised; keep pickles reference-sized
+        self._queue_library = None  # the device context is not picklable
         return dict.__reduce_ex__(self, protocol)
 
     def __repr__(self):
@@ -113,10 +164,10 @@ class Results(dict):
         slot["len_data"] += 1
         slot["data"].append(entry)
         index = self.index
-        index["files"].add(key.file_name)
-        index["charges"].add(key.charge)
-        index["formulas"].add(key.formula)
-        index["label_percentiles"].add(key.label_percentiles)
+        dict.__getitem__(index, "files").add(key.file_name)
+        dict.__getitem__(index, "charges").add(key.charge)
+        dict.__getitem__(index, "formulas").add(key.formula)
+        dict.__getitem__(index, "label_percentiles").add(key.label_percentiles)
         return key
 
     def extract_results(self, molecules=None, charges=None, file_names=None, label_percentiles=None, formulas=None):

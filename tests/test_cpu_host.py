@@ -2,6 +2,7 @@
 planning layer (string work) matches the reference's golden dumps, sharding helpers, synthetic generators."""
 import ctypes
 import re
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -21,6 +22,10 @@ def declared_symbols():
 
 def test_library_exports_every_declared_symbol():
     from pyqms_b200 import _capi
+    if not _capi.LIB_PATH.exists():                 # fresh checkout: compile first (nvcc cross-compiles without a GPU)
+        sys.path.insert(0, str(ROOT))
+        import __graft_entry__
+        __graft_entry__.build()
     lib = ctypes.CDLL(str(_capi.LIB_PATH))          # built by __graft_entry__.build() / make -C pyqms_b200/csrc
     names = declared_symbols()
     assert len(names) >= 25

