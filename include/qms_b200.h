@@ -214,6 +214,17 @@ int qms_score_matches(qms_ctx* ctx, int32_t n, const double* mmz, const double* 
                       const double* cmz, const double* ci, double mz_score_percentile, double* score,
                       double* scaling);
 
+/* ---- next row N2: amounts of matched isotope chromatograms -----------------------------------
+ * Replaces pyqms.adaptors.calc_amount_function (adaptors.py:509-569) inside the retention-time window
+ * walk of Results.calc_amounts_from_rt_info_file (results.py:1238-1262).  Key k owns the profile
+ * entries [seg_off[k], seg_off[k+1]) in stored (spectrum) order: rt (minutes), intensity (= scaling
+ * factor) and score.  win_start / win_stop: per-key window in minutes, NaN = unbounded, NULL = no windows.
+ * out5[k] = {max I, rt at max, score at max, sum I, area under curve}; out_n[k] = entries inside the
+ * window (0 -> the reference returns None).  Host arrays. */
+int qms_calc_amounts(qms_ctx* ctx, int64_t n_keys, const int64_t* seg_off, const double* rt,
+                     const double* intensity, const double* score, const double* win_start,
+                     const double* win_stop, double* out5, int32_t* out_n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -669,3 +669,46 @@ class OracleLibrary(dict):
         mz_score = mz_score / ri_sum
         i_score = i_score / ri_sum
         return mz_score * xi + i_score * (1 - xi), scaling
+
+
+# ---------------------------------------------------------------- next row N2: amounts
+def calc_amount(profile):
+    """pyqms/adaptors.py:509-569 (calc_amount_function): max / sum / area under curve of one profile
+    {"rt": [...], "i": [...], "scores": [...]}; None for an empty profile."""
+    if len(profile["i"]) == 0:
+        return None
+    top = max(profile["i"])
+    at = profile["i"].index(top)
+    out = {"max I in window": top, "max I in window (rt)": profile["rt"][at], "max I in window (score)": profile["scores"][at],
+           "sum I in window": sum(profile["i"]), "auc in window": 0}
+    for pos, y1 in enumerate(profile["i"]):
+        if pos == 0:
+            continue
+        x0, y0, x1 = profile["rt"][pos - 1], profile["i"][pos - 1], profile["rt"][pos]
+        xspace = x1 - x0
+        triangle = 0.5 * (xspace * abs(y1 - y0))
+        out["auc in window"] += xspace * y0
+        if y0 < y1:
+            out["auc in window"] += triangle
+        elif y0 > y1:
+            out["auc in window"] -= triangle
+    return out
+
+
+def windowed_profile(matches, start=None, stop=None):
+    """pyqms/results.py:1238-1262: the rt window walk of calc_amounts_from_rt_info_file over one key's matches."""
+    profile = {"rt": [], "i": [], "scores": [], "spec_ids": []}
+    for entry in matches:
+        try:
+            rt = entry.rt[0] / 60 if entry.rt[1] == "second" else entry.rt[0]
+        except TypeError:
+            rt = entry.rt
+        if start is not None and rt < start:
+            continue
+        elif stop is not None and rt > stop:
+            break
+        profile["rt"].append(rt)
+        profile["i"].append(entry.scaling_factor)
+        profile["scores"].append(entry.score)
+        profile["spec_ids"].append(entry.spec_id)
+    return profile

@@ -1046,3 +1046,88 @@ extern "C" int qms_score_matches(qms_ctx* ctx, int32_t n, const double* mmz, con
     *scaling = res[1];
     return QMS_OK;
 }
+
+// ---- amounts of matched isotope chromatograms -------------------------------------
+// Replaces pyqms.adaptors.calc_amount_function (adaptors.py:509-569) applied inside the retention-time window
+// logic of Results.calc_amounts_from_rt_info_file (results.py:1238-1262): per key the matches are visited in
+// stored order, entries before the window are skipped, the first entry after it ends the profile.  One thread
+// per key, strictly sequential FP64 in the reference's operation order (sum() compensated like CPython >= 3.12).
+__global__ void calc_amounts_kernel(int64_t n_keys, const int64_t* __restrict__ seg_off, const double* __restrict__ rt,
+                                    const double* __restrict__ inten, const double* __restrict__ score,
+                                    const double* __restrict__ win_start, const double* __restrict__ win_stop,
+                                    double* __restrict__ out /* [n_keys][5] */, int32_t* __restrict__ out_n) {
+    const int64_t key = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    const double start = win_start ? win_start[key] : __longlong_as_double(0x7ff8000000000000ll);
+    const double stop = win_stop ? win_stop[key] : __longlong_as_double(0x7ff8000000000000ll);
+    int n = 0;
+    double max_i = 0.0, max_rt = 0.0, max_score = 0.0, sum_hi = 0.0, sum_lo = 0.0, auc = 0.0, x0 = 0.0, y0 = 0.0;
+    for (int64_t h = seg_off[key]; h < seg_off[key + 1]; ++h) {
+        const double x1 = rt[h], y1 = inten[h];
+        if (start == start && x1 < start) continue;   // NaN window edge = no limit
+        if (stop == stop && x1 > stop) break;
+        if (n == 0 || y1 > max_i) {                   // max() / list.index(): first occurrence of the maximum
+            max_i = y1;
+            max_rt = x1;
+            max_score = score[h];
+        }
+        const double t = __dadd_rn(sum_hi, y1);       // Neumaier step
+        if (fabs(sum_hi) >= fabs(y1))
+            sum_lo = __dadd_rn(sum_lo, __dadd_rn(__dsub_rn(sum_hi, t), y1));
+        else
+            sum_lo = __dadd_rn(sum_lo, __dadd_rn(__dsub_rn(y1, t), sum_hi));
+        sum_hi = t;
+        if (n > 0) {                                  // adaptors.py:545-566
+            const double xspace = __dsub_rn(x1, x0);
+            const double triangle = __dmul_rn(0.5, __dmul_rn(xspace, fabs(__dsub_rn(y1, y0))));
+            auc = __dadd_rn(auc, __dmul_rn(xspace, y0));
+            if (y0 < y1)
+                auc = __dadd_rn(auc, triangle);
+            else if (y0 > y1)
+                auc = __dsub_rn(auc, triangle);
+        }
+        x0 = x1;
+        y0 = y1;
+        ++n;
+    }
+    out_n[key] = n;
+    out[key * 5 + 0] = max_i;
+    out[key * 5 + 1] = max_rt;
+    out[key * 5 + 2] = max_score;
+    out[key * 5 + 3] = __dadd_rn(sum_hi, sum_lo);
+    out[key * 5 + 4] = auc;
+}
+
+extern "C" int qms_calc_amounts(qms_ctx* ctx, int64_t n_keys, const int64_t* seg_off, const double* rt, const double* intensity,
+                                const double* score, const double* win_start, const double* win_stop, double* out5,
+                                int32_t* out_n) {
+    if (!ctx || n_keys < 0 || !seg_off || !out5 || !out_n) return qms_fail(ctx, QMS_E_ARG, "qms_calc_amounts: bad arguments");
+    if (n_keys == 0) return QMS_OK;
+    QMS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n_hits = seg_off[n_keys];
+    if (n_hits > 0 && (!rt || !intensity || !score)) return qms_fail(ctx, QMS_E_ARG, "qms_calc_amounts: NULL profile arrays");
+    TmpBuf<int64_t> d_off(ctx);
+    TmpBuf<double> d_prof(ctx), d_win(ctx), d_out(ctx);
+    TmpBuf<int32_t> d_n(ctx);
+    QMS_TRY(qms_upload(ctx, d_off.b, seg_off, (size_t)n_keys + 1));
+    QMS_TRY(qms_reserve(ctx, d_prof.b, (size_t)3 * n_hits + 1));
+    if (n_hits) {
+        QMS_CUDA(ctx, cudaMemcpyAsync(d_prof.b.p, rt, n_hits * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        QMS_CUDA(ctx, cudaMemcpyAsync(d_prof.b.p + n_hits, intensity, n_hits * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        QMS_CUDA(ctx, cudaMemcpyAsync(d_prof.b.p + 2 * n_hits, score, n_hits * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    QMS_TRY(qms_reserve(ctx, d_win.b, (size_t)2 * n_keys));
+    if (win_start) QMS_CUDA(ctx, cudaMemcpyAsync(d_win.b.p, win_start, n_keys * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (win_stop) QMS_CUDA(ctx, cudaMemcpyAsync(d_win.b.p + n_keys, win_stop, n_keys * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    QMS_TRY(qms_reserve(ctx, d_out.b, (size_t)5 * n_keys));
+    QMS_TRY(qms_reserve(ctx, d_n.b, (size_t)n_keys));
+    calc_amounts_kernel<<<qms_blocks(n_keys, 128), 128, 0, ctx->stream>>>(n_keys, d_off.b.p, d_prof.b.p, d_prof.b.p + n_hits,
+                                                                         d_prof.b.p + 2 * n_hits, win_start ? d_win.b.p : nullptr,
+                                                                         win_stop ? d_win.b.p + n_keys : nullptr, d_out.b.p, d_n.b.p);
+    QMS_CUDA(ctx, cudaGetLastError());
+    ctx->cnt.kernel_launches++;
+    QMS_TRY(qms_download(ctx, out5, d_out.b.p, (size_t)5 * n_keys));
+    QMS_TRY(qms_download(ctx, out_n, d_n.b.p, (size_t)n_keys));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return QMS_OK;
+}

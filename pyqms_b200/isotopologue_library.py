@@ -759,6 +759,41 @@ class IsotopologueLibrary(dict):
         collected = self._emit(out, _Collector(), None, [None], [None], kind == 1 or mz_i_list is None)
         return collected.rows[0]
 
+    def calc_amounts(self, results, rt_windows=None):
+        """Amounts of every matched isotope chromatogram in ``results``.
+
+        Per key the matches inside the retention-time window ``rt_windows[key] = (start_min, stop_min)`` (whole
+        profile if absent) give ``{"max I in window", "max I in window (rt)", "max I in window (score)",
+        "sum I in window", "auc in window"}`` exactly like ``pyqms.adaptors.calc_amount_function``
+        (adaptors.py:509-569) driven by ``Results.calc_amounts_from_rt_info_file`` (results.py:1238-1262);
+        ``None`` for a key without a match in its window.  Computed by ``qms_calc_amounts`` (one thread per key)."""
+        keys = list(results.keys())
+        seg_off = np.zeros(len(keys) + 1, dtype=np.int64)
+        rts, intensities, scores = [], [], []
+        for n, key in enumerate(keys):
+            for entry in results[key]["data"]:
+                try:                                        # results.py:1240-1246
+                    rt = entry.rt[0] / 60 if entry.rt[1] == "second" else entry.rt[0]
+                except TypeError:
+                    rt = entry.rt
+                rts.append(rt)
+                intensities.append(entry.scaling_factor)
+                scores.append(entry.score)
+            seg_off[n + 1] = len(rts)
+        rt = np.array(rts, dtype=np.float64)
+        inten = np.array(intensities, dtype=np.float64)
+        score = np.array(scores, dtype=np.float64)
+        start = stop = None
+        if rt_windows is not None:
+            start = np.array([rt_windows.get(k, (_NAN, _NAN))[0] for k in keys], dtype=np.float64)
+            stop = np.array([rt_windows.get(k, (_NAN, _NAN))[1] for k in keys], dtype=np.float64)
+        out = np.zeros((len(keys), 5), dtype=np.float64)
+        count = np.zeros(len(keys), dtype=np.int32)
+        self._ctx.call("qms_calc_amounts", len(keys), ptr(seg_off), ptr(rt), ptr(inten), ptr(score), ptr(start), ptr(stop),
+                       ptr(out), ptr(count))
+        names = ("max I in window", "max I in window (rt)", "max I in window (score)", "sum I in window", "auc in window")
+        return {key: (dict(zip(names, out[n].tolist())) if count[n] else None) for n, key in enumerate(keys)}
+
     def score_matches(self, matched_peaks, mz_score_percentile):
         """mScore and scaling factor of one list of (mmz, mi, ri, cmz, ci) tuples (IL:2441-2498), on the device."""
         rows = list(matched_peaks)

@@ -170,28 +170,61 @@ class Results(dict):
         dict.__getitem__(index, "label_percentiles").add(key.label_percentiles)
         return key
 
-    def extract_results(self, molecules=None, charges=None, file_names=None, label_percentiles=None, formulas=None):
-        """Yield (key, i, match) for every stored match that passes the given filters (results.py:305-341)."""
-        self._flush()
-        wanted_formulas = set(formulas or [])
-        for molecule in molecules or []:
-            wanted_formulas.add(self.lookup.get("molecule to formula", {}).get(molecule, molecule))
-        for key, slot in self.items():
-            if wanted_formulas and key.formula not in wanted_formulas:
+    def _translate_molecules_to_formulas(self, molecules, formulas):
+        """Formulas of ``molecules`` (via ``lookup["molecule to formula"]``) added to ``formulas`` (results.py:343-358)."""
+        formulas = set(formulas) if formulas is not None else set()
+        table = self.lookup.get("molecule to formula", {})
+        for molecule in molecules:
+            if molecule in table:
+                formulas.add(table[molecule])
+        return formulas
+
+    def _parse_and_filter(self, molecules=None, charges=None, file_names=None, label_percentiles=None, formulas=None):
+        """Yield the keys that pass the given filters; ``None`` = do not filter (results.py:205-248)."""
+        if molecules is not None:
+            formulas = self._translate_molecules_to_formulas(molecules, formulas)
+        for key in self.keys():
+            if file_names is not None and key[0] not in file_names:
                 continue
-            if charges is not None and key.charge not in charges:
+            if formulas is not None and key[1] not in formulas:
                 continue
-            if file_names is not None and key.file_name not in file_names:
+            if charges is not None and key[2] not in charges:
                 continue
-            if label_percentiles is not None and key.label_percentiles not in label_percentiles:
+            if label_percentiles is not None and key[3] not in label_percentiles:
                 continue
-            for i, entry in enumerate(slot["data"]):
+            yield key
+
+    def extract_results(self, molecules=None, charges=None, file_names=None, label_percentiles=None, formulas=None,
+                        score_threshold=None):
+        """Yield (key, i, match) of every stored match that passes the filters (results.py:250-307)."""
+        for key in self._parse_and_filter(molecules=molecules, charges=charges, file_names=file_names,
+                                          label_percentiles=label_percentiles, formulas=formulas):
+            for i, entry in enumerate(self[key]["data"]):
+                if score_threshold is not None and entry.score < score_threshold:
+                    continue
                 yield key, i, entry
 
-    def max_score(self, **filters):
-        """(key, index, match) of the best-scoring match under the filters, or (None, None, None)."""
-        best = (None, None, None)
-        for key, i, entry in self.extract_results(**filters):
-            if best[2] is None or entry.score > best[2].score:
-                best = (key, i, entry)
+    def format_all_results(self):
+        """All matches as a pandas DataFrame with the m_key and match fields as columns (results.py:309-341)."""
+        import pandas as pd
+        rows = [self._combined_class(*key, *entry) for key in self.keys() for entry in self[key]["data"]]
+        return pd.DataFrame(rows)
+
+    def max_score(self, molecules=None, charges=None, file_names=None, label_percentiles=None, formulas=None):
+        """[best score, key, index, match] under the filters; [0, None, None, None] if nothing matches
+        (results.py:360-398)."""
+        best = [0, None, None, None]
+        for key, i, entry in self.extract_results(molecules=molecules, charges=charges, file_names=file_names,
+                                                  label_percentiles=label_percentiles, formulas=formulas):
+            if entry.score > best[0]:
+                best = [entry.score, key, i, entry]
         return best
+
+    def determine_max_itensity(self, obj_for_calc_amount):
+        """Default amount function: maximum intensity of an elution profile (results.py:400-447)."""
+        if len(obj_for_calc_amount["i"]) == 0:
+            return None
+        top = max(obj_for_calc_amount["i"])
+        at = obj_for_calc_amount["i"].index(top)
+        return {"max I in window": top, "max I in window (rt)": obj_for_calc_amount["rt"][at],
+                "max I in window (score)": obj_for_calc_amount["scores"][at]}

@@ -109,8 +109,14 @@ def test_results_container():
     assert slot["len_data"] == 2 and slot["max_score"] == 0.9 and slot["max_score_index"] == 1
     assert isinstance(slot["data"][0], pyqms_b200.match) and slot["data"][1].spec_id == 2
     assert res.index["formulas"] == {"C(2)H(4)"} and res.index["charges"] == {2}
-    assert res.max_score()[2].score == 0.9
+    assert res.max_score()[0] == 0.9 and res.max_score()[2] == 1          # [score, key, index, match] (results.py:360-398)
+    assert res.max_score(charges=[3]) == [0, None, None, None]
     assert len(list(res.extract_results(charges=[3]))) == 0
+    assert len(list(res.extract_results(score_threshold=0.8))) == 1
+    frame = res.format_all_results()
+    assert list(frame.columns) == ["file_name", "formula", "charge", "label_percentiles", "spec_id", "rt", "score",
+                                   "scaling_factor", "peaks"] and len(frame) == 2
+    assert res.determine_max_itensity({"rt": [1, 2], "i": [5, 9], "scores": [0.6, 0.7]})["max I in window (rt)"] == 2
 
 
 def test_shard_ranges_cover_exactly():

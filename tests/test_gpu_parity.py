@@ -272,3 +272,38 @@ def test_deferred_loop_equals_eager_loop(pyqms):
             assert type(a.score) is type(b.score)
             assert [type(p[0]) for p in a.peaks] == [type(p[0]) for p in b.peaks]
     assert res_l.index["formulas"] == res_e.index["formulas"]
+
+
+def test_calc_amounts(pyqms):
+    """N2: amounts on the device vs the reference's known answers (tests/adaptor_calc_amount_test.py:8-70) and
+    vs the oracle restatement on matched chromatograms of a synthetic run, with and without rt windows."""
+    from oracle.qms_oracle import calc_amount, windowed_profile
+    lib = pyqms.IsotopologueLibrary(verbose=False, **CASES["bsa_14n15n"]["lib"])
+    kats = [([1, 2, 3], [0, 10, 100], [0.7, 0.8, 0.9], (100, 3, 0.9, 110, 60)),
+            ([1, 2, 3, 4], [10, 100, 100, 10], [0.7, 0.8, 0.9, 0.8], (100, 2, 0.8, 220, 210)),
+            ([1, 2, 3, 4], [10, 100, 120, 10], [0.7, 0.8, 0.9, 0.8], (120, 3, 0.9, 240, 230)),
+            ([1, 2, 3, 4], [10, 10, 10, 10], [0.8, 0.8, 0.8, 0.8], (10, 1, 0.8, 40, 30))]
+    res = pyqms.Results(params=lib.params)
+    for n, (rt, inten, score, want) in enumerate(kats):
+        for r, i, sc in zip(rt, inten, score):
+            res.add(("kat", "F%d" % n, 1, (("N", "0.000"),)), (0, r, sc, i, ()))
+    got = lib.calc_amounts(res)
+    for n, (rt, inten, score, want) in enumerate(kats):
+        amount = got[pyqms.m_key("kat", "F%d" % n, 1, (("N", "0.000"),))]
+        assert tuple(amount.values()) == tuple(float(x) for x in want)
+    blob, peaks, offsets = load_case("bsa_14n15n")
+    n = len(offsets) - 1
+    res = lib.match_many(peaks, file_name="run", spec_ids=list(range(n)), spec_rts=[(s * 12.0, "second") for s in range(n)],
+                         offsets=offsets)
+    windows = {key: (1.0, 4.0) for i, key in enumerate(res.keys()) if i % 2 == 0}
+    for rt_windows in (None, windows):
+        got = lib.calc_amounts(res, rt_windows)
+        for key in res.keys():
+            lo, hi = (rt_windows or {}).get(key, (None, None))
+            want = calc_amount(windowed_profile(res[key]["data"], lo, hi))
+            if want is None:
+                assert got[key] is None
+                continue
+            for name, value in want.items():
+                assert abs(got[key][name] - value) <= 1e-6 * max(1.0, abs(value)), (key, name)
+            assert got[key]["max I in window"] == want["max I in window"]
