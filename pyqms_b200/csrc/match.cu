@@ -436,7 +436,7 @@ __device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, in
     return j;
 }
 
-#define K6_LOCAL 24
+#define K6_LOCAL 16
 
 __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys,
                                                              const unsigned long long* __restrict__ vals, int entry_bits,

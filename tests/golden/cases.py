@@ -95,6 +95,15 @@ CASES = {
     "dense": dict(
         lib=dict(molecules=BSA_MOLECULES[:5], charges=[2, 3], fixed_labels=CAM_FIXED_LABEL),
         run=dict(n_spectra=24, mean_peaks=120, seed=21, elution_sigma=3.0, dense=True)),
+    # wide windows at high charge: neighbouring isotope windows overlap, one bucket can sit in two windows (Q10)
+    "overlap_windows": dict(
+        lib=dict(molecules=BSA_MOLECULES[:6], charges=[4, 5], params={"REL_MZ_RANGE": 5e-4, "REL_I_RANGE": 0.5,
+                                                                     "M_SCORE_THRESHOLD": 0.2}),
+        run=dict(n_spectra=16, mean_peaks=150, seed=23, elution_sigma=3.0, ppm_sd=100.0)),
+    # one ~22 kDa molecule: more than 24 matchable peaks per entry (the matcher's long-entry path)
+    "huge_formula": dict(
+        lib=dict(molecules=["+C980H1540N270O290S8"], charges=[10, 14, 18], params={"UPPER_MZ_LIMIT": 3000}),
+        run=dict(n_spectra=8, mean_peaks=150, seed=24, elution_sigma=3.0), skip_trees=True),
     "big_formula": dict(
         lib=dict(molecules=["+C222H349N61O66S2", "+C444H698N122O133S4", "+C130H210N30O45S1"], charges=[3, 5, 8]),
         run=dict(n_spectra=10, mean_peaks=150, seed=22, elution_sigma=3.0)),

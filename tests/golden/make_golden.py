@@ -35,7 +35,7 @@ def f(x):
     return None if x is None else float(x)
 
 
-def dump_library(lib):
+def dump_library(lib, skip_trees=False):
     formulas = list(lib.keys())
     lps = list(lib.labled_percentiles)
     env = {}
@@ -51,7 +51,7 @@ def dump_library(lib):
                                "n_atmzs": len(e[z]["atmzs"])} for z in lib.charges}})
         env[formula] = rows
     trees = {}
-    for el, by_label in lib.element_trees.items():
+    for el, by_label in ({} if skip_trees else lib.element_trees).items():
         trees[el] = {}
         for label, levels in by_label.items():
             out = {}
@@ -108,7 +108,7 @@ def main():
             continue
         lib = pyqms.IsotopologueLibrary(verbose=False, **case["lib"])
         peaks, offsets = draw_case_spectra(lib, case["run"], name)
-        blob = {"library": dump_library(lib),
+        blob = {"library": dump_library(lib, case.get("skip_trees", False)),
                 "results_numpy": dump_results(run_matches(lib, peaks, offsets, False)),
                 "results_list": dump_results(run_matches(lib, peaks, offsets, True))}
         with gzip.open(HERE / (name + ".json.gz"), "wt") as fh:

@@ -307,3 +307,50 @@ def test_calc_amounts(pyqms):
             for name, value in want.items():
                 assert abs(got[key][name] - value) <= 1e-6 * max(1.0, abs(value)), (key, name)
             assert got[key]["max I in window"] == want["max I in window"]
+
+
+def test_crafted_edge_spectra_vs_oracle(pyqms):
+    """Hand-made spectra around the window edges and bucket boundaries, duplicated rows, zero intensities,
+    shuffled numpy input -- CUDA path vs oracle, numpy and list semantics."""
+    from oracle.qms_oracle import OracleLibrary
+    kw = dict(molecules=["DDSPDLPK", "LVTDLTK", "HLVDEPQNLIK"], charges=[1, 2, 3])
+    ora = OracleLibrary(**kw)
+    lib = pyqms.IsotopologueLibrary(verbose=False, **kw)
+    rng = np.random.default_rng(123)
+    P, r = 1000.0, 5e-6
+    spectra = []
+    for lo, hi, z, lp, formula in ora.formulas_sorted_by_mz:
+        env = ora[formula]["env"][lp]
+        cpk = [n for n, p in enumerate(env["c_peak_pos"]) if p is not None]
+        rows = []
+        for n in cpk:
+            mz = env[z]["mz"][n]
+            win = sorted(env[z]["tmzs"][n])
+            # exactly on, just inside and just outside both window edges; bucket boundaries x.5/P
+            for t in (win[0] - 1, win[0], win[-1], win[-1] + 1):
+                for frac in (-0.4999, 0.0, 0.4999):
+                    rows.append(((t + frac) / P, float(env["abun"][n]) * rng.uniform(50, 150)))
+            rows.append((mz, 0.0))                       # zero intensity in the centre bucket
+            rows.append((mz, float(env["abun"][n]) * 100))
+            rows.append((mz, float(env["abun"][n]) * 100))   # exact duplicate row
+        rows.sort()
+        spectra.append(np.array(rows))
+        spectra.append(np.array(rows[::3]))
+        spectra.append(np.array([row for row in rows if row[1] > 0][::2]))
+    want_np, want_list = {}, {}
+    for s, spec in enumerate(spectra):
+        ora.match_all(spec, "crafted", s, float(s), want_np)
+        ora.match_all([(float(a), float(b)) for a, b in spec], "crafted", s, float(s), want_list)
+    ids, rts = list(range(len(spectra))), [float(s) for s in range(len(spectra))]
+    got = lib.match_many(spectra, file_name="crafted", spec_ids=ids, spec_rts=rts)
+    assert_results_equal(results_to_rows(got), results_to_rows(want_np), score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+    got = lib.match_many([[(float(a), float(b)) for a, b in spec] for spec in spectra], file_name="crafted", spec_ids=ids, spec_rts=rts)
+    assert_results_equal(results_to_rows(got), results_to_rows(want_list), score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+    assert sum(len(v) for v in want_np.values()) > 10
+    # shuffled numpy input: the reference keeps array order inside a bucket (IL:2592-2600)
+    want, got = {}, None
+    for s, spec in enumerate(spectra[:12]):
+        shuffled = spec[rng.permutation(len(spec))]
+        ora.match_all(shuffled, "shuffled", s, float(s), want)
+        got = lib.match_all(mz_i_list=shuffled, file_name="shuffled", spec_id=s, spec_rt=float(s), results=got)
+    assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
