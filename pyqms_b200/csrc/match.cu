@@ -490,12 +490,80 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
         n_matched += first[m] >= 0;
     }
     PairRows rows{&v, w0, nc, cur};
+    // Fast path (entries with <= K6_LOCAL windows): everything of score_matches that does not depend on
+    // the combination is computed once -- sum(ci*ri), sum(ri) -- or once per chosen candidate -- mi*ri and
+    // the m/z term -- so a combination costs one pass of adds, one division for the scaling factor and the
+    // intensity terms, which are independent of each other (instruction-level parallelism) before they are
+    // summed in window order.  Same operations in the same order as score_rows / IL:2441-2498.
+    const bool fast = nc <= K6_LOCAL;
+    double c_p[K6_LOCAL], c_mi[K6_LOCAL], c_mz[K6_LOCAL], k_ri[K6_LOCAL], k_ci[K6_LOCAL], t_i[K6_LOCAL];
+    double calculated = 0.0, ri_sum = 0.0;
+    uint32_t active = 0;   // windows that are matched and pass the relative-intensity floor
+    auto refresh = [&](int m) {
+        const double2 row = __ldg(&v.peaks[cur[m]]);
+        const double cmz = __ldg(&v.win_cmz[w0 + m]);
+        c_mi[m] = row.y;
+        c_p[m] = __dmul_rn(row.y, k_ri[m]);
+        double term = 0.0;
+        if (cmz > QMS_DBL_EPS) {
+            const double err = __ddiv_rn(fabs(__dsub_rn(row.x, cmz)), cmz);
+            const double local = err > v.rel_mz ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, v.rel_mz));
+            term = __dmul_rn(local, k_ri[m]);
+        }
+        c_mz[m] = term;
+    };
+    if (fast) {
+        for (int m = 0; m < nc; ++m) {
+            const double ri = __ldg(&v.win_ri[w0 + m]);
+            k_ri[m] = ri;
+            k_ci[m] = (double)__ldg(&v.win_ci[w0 + m]);
+            if (ri < v.min_rel) continue;
+            if (cur[m] >= 0) {
+                calculated = __dadd_rn(calculated, __dmul_rn(k_ci[m], ri));
+                active |= 1u << m;
+                refresh(m);
+            }
+            ri_sum = __dadd_rn(ri_sum, ri);
+        }
+    }
+    const double one_minus_xi = __dsub_rn(1.0, v.xi);
+    const double one_plus_reli = __dadd_rn(1.0, v.rel_i);
     double best_score = 0.0, best_scaling = 0.0;
     bool have = false;
     unsigned long long combos = 0;
     while (n_matched > 0) {
         double score, scaling;
-        score_rows(rows, v.min_rel, v.rel_mz, v.rel_i, v.xi, score, scaling);
+        if (fast) {
+            double measured = 0.0;
+            for (int m = 0; m < nc; ++m)
+                if ((active >> m) & 1u) measured = __dadd_rn(measured, c_p[m]);
+            scaling = __ddiv_rn(measured, calculated);
+#pragma unroll 4
+            for (int m = 0; m < nc; ++m) {            // independent of each other
+                double term = 0.0;
+                if ((active >> m) & 1u) {
+                    const double si = __dmul_rn(k_ci[m], scaling);
+                    if (si > QMS_DBL_EPS) {
+                        const double err = __ddiv_rn(fabs(__dsub_rn(c_mi[m], si)), si);
+                        const double span = __dsub_rn(one_plus_reli, k_ri[m]);
+                        const double local = err > span ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, span));
+                        term = __dmul_rn(local, k_ri[m]);
+                    }
+                }
+                t_i[m] = term;
+            }
+            double mz_score = 0.0, i_score = 0.0;
+            for (int m = 0; m < nc; ++m)
+                if ((active >> m) & 1u) {
+                    mz_score = __dadd_rn(mz_score, c_mz[m]);
+                    i_score = __dadd_rn(i_score, t_i[m]);
+                }
+            mz_score = __ddiv_rn(mz_score, ri_sum);
+            i_score = __ddiv_rn(i_score, ri_sum);
+            score = __dadd_rn(__dmul_rn(mz_score, v.xi), __dmul_rn(i_score, one_minus_xi));
+        } else {
+            score_rows(rows, v.min_rel, v.rel_mz, v.rel_i, v.xi, score, scaling);
+        }
         ++combos;
         // max under Python tuple order (score, scaling_factor, peaks) -- IL:2022-2034
         bool better = !have;
@@ -533,9 +601,13 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
                 const int64_t nx = next_bucket(v, cur[m], cb, __ldg(&v.win_hi[w0 + m]));
                 if (nx >= 0) {
                     cur[m] = nx;
+                    if (fast && ((active >> m) & 1u)) refresh(m);
                     break;
                 }
-                cur[m] = first[m];
+                if (cur[m] != first[m]) {
+                    cur[m] = first[m];
+                    if (fast && ((active >> m) & 1u)) refresh(m);
+                }
             }
             --m;
         }
