@@ -269,11 +269,12 @@ __global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_kernel(MatchView
             const int32_t t = qms_tmz(row[u].x, v.precision);
             int32_t t_prev = __shfl_up_sync(0xffffffffu, t, 1);
             if (lane == 0) t_prev = (valid && i > p_begin) ? tmz_at(v.peaks, i - 1, v.precision) : t;
-            bool live = false;
-            if (valid && t >= v.t_min && t <= v.t_max) {
-                const uint32_t c = (uint32_t)(t - v.t_min);
-                if ((__ldg(&v.cover2[c >> 10]) >> ((c >> 5) & 31)) & 1u) live = (__ldg(&v.cover[c >> 5]) >> (c & 31)) & 1u;
-            }
+            // branch-free coarse test (the few-KB coarse bitmap is L1-resident; index clamped when out of range),
+            // only the ~3 % of rows that pass it touch the fine bitmap
+            const bool in_range = valid && t >= v.t_min && t <= v.t_max;
+            const uint32_t c = in_range ? (uint32_t)(t - v.t_min) : 0u;
+            bool live = in_range && ((__ldg(&v.cover2[c >> 10]) >> ((c >> 5) & 31)) & 1u);
+            if (live) live = (__ldg(&v.cover[c >> 5]) >> (c & 31)) & 1u;
             const bool descends = valid && t < t_prev;
             const bool push = live || descends;
             const unsigned mask = __ballot_sync(0xffffffffu, push);
