@@ -137,6 +137,7 @@ __global__ void probe_records_kernel(int64_t n_windows, const int64_t* __restric
     probe[i] = r;
     atomicMax(&stats[0], r.hi);
     atomicMax(&stats[1], r.hi - r.lo + 1);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 2), (unsigned long long)(r.hi - r.lo + 1));   // sum of widths
 }
 
 __global__ void iota_i64_kernel(int64_t n, int64_t* __restrict__ dst) {
@@ -177,6 +178,13 @@ __global__ void cover2_kernel(int64_t n_words, const uint32_t* __restrict__ cove
         if (w < n_words && cover[w]) out |= 1u << b;
     }
     cover2[i] = out;
+}
+
+__global__ void cover_popcount_kernel(int64_t n_words, const uint32_t* __restrict__ cover, unsigned long long* __restrict__ total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bits = i < n_words ? (unsigned long long)__popc(cover[i]) : 0ull;
+    for (int s = 16; s > 0; s >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, s);
+    if ((threadIdx.x & 31) == 0 && bits) atomicAdd(total, bits);
 }
 
 template <class K, class V>
@@ -325,6 +333,8 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         ctx->t_min = first_lo;
         ctx->t_max = h_stats[0];
         ctx->max_width = h_stats[1];
+        unsigned long long width_sum = 0;
+        memcpy(&width_sum, &h_stats[2], sizeof(width_sum));
         const int64_t span = (int64_t)ctx->t_max - ctx->t_min + 1;
         QMS_TRY(qms_reserve(ctx, ctx->cell_start, (size_t)span + 2));
         const int64_t cover_words = (span + 31) / 32, cover2_words = (cover_words + 31) / 32;
@@ -335,9 +345,15 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         cover_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->t_min, ctx->probe.p, ctx->cover.p);
         cover2_kernel<<<qms_blocks(cover2_words, threads), threads, 0, ctx->stream>>>(cover_words, ctx->cover.p,
                                                                                      ctx->cover.p + cover_words + 1);
-        ctx->cnt.kernel_launches += 4;
+        // windows per COVERED cell (libraries of label-percentile variants pile many windows on few cells)
+        QMS_CUDA(ctx, cudaMemsetAsync(ctx->dev_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+        cover_popcount_kernel<<<qms_blocks(cover_words, threads), threads, 0, ctx->stream>>>(cover_words, ctx->cover.p,
+                                                                                            ctx->dev_counters.p);
+        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->cnt.kernel_launches += 5;
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->window_density = ctx->h_pinned[0] ? (double)width_sum / (double)ctx->h_pinned[0] : 0.0;
     }
     QMS_CUDA(ctx, cudaGetLastError());
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -363,6 +363,78 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_kernel(MatchView v, i
     }
 }
 
+// K5b for dense libraries (many windows per grid cell): one WARP per surviving row, the lanes take the row's
+// incidences.  With one thread per row the lanes of a warp sit in different entries' gates (ncu on the
+// 100 k-peptide library: 3.4 of 32 lanes active, issue-bound); here all lanes of a warp walk the same
+// neighbourhood of the same spectrum and differ only in the window list they test against.
+__global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView v, int64_t p_begin, int64_t seg_cap,
+                                                                        const uint32_t* __restrict__ live_rows,
+                                                                        const uint32_t* __restrict__ live_count,
+                                                                        const int32_t* __restrict__ tile_spec, int shift,
+                                                                        int entry_bits, unsigned long long* __restrict__ pair_keys,
+                                                                        unsigned long long* __restrict__ pair_vals,
+                                                                        unsigned long long pair_cap,
+                                                                        unsigned long long* __restrict__ counters) {
+    unsigned long long n_live = 0, n_inc = 0;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_rows = live_count[blockIdx.x];
+    const uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
+    for (uint32_t r = threadIdx.x >> 5; r < n_rows; r += blockDim.x >> 5) {   // warp-uniform from here on
+        const uint32_t word = segment[r];
+        const int64_t i = p_begin + (int64_t)(word & ~ROW_CHECK_ONLY);
+        const int64_t tile_id = (int64_t)(word & ~ROW_CHECK_ONLY) >> shift;
+        int64_t s = __ldg(&tile_spec[tile_id]);
+        {
+            int64_t s_hi = __ldg(&tile_spec[tile_id + 1]) + 1;
+            while (s_hi - s > 1) {
+                const int64_t mid = s + ((s_hi - s) >> 1);
+                if (__ldg(&v.offsets[mid]) <= i)
+                    s = mid;
+                else
+                    s_hi = mid;
+            }
+        }
+        const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
+        const int32_t t = tmz_at(v.peaks, i, v.precision);
+        const int32_t t_prev = i > sb ? tmz_at(v.peaks, i - 1, v.precision) : INT32_MIN;
+        if (t < t_prev && lane == 0) atomicAdd(&counters[C_UNSORTED], 1ull);
+        if (word & ROW_CHECK_ONLY) continue;
+        if (lane == 0) ++n_live;
+        if (v.input_kind == 0 && t_prev == t) continue;
+        int32_t c_lo = t - v.max_width + 1;
+        if (c_lo < v.t_min) c_lo = v.t_min;
+        const int32_t j0 = __ldg(&v.cell_start[c_lo - v.t_min]);
+        const int32_t j1 = __ldg(&v.cell_start[t + 1 - v.t_min]);
+        for (int32_t jb = j0; jb < j1; jb += 32) {          // 32 probe records per step, one coalesced 512-byte read
+            const int32_t j = jb + lane;
+            int4 raw = make_int4(0, INT32_MIN, 0, 0);
+            if (j < j1) raw = __ldg(reinterpret_cast<const int4*>(&v.probe[j]));  // lo, hi, entry, k
+            const bool incident = j < j1 && raw.y >= t && (v.only_entry < 0 || raw.z == v.only_entry);
+            n_inc += incident;
+            const bool pass = incident && gate_incidence(v, sb, se, i, t, raw.z, raw.w);
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (mask) {
+                unsigned long long slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&counters[C_PAIRS], (unsigned long long)__popc(mask));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                const unsigned long long slot = slot0 + __popc(mask & ((1u << lane) - 1u));
+                if (pass && slot < pair_cap) {
+                    pair_keys[slot] = ((unsigned long long)s << entry_bits) | (unsigned long long)(uint32_t)raw.z;
+                    pair_vals[slot] = ((unsigned long long)(word & ~ROW_CHECK_ONLY) << 16) | (unsigned long long)(raw.w & 0xffff);
+                }
+            }
+        }
+    }
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        n_live += __shfl_xor_sync(0xffffffffu, n_live, sft);
+        n_inc += __shfl_xor_sync(0xffffffffu, n_inc, sft);
+    }
+    if (lane == 0) {
+        if (n_live) atomicAdd(&counters[C_LIVE], n_live);
+        if (n_inc) atomicAdd(&counters[C_INCID], n_inc);
+    }
+}
+
 // ---- scoring (IL:2441-2498), sequential FP64, no FMA ------------------------------------------------
 struct ScoreAcc {
     double measured, calculated, ri_sum;
@@ -889,10 +961,21 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
         tile_spectrum_kernel<<<qms_blocks(tiles_total + 1, 256), 256, 0, ctx->stream>>>(tiles_total, p_begin, tile, d_off, n_spectra,
                                                                                       ctx->tile_spec.p);
-        gate_rows_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p,
-                                                                             ctx->tile_spec.p, tile_shift, entry_bits, ctx->pair_keys.p,
-                                                                             ctx->pair_vals.p, (unsigned long long)pair_cap,
-                                                                             ctx->dev_counters.p);
+        // library density = windows over an average covered grid cell: dense libraries gate warp-cooperatively
+        static int gate_mode = -1;   // QMS_GATE_MODE: 0 thread per row, 1 warp per row, default by density
+        if (gate_mode < 0) {
+            const char* e = getenv("QMS_GATE_MODE");
+            gate_mode = e ? atoi(e) : 2;
+        }
+        const bool warp_gate = gate_mode == 1 || (gate_mode == 2 && ctx->window_density >= 4.0);
+        if (warp_gate)
+            gate_rows_warp_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(
+                v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p, ctx->tile_spec.p, tile_shift, entry_bits, ctx->pair_keys.p,
+                ctx->pair_vals.p, (unsigned long long)pair_cap, ctx->dev_counters.p);
+        else
+            gate_rows_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(
+                v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p, ctx->tile_spec.p, tile_shift, entry_bits, ctx->pair_keys.p,
+                ctx->pair_vals.p, (unsigned long long)pair_cap, ctx->dev_counters.p);
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
         ctx->cnt.kernel_launches += 3;
