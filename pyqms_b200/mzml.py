@@ -1,0 +1,142 @@
+"""mzML -> packed spectra (the step before the matching path).
+
+The reference's scripts loop ``pymzml.run.Reader`` and hand every MS1 spectrum's ``centroidedPeaks`` to
+``match_all`` (example_scripts/quantify_mzml.py:59-73).  This reader goes from the file straight to the packed
+layout the batched matcher consumes -- one (N, 2) float64 array of (m/z, intensity) rows plus row offsets --
+without a Python object per peak: binary arrays are base64/zlib-decoded into numpy buffers (mzML 1.1: MS:1000514
+m/z array, MS:1000515 intensity array, MS:1000521/523 32/64-bit float, MS:1000574 zlib, MS:1000576 none).
+
+    run = read_mzml("BSA1.mzML", ms_level=1)
+    results = lib.match_many(run.peaks, file_name=run.name, spec_ids=run.spec_ids, spec_rts=run.rts, offsets=run.offsets)
+"""
+import base64
+import os
+import re
+import zlib
+from collections import namedtuple
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+Run = namedtuple("Run", ["name", "peaks", "offsets", "spec_ids", "rts", "ms_levels"])
+
+_MZ, _INTENSITY = "MS:1000514", "MS:1000515"
+_F32, _F64, _ZLIB = "MS:1000521", "MS:1000523", "MS:1000574"
+_MS_LEVEL, _SCAN_START = "MS:1000511", "MS:1000016"
+_ID_NUMBER = re.compile(r"(?:scan|index|spectrum)=(\d+)")
+
+
+def _local(tag):
+    return tag.rsplit("}", 1)[-1]
+
+
+def _decode(array_element):
+    kind, dtype, compressed, text = None, np.float64, False, ""
+    for child in array_element:
+        name = _local(child.tag)
+        if name == "cvParam":
+            accession = child.get("accession")
+            if accession in (_MZ, _INTENSITY):
+                kind = accession
+            elif accession == _F32:
+                dtype = np.float32
+            elif accession == _F64:
+                dtype = np.float64
+            elif accession == _ZLIB:
+                compressed = True
+        elif name == "binary":
+            text = child.text or ""
+    raw = base64.b64decode(text) if text.strip() else b""
+    if compressed and raw:
+        raw = zlib.decompress(raw)
+    return kind, np.frombuffer(raw, dtype=np.dtype(dtype).newbyteorder("<")).astype(np.float64)
+
+
+def spectrum_id(native_id, index):
+    """pymzml-style integer id: the scan number of the native id if there is one, else index + 1."""
+    found = _ID_NUMBER.search(native_id or "")
+    return int(found.group(1)) if found else index + 1
+
+
+def read_mzml(path, ms_level=1, sort_peaks=True):
+    """Read every spectrum of ``ms_level`` (None = all) into a packed ``Run``.
+
+    ``rts`` holds ``(value, unit)`` tuples like pymzml's ``scan_time`` (unit 'minute' or 'second'), which is
+    what ``Results``/``calc_amounts`` understand (results.py:1240-1246)."""
+    mz_parts, int_parts, lengths, ids, rts, levels = [], [], [], [], [], []
+    index = -1
+    for _, element in ET.iterparse(str(path), events=("end",)):
+        if _local(element.tag) != "spectrum":
+            continue
+        index += 1
+        level, scan_time = None, None
+        for param in element.iter():
+            if _local(param.tag) != "cvParam":
+                continue
+            accession = param.get("accession")
+            if accession == _MS_LEVEL:
+                level = int(param.get("value"))
+            elif accession == _SCAN_START and scan_time is None:
+                unit = (param.get("unitName") or "minute").lower()
+                scan_time = (float(param.get("value")), "second" if unit.startswith("sec") else "minute")
+        if ms_level is None or level == ms_level:
+            mz = intensity = None
+            for array_element in element.iter():
+                if _local(array_element.tag) != "binaryDataArray":
+                    continue
+                kind, values = _decode(array_element)
+                if kind == _MZ:
+                    mz = values
+                elif kind == _INTENSITY:
+                    intensity = values
+            if mz is None or intensity is None or len(mz) != len(intensity):
+                raise ValueError("spectrum %r: m/z and intensity arrays missing or of different length" % element.get("id"))
+            if sort_peaks and len(mz) > 1 and np.any(mz[1:] < mz[:-1]):
+                order = np.argsort(mz, kind="stable")
+                mz, intensity = mz[order], intensity[order]
+            mz_parts.append(mz)
+            int_parts.append(intensity)
+            lengths.append(len(mz))
+            ids.append(spectrum_id(element.get("id"), index))
+            rts.append(scan_time)
+            levels.append(level)
+        element.clear()
+    offsets = np.zeros(len(lengths) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    peaks = np.empty((int(offsets[-1]), 2), dtype=np.float64)
+    if lengths:
+        peaks[:, 0] = np.concatenate(mz_parts)
+        peaks[:, 1] = np.concatenate(int_parts)
+    return Run(os.path.basename(str(path)), peaks, offsets, ids, rts, levels)
+
+
+def write_mzml(path, spectra, rts_minutes=None, ms_levels=None, precision=64, compress=True):
+    """Minimal mzML 1.1 writer (test fixtures and synthetic runs): ``spectra`` = list of (n, 2) arrays."""
+    dtype = np.dtype("<f8" if precision == 64 else "<f4")
+
+    def binary(values, accession, name):
+        raw = np.ascontiguousarray(values, dtype=dtype).tobytes()
+        if compress:
+            raw = zlib.compress(raw)
+        text = base64.b64encode(raw).decode()
+        return ('<binaryDataArray encodedLength="%d"><cvParam cvRef="MS" accession="%s" name="%d-bit float"/>'
+                '<cvParam cvRef="MS" accession="%s" name="%s"/><cvParam cvRef="MS" accession="%s" name="%s"/>'
+                "<binary>%s</binary></binaryDataArray>") % (
+                    len(text), _F64 if precision == 64 else _F32, precision, _ZLIB if compress else "MS:1000576",
+                    "zlib compression" if compress else "no compression", accession, name, text)
+
+    with open(path, "w") as out:
+        out.write('<?xml version="1.0" encoding="utf-8"?>\n<mzML xmlns="http://psi.hupo.org/ms/mzml" version="1.1.0">\n'
+                  '<run id="synthetic"><spectrumList count="%d">\n' % len(spectra))
+        for n, spectrum in enumerate(spectra):
+            spectrum = np.asarray(spectrum, dtype=np.float64).reshape(-1, 2)
+            level = 1 if ms_levels is None else ms_levels[n]
+            rt = 0.01 * n if rts_minutes is None else rts_minutes[n]
+            out.write('<spectrum index="%d" id="controllerType=0 controllerNumber=1 scan=%d" defaultArrayLength="%d">'
+                      '<cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="%d"/>'
+                      '<scanList count="1"><scan><cvParam cvRef="MS" accession="MS:1000016" name="scan start time" '
+                      'value="%r" unitName="minute"/></scan></scanList><binaryDataArrayList count="2">%s%s'
+                      "</binaryDataArrayList></spectrum>\n" % (
+                          n, n + 1, len(spectrum), level, rt, binary(spectrum[:, 0], _MZ, "m/z array"),
+                          binary(spectrum[:, 1], _INTENSITY, "intensity array")))
+        out.write("</spectrumList></run></mzML>\n")

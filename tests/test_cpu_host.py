@@ -142,3 +142,32 @@ def test_synthetic_generators_are_deterministic():
     for s in range(10):
         seg = p1[o1[s]:o1[s + 1], 0]
         assert np.all(seg[1:] >= seg[:-1])
+
+
+def test_mzml_round_trip(tmp_path):
+    """N3: mzML -> packed spectra; 64/32-bit floats, zlib or plain, MS-level filter, unsorted peaks."""
+    from pyqms_b200.mzml import read_mzml, write_mzml
+    rng = np.random.default_rng(8)
+    spectra = []
+    for n in range(7):
+        mz = np.sort(rng.uniform(150, 2000, size=int(rng.integers(0, 40))))
+        spectra.append(np.column_stack([mz, 10 ** rng.uniform(3, 6, size=len(mz))]))
+    spectra[3] = spectra[3][::-1].copy()                     # a file with descending m/z
+    levels = [1, 2, 1, 1, 2, 1, 1]
+    for precision, compress in ((64, True), (64, False), (32, True)):
+        path = tmp_path / ("run_%d_%d.mzML" % (precision, compress))
+        write_mzml(path, spectra, rts_minutes=[0.5 * n for n in range(7)], ms_levels=levels, precision=precision, compress=compress)
+        run = read_mzml(path, ms_level=1)
+        keep = [n for n, level in enumerate(levels) if level == 1]
+        assert run.name == path.name and run.spec_ids == [n + 1 for n in keep]
+        assert run.rts == [(0.5 * n, "minute") for n in keep]
+        assert list(np.diff(run.offsets)) == [len(spectra[n]) for n in keep]
+        for k, n in enumerate(keep):
+            got = run.peaks[run.offsets[k]:run.offsets[k + 1]]
+            want = spectra[n][np.argsort(spectra[n][:, 0], kind="stable")]
+            if precision == 64:
+                assert np.array_equal(got, want)
+            else:
+                assert np.allclose(got, want, rtol=1e-6)
+            assert np.all(got[1:, 0] >= got[:-1, 0])
+        assert len(read_mzml(path, ms_level=None).spec_ids) == 7

@@ -354,3 +354,22 @@ def test_crafted_edge_spectra_vs_oracle(pyqms):
         ora.match_all(shuffled, "shuffled", s, float(s), want)
         got = lib.match_all(mz_i_list=shuffled, file_name="shuffled", spec_id=s, spec_rt=float(s), results=got)
     assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+
+
+def test_mzml_to_results_end_to_end(pyqms, tmp_path):
+    """N3 + P2 + N2: synthetic run -> mzML file -> packed reader -> match_many -> amounts equals the direct path."""
+    from pyqms_b200.mzml import read_mzml, write_mzml
+    blob, peaks, offsets = load_case("bsa_14n15n")
+    n = len(offsets) - 1
+    path = tmp_path / "run.mzML"
+    write_mzml(path, [peaks[offsets[s]:offsets[s + 1]] for s in range(n)], rts_minutes=[0.2 * s for s in range(n)])
+    run = read_mzml(path)
+    assert np.array_equal(run.peaks, peaks) and np.array_equal(run.offsets, offsets)
+    lib = pyqms.IsotopologueLibrary(verbose=False, **CASES["bsa_14n15n"]["lib"])
+    from_file = lib.match_many(run.peaks, file_name="run", spec_ids=[i - 1 for i in run.spec_ids], spec_rts=[s * 0.2 for s in range(n)],
+                               offsets=run.offsets)
+    assert_results_equal(results_to_rows(from_file), blob["results_numpy"], score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+    sys.path.insert(0, str(GOLDEN.parent.parent / "examples"))
+    import quantify_mzml
+    res = quantify_mzml.main(str(path), ["DDSPDLPK", "LVTDLTK"])
+    assert len(res) > 0
