@@ -73,7 +73,7 @@ def test_host_planning_matches_reference(name):
     term_off = lib._terms[0]
     assert len(term_off) == len(ref["formulas"]) * len(ref["labled_percentiles"]) + 1
     # envelope terms: (pool, level) in the reference's element order -> levels must exist in its trees
-    for e in range(len(term_off) - 1):
+    for e in range(len(term_off) - 1 if ref["trees"] else 0):      # (tree dumps are skipped for the 22 kDa fixture)
         for t in range(term_off[e], term_off[e + 1]):
             element, label = lib._pools[lib._terms[1][t]]
             assert str(lib._terms[2][t]) in ref["trees"][element][label], (element, label, lib._terms[2][t])
