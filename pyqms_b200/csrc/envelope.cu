@@ -6,16 +6,19 @@
 // the elements' pruned slices [minPos,maxPos], carried here as two arrays per envelope:
 //     A[p] = sum over combinations landing on p of prod(abun)
 //     W[p] = sum over combinations landing on p of prod(abun) * sum(mass)
-// so that total = A[p] and mass = W[p]/A[p] (IL:722-741).  One warp owns one envelope: lanes are
-// parallel over output positions, the element slice is staged in shared memory, A/W ping-pong in
-// shared memory.  Finalisation (IL:742-775): abun = int(round(total*F)), relabun = total/max,
+// so that total = A[p] and mass = W[p]/A[p] (IL:722-741).  Eight lanes own one envelope (four envelopes
+// per warp): every lane holds four consecutive output positions in registers, the element slice is staged
+// in shared memory, A/W ping-pong in shared memory.  Finalisation (IL:742-775): abun = int(round(total*F)), relabun = total/max,
 // c_peak = relabun >= MIN_REL, peaks with total < 2.22e-16 dropped; kept peaks are compacted with
 // a warp ballot.  FP64, -fmad=false.
 #include "qms_internal.cuh"
 
 #define QMS_DBL_EPS 2.220446049250313e-16
 
-__global__ void envelope_convolve_kernel(int64_t e_begin, int64_t e_end, const int64_t* __restrict__ term_off,
+#define ENV_GROUP 8      // lanes that share one envelope (4 envelopes per warp)
+#define ENV_TILE 4       // consecutive output positions per lane, held in registers
+
+__global__ void __launch_bounds__(256, 2) envelope_convolve_kernel(int64_t e_begin, int64_t e_end, const int64_t* __restrict__ term_off,
                                          const int32_t* __restrict__ term_pool, const int32_t* __restrict__ term_level,
                                          const int32_t* __restrict__ lvl_base, const int32_t* __restrict__ lvl_min,
                                          const int32_t* __restrict__ lvl_max, const int64_t* __restrict__ lvl_off,
@@ -25,12 +28,21 @@ __global__ void envelope_convolve_kernel(int64_t e_begin, int64_t e_end, const i
                                          int32_t* __restrict__ env_abun, int32_t* __restrict__ env_pos,
                                          uint8_t* __restrict__ env_cflag, int32_t* __restrict__ env_len,
                                          int32_t* __restrict__ env_nc, unsigned long long* __restrict__ flops) {
+    // ENV_GROUP lanes own one envelope.  Every lane keeps ENV_TILE consecutive output positions and the
+    // matching window of the previous arrays in registers: per slice entry it loads ONE new (A, W) pair and
+    // the slice's (abundance, mass) -- a broadcast inside the group -- for 6*ENV_TILE FP64 operations, instead
+    // of four shared-memory loads per 6 operations with one position per lane.  Positions outside the
+    // previous envelope enter as +0.0, which leaves every partial sum bit-identical to the plain loop.
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int64_t e = e_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (e >= e_end) return;
-    double* base = smem + (size_t)warp * (4 * (size_t)cap_len + 2 * (size_t)cap_slice);
+    const int gl = lane & (ENV_GROUP - 1);                    // lane inside the group
+    const int group_in_warp = lane / ENV_GROUP;
+    const unsigned gmask = ((1u << ENV_GROUP) - 1u) << (group_in_warp * ENV_GROUP);
+    const int groups_per_block = blockDim.x / ENV_GROUP;
+    const int group = threadIdx.x / ENV_GROUP;
+    const int64_t e = e_begin + (int64_t)blockIdx.x * groups_per_block + group;
+    if (e >= e_end) return;                                   // whole groups leave together
+    double* base = smem + (size_t)group * (4 * (size_t)cap_len + 2 * (size_t)cap_slice);
     double* a_prev = base;
     double* w_prev = base + cap_len;
     double* a_cur = base + 2 * cap_len;
@@ -40,70 +52,115 @@ __global__ void envelope_convolve_kernel(int64_t e_begin, int64_t e_end, const i
 
     int len = 1;
     int zero_pos = 0;
+    unsigned long long pairs = 0;
     // The first and the last position are reached by exactly one combination (every element at its
     // minPos / maxPos); their mass is the plain sum of the slice-edge masses in element order, which is
     // what the reference's mass*abun/total collapses to (IL:731-737).  Keeping it free of the abundance
     // round trip makes equal formulas under different label percentiles tie exactly on lower_mz, so the
     // index sort falls through to upper_mz like the reference's tuple sort.
     double edge_lo = 0.0, edge_hi = 0.0;
-    unsigned long long pairs = 0;
-    if (lane == 0) {
+    if (gl == 0) {
         a_prev[0] = 1.0;  // abun = 1, mass = 0 (IL:662-663)
         w_prev[0] = 0.0;
     }
-    __syncwarp();
-    for (int64_t t = term_off[e]; t < term_off[e + 1]; ++t) {
-        const int idx = lvl_base[term_pool[t]] + term_level[t];
-        const int lo = lvl_min[idx];
-        const int r = lvl_max[idx] - lo + 1;
-        const int64_t off = lvl_off[idx];
+    __syncwarp(gmask);
+    const int64_t t_first = term_off[e];
+    const int n_terms = (int)(term_off[e + 1] - t_first);
+    for (int tb = 0; tb < n_terms; tb += ENV_GROUP) {
+      // the (pool, level) -> (minPos, range, offset) lookups of ENV_GROUP terms are issued by different lanes at
+      // once (a chain of four dependent loads per term otherwise) and handed round with shuffles
+      int m_lo = 0, m_r = 1;
+      long long m_off = 0;
+      if (tb + gl < n_terms) {
+          const int idx = lvl_base[term_pool[t_first + tb + gl]] + term_level[t_first + tb + gl];
+          m_lo = lvl_min[idx];
+          m_r = lvl_max[idx] - m_lo + 1;
+          m_off = lvl_off[idx];
+      }
+      const int batch = n_terms - tb < ENV_GROUP ? n_terms - tb : ENV_GROUP;
+      for (int k = 0; k < batch; ++k) {
+        const int src_lane = group_in_warp * ENV_GROUP + k;
+        const int lo = __shfl_sync(gmask, m_lo, src_lane);
+        const int r = __shfl_sync(gmask, m_r, src_lane);
+        const int64_t off = __shfl_sync(gmask, m_off, src_lane);
         zero_pos += lo;
-        for (int j = lane; j < r; j += 32) {  // stage the element slice
+        for (int j = gl; j < r; j += ENV_GROUP) {  // stage the element slice
             s_abun[j] = tree_abun[off + j];
             s_mass[j] = tree_mass[off + j];
         }
-        __syncwarp();
+        __syncwarp(gmask);
         edge_lo = __dadd_rn(edge_lo, s_mass[0]);
         edge_hi = __dadd_rn(edge_hi, s_mass[r - 1]);
         const int new_len = len + r - 1;
-        for (int p = lane; p < new_len; p += 32) {
-            double acc_a = 0.0, acc_w = 0.0;
-            const int j0 = p - len + 1 > 0 ? p - len + 1 : 0;
-            const int j1 = p < r - 1 ? p : r - 1;
-            for (int j = j0; j <= j1; ++j) {
-                const double pa = a_prev[p - j];
-                const double prod = __dmul_rn(pa, s_abun[j]);
-                acc_a = __dadd_rn(acc_a, prod);
-                acc_w = __dadd_rn(acc_w, __dadd_rn(__dmul_rn(w_prev[p - j], s_abun[j]), __dmul_rn(prod, s_mass[j])));
+        for (int pb = 0; pb < new_len; pb += ENV_GROUP * ENV_TILE) {
+            const int p0 = pb + gl * ENV_TILE;
+            if (p0 < new_len) {
+                // slice entries that touch at least one of this lane's positions
+                const int j_lo = p0 - len + 1 > 0 ? p0 - len + 1 : 0;
+                const int j_hi = p0 + ENV_TILE - 1 < r - 1 ? p0 + ENV_TILE - 1 : r - 1;
+                double pa[ENV_TILE], pw[ENV_TILE], acc_a[ENV_TILE], acc_w[ENV_TILE];
+#pragma unroll
+                for (int q = 0; q < ENV_TILE; ++q) {
+                    const int src = p0 + q - j_lo;
+                    const bool in = src >= 0 && src < len;
+                    pa[q] = in ? a_prev[src] : 0.0;
+                    pw[q] = in ? w_prev[src] : 0.0;
+                    acc_a[q] = 0.0;
+                    acc_w[q] = 0.0;
+                }
+                for (int j = j_lo; j <= j_hi; ++j) {
+                    const double sa = s_abun[j], sm = s_mass[j];
+#pragma unroll
+                    for (int q = 0; q < ENV_TILE; ++q) {
+                        const double prod = __dmul_rn(pa[q], sa);
+                        acc_a[q] = __dadd_rn(acc_a[q], prod);
+                        acc_w[q] = __dadd_rn(acc_w[q], __dadd_rn(__dmul_rn(pw[q], sa), __dmul_rn(prod, sm)));
+                    }
+#pragma unroll
+                    for (int q = ENV_TILE - 1; q > 0; --q) {  // slide the window: position p needs prev[p - (j+1)]
+                        pa[q] = pa[q - 1];
+                        pw[q] = pw[q - 1];
+                    }
+                    const int src = p0 - (j + 1);
+                    const bool in = src >= 0 && src < len;
+                    pa[0] = in ? a_prev[src] : 0.0;
+                    pw[0] = in ? w_prev[src] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < ENV_TILE; ++q)
+                    if (p0 + q < new_len) {
+                        a_cur[p0 + q] = acc_a[q];
+                        w_cur[p0 + q] = acc_w[q];
+                    }
             }
-            a_cur[p] = acc_a;
-            w_cur[p] = acc_w;
-            pairs += (unsigned long long)(j1 - j0 + 1);
         }
-        __syncwarp();
+        pairs += (unsigned long long)len * (unsigned long long)r;
+        __syncwarp(gmask);
         double* t0 = a_prev; a_prev = a_cur; a_cur = t0;
         double* t1 = w_prev; w_prev = w_cur; w_cur = t1;
         len = new_len;
+      }
     }
     // max over positions (IL:721-725)
     double top = 0.0;
-    for (int p = lane; p < len; p += 32) top = a_prev[p] > top ? a_prev[p] : top;
-    for (int s = 16; s > 0; s >>= 1) {
-        double o = __shfl_xor_sync(0xffffffffu, top, s);
+    for (int p = gl; p < len; p += ENV_GROUP) top = a_prev[p] > top ? a_prev[p] : top;
+    for (int s = ENV_GROUP / 2; s > 0; s >>= 1) {
+        double o = __shfl_xor_sync(gmask, top, s);
         top = o > top ? o : top;
     }
     // finalise + ballot compaction of the kept peaks, ascending position
     const int64_t out0 = slot_off[e];
+    const unsigned below = (1u << gl) - 1u;
     int kept = 0, n_c = 0;
-    for (int p0 = 0; p0 < len; p0 += 32) {
-        const int p = p0 + lane;
+    for (int p0 = 0; p0 < len; p0 += ENV_GROUP) {
+        const int p = p0 + gl;
         double total = p < len ? a_prev[p] : 0.0;
         const bool keep = p < len && !(total < QMS_DBL_EPS);
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const unsigned mask = (__ballot_sync(gmask, keep) >> (group_in_warp * ENV_GROUP)) & ((1u << ENV_GROUP) - 1u);
         double rel = 0.0;
         bool c_peak = false;
         if (keep) {
-            const int64_t o = out0 + kept + __popc(mask & ((1u << lane) - 1u));
+            const int64_t o = out0 + kept + __popc(mask & below);
             rel = __ddiv_rn(total, top);
             c_peak = rel >= min_rel;
             env_mass[o] = p == 0 ? edge_lo : (p == len - 1 ? edge_hi : __ddiv_rn(w_prev[p], total));
@@ -112,17 +169,16 @@ __global__ void envelope_convolve_kernel(int64_t e_begin, int64_t e_end, const i
             env_pos[o] = zero_pos + p;
             env_cflag[o] = c_peak ? 1 : 0;
         }
-        n_c += __popc(__ballot_sync(0xffffffffu, c_peak));
+        n_c += __popc((__ballot_sync(gmask, c_peak) >> (group_in_warp * ENV_GROUP)) & ((1u << ENV_GROUP) - 1u));
         kept += __popc(mask);
     }
     // mark the unused tail of the slot range (upper bound layout) as dropped
     const int64_t out1 = slot_off[e + 1];
-    for (int64_t o = out0 + kept + lane; o < out1; o += 32) {
+    for (int64_t o = out0 + kept + gl; o < out1; o += ENV_GROUP) {
         env_pos[o] = -1;
         env_cflag[o] = 0;
     }
-    for (int s = 16; s > 0; s >>= 1) pairs += __shfl_xor_sync(0xffffffffu, pairs, s);
-    if (lane == 0) {
+    if (gl == 0) {
         env_len[e] = kept;
         env_nc[e] = n_c;
         atomicAdd(flops, pairs * 6ull);  // 3 mul + 3 add per (position, slice entry) pair
@@ -196,18 +252,18 @@ extern "C" int qms_build_envelopes(qms_ctx* ctx, int64_t e_begin, int64_t e_end)
                         (long long)ctx->n_env);
     if (e_begin == e_end) return QMS_OK;
     QMS_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t per_warp = (4 * (size_t)ctx->max_slots_per_env + 2 * (size_t)ctx->max_slice) * sizeof(double);
-    int warps = 8;
-    while (warps > 1 && warps * per_warp > 96 * 1024) warps >>= 1;
-    const size_t smem = warps * per_warp;
+    const size_t per_group = (4 * (size_t)ctx->max_slots_per_env + 2 * (size_t)ctx->max_slice) * sizeof(double);
+    int groups = 32;                                        // envelopes per CTA: 8 warps x 4 groups
+    while (groups > 4 && groups * per_group > 96 * 1024) groups >>= 1;
+    const size_t smem = groups * per_group;
     if (smem > 220 * 1024)
-        return qms_fail(ctx, QMS_E_LIMIT, "envelope of %d peaks needs %zu B shared memory per warp (> 220 KiB)",
-                        ctx->max_slots_per_env, per_warp);
+        return qms_fail(ctx, QMS_E_LIMIT, "envelope of %d peaks needs %zu B shared memory per envelope (> 55 KiB)",
+                        ctx->max_slots_per_env, per_group);
     if (smem > 48 * 1024)
         QMS_CUDA(ctx, cudaFuncSetAttribute(envelope_convolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n = e_end - e_begin;
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    envelope_convolve_kernel<<<(unsigned)((n + warps - 1) / warps), warps * 32, smem, ctx->stream>>>(
+    envelope_convolve_kernel<<<(unsigned)((n + groups - 1) / groups), groups * ENV_GROUP, smem, ctx->stream>>>(
         e_begin, e_end, ctx->term_off.p, ctx->term_pool.p, ctx->term_level.p, ctx->lvl_base.p, ctx->lvl_min.p, ctx->lvl_max.p,
         ctx->lvl_off.p, ctx->tree_abun.p, ctx->tree_mass.p, ctx->slot_off.p, ctx->max_slots_per_env, ctx->max_slice,
         ctx->prm.intensity_transformation, ctx->prm.min_rel_peak_intensity, ctx->env_mass.p, ctx->env_relabun.p, ctx->env_abun.p,
