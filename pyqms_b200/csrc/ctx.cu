@@ -120,7 +120,7 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     REL(d_peaks); REL(d_offsets); REL(pair_keys); REL(pair_keys_alt); REL(cub_tmp); REL(dev_counters);
     REL(pair_score); REL(pair_scaling); REL(pair_flag); REL(pair_win_off); REL(pair_best);
     REL(blk_hits); REL(blk_wins); REL(live_rows); REL(live_count); REL(pair_vals); REL(pair_vals_alt);
-    REL(pair_nc); REL(scr_first); REL(scr_cur); REL(scr_best); REL(tile_spec);
+    REL(pair_nc); REL(scr_first); REL(scr_cur); REL(scr_best); REL(heavy_list); REL(tile_spec);
     REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak);
 #undef REL
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);

@@ -29,7 +29,7 @@
 
 #define QMS_DBL_EPS 2.220446049250313e-16
 
-enum { C_PEAKS = 0, C_LIVE, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_PAIR_WINDOWS, C_N };
+enum { C_LIVE = 0, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_HEAVY, C_N };   // slots of the device counter block
 
 struct MatchView {
     const double2* peaks;
@@ -58,18 +58,6 @@ struct MatchView {
 
 __device__ __forceinline__ int32_t tmz_at(const double2* __restrict__ peaks, int64_t i, double precision) {
     return qms_tmz(__ldg(&peaks[i].x), precision);
-}
-
-// first index in [a,b) whose bucket is >= t
-__device__ __forceinline__ int64_t lower_bound_t(const double2* __restrict__ peaks, int64_t a, int64_t b, int32_t t, double precision) {
-    while (a < b) {
-        const int64_t mid = a + ((b - a) >> 1);
-        if (tmz_at(peaks, mid, precision) < t)
-            a = mid + 1;
-        else
-            b = mid;
-    }
-    return a;
 }
 
 // bisect.bisect_right of the tuple (mz, inten) in a list of (mz, intensity) tuples (IL:2511-2516)
@@ -119,41 +107,6 @@ __device__ __forceinline__ int64_t spectrum_of(const int64_t* __restrict__ offse
             b = mid;
     }
     return a;
-}
-
-// first index j in [from, end) whose bucket is >= t, searching forward exponentially from `from`
-// (consecutive windows of an entry are ~1/z Da apart, i.e. a handful of rows: 1-3 probes instead of log2(P))
-__device__ __forceinline__ int64_t gallop_forward(const double2* __restrict__ peaks, int64_t from, int64_t end, int32_t t, double precision) {
-    if (from >= end || tmz_at(peaks, from, precision) >= t) return from < end ? from : end;
-    int64_t step = 1, lo = from;  // bucket(lo) < t
-    while (lo + step < end && tmz_at(peaks, lo + step, precision) < t) {
-        lo += step;
-        step <<= 1;
-    }
-    int64_t hi = lo + step < end ? lo + step : end;  // bucket(hi) >= t or hi == end
-    return lower_bound_t(peaks, lo + 1, hi, t, precision);
-}
-
-// last index j in [begin, from] whose bucket is <= t, searching backward from `from`; begin-1 if none
-__device__ __forceinline__ int64_t gallop_backward(const double2* __restrict__ peaks, int64_t begin, int64_t from, int32_t t, double precision) {
-    if (from < begin) return begin - 1;
-    if (tmz_at(peaks, from, precision) <= t) return from;
-    int64_t step = 1, hi = from;  // bucket(hi) > t
-    while (hi - step >= begin && tmz_at(peaks, hi - step, precision) > t) {
-        hi -= step;
-        step <<= 1;
-    }
-    const int64_t lo = hi - step >= begin ? hi - step : begin - 1;  // bucket(lo) <= t or lo == begin-1
-    // first index in (lo, hi) whose bucket is > t, minus one
-    int64_t a = lo + 1, b = hi;
-    while (a < b) {
-        const int64_t mid = a + ((b - a) >> 1);
-        if (tmz_at(peaks, mid, precision) <= t)
-            a = mid + 1;
-        else
-            b = mid;
-    }
-    return a - 1;
 }
 
 // Is bucket t inside any window of the entry?  Windows normally ascend with the isotope position
@@ -229,11 +182,10 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
 }
 
 #define PROBE_THREADS 256
-#define PROBE_UNROLL 4
 #define ROW_CHECK_ONLY 0x80000000u   // row listed only because its bucket is below its predecessor's
 
 // K5a: the streaming half.  Every (m/z, intensity) row is read once with one LDG.128, coalesced (a warp
-// covers 512 contiguous bytes per load, PROBE_UNROLL independent loads in flight per thread).  A row
+// covers 512 contiguous bytes per load, UNROLL independent loads in flight per thread).  A row
 // survives if its bucket is covered by a library window (two-level bitmap, the coarse level is a few KB
 // and stays in L1) or if its bucket descends against the previous row (sortedness is verified by K5b,
 // which knows the spectrum boundaries).  Survivors are appended to the block's own segment of
@@ -436,10 +388,6 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView
 }
 
 // ---- scoring (IL:2441-2498), sequential FP64, no FMA ------------------------------------------------
-struct ScoreAcc {
-    double measured, calculated, ri_sum;
-};
-
 template <class Rows>  // Rows: n(), matched(m), mmz(m), mi(m), ri(m), cmz(m), ci(m)
 __device__ void score_rows(const Rows& r, double min_rel, double rel_mz, double rel_i, double xi, double& score, double& scaling) {
     double measured = 0.0, calculated = 0.0, ri_sum = 0.0;
@@ -510,6 +458,7 @@ __device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, in
 }
 
 #define K6_LOCAL 16
+#define K6B_CANDS 8      // most candidate buckets per window a pair may have to be scored by K6b
 
 __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys,
                                                              const unsigned long long* __restrict__ vals, int entry_bits,
@@ -518,7 +467,8 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
                                                              int64_t* __restrict__ scr_cur, int64_t* __restrict__ scr_best,
                                                              int64_t* __restrict__ pair_best,
                                                              double* __restrict__ pair_score, double* __restrict__ pair_scaling,
-                                                             int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters) {
+                                                             int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters,
+                                                             int64_t* __restrict__ heavy_list, int heavy_min) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     const int64_t s = (int64_t)(keys[p] >> entry_bits);
@@ -562,6 +512,25 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
         cur[m] = best[m] = first[m];
         n_matched += first[m] >= 0;
     }
+    // Pairs with many candidate combinations go to the warp-cooperative kernel (K6b): there the 32 lanes score
+    // different combinations of the same pair with identical control flow instead of one lane grinding through
+    // all of them while its neighbours idle.
+    if (heavy_list != nullptr && nc <= K6_LOCAL && n_matched > 0) {
+        unsigned long long total = 1;
+        bool fits = true;
+        for (int m = 0; m < nc && fits; ++m) {
+            if (first[m] < 0) continue;
+            int count = 1;
+            for (int64_t j = next_bucket(v, first[m], cb, __ldg(&whi[m])); j >= 0; j = next_bucket(v, j, cb, __ldg(&whi[m]))) ++count;
+            fits = count <= K6B_CANDS;
+            total *= (unsigned long long)count;
+            if (total > (1ull << 40)) fits = false;
+        }
+        if (fits && total >= (unsigned long long)heavy_min) {
+            heavy_list[atomicAdd(&counters[C_HEAVY], 1ull)] = p;
+            return;
+        }
+    }
     PairRows rows{&v, w0, nc, cur};
     // Fast path (entries with <= K6_LOCAL windows): everything of score_matches that does not depend on
     // the combination is computed once -- sum(ci*ri), sum(ri) -- or once per chosen candidate -- mi*ri and
@@ -572,16 +541,16 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
     double c_p[K6_LOCAL], c_mi[K6_LOCAL], c_mz[K6_LOCAL], k_ri[K6_LOCAL], k_ci[K6_LOCAL], t_i[K6_LOCAL];
     double calculated = 0.0, ri_sum = 0.0;
     uint32_t active = 0;   // windows that are matched and pass the relative-intensity floor
-    auto refresh = [&](int m) {
+    auto refresh = [&](int m, double ri_m) {
         const double2 row = __ldg(&v.peaks[cur[m]]);
         const double cmz = __ldg(&v.win_cmz[w0 + m]);
         c_mi[m] = row.y;
-        c_p[m] = __dmul_rn(row.y, k_ri[m]);
+        c_p[m] = __dmul_rn(row.y, ri_m);
         double term = 0.0;
         if (cmz > QMS_DBL_EPS) {
             const double err = __ddiv_rn(fabs(__dsub_rn(row.x, cmz)), cmz);
             const double local = err > v.rel_mz ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, v.rel_mz));
-            term = __dmul_rn(local, k_ri[m]);
+            term = __dmul_rn(local, ri_m);
         }
         c_mz[m] = term;
     };
@@ -594,7 +563,7 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
             if (cur[m] >= 0) {
                 calculated = __dadd_rn(calculated, __dmul_rn(k_ci[m], ri));
                 active |= 1u << m;
-                refresh(m);
+                refresh(m, ri);
             }
             ri_sum = __dadd_rn(ri_sum, ri);
         }
@@ -674,12 +643,12 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
                 const int64_t nx = next_bucket(v, cur[m], cb, __ldg(&v.win_hi[w0 + m]));
                 if (nx >= 0) {
                     cur[m] = nx;
-                    if (fast && ((active >> m) & 1u)) refresh(m);
+                    if (fast && ((active >> m) & 1u)) refresh(m, k_ri[m]);
                     break;
                 }
                 if (cur[m] != first[m]) {
                     cur[m] = first[m];
-                    if (fast && ((active >> m) & 1u)) refresh(m);
+                    if (fast && ((active >> m) & 1u)) refresh(m, k_ri[m]);
                 }
             }
             --m;
@@ -699,6 +668,179 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
     pair_scaling[p] = best_scaling;
     pair_flag[p] = pass ? 1 : 0;
     atomicAdd(&counters[C_COMBOS], combos);
+}
+
+// K6b: one warp per combination-heavy pair.  Candidate tables (row, mi, mi*ri, m/z term per window and candidate)
+// are built once in shared memory; combination k is decoded in mixed radix (last window fastest, like the
+// odometer of K6) and scored by lane k % 32 with the arithmetic of the K6 fast path; the best under the
+// reference's (score, scaling, peaks) order is found per lane and then across the warp.
+struct HeavyTables {
+    int64_t row[K6_LOCAL][K6B_CANDS];
+    double mmz[K6_LOCAL][K6B_CANDS], mi[K6_LOCAL][K6B_CANDS], p[K6_LOCAL][K6B_CANDS], mz_term[K6_LOCAL][K6B_CANDS];
+    double ri[K6_LOCAL], ci[K6_LOCAL];
+    int count[K6_LOCAL];
+};
+
+__device__ __forceinline__ bool combo_greater(const HeavyTables& T, int nc, double s_a, double f_a, unsigned long long d_a, double s_b,
+                                              double f_b, unsigned long long d_b) {
+    // tuple order (score, scaling_factor, peaks): peaks differ first at the lowest window whose candidates differ
+    if (s_a != s_b) return s_a > s_b;
+    if (f_a != f_b) return f_a > f_b;
+    for (int m = 0; m < nc; ++m) {
+        if (T.count[m] == 0) continue;
+        const int a = (int)((d_a >> (4 * m)) & 15ull), b = (int)((d_b >> (4 * m)) & 15ull);
+        if (a == b) continue;
+        if (T.mmz[m][a] != T.mmz[m][b]) return T.mmz[m][a] > T.mmz[m][b];
+        if (T.mi[m][a] != T.mi[m][b]) return T.mi[m][a] > T.mi[m][b];
+    }
+    return false;
+}
+
+#define K6B_WARPS 4
+
+__global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v, const unsigned long long* __restrict__ keys,
+                                                                     const unsigned long long* __restrict__ vals, int entry_bits,
+                                                                     int64_t p_begin, const int64_t* __restrict__ pair_win_off,
+                                                                     const int64_t* __restrict__ heavy_list,
+                                                                     int64_t* __restrict__ pair_best, double* __restrict__ pair_score,
+                                                                     double* __restrict__ pair_scaling, int32_t* __restrict__ pair_flag,
+                                                                     unsigned long long* __restrict__ counters) {
+    __shared__ HeavyTables tables[K6B_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    HeavyTables& T = tables[warp];
+    const int64_t n_heavy = (int64_t)counters[C_HEAVY];
+    const int64_t n_warps = (int64_t)gridDim.x * K6B_WARPS;
+    const double one_minus_xi = __dsub_rn(1.0, v.xi);
+    const double one_plus_reli = __dadd_rn(1.0, v.rel_i);
+    for (int64_t h = (int64_t)blockIdx.x * K6B_WARPS + warp; h < n_heavy; h += n_warps) {
+        const int64_t p = heavy_list[h];
+        const int64_t s = (int64_t)(keys[p] >> entry_bits);
+        const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
+        const int64_t row0 = p_begin + (int64_t)(vals[p] >> 16);
+        const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
+        int64_t ca, cb;
+        entry_clamp(v, sb, se, x, ca, cb);
+        const int64_t w0 = __ldg(&v.ent_win_off[x]);
+        const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
+        __syncwarp();
+        // lane m builds the candidate list of window m (K6 has verified nc <= K6_LOCAL and <= K6B_CANDS per window)
+        if (lane < nc) {
+            const int m = lane;
+            const int32_t lo = __ldg(&v.win_lo[w0 + m]), hi = __ldg(&v.win_hi[w0 + m]);
+            const double ri = __ldg(&v.win_ri[w0 + m]), cmz = __ldg(&v.win_cmz[w0 + m]);
+            T.ri[m] = ri;
+            T.ci[m] = (double)__ldg(&v.win_ci[w0 + m]);
+            int count = 0;
+            int32_t last = INT32_MIN;
+            for (int64_t j = row0; j < cb && count < K6B_CANDS; ++j) {
+                const int32_t tj = tmz_at(v.peaks, j, v.precision);
+                if (tj > hi) break;
+                if (tj == last || tj < lo) {
+                    last = tj;
+                    continue;
+                }
+                last = tj;
+                const double2 row = __ldg(&v.peaks[j]);
+                T.row[m][count] = j;
+                T.mmz[m][count] = row.x;
+                T.mi[m][count] = row.y;
+                T.p[m][count] = __dmul_rn(row.y, ri);
+                double term = 0.0;
+                if (cmz > QMS_DBL_EPS) {
+                    const double err = __ddiv_rn(fabs(__dsub_rn(row.x, cmz)), cmz);
+                    const double local = err > v.rel_mz ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, v.rel_mz));
+                    term = __dmul_rn(local, ri);
+                }
+                T.mz_term[m][count] = term;
+                ++count;
+            }
+            T.count[m] = ri < v.min_rel ? -count : count;   // negative: matched but below the intensity floor (ignored by the score)
+        }
+        __syncwarp();
+        // combination-independent sums, in window order (every lane redundantly: uniform)
+        double calculated = 0.0, ri_sum = 0.0;
+        unsigned long long total = 1;
+        int n_matched = 0;
+        for (int m = 0; m < nc; ++m) {
+            const int c = T.count[m];
+            if (c != 0) ++n_matched;
+            if (T.ri[m] < v.min_rel) continue;
+            if (c > 0) {
+                calculated = __dadd_rn(calculated, __dmul_rn(T.ci[m], T.ri[m]));
+                total *= (unsigned long long)c;
+            }
+            ri_sum = __dadd_rn(ri_sum, T.ri[m]);
+        }
+        double b_score = 0.0, b_scaling = 0.0;
+        unsigned long long b_digits = 0;
+        bool have = false;
+        for (unsigned long long k = lane; k < total; k += 32) {
+            unsigned long long rest = k, digits = 0;
+            for (int m = nc - 1; m >= 0; --m) {            // last window fastest
+                const int c = T.count[m];
+                if (c <= 0) continue;
+                digits |= (rest % (unsigned long long)c) << (4 * m);
+                rest /= (unsigned long long)c;
+            }
+            double measured = 0.0;
+            for (int m = 0; m < nc; ++m)
+                if (T.count[m] > 0) measured = __dadd_rn(measured, T.p[m][(digits >> (4 * m)) & 15ull]);
+            const double scaling = __ddiv_rn(measured, calculated);
+            double mz_score = 0.0, i_score = 0.0;
+            for (int m = 0; m < nc; ++m) {
+                if (T.count[m] <= 0) continue;
+                const int d = (int)((digits >> (4 * m)) & 15ull);
+                double term = 0.0;
+                const double si = __dmul_rn(T.ci[m], scaling);
+                if (si > QMS_DBL_EPS) {
+                    const double err = __ddiv_rn(fabs(__dsub_rn(T.mi[m][d], si)), si);
+                    const double span = __dsub_rn(one_plus_reli, T.ri[m]);
+                    const double local = err > span ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, span));
+                    term = __dmul_rn(local, T.ri[m]);
+                }
+                mz_score = __dadd_rn(mz_score, T.mz_term[m][d]);
+                i_score = __dadd_rn(i_score, term);
+            }
+            mz_score = __ddiv_rn(mz_score, ri_sum);
+            i_score = __ddiv_rn(i_score, ri_sum);
+            const double score = __dadd_rn(__dmul_rn(mz_score, v.xi), __dmul_rn(i_score, one_minus_xi));
+            if (!have || combo_greater(T, nc, score, scaling, digits, b_score, b_scaling, b_digits)) {
+                have = true;
+                b_score = score;
+                b_scaling = scaling;
+                b_digits = digits;
+            }
+        }
+        // best across the warp (lanes without a combination carry have = false)
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const double o_score = __shfl_xor_sync(0xffffffffu, b_score, sft);
+            const double o_scaling = __shfl_xor_sync(0xffffffffu, b_scaling, sft);
+            const unsigned long long o_digits = __shfl_xor_sync(0xffffffffu, b_digits, sft);
+            const int o_have = __shfl_xor_sync(0xffffffffu, (int)have, sft);
+            if (o_have && (!have || combo_greater(T, nc, o_score, o_scaling, o_digits, b_score, b_scaling, b_digits))) {
+                have = true;
+                b_score = o_score;
+                b_scaling = o_scaling;
+                b_digits = o_digits;
+            }
+        }
+        if (lane == 0) {
+            bool pass = have;
+            if (v.only_entry < 0) {
+                if (b_score < v.score_thr) pass = false;          // IL:1860
+                if (n_matched < v.min_match) pass = false;        // IL:1862-1870
+            }
+            int64_t* out_best = pair_best + pair_win_off[p];
+            for (int m = 0; m < nc; ++m) {
+                const int c = T.count[m];
+                out_best[m] = c == 0 ? -1 : T.row[m][c > 0 ? (int)((b_digits >> (4 * m)) & 15ull) : 0];
+            }
+            pair_score[p] = b_score;
+            pair_scaling[p] = b_scaling;
+            pair_flag[p] = pass ? 1 : 0;
+            atomicAdd(&counters[C_COMBOS], total);
+        }
+    }
 }
 
 // ---- K7: order-preserving warp-ballot compaction -----------------------------------------------------
@@ -1047,9 +1189,26 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     QMS_TRY(qms_reserve(ctx, ctx->pair_score, (size_t)n_pairs));
     QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)n_pairs));
     QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)n_pairs));
+    static int heavy_min = -1;   // QMS_HEAVY_MIN: combinations from which a pair is scored warp-cooperatively (0 = never)
+    if (heavy_min < 0) {
+        const char* e = getenv("QMS_HEAVY_MIN");
+        heavy_min = e ? atoi(e) : 16;
+    }
+    QMS_TRY(qms_reserve(ctx, ctx->heavy_list, (size_t)n_pairs + 1));
     assemble_score_kernel<<<qms_blocks((int64_t)n_pairs, 128), 128, 0, ctx->stream>>>(
         v, (int64_t)n_pairs, keys, vals, entry_bits, p_begin, max_nc, ctx->pair_win_off.p, ctx->scr_first.p, ctx->scr_cur.p,
-        ctx->scr_best.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
+        ctx->scr_best.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p,
+        heavy_min > 0 ? ctx->heavy_list.p : nullptr, heavy_min);
+    QMS_CUDA(ctx, cudaGetLastError());
+    if (heavy_min > 0) {
+        int64_t hblocks = ((int64_t)n_pairs + K6B_WARPS - 1) / K6B_WARPS;
+        const int64_t hmax = (int64_t)ctx->sm_count * 8;
+        if (hblocks > hmax) hblocks = hmax;
+        score_heavy_kernel<<<(unsigned)hblocks, 32 * K6B_WARPS, 0, ctx->stream>>>(
+            v, keys, vals, entry_bits, p_begin, ctx->pair_win_off.p, ctx->heavy_list.p, ctx->pair_best.p, ctx->pair_score.p,
+            ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
+        ctx->cnt.kernel_launches++;
+    }
     QMS_CUDA(ctx, cudaGetLastError());
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->cnt.kernel_launches++;

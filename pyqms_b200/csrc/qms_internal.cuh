@@ -10,8 +10,6 @@
 
 #include "../../include/qms_b200.h"
 
-#define QMS_WARP 32
-
 // ---- host-side phase tracing (QMS_TRACE=1): wall ms since the previous mark, to stderr ----
 void qms_trace(qms_ctx* ctx, const char* label);
 
@@ -105,7 +103,7 @@ struct qms_ctx {
     DBuf<double> d_peaks;
     DBuf<int64_t> d_offsets;
     DBuf<unsigned long long> pair_keys, pair_keys_alt, pair_vals, pair_vals_alt;
-    DBuf<int64_t> pair_nc, scr_first, scr_cur, scr_best;
+    DBuf<int64_t> pair_nc, scr_first, scr_cur, scr_best, heavy_list;
     DBuf<int32_t> tile_spec;
     int32_t max_nc = 0;            // most c-peak windows of any index entry
     double window_density = 0.0;   // sum of window widths / covered grid cells = windows over an average covered cell

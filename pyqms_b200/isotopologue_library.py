@@ -22,7 +22,7 @@ import numpy as np
 
 from . import knowledge_base
 from .params import params as _default_params
-from ._capi import QMS_E_INPUT, Context, QmsError, QmsHits, QmsIndexInfo, QmsParams, ptr
+from ._capi import Context, QmsHits, QmsIndexInfo, QmsParams, ptr
 from .chemistry import ChemicalComposition
 from .results import Results
 
