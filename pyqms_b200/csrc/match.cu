@@ -315,10 +315,13 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_kernel(MatchView v, i
     }
 }
 
-// K5b for dense libraries (many windows per grid cell): one WARP per surviving row, the lanes take the row's
-// incidences.  With one thread per row the lanes of a warp sit in different entries' gates (ncu on the
-// 100 k-peptide library: 3.4 of 32 lanes active, issue-bound); here all lanes of a warp walk the same
-// neighbourhood of the same spectrum and differ only in the window list they test against.
+// K5b for dense libraries (many windows per covered grid cell): a warp walks its rows, the lanes read the
+// row's probe records (one coalesced 512-byte read per 32 records) and the incident ones are compacted into
+// a per-warp shared-memory queue; whenever the queue holds 32 incidences they are gated together, one per
+// lane.  With one thread per row the lanes of a warp sat in different rows' record loops (ncu on the
+// 100 k-peptide library: 3.4 of 32 lanes active, issue-bound); gating straight from the record loop still
+// left the lanes of non-incident records idle (4.4 of 32).
+#define GATE_QUEUE 64
 __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView v, int64_t p_begin, int64_t seg_cap,
                                                                         const uint32_t* __restrict__ live_rows,
                                                                         const uint32_t* __restrict__ live_count,
@@ -327,14 +330,45 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView
                                                                         unsigned long long* __restrict__ pair_vals,
                                                                         unsigned long long pair_cap,
                                                                         unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t q_row[PROBE_THREADS / 32][GATE_QUEUE];
+    __shared__ int32_t q_entry[PROBE_THREADS / 32][GATE_QUEUE], q_k[PROBE_THREADS / 32][GATE_QUEUE],
+        q_spec[PROBE_THREADS / 32][GATE_QUEUE];
     unsigned long long n_live = 0, n_inc = 0;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    int q_n = 0;   // warp-uniform
+    auto gate_batch = [&](int first, int count) {   // gate queue entries [first, first+count), one per lane
+        bool pass = false;
+        uint32_t row_off = 0;
+        int32_t x = 0, k = 0, sp = 0;
+        if (lane < count) {
+            row_off = q_row[warp][first + lane];
+            x = q_entry[warp][first + lane];
+            k = q_k[warp][first + lane];
+            sp = q_spec[warp][first + lane];
+            const int64_t i = p_begin + (int64_t)row_off;
+            const int64_t sb = __ldg(&v.offsets[sp]), se = __ldg(&v.offsets[sp + 1]);
+            pass = gate_incidence(v, sb, se, i, tmz_at(v.peaks, i, v.precision), x, k);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (mask) {
+            unsigned long long slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(&counters[C_PAIRS], (unsigned long long)__popc(mask));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            const unsigned long long slot = slot0 + __popc(mask & below);
+            if (pass && slot < pair_cap) {
+                pair_keys[slot] = ((unsigned long long)sp << entry_bits) | (unsigned long long)(uint32_t)x;
+                pair_vals[slot] = ((unsigned long long)row_off << 16) | (unsigned long long)(k & 0xffff);
+            }
+        }
+    };
     const uint32_t n_rows = live_count[blockIdx.x];
     const uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
-    for (uint32_t r = threadIdx.x >> 5; r < n_rows; r += blockDim.x >> 5) {   // warp-uniform from here on
+    for (uint32_t r = warp; r < n_rows; r += blockDim.x >> 5) {   // warp-uniform from here on
         const uint32_t word = segment[r];
-        const int64_t i = p_begin + (int64_t)(word & ~ROW_CHECK_ONLY);
-        const int64_t tile_id = (int64_t)(word & ~ROW_CHECK_ONLY) >> shift;
+        const uint32_t row_off = word & ~ROW_CHECK_ONLY;
+        const int64_t i = p_begin + (int64_t)row_off;
+        const int64_t tile_id = (int64_t)row_off >> shift;
         int64_t s = __ldg(&tile_spec[tile_id]);
         {
             int64_t s_hi = __ldg(&tile_spec[tile_id + 1]) + 1;
@@ -346,7 +380,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView
                     s_hi = mid;
             }
         }
-        const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
+        const int64_t sb = __ldg(&v.offsets[s]);
         const int32_t t = tmz_at(v.peaks, i, v.precision);
         const int32_t t_prev = i > sb ? tmz_at(v.peaks, i - 1, v.precision) : INT32_MIN;
         if (t < t_prev && lane == 0) atomicAdd(&counters[C_UNSORTED], 1ull);
@@ -357,26 +391,30 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView
         if (c_lo < v.t_min) c_lo = v.t_min;
         const int32_t j0 = __ldg(&v.cell_start[c_lo - v.t_min]);
         const int32_t j1 = __ldg(&v.cell_start[t + 1 - v.t_min]);
-        for (int32_t jb = j0; jb < j1; jb += 32) {          // 32 probe records per step, one coalesced 512-byte read
+        for (int32_t jb = j0; jb < j1; jb += 32) {
             const int32_t j = jb + lane;
             int4 raw = make_int4(0, INT32_MIN, 0, 0);
             if (j < j1) raw = __ldg(reinterpret_cast<const int4*>(&v.probe[j]));  // lo, hi, entry, k
             const bool incident = j < j1 && raw.y >= t && (v.only_entry < 0 || raw.z == v.only_entry);
-            n_inc += incident;
-            const bool pass = incident && gate_incidence(v, sb, se, i, t, raw.z, raw.w);
-            const unsigned mask = __ballot_sync(0xffffffffu, pass);
-            if (mask) {
-                unsigned long long slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&counters[C_PAIRS], (unsigned long long)__popc(mask));
-                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                const unsigned long long slot = slot0 + __popc(mask & ((1u << lane) - 1u));
-                if (pass && slot < pair_cap) {
-                    pair_keys[slot] = ((unsigned long long)s << entry_bits) | (unsigned long long)(uint32_t)raw.z;
-                    pair_vals[slot] = ((unsigned long long)(word & ~ROW_CHECK_ONLY) << 16) | (unsigned long long)(raw.w & 0xffff);
-                }
+            const unsigned mask = __ballot_sync(0xffffffffu, incident);
+            if (incident) {
+                const int slot = q_n + __popc(mask & below);
+                q_row[warp][slot] = row_off;
+                q_entry[warp][slot] = raw.z;
+                q_k[warp][slot] = raw.w;
+                q_spec[warp][slot] = (int32_t)s;
+            }
+            q_n += __popc(mask);
+            if (lane == 0) n_inc += __popc(mask);
+            __syncwarp();
+            if (q_n >= 32) {
+                gate_batch(q_n - 32, 32);
+                q_n -= 32;
+                __syncwarp();
             }
         }
     }
+    if (q_n > 0) gate_batch(0, q_n);
     for (int sft = 16; sft > 0; sft >>= 1) {
         n_live += __shfl_xor_sync(0xffffffffu, n_live, sft);
         n_inc += __shfl_xor_sync(0xffffffffu, n_inc, sft);
