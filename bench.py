@@ -198,6 +198,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    from pyqms_b200.distributed import bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None    # before any pinned allocation
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
@@ -362,7 +364,7 @@ def run_ours(args):
             "config": {"workload": wl["name"], "spectra_per_gpu": n_spec, "peaks_per_gpu": int(len(peaks)),
                        "library_entries": int(lib._n_entries), "library_windows": int(lib._n_windows),
                        "l2_policy": "inputs (%d MB of peaks per step) larger than L2" % (peaks.nbytes >> 20),
-                       "input_kind": "numpy (N,2) float64", "hits_per_step": int(nh.value)},
+                       "input_kind": "numpy (N,2) float64", "hits_per_step": int(nh.value), "numa_node_rank0": numa_node},
             "e2e": {"value": e2e_value, "unit": "spectra/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,

@@ -30,6 +30,32 @@ def rank():
     return d.get_rank() if d else 0
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned spectrum buffers
+    (first touch) and the staging copies live next to the GPU's PCIe root.  Returns the node or None."""
+    import os
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def shard_range(n, r, world):
     """Contiguous block partition of range(n): rank r gets [begin, end); sizes differ by at most 1."""
     base, extra = divmod(int(n), int(world))
