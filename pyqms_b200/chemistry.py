@@ -74,6 +74,24 @@ class ChemicalComposition(dict):
             del self[symbol]
         return self
 
+    def composition_of(self, molecule):
+        """A fresh ``ChemicalComposition`` of one molecule string (``use`` + ``generate_cc_dict`` without touching
+        this object); plain ``+formula`` molecules skip the peptide machinery."""
+        out = ChemicalComposition.__new__(ChemicalComposition)
+        dict.__init__(out)
+        out.aa_compositions = self.aa_compositions
+        out.isotopic_distributions = self.isotopic_distributions
+        out.unimod_file_list = self.unimod_file_list
+        out.add_default_files = self.add_default_files
+        if molecule[:1] == "+" and "#" not in molecule:
+            for isotope, element, bracketed, bare in _TOKEN.findall(molecule.replace(" ", "")[1:]):
+                key = isotope + element
+                out[key] = out.get(key, 0) + (int(bracketed) if bracketed != "" else int(bare or 1))
+            for symbol in [s for s, n in out.items() if n == 0]:
+                del out[symbol]
+            return out
+        return out.use(deprecated_format=molecule)
+
     def _modification(self, title):
         for path in self.unimod_file_list:
             table = load_unimod_xml(path)

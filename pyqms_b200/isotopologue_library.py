@@ -291,53 +291,62 @@ class IsotopologueLibrary(dict):
         two_iso = self._range_for_elements_with_two_isotopes
         # the reference iterates set(molecules) (hash order); sorted() makes the envelope order identical in
         # every process, which the sharded multi-GPU build relies on
+        known = self.isotopic_distributions
+        highest = self._highest_element_count
+        two_isotopes = {}                                   # element -> has a 2-isotope table (IL:448-460)
+        hill_order = {}                                     # element tuple -> Hill order (C, H, then sorted)
+        to_formula = self.lookup["molecule to formula"]
+        to_molecule = self.lookup["formula to molecule"]
         for molecule in sorted(set(molecules)):
             if molecule.count("#") > 1:
                 raise ValueError(f"{molecule} contains too many '#' {molecule.count('#') + 1} only one allowed")
-            factory.use(deprecated_format=molecule)
-            composition = factory.generate_cc_dict()
-            formula = factory.hill_notation_unimod()
+            composition = factory.composition_of(molecule)
+            elements = tuple(composition)
+            order = hill_order.get(elements)
+            if order is None:
+                order = hill_order[elements] = [e for e in ("C", "H") if e in composition] + \
+                    sorted(e for e in elements if e not in ("C", "H"))
+            formula = "".join(["%s(%d)" % (e, composition[e]) for e in order])
             if trivial_names is not None:
                 name = trivial_names.get(molecule, None)
                 if name is not None:
                     self.lookup["formula to trivial name"].setdefault(formula, []).append(name)
                 else:
                     print("No trivial name for molecule", molecule)
-            self.lookup["molecule to formula"][molecule] = formula
-            self.lookup["formula to molecule"].setdefault(formula, []).append(molecule)
+            to_formula[molecule] = formula
+            to_molecule.setdefault(formula, []).append(molecule)
             if formula not in self:
                 self[formula] = {"env": _LazyEnvelopes(self, formula, self.labled_percentiles), "cc": composition}
-            for element in composition:
-                if element in self.isotopic_distributions:
-                    continue
-                # isotope-labelled element introduced by a modification (e.g. 13C of a SILAC/TMT unimod), IL:378-436
-                found = _ISOTOPE_ELEMENT.match(element)
-                try:
-                    enriched = int(round(float(found.group("isotope"))))
-                except Exception:
-                    print("Failed on", element)
-                    print("Maybe element is not in pyqms.knowledge_base.py ?")
-                    raise SystemExit(1)
-                template = found.group("element")
-                target = levels.get("{0}{1}".format(enriched, template)) or 0.994
-                if self.verbose:
-                    print("> Extending isotopic distribution that are within the modifications for "
-                          "element {0}{1}, enrichment levels set to {2}".format(enriched, template, target))
-                self.isotopic_distributions[element] = {self.zero_labeled_percentile: self._recalc_isotopic_distribution(
-                    element=template, target_percentile=target, enriched_isotope=enriched)}
-            highest = self._highest_element_count
+            for element, count in composition.items():
+                if element not in known:
+                    # isotope-labelled element introduced by a modification (e.g. 13C of a SILAC/TMT unimod), IL:378-436
+                    found = _ISOTOPE_ELEMENT.match(element)
+                    try:
+                        enriched = int(round(float(found.group("isotope"))))
+                    except Exception:
+                        print("Failed on", element)
+                        print("Maybe element is not in pyqms.knowledge_base.py ?")
+                        raise SystemExit(1)
+                    template = found.group("element")
+                    target = levels.get("{0}{1}".format(enriched, template)) or 0.994
+                    if self.verbose:
+                        print("> Extending isotopic distribution that are within the modifications for "
+                              "element {0}{1}, enrichment levels set to {2}".format(enriched, template, target))
+                    known[element] = {self.zero_labeled_percentile: self._recalc_isotopic_distribution(
+                        element=template, target_percentile=target, enriched_isotope=enriched)}
             for element, count in composition.items():
                 if element not in highest:
                     highest[element] = 0
                 if highest[element] < count:
                     highest[element] = count
-                for table in self.isotopic_distributions[element].values():
-                    if len(table) == 2:
-                        if two_iso[0] is None or count < two_iso[0]:
-                            two_iso[0] = count
-                        if two_iso[1] is None or count > two_iso[1]:
-                            two_iso[1] = count
-                        break                               # one 2-isotope label of the element is enough (IL:448-460)
+                has_two = two_isotopes.get(element)
+                if has_two is None:
+                    has_two = two_isotopes[element] = any(len(table) == 2 for table in known[element].values())
+                if has_two:
+                    if two_iso[0] is None or count < two_iso[0]:
+                        two_iso[0] = count
+                    if two_iso[1] is None or count > two_iso[1]:
+                        two_iso[1] = count
         # fold the isotope-labelled counts into their template element (IL:467-497)
         for element in list(self._highest_element_count):
             if element.isalpha():
