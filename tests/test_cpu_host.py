@@ -171,3 +171,25 @@ def test_mzml_round_trip(tmp_path):
                 assert np.allclose(got, want, rtol=1e-6)
             assert np.all(got[1:, 0] >= got[:-1, 0])
         assert len(read_mzml(path, ms_level=None).spec_ids) == 7
+
+
+def build_c_demo(tmp_path):
+    import subprocess
+    exe = tmp_path / "c_abi_demo"
+    lib_dir = ROOT / "pyqms_b200"
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I" + str(ROOT / "include"), str(ROOT / "examples" / "c_abi_demo.c"), "-o", str(exe),
+           "-L" + str(lib_dir), "-lqms_b200", "-Wl,-rpath," + str(lib_dir), "-lm"]
+    done = subprocess.run(cmd, capture_output=True, text=True)
+    assert done.returncode == 0, done.stderr
+    return exe
+
+
+def test_c_abi_links_from_plain_c(tmp_path):
+    """The boundary is a C ABI: a plain C program (no Python, no torch) compiles against include/qms_b200.h and links
+    libqms_b200.so; without a GPU it must fail loudly (there is no CPU fallback)."""
+    import subprocess
+    import torch
+    exe = build_c_demo(tmp_path)
+    if not torch.cuda.is_available():
+        done = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert done.returncode == 2 and "no CPU fallback" in done.stderr

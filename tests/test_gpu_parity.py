@@ -373,3 +373,12 @@ def test_mzml_to_results_end_to_end(pyqms, tmp_path):
     import quantify_mzml
     res = quantify_mzml.main(str(path), ["DDSPDLPK", "LVTDLTK"])
     assert len(res) > 0
+
+
+def test_c_abi_demo_runs(tmp_path):
+    """Plain C driver of the C ABI reproduces the docs' quick-start answer (examples/c_abi_demo.c)."""
+    import subprocess
+    from tests.test_cpu_host import build_c_demo
+    done = subprocess.run([str(build_c_demo(tmp_path))], capture_output=True, text=True, timeout=120)
+    assert done.returncode == 0 and done.stdout.strip().endswith("OK"), done.stdout + done.stderr
+    assert "mScore 0.96066097" in done.stdout
