@@ -229,7 +229,7 @@ def run_ours(args):
                "mi": torch.empty(cap_w, dtype=torch.float64, device="cuda"), "peak": torch.empty(cap_w, dtype=torch.int64, device="cuda")}
         hits = QmsHits(cap_h, cap_w, *[dev[k].data_ptr() for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
         nh, nw = C.c_int64(), C.c_int64()
-        rc = ctx.lib.qms_match_batch(ctx.handle, d_peaks.data_ptr(), d_offsets.data_ptr(), n_spec, 0, xi, C.byref(hits), C.byref(nh),
+        rc = ctx.lib.qms_match_batch(ctx.handle, d_peaks.data_ptr(), offsets.ctypes.data, n_spec, 0, xi, C.byref(hits), C.byref(nh),
                                      C.byref(nw))
         if rc == -3:
             cap_h, cap_w = nh.value + 1024, nw.value + 8192
@@ -238,7 +238,8 @@ def run_ours(args):
         break
 
     def device_step():
-        ctx.check(ctx.lib.qms_match_batch(ctx.handle, d_peaks.data_ptr(), d_offsets.data_ptr(), n_spec, 0, xi, C.byref(hits),
+        # peaks resident in HBM; the 240 KB of row offsets stay a host array (the library needs the row count on the host)
+        ctx.check(ctx.lib.qms_match_batch(ctx.handle, d_peaks.data_ptr(), offsets.ctypes.data, n_spec, 0, xi, C.byref(hits),
                                           C.byref(nh), C.byref(nw)))
 
     def barrier():

@@ -98,7 +98,7 @@ int qms_ctx_create(int device, qms_ctx** out) {
         delete ctx;
         return QMS_E_CUDA;
     }
-    for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 12; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaHostAlloc((void**)&ctx->h_pinned, 64 * sizeof(unsigned long long), cudaHostAllocDefault);
     *out = ctx;
@@ -123,7 +123,7 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     REL(pair_nc); REL(scr_first); REL(scr_cur); REL(scr_best); REL(heavy_list); REL(tile_spec);
     REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak);
 #undef REL
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 12; ++i) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

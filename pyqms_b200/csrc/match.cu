@@ -29,7 +29,7 @@
 
 #define QMS_DBL_EPS 2.220446049250313e-16
 
-enum { C_LIVE = 0, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_HEAVY, C_N };   // slots of the device counter block
+enum { C_LIVE = 0, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_HEAVY, C_PAIR_WINDOWS, C_N };   // slots of the device counter block
 
 struct MatchView {
     const double2* peaks;
@@ -477,14 +477,6 @@ struct PairRows {  // rows of one (spectrum, entry) pair under the current candi
     __device__ double ci(int m) const { return (double)__ldg(&v->win_ci[w0 + m]); }
 };
 
-__global__ void pair_windows_kernel(int64_t n_pairs, const unsigned long long* __restrict__ keys, int entry_bits,
-                                    const int64_t* __restrict__ ent_win_off, int64_t* __restrict__ pair_nc) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
-    pair_nc[p] = ent_win_off[x + 1] - ent_win_off[x];
-}
-
 // next first-of-bucket row after row j (bucket tj) that still lies inside [.., hi]; -1 if none
 __device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, int64_t cb, int32_t hi) {
     const int32_t tj = tmz_at(v.peaks, j, v.precision);
@@ -500,15 +492,14 @@ __device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, in
 
 __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys,
                                                              const unsigned long long* __restrict__ vals, int entry_bits,
-                                                             int64_t p_begin, int max_nc,
-                                                             const int64_t* __restrict__ pair_win_off, int64_t* __restrict__ scr_first,
+                                                             int64_t p_begin, int max_nc, int64_t* __restrict__ scr_first,
                                                              int64_t* __restrict__ scr_cur, int64_t* __restrict__ scr_best,
                                                              int64_t* __restrict__ pair_best,
                                                              double* __restrict__ pair_score, double* __restrict__ pair_scaling,
                                                              int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters,
                                                              int64_t* __restrict__ heavy_list, int heavy_min) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
+    if (p >= n_pairs || keys[p] == ~0ull) return;              // n_pairs = list capacity; all-ones = unused slot
     const int64_t s = (int64_t)(keys[p] >> entry_bits);
     const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
     const int64_t row0 = p_begin + (int64_t)(vals[p] >> 16);   // canonical incidence: first bucket of the
@@ -699,13 +690,14 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
         if (n_matched < v.min_match) pass = false;           // IL:1862-1870
     }
     {
-        int64_t* out_best = pair_best + pair_win_off[p];
+        int64_t* out_best = pair_best + p * max_nc;
         for (int m = 0; m < nc; ++m) out_best[m] = best[m];
     }
     pair_score[p] = best_score;
     pair_scaling[p] = best_scaling;
-    pair_flag[p] = pass ? 1 : 0;
+    pair_flag[p] = pass ? nc : 0;                 // a passing pair records its window count (the hit's length)
     atomicAdd(&counters[C_COMBOS], combos);
+    atomicAdd(&counters[C_PAIR_WINDOWS], (unsigned long long)nc);
 }
 
 // K6b: one warp per combination-heavy pair.  Candidate tables (row, mi, mi*ri, m/z term per window and candidate)
@@ -738,7 +730,7 @@ __device__ __forceinline__ bool combo_greater(const HeavyTables& T, int nc, doub
 
 __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v, const unsigned long long* __restrict__ keys,
                                                                      const unsigned long long* __restrict__ vals, int entry_bits,
-                                                                     int64_t p_begin, const int64_t* __restrict__ pair_win_off,
+                                                                     int64_t p_begin, int max_nc,
                                                                      const int64_t* __restrict__ heavy_list,
                                                                      int64_t* __restrict__ pair_best, double* __restrict__ pair_score,
                                                                      double* __restrict__ pair_scaling, int32_t* __restrict__ pair_flag,
@@ -868,15 +860,16 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
                 if (b_score < v.score_thr) pass = false;          // IL:1860
                 if (n_matched < v.min_match) pass = false;        // IL:1862-1870
             }
-            int64_t* out_best = pair_best + pair_win_off[p];
+            int64_t* out_best = pair_best + p * max_nc;
             for (int m = 0; m < nc; ++m) {
                 const int c = T.count[m];
                 out_best[m] = c == 0 ? -1 : T.row[m][c > 0 ? (int)((b_digits >> (4 * m)) & 15ull) : 0];
             }
             pair_score[p] = b_score;
             pair_scaling[p] = b_scaling;
-            pair_flag[p] = pass ? 1 : 0;
+            pair_flag[p] = pass ? nc : 0;
             atomicAdd(&counters[C_COMBOS], total);
+            atomicAdd(&counters[C_PAIR_WINDOWS], (unsigned long long)nc);
         }
     }
 }
@@ -885,12 +878,11 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
 #define CMP_THREADS 256
 
 __global__ void __launch_bounds__(CMP_THREADS) compact_count_kernel(int64_t n_pairs, const int32_t* __restrict__ pair_flag,
-                                                                    const int64_t* __restrict__ pair_win_off,
                                                                     int64_t* __restrict__ blk_hits, int64_t* __restrict__ blk_wins) {
     __shared__ int64_t s_h[CMP_THREADS / 32], s_w[CMP_THREADS / 32];
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool flag = p < n_pairs && pair_flag[p];
-    int64_t wins = flag ? pair_win_off[p + 1] - pair_win_off[p] : 0;
+    int64_t wins = p < n_pairs ? pair_flag[p] : 0;   // window count of a passing pair, 0 otherwise
+    const bool flag = wins > 0;
     const unsigned mask = __ballot_sync(0xffffffffu, flag);
     for (int s = 16; s > 0; s >>= 1) wins += __shfl_xor_sync(0xffffffffu, wins, s);
     if ((threadIdx.x & 31) == 0) {
@@ -944,7 +936,7 @@ __global__ void compact_scan_kernel(int64_t n_blocks, int64_t* __restrict__ blk_
 
 __global__ void __launch_bounds__(CMP_THREADS) compact_emit_kernel(
     MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys, const int32_t* __restrict__ pair_flag,
-    const int64_t* __restrict__ pair_win_off, const int64_t* __restrict__ pair_best, const double* __restrict__ pair_score,
+    int max_nc, const int64_t* __restrict__ pair_best, const double* __restrict__ pair_score,
     const double* __restrict__ pair_scaling, const int64_t* __restrict__ blk_hits, const int64_t* __restrict__ blk_wins,
     int32_t* __restrict__ o_spec, int32_t* __restrict__ o_entry, double* __restrict__ o_score, double* __restrict__ o_scaling,
     int64_t* __restrict__ o_win_off, double* __restrict__ o_mmz, double* __restrict__ o_mi, int64_t* __restrict__ o_peak,
@@ -952,8 +944,8 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_emit_kernel(
     __shared__ int64_t s_h[CMP_THREADS / 32], s_w[CMP_THREADS / 32];
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool flag = p < n_pairs && pair_flag[p];
-    const int64_t nc = flag ? pair_win_off[p + 1] - pair_win_off[p] : 0;
+    const int64_t nc = p < n_pairs ? pair_flag[p] : 0;
+    const bool flag = nc > 0;
     const unsigned mask = __ballot_sync(0xffffffffu, flag);
     int64_t wpre = nc;  // inclusive prefix of windows inside the warp
     for (int s = 1; s < 32; s <<= 1) {
@@ -978,7 +970,7 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_emit_kernel(
     o_score[h] = pair_score[p];
     o_scaling[h] = pair_scaling[p];
     o_win_off[h] = w;
-    const int64_t* best = pair_best + pair_win_off[p];
+    const int64_t* best = pair_best + p * max_nc;
     for (int64_t m = 0; m < nc; ++m) {
         const int64_t row = best[m];
         o_peak[w + m] = row < 0 ? -1 : row - peak_base;
@@ -1094,15 +1086,12 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     v.xi = mz_score_percentile;
     v.score_thr = P.m_score_threshold;
 
-    // ---- K5a + K5b ----
+    // ---- K5a .. K7a are enqueued back to back; the host looks at the counters once, after the hit count ----
+    // The pair list has a power-of-two capacity learned from the previous batch; unused slots hold an all-ones
+    // sentinel key that sorts behind every real (spectrum, entry) key, so the sort, the window scan and the scoring
+    // kernels can be launched over the capacity without knowing the pair count (no host round trip after the gate).
     if (n_peaks >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 peaks per batch (split the run)");
     QMS_TRY(qms_reserve(ctx, ctx->dev_counters, 64));
-    size_t pair_cap = ctx->pair_keys.cap < ctx->pair_vals.cap ? ctx->pair_keys.cap : ctx->pair_vals.cap;
-    if (pair_cap < 65536) {
-        QMS_TRY(qms_reserve(ctx, ctx->pair_keys, 65536));
-        QMS_TRY(qms_reserve(ctx, ctx->pair_vals, 65536));
-        pair_cap = ctx->pair_keys.cap < ctx->pair_vals.cap ? ctx->pair_keys.cap : ctx->pair_vals.cap;
-    }
     int entry_bits = 1, spec_bits = 1;
     while ((1ll << entry_bits) < ctx->n_entries) ++entry_bits;
     while ((1ll << spec_bits) < n_spectra) ++spec_bits;
@@ -1127,9 +1116,50 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     QMS_TRY(qms_reserve(ctx, ctx->live_rows, (size_t)(seg_cap * blocks)));
     QMS_TRY(qms_reserve(ctx, ctx->live_count, (size_t)blocks));
     QMS_TRY(qms_reserve(ctx, ctx->tile_spec, (size_t)tiles_total + 2));
+    static int gate_mode = -1;   // QMS_GATE_MODE: 0 thread per row, 1 warp per row, default by library density
+    if (gate_mode < 0) {
+        const char* e = getenv("QMS_GATE_MODE");
+        gate_mode = e ? atoi(e) : 2;
+    }
+    // library density = windows over an average covered grid cell: dense libraries gate warp-cooperatively
+    const bool warp_gate = gate_mode == 1 || (gate_mode == 2 && ctx->window_density >= 4.0);
+    static int heavy_min = -1;   // QMS_HEAVY_MIN: combinations from which a pair is scored warp-cooperatively (0 = never)
+    if (heavy_min < 0) {
+        const char* e = getenv("QMS_HEAVY_MIN");
+        heavy_min = e ? atoi(e) : 16;
+    }
+    const int max_nc = ctx->max_nc > 0 ? ctx->max_nc : 1;
+    int64_t cap = ctx->pair_cap_hint > 0 ? ctx->pair_cap_hint : 65536;
     unsigned long long n_pairs = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    const unsigned long long* keys = nullptr;
+    const unsigned long long* vals = nullptr;
+    int64_t cblocks = 0;
+    for (int attempt = 0;; ++attempt) {
+        QMS_TRY(qms_reserve(ctx, ctx->pair_keys, (size_t)cap));
+        QMS_TRY(qms_reserve(ctx, ctx->pair_vals, (size_t)cap));
+        QMS_TRY(qms_reserve(ctx, ctx->pair_keys_alt, (size_t)cap));
+        QMS_TRY(qms_reserve(ctx, ctx->pair_vals_alt, (size_t)cap));
+        const size_t scratch = max_nc > K6_LOCAL ? (size_t)cap * (size_t)max_nc + 1 : 1;
+        QMS_TRY(qms_reserve(ctx, ctx->scr_first, scratch));
+        QMS_TRY(qms_reserve(ctx, ctx->scr_cur, scratch));
+        QMS_TRY(qms_reserve(ctx, ctx->scr_best, scratch));
+        QMS_TRY(qms_reserve(ctx, ctx->pair_best, (size_t)cap * (size_t)max_nc + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->pair_score, (size_t)cap));
+        QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)cap));
+        QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)cap));
+        QMS_TRY(qms_reserve(ctx, ctx->heavy_list, (size_t)cap + 1));
+        cblocks = qms_blocks(cap, CMP_THREADS);
+        QMS_TRY(qms_reserve(ctx, ctx->blk_hits, (size_t)cblocks + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->blk_wins, (size_t)cblocks + 1));
+        size_t sort_bytes = 0;
+        const int key_bits = entry_bits + spec_bits + 1;   // + the bit that only the sentinel has set
+        QMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, ctx->pair_vals.p,
+                                                      ctx->pair_vals_alt.p, cap, 0, key_bits, ctx->stream));
+        QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, sort_bytes + 16));
+
         QMS_CUDA(ctx, cudaMemsetAsync(ctx->dev_counters.p, 0, 64 * sizeof(unsigned long long), ctx->stream));
+        QMS_CUDA(ctx, cudaMemsetAsync(ctx->pair_keys.p, 0xFF, (size_t)cap * sizeof(unsigned long long), ctx->stream));
+        QMS_CUDA(ctx, cudaMemsetAsync(ctx->pair_flag.p, 0, (size_t)cap * sizeof(int32_t), ctx->stream));
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
         switch (variant) {
             case 1: spectrum_probe_kernel<4, true><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
@@ -1141,44 +1171,75 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
         tile_spectrum_kernel<<<qms_blocks(tiles_total + 1, 256), 256, 0, ctx->stream>>>(tiles_total, p_begin, tile, d_off, n_spectra,
                                                                                       ctx->tile_spec.p);
-        // library density = windows over an average covered grid cell: dense libraries gate warp-cooperatively
-        static int gate_mode = -1;   // QMS_GATE_MODE: 0 thread per row, 1 warp per row, default by density
-        if (gate_mode < 0) {
-            const char* e = getenv("QMS_GATE_MODE");
-            gate_mode = e ? atoi(e) : 2;
-        }
-        const bool warp_gate = gate_mode == 1 || (gate_mode == 2 && ctx->window_density >= 4.0);
         if (warp_gate)
             gate_rows_warp_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(
                 v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p, ctx->tile_spec.p, tile_shift, entry_bits, ctx->pair_keys.p,
-                ctx->pair_vals.p, (unsigned long long)pair_cap, ctx->dev_counters.p);
+                ctx->pair_vals.p, (unsigned long long)cap, ctx->dev_counters.p);
         else
             gate_rows_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(
                 v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p, ctx->tile_spec.p, tile_shift, entry_bits, ctx->pair_keys.p,
-                ctx->pair_vals.p, (unsigned long long)pair_cap, ctx->dev_counters.p);
+                ctx->pair_vals.p, (unsigned long long)cap, ctx->dev_counters.p);
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
-        ctx->cnt.kernel_launches += 3;
-        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, C_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+        // sort pairs by (spectrum, entry): only the populated key bits are radix-sorted, sentinels end up last
+        QMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, sort_bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p,
+                                                      ctx->pair_vals.p, ctx->pair_vals_alt.p, cap, 0, key_bits, ctx->stream));
+        keys = ctx->pair_keys_alt.p;
+        vals = ctx->pair_vals_alt.p;
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+        // K6 / K6b
+        assemble_score_kernel<<<qms_blocks(cap, 128), 128, 0, ctx->stream>>>(
+            v, cap, keys, vals, entry_bits, p_begin, max_nc, ctx->scr_first.p, ctx->scr_cur.p, ctx->scr_best.p,
+            ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p,
+            heavy_min > 0 ? ctx->heavy_list.p : nullptr, heavy_min);
+        QMS_CUDA(ctx, cudaGetLastError());
+        if (heavy_min > 0) {
+            int64_t hblocks = (cap + K6B_WARPS - 1) / K6B_WARPS;
+            const int64_t hmax = (int64_t)ctx->sm_count * 8;
+            if (hblocks > hmax) hblocks = hmax;
+            score_heavy_kernel<<<(unsigned)hblocks, 32 * K6B_WARPS, 0, ctx->stream>>>(
+                v, keys, vals, entry_bits, p_begin, max_nc, ctx->heavy_list.p, ctx->pair_best.p, ctx->pair_score.p,
+                ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
+            ctx->cnt.kernel_launches++;
+        }
+        QMS_CUDA(ctx, cudaGetLastError());
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+        // K7a: hit and window counts
+        compact_count_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(cap, ctx->pair_flag.p, ctx->blk_hits.p,
+                                                                                ctx->blk_wins.p);
+        compact_scan_kernel<<<1, 32, 0, ctx->stream>>>(cblocks, ctx->blk_hits.p, ctx->blk_wins.p, ctx->dev_counters.p + 40);
+        QMS_CUDA(ctx, cudaGetLastError());
+        ctx->cnt.kernel_launches += 10;
+        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                       ctx->stream));
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->cnt.ms_probe += elapsed(ctx, 2, 3);
         ctx->cnt.ms_gate += elapsed(ctx, 3, 5);
+        ctx->cnt.ms_compact += elapsed(ctx, 5, 6) + elapsed(ctx, 7, 8);
+        ctx->cnt.ms_score += elapsed(ctx, 6, 7);
         if (ctx->h_pinned[C_UNSORTED])
             return qms_fail(ctx, QMS_E_INPUT, "m/z values are not ascending inside %llu spectrum position(s)",
                             (unsigned long long)ctx->h_pinned[C_UNSORTED]);
         n_pairs = ctx->h_pinned[C_PAIRS];
-        if (n_pairs <= pair_cap) break;
+        int64_t want = 4096;
+        while (want < (int64_t)(n_pairs + n_pairs / 2)) want <<= 1;
+        ctx->pair_cap_hint = want;
+        if ((int64_t)n_pairs <= cap) break;
         if (attempt == 1) return qms_fail(ctx, QMS_E_LIMIT, "pair list overflow after regrow");
-        QMS_TRY(qms_reserve(ctx, ctx->pair_keys, (size_t)n_pairs + 1024));
-        QMS_TRY(qms_reserve(ctx, ctx->pair_vals, (size_t)n_pairs + 1024));
-        pair_cap = ctx->pair_keys.cap < ctx->pair_vals.cap ? ctx->pair_keys.cap : ctx->pair_vals.cap;
+        cap = want;                                        // rare: the batch holds more pairs than the hint; run it again
     }
     ctx->cnt.ms_h2d += elapsed(ctx, 0, 1);
     ctx->cnt.live_peaks += (int64_t)ctx->h_pinned[C_LIVE];
     ctx->cnt.incidences += (int64_t)ctx->h_pinned[C_INCID];
     ctx->cnt.candidates += (int64_t)n_pairs;
+    ctx->cnt.candidate_windows += (int64_t)ctx->h_pinned[C_PAIR_WINDOWS];
+    ctx->cnt.combinations += (int64_t)ctx->h_pinned[C_COMBOS];
+    const int64_t nh = (int64_t)ctx->h_pinned[40], nw = (int64_t)ctx->h_pinned[41];
+    *n_hits = nh;
+    *n_hit_windows = nw;
     if (n_pairs == 0) {
+        ctx->last_hits = ctx->last_windows = 0;
         if (out && out->hit_win_off) {
             const int64_t zero = 0;
             QMS_CUDA(ctx, cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t),
@@ -1186,90 +1247,6 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         }
         return QMS_OK;
     }
-    // ---- sort pairs by (spectrum, entry): only the populated key bits are radix-sorted ----
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_keys_alt, (size_t)n_pairs + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_vals_alt, (size_t)n_pairs + 1));
-    {
-        size_t bytes = 0;
-        QMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, ctx->pair_vals.p,
-                                                      ctx->pair_vals_alt.p, (int64_t)n_pairs, 0, entry_bits + spec_bits, ctx->stream));
-        QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
-        QMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, bytes, ctx->pair_keys.p, ctx->pair_keys_alt.p, ctx->pair_vals.p,
-                                                      ctx->pair_vals_alt.p, (int64_t)n_pairs, 0, entry_bits + spec_bits, ctx->stream));
-        ctx->cnt.kernel_launches += 3;
-    }
-    const unsigned long long* keys = ctx->pair_keys_alt.p;
-    const unsigned long long* vals = ctx->pair_vals_alt.p;
-    // ---- per-pair window offsets (output layout); scratch is bounded by max_nc, so no host round trip ----
-    const int max_nc = ctx->max_nc > 0 ? ctx->max_nc : 1;
-    QMS_TRY(qms_reserve(ctx, ctx->pair_nc, (size_t)n_pairs + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_win_off, (size_t)n_pairs + 1));
-    QMS_CUDA(ctx, cudaMemsetAsync(ctx->pair_nc.p + n_pairs, 0, sizeof(int64_t), ctx->stream));
-    pair_windows_kernel<<<qms_blocks((int64_t)n_pairs, 256), 256, 0, ctx->stream>>>((int64_t)n_pairs, keys, entry_bits,
-                                                                                   ctx->ent_win_off.p, ctx->pair_nc.p);
-    {
-        size_t bytes = 0;
-        QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, bytes, ctx->pair_nc.p, ctx->pair_win_off.p, (int64_t)n_pairs + 1, ctx->stream));
-        QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, bytes + 16));
-        QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, bytes, ctx->pair_nc.p, ctx->pair_win_off.p, (int64_t)n_pairs + 1,
-                                                    ctx->stream));
-        ctx->cnt.kernel_launches += 3;
-    }
-    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 32, ctx->pair_win_off.p + n_pairs, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    // ---- K6 ----
-    const size_t scratch = max_nc > K6_LOCAL ? (size_t)n_pairs * (size_t)max_nc + 1 : 1;
-    QMS_TRY(qms_reserve(ctx, ctx->scr_first, scratch));
-    QMS_TRY(qms_reserve(ctx, ctx->scr_cur, scratch));
-    QMS_TRY(qms_reserve(ctx, ctx->scr_best, scratch));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_best, (size_t)n_pairs * (size_t)max_nc + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_score, (size_t)n_pairs));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)n_pairs));
-    QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)n_pairs));
-    static int heavy_min = -1;   // QMS_HEAVY_MIN: combinations from which a pair is scored warp-cooperatively (0 = never)
-    if (heavy_min < 0) {
-        const char* e = getenv("QMS_HEAVY_MIN");
-        heavy_min = e ? atoi(e) : 16;
-    }
-    QMS_TRY(qms_reserve(ctx, ctx->heavy_list, (size_t)n_pairs + 1));
-    assemble_score_kernel<<<qms_blocks((int64_t)n_pairs, 128), 128, 0, ctx->stream>>>(
-        v, (int64_t)n_pairs, keys, vals, entry_bits, p_begin, max_nc, ctx->pair_win_off.p, ctx->scr_first.p, ctx->scr_cur.p,
-        ctx->scr_best.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p,
-        heavy_min > 0 ? ctx->heavy_list.p : nullptr, heavy_min);
-    QMS_CUDA(ctx, cudaGetLastError());
-    if (heavy_min > 0) {
-        int64_t hblocks = ((int64_t)n_pairs + K6B_WARPS - 1) / K6B_WARPS;
-        const int64_t hmax = (int64_t)ctx->sm_count * 8;
-        if (hblocks > hmax) hblocks = hmax;
-        score_heavy_kernel<<<(unsigned)hblocks, 32 * K6B_WARPS, 0, ctx->stream>>>(
-            v, keys, vals, entry_bits, p_begin, ctx->pair_win_off.p, ctx->heavy_list.p, ctx->pair_best.p, ctx->pair_score.p,
-            ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
-        ctx->cnt.kernel_launches++;
-    }
-    QMS_CUDA(ctx, cudaGetLastError());
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
-    ctx->cnt.kernel_launches++;
-    // ---- K7 ----
-    const int64_t cblocks = qms_blocks((int64_t)n_pairs, CMP_THREADS);
-    QMS_TRY(qms_reserve(ctx, ctx->blk_hits, (size_t)cblocks + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->blk_wins, (size_t)cblocks + 1));
-    compact_count_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>((int64_t)n_pairs, ctx->pair_flag.p, ctx->pair_win_off.p,
-                                                                            ctx->blk_hits.p, ctx->blk_wins.p);
-    compact_scan_kernel<<<1, 32, 0, ctx->stream>>>(cblocks, ctx->blk_hits.p, ctx->blk_wins.p, ctx->dev_counters.p + 40);
-    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 40, ctx->dev_counters.p + 40, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + C_COMBOS, ctx->dev_counters.p + C_COMBOS, sizeof(unsigned long long),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->cnt.kernel_launches += 2;
-    ctx->cnt.ms_compact += elapsed(ctx, 2, 3);
-    ctx->cnt.ms_score += elapsed(ctx, 3, 5);
-    ctx->cnt.candidate_windows += (int64_t)ctx->h_pinned[32];
-    ctx->cnt.combinations += (int64_t)ctx->h_pinned[C_COMBOS];
-    const int64_t nh = (int64_t)ctx->h_pinned[40], nw = (int64_t)ctx->h_pinned[41];
-    *n_hits = nh;
-    *n_hit_windows = nw;
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     QMS_TRY(qms_reserve(ctx, ctx->o_spec, (size_t)nh + 1));
     QMS_TRY(qms_reserve(ctx, ctx->o_entry, (size_t)nh + 1));
@@ -1279,18 +1256,27 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     QMS_TRY(qms_reserve(ctx, ctx->o_mmz, (size_t)nw + 1));
     QMS_TRY(qms_reserve(ctx, ctx->o_mi, (size_t)nw + 1));
     QMS_TRY(qms_reserve(ctx, ctx->o_peak, (size_t)nw + 1));
+    const bool fits = out && nh <= out->cap_hits && nw <= out->cap_windows;
+    // caller buffers in device memory are written by the emit kernel itself (no staging copy); the hits then are
+    // not retained for qms_fetch_hits
+    const bool direct = fits && out->hit_spec && out->hit_entry && out->hit_score && out->hit_scaling && out->hit_win_off &&
+                        out->hit_mmz && out->hit_mi && out->hit_peak && qms_is_device_ptr(out->hit_spec) &&
+                        qms_is_device_ptr(out->hit_entry) && qms_is_device_ptr(out->hit_score) && qms_is_device_ptr(out->hit_scaling) &&
+                        qms_is_device_ptr(out->hit_win_off) && qms_is_device_ptr(out->hit_mmz) && qms_is_device_ptr(out->hit_mi) &&
+                        qms_is_device_ptr(out->hit_peak);
+    int64_t* t_win_off = direct ? out->hit_win_off : ctx->o_win_off.p;
     compact_emit_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(
-        v, (int64_t)n_pairs, keys, ctx->pair_flag.p, ctx->pair_win_off.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p,
-        ctx->blk_hits.p, ctx->blk_wins.p, ctx->o_spec.p, ctx->o_entry.p, ctx->o_score.p, ctx->o_scaling.p, ctx->o_win_off.p,
-        ctx->o_mmz.p, ctx->o_mi.p, ctx->o_peak.p, 0, entry_bits);
+        v, cap, keys, ctx->pair_flag.p, max_nc, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->blk_hits.p,
+        ctx->blk_wins.p, direct ? out->hit_spec : ctx->o_spec.p, direct ? out->hit_entry : ctx->o_entry.p,
+        direct ? out->hit_score : ctx->o_score.p, direct ? out->hit_scaling : ctx->o_scaling.p, t_win_off,
+        direct ? out->hit_mmz : ctx->o_mmz.p, direct ? out->hit_mi : ctx->o_mi.p, direct ? out->hit_peak : ctx->o_peak.p, 0, entry_bits);
     QMS_CUDA(ctx, cudaGetLastError());
-    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->o_win_off.p + nh, &ctx->h_pinned[41], sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    QMS_CUDA(ctx, cudaMemcpyAsync(t_win_off + nh, &ctx->h_pinned[41], sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->cnt.kernel_launches++;
-    ctx->last_hits = nh;            // retained in the o_* buffers for qms_fetch_hits
-    ctx->last_windows = nw;
-    const bool fits = out && nh <= out->cap_hits && nw <= out->cap_windows;
-    if (fits) {
+    ctx->last_hits = direct ? 0 : nh;            // retained in the o_* buffers for qms_fetch_hits
+    ctx->last_windows = direct ? 0 : nw;
+    if (fits && !direct) {
         QMS_TRY(copy_out(ctx, out->hit_spec, ctx->o_spec.p, (size_t)nh));
         QMS_TRY(copy_out(ctx, out->hit_entry, ctx->o_entry.p, (size_t)nh));
         QMS_TRY(copy_out(ctx, out->hit_score, ctx->o_score.p, (size_t)nh));
