@@ -490,16 +490,12 @@ __device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, in
 #define K6_LOCAL 16
 #define K6B_CANDS 8      // most candidate buckets per window a pair may have to be scored by K6b
 
-__global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys,
-                                                             const unsigned long long* __restrict__ vals, int entry_bits,
-                                                             int64_t p_begin, int max_nc, int64_t* __restrict__ scr_first,
-                                                             int64_t* __restrict__ scr_cur, int64_t* __restrict__ scr_best,
-                                                             int64_t* __restrict__ pair_best,
-                                                             double* __restrict__ pair_score, double* __restrict__ pair_scaling,
-                                                             int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters,
-                                                             int64_t* __restrict__ heavy_list, int heavy_min) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs || keys[p] == ~0ull) return;              // n_pairs = list capacity; all-ones = unused slot
+__device__ void score_pair(const MatchView& v, int64_t p, const unsigned long long* __restrict__ keys,
+                           const unsigned long long* __restrict__ vals, int entry_bits, int64_t p_begin, int max_nc,
+                           int64_t* __restrict__ scr_first, int64_t* __restrict__ scr_cur, int64_t* __restrict__ scr_best,
+                           int64_t* __restrict__ pair_best, double* __restrict__ pair_score, double* __restrict__ pair_scaling,
+                           int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters,
+                           int64_t* __restrict__ heavy_list, int heavy_min, unsigned long long& combos_out, int& windows_out) {
     const int64_t s = (int64_t)(keys[p] >> entry_bits);
     const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
     const int64_t row0 = p_begin + (int64_t)(vals[p] >> 16);   // canonical incidence: first bucket of the
@@ -696,8 +692,39 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
     pair_score[p] = best_score;
     pair_scaling[p] = best_scaling;
     pair_flag[p] = pass ? nc : 0;                 // a passing pair records its window count (the hit's length)
-    atomicAdd(&counters[C_COMBOS], combos);
-    atomicAdd(&counters[C_PAIR_WINDOWS], (unsigned long long)nc);
+    combos_out = combos;
+    windows_out = nc;
+}
+
+__global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_t n_pairs, const unsigned long long* __restrict__ keys,
+                                                             const unsigned long long* __restrict__ vals, int entry_bits,
+                                                             int64_t p_begin, int max_nc, int64_t* __restrict__ scr_first,
+                                                             int64_t* __restrict__ scr_cur, int64_t* __restrict__ scr_best,
+                                                             int64_t* __restrict__ pair_best,
+                                                             double* __restrict__ pair_score, double* __restrict__ pair_scaling,
+                                                             int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters,
+                                                             int64_t* __restrict__ heavy_list, int heavy_min) {
+    // statistics go through shared memory: one global atomic per CTA instead of one per pair (12 M same-address
+    // atomics cost more than the scoring itself on the dense libraries)
+    __shared__ unsigned long long s_combos, s_windows;
+    if (threadIdx.x == 0) {
+        s_combos = 0;
+        s_windows = 0;
+    }
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long combos = 0;
+    int windows = 0;
+    if (p < n_pairs && keys[p] != ~0ull)          // n_pairs = list capacity; all-ones = unused slot
+        score_pair(v, p, keys, vals, entry_bits, p_begin, max_nc, scr_first, scr_cur, scr_best, pair_best, pair_score, pair_scaling,
+                   pair_flag, counters, heavy_list, heavy_min, combos, windows);
+    if (combos) atomicAdd(&s_combos, combos);
+    if (windows) atomicAdd(&s_windows, (unsigned long long)windows);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_combos) atomicAdd(&counters[C_COMBOS], s_combos);
+        if (s_windows) atomicAdd(&counters[C_PAIR_WINDOWS], s_windows);
+    }
 }
 
 // K6b: one warp per combination-heavy pair.  Candidate tables (row, mi, mi*ri, m/z term per window and candidate)
@@ -742,6 +769,7 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
     const int64_t n_warps = (int64_t)gridDim.x * K6B_WARPS;
     const double one_minus_xi = __dsub_rn(1.0, v.xi);
     const double one_plus_reli = __dadd_rn(1.0, v.rel_i);
+    unsigned long long stat_combos = 0, stat_windows = 0;   // lane 0 only; one global atomic per warp at the end
     for (int64_t h = (int64_t)blockIdx.x * K6B_WARPS + warp; h < n_heavy; h += n_warps) {
         const int64_t p = heavy_list[h];
         const int64_t s = (int64_t)(keys[p] >> entry_bits);
@@ -868,9 +896,13 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
             pair_score[p] = b_score;
             pair_scaling[p] = b_scaling;
             pair_flag[p] = pass ? nc : 0;
-            atomicAdd(&counters[C_COMBOS], total);
-            atomicAdd(&counters[C_PAIR_WINDOWS], (unsigned long long)nc);
+            stat_combos += total;
+            stat_windows += (unsigned long long)nc;
         }
+    }
+    if (lane == 0) {
+        if (stat_combos) atomicAdd(&counters[C_COMBOS], stat_combos);
+        if (stat_windows) atomicAdd(&counters[C_PAIR_WINDOWS], stat_windows);
     }
 }
 
@@ -1087,7 +1119,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     v.score_thr = P.m_score_threshold;
 
     // ---- K5a .. K7a are enqueued back to back; the host looks at the counters once, after the hit count ----
-    // The pair list has a power-of-two capacity learned from the previous batch; unused slots hold an all-ones
+    // The pair list has a capacity learned from the previous batch (its pair count + 25 %); unused slots hold an all-ones
     // sentinel key that sorts behind every real (spectrum, entry) key, so the sort, the window scan and the scoring
     // kernels can be launched over the capacity without knowing the pair count (no host round trip after the gate).
     if (n_peaks >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 peaks per batch (split the run)");
@@ -1222,8 +1254,8 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
             return qms_fail(ctx, QMS_E_INPUT, "m/z values are not ascending inside %llu spectrum position(s)",
                             (unsigned long long)ctx->h_pinned[C_UNSORTED]);
         n_pairs = ctx->h_pinned[C_PAIRS];
-        int64_t want = 4096;
-        while (want < (int64_t)(n_pairs + n_pairs / 2)) want <<= 1;
+        int64_t want = ((int64_t)(n_pairs + n_pairs / 4) + 4095) / 4096 * 4096;   // 25 % head room, 4 Ki granules
+        if (want < 4096) want = 4096;
         ctx->pair_cap_hint = want;
         if ((int64_t)n_pairs <= cap) break;
         if (attempt == 1) return qms_fail(ctx, QMS_E_LIMIT, "pair list overflow after regrow");

@@ -107,7 +107,7 @@ struct qms_ctx {
     DBuf<int32_t> tile_spec;
     int32_t max_nc = 0;            // most c-peak windows of any index entry
     double window_density = 0.0;   // sum of window widths / covered grid cells = windows over an average covered cell
-    int64_t pair_cap_hint = 0;     // power-of-two capacity of the pair list, learned from the previous batch
+    int64_t pair_cap_hint = 0;     // capacity of the pair list, learned from the previous batch (+25 %)
     int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
     DBuf<uint8_t> cub_tmp;
     DBuf<unsigned long long> dev_counters;   // see match.cu
