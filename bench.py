@@ -309,7 +309,7 @@ def run_ours(args):
     peaks_json = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak_gbs = float(peaks_json.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (probe_ms * 1e-3) / 1e9 if probe_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "spectrum_probe_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "spectrum_probe_warp_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks_json else "fallback",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": probe_ms,
                 "step_algorithmic_bytes": step_alg_bytes, "step_achieved_gbs": step_alg_bytes / (ms_max / args.steps * 1e-3) / 1e9,

@@ -29,7 +29,7 @@
 
 #define QMS_DBL_EPS 2.220446049250313e-16
 
-enum { C_LIVE = 0, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_HEAVY, C_PAIR_WINDOWS, C_N };   // slots of the device counter block
+enum { C_LIVE = 0, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_HEAVY, C_PAIR_WINDOWS, C_GATE_TICKET, C_N };   // slots of the device counter block
 
 struct MatchView {
     const double2* peaks;
@@ -243,29 +243,134 @@ __global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_kernel(MatchView
     if (threadIdx.x == 0) live_count[blockIdx.x] = s_cursor;
 }
 
+// K5a, warp-contiguous layout: a warp owns 32*UNROLL consecutive rows of the tile, so the predecessor of a
+// lane-0 row is lane 31 of the same warp one load earlier (register shuffle); only the first row of the
+// warp's chunk needs its predecessor from memory and that load is issued together with the row loads, which
+// leaves the cover look-ups as the only dependent loads after the stream loads return.
+template <int UNROLL>
+__global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_warp_kernel(MatchView v, int64_t p_begin, int64_t p_end,
+                                                                             int64_t seg_cap, uint32_t* __restrict__ live_rows,
+                                                                             uint32_t* __restrict__ live_count) {
+    __shared__ uint32_t s_cursor;
+    if (threadIdx.x == 0) s_cursor = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
+    const int64_t tile = (int64_t)PROBE_THREADS * UNROLL;
+    for (int64_t base = p_begin + (int64_t)blockIdx.x * tile; base < p_end; base += (int64_t)gridDim.x * tile) {
+        const int64_t first = base + (int64_t)warp * (32 * UNROLL);
+        double x[UNROLL];
+        double x_before = 0.0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = first + u * 32 + lane;
+            x[u] = i < p_end ? __ldg(&v.peaks[i].x) : 0.0;
+        }
+        const bool has_before = lane == 0 && first > p_begin && first < p_end;
+        if (has_before) x_before = __ldg(&v.peaks[first - 1].x);
+        int32_t t_last = 0;   // bucket of the previous load's lane 31
+        uint32_t word[UNROLL];
+        bool any_push = false;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = first + u * 32 + lane;
+            const bool valid = i < p_end;
+            const int32_t t = qms_tmz(x[u], v.precision);
+            int32_t t_prev = __shfl_up_sync(0xffffffffu, t, 1);
+            if (lane == 0) t_prev = u == 0 ? (has_before ? qms_tmz(x_before, v.precision) : t) : t_last;
+            t_last = __shfl_sync(0xffffffffu, t, 31);
+            const bool in_range = valid && t >= v.t_min && t <= v.t_max;
+            const uint32_t c = in_range ? (uint32_t)(t - v.t_min) : 0u;
+            bool live = in_range && ((__ldg(&v.cover2[c >> 10]) >> ((c >> 5) & 31)) & 1u);
+            if (live) live = (__ldg(&v.cover[c >> 5]) >> (c & 31)) & 1u;
+            const bool descends = valid && t < t_prev;
+            const bool push = live || descends;
+            word[u] = push ? ((uint32_t)(i - p_begin) | (live ? 0u : ROW_CHECK_ONLY)) : 0xffffffffu;
+            any_push |= push;
+        }
+        if (__any_sync(0xffffffffu, any_push)) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const bool push = word[u] != 0xffffffffu;
+                const unsigned mask = __ballot_sync(0xffffffffu, push);
+                if (mask) {
+                    uint32_t warp_base = 0;
+                    if (lane == 0) warp_base = atomicAdd(&s_cursor, (uint32_t)__popc(mask));
+                    warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+                    if (push) segment[warp_base + __popc(mask & ((1u << lane) - 1u))] = word[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) live_count[blockIdx.x] = s_cursor;
+}
+
 // K5b: the gating half, one thread per surviving row (all lanes of a warp are in the slow path together).
 // Spectrum lookup, bucket dedupe (Q9), window lookup through the cell table, entry gating (IL:1968-1976).
-__global__ void tile_spectrum_kernel(int64_t n_tiles, int64_t p_begin, int64_t tile, const int64_t* __restrict__ offsets,
-                                     int64_t n_spectra, int32_t* __restrict__ tile_spec) {
+__global__ void __launch_bounds__(256) tile_spectrum_kernel(int64_t n_tiles, int64_t p_begin, int64_t tile,
+                                                            const int64_t* __restrict__ offsets, int64_t n_spectra,
+                                                            int32_t* __restrict__ tile_spec, const uint32_t* __restrict__ live_count,
+                                                            int n_segments, uint32_t* __restrict__ live_prefix) {
+    if (blockIdx.x == gridDim.x - 1) {
+        // last CTA: exclusive prefix sum of the probe blocks' survivor counts, so that K5b can spread the
+        // surviving rows evenly over its threads whatever the probe grid was
+        __shared__ uint32_t s_warp[8];
+        const int chunk = (n_segments + 255) / 256;
+        const int a = min((int)threadIdx.x * chunk, n_segments), b = min(a + chunk, n_segments);
+        uint32_t sum = 0;
+        for (int k = a; k < b; ++k) sum += live_count[k];
+        uint32_t incl = sum;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        uint32_t run = before + incl - sum;
+        for (int k = a; k < b; ++k) {
+            live_prefix[k] = run;
+            run += live_count[k];
+        }
+        if (threadIdx.x == 255) live_prefix[n_segments] = run;
+        return;
+    }
     // spectrum holding the first row of every probe tile: bounds the per-row lookup of K5b to 1-2 steps
     const int64_t tidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tidx > n_tiles) return;
     tile_spec[tidx] = tidx == n_tiles ? (int32_t)(n_spectra - 1) : (int32_t)spectrum_of(offsets, n_spectra, p_begin + tidx * tile);
 }
 
+// surviving row g of the batch -> its word in the probe blocks' segments
+__device__ __forceinline__ uint32_t live_row_word(const uint32_t* __restrict__ live_rows, const uint32_t* __restrict__ live_prefix,
+                                                  int n_segments, int64_t seg_cap, uint32_t g) {
+    int a = 0, b = n_segments;   // last segment whose prefix is <= g
+    while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (__ldg(&live_prefix[mid]) <= g)
+            a = mid;
+        else
+            b = mid;
+    }
+    return live_rows[(int64_t)a * seg_cap + (g - __ldg(&live_prefix[a]))];
+}
+
 __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_kernel(MatchView v, int64_t p_begin, int64_t seg_cap,
                                                                    const uint32_t* __restrict__ live_rows,
-                                                                   const uint32_t* __restrict__ live_count,
+                                                                   const uint32_t* __restrict__ live_prefix, int n_segments,
                                                                    const int32_t* __restrict__ tile_spec, int shift, int entry_bits,
                                                                    unsigned long long* __restrict__ pair_keys,
                                                                    unsigned long long* __restrict__ pair_vals,
                                                                    unsigned long long pair_cap,
                                                                    unsigned long long* __restrict__ counters) {
     unsigned long long n_live = 0, n_inc = 0;
-    const uint32_t n_rows = live_count[blockIdx.x];
-    const uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
-    for (uint32_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
-        const uint32_t word = segment[r];
+    const uint32_t n_rows = live_prefix[n_segments];
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
+        const uint32_t word = live_row_word(live_rows, live_prefix, n_segments, seg_cap, r);
         const int64_t i = p_begin + (int64_t)(word & ~ROW_CHECK_ONLY);
         const int64_t tile_id = (int64_t)(word & ~ROW_CHECK_ONLY) >> shift;
         int64_t s = __ldg(&tile_spec[tile_id]);
@@ -324,8 +429,8 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_kernel(MatchView v, i
 #define GATE_QUEUE 64
 __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView v, int64_t p_begin, int64_t seg_cap,
                                                                         const uint32_t* __restrict__ live_rows,
-                                                                        const uint32_t* __restrict__ live_count,
-                                                                        const int32_t* __restrict__ tile_spec, int shift,
+                                                                        const uint32_t* __restrict__ live_prefix, int n_segments,
+                                                                        uint32_t gate_chunk, const int32_t* __restrict__ tile_spec, int shift,
                                                                         int entry_bits, unsigned long long* __restrict__ pair_keys,
                                                                         unsigned long long* __restrict__ pair_vals,
                                                                         unsigned long long pair_cap,
@@ -362,10 +467,18 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView
             }
         }
     };
-    const uint32_t n_rows = live_count[blockIdx.x];
-    const uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
-    for (uint32_t r = warp; r < n_rows; r += blockDim.x >> 5) {   // warp-uniform from here on
-        const uint32_t word = segment[r];
+    const uint32_t n_rows = live_prefix[n_segments];
+    // Rows differ in cost by orders of magnitude (records per cell), so the warps draw chunks of gate_chunk
+    // consecutive surviving rows from a device-wide ticket instead of a fixed stride (a static split left
+    // 9 % of the kernel as tail on the 100 k-peptide library).
+    for (;;) {
+    uint32_t chunk = 0;
+    if (lane == 0) chunk = (uint32_t)atomicAdd(&counters[C_GATE_TICKET], 1ull);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if ((unsigned long long)chunk * gate_chunk >= n_rows) break;
+    chunk *= gate_chunk;
+    for (uint32_t r = chunk; r < min(chunk + gate_chunk, n_rows); ++r) {   // warp-uniform from here on
+        const uint32_t word = live_row_word(live_rows, live_prefix, n_segments, seg_cap, r);
         const uint32_t row_off = word & ~ROW_CHECK_ONLY;
         const int64_t i = p_begin + (int64_t)row_off;
         const int64_t tile_id = (int64_t)row_off >> shift;
@@ -413,6 +526,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView
                 __syncwarp();
             }
         }
+    }
     }
     if (q_n > 0) gate_batch(0, q_n);
     for (int sft = 16; sft > 0; sft >>= 1) {
@@ -1130,9 +1244,9 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     static int variant = -1;   // QMS_PROBE_VARIANT: tuning switch for profiling runs (default = best measured)
     if (variant < 0) {
         const char* e = getenv("QMS_PROBE_VARIANT");
-        variant = e ? atoi(e) : 0;
+        variant = e ? atoi(e) : 4;
     }
-    const int unroll = (variant == 2 || variant == 3) ? 8 : 4;
+    const int unroll = (variant == 2 || variant == 3 || variant == 5) ? 8 : 4;
     const int tile_shift = unroll == 8 ? 11 : 10;
     const int64_t tile = (int64_t)PROBE_THREADS * unroll;
     const int64_t tiles_total = (n_peaks + tile - 1) / tile;
@@ -1140,13 +1254,25 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     static int ctas_per_sm = -1;
     if (ctas_per_sm < 0) {
         const char* e = getenv("QMS_PROBE_CTAS");
-        ctas_per_sm = e ? atoi(e) : 16;
+        ctas_per_sm = e ? atoi(e) : 48;
     }
-    const int64_t max_blocks = (int64_t)ctx->sm_count * ctas_per_sm;   // CTAs of 256 threads per SM: 8 are resident, 16 measured best (tail balance)
+    const int64_t max_blocks = (int64_t)ctx->sm_count * ctas_per_sm;   // CTAs of 256 threads per SM: 8 are resident; 6 waves of short CTAs keep the tail short (measured: 8 -> 0.86, 32 -> 0.89, 48 -> 0.90 of HBM peak)
     if (blocks > max_blocks) blocks = max_blocks;
     const int64_t seg_cap = ((tiles_total + blocks - 1) / blocks) * tile;   // every row of a block could survive
     QMS_TRY(qms_reserve(ctx, ctx->live_rows, (size_t)(seg_cap * blocks)));
     QMS_TRY(qms_reserve(ctx, ctx->live_count, (size_t)blocks));
+    QMS_TRY(qms_reserve(ctx, ctx->live_prefix, (size_t)blocks + 1));
+    static int gate_ctas = -1;   // QMS_GATE_CTAS: CTAs per SM of the gate kernels (grid-stride over the surviving rows)
+    if (gate_ctas < 0) {
+        const char* e = getenv("QMS_GATE_CTAS");
+        gate_ctas = e ? atoi(e) : 8;
+    }
+    const int64_t gate_blocks = (int64_t)ctx->sm_count * (gate_ctas > 0 ? gate_ctas : 8);
+    static int gate_chunk = -1;  // QMS_GATE_CHUNK: consecutive surviving rows a warp of the warp-per-row gate draws at a time
+    if (gate_chunk < 0) {
+        const char* e = getenv("QMS_GATE_CHUNK");
+        gate_chunk = e && atoi(e) > 0 ? atoi(e) : 32;
+    }
     QMS_TRY(qms_reserve(ctx, ctx->tile_spec, (size_t)tiles_total + 2));
     static int gate_mode = -1;   // QMS_GATE_MODE: 0 thread per row, 1 warp per row, default by library density
     if (gate_mode < 0) {
@@ -1197,20 +1323,22 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
             case 1: spectrum_probe_kernel<4, true><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
             case 2: spectrum_probe_kernel<8, false><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
             case 3: spectrum_probe_kernel<8, true><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
-            default: spectrum_probe_kernel<4, false><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
+            case 5: spectrum_probe_warp_kernel<8><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
+            case 0: spectrum_probe_kernel<4, false><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
+            default: spectrum_probe_warp_kernel<4><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
         }
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-        tile_spectrum_kernel<<<qms_blocks(tiles_total + 1, 256), 256, 0, ctx->stream>>>(tiles_total, p_begin, tile, d_off, n_spectra,
-                                                                                      ctx->tile_spec.p);
+        tile_spectrum_kernel<<<qms_blocks(tiles_total + 1, 256) + 1, 256, 0, ctx->stream>>>(
+            tiles_total, p_begin, tile, d_off, n_spectra, ctx->tile_spec.p, ctx->live_count.p, (int)blocks, ctx->live_prefix.p);
         if (warp_gate)
-            gate_rows_warp_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(
-                v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p, ctx->tile_spec.p, tile_shift, entry_bits, ctx->pair_keys.p,
-                ctx->pair_vals.p, (unsigned long long)cap, ctx->dev_counters.p);
+            gate_rows_warp_kernel<<<(unsigned)gate_blocks, PROBE_THREADS, 0, ctx->stream>>>(
+                v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_prefix.p, (int)blocks, (uint32_t)gate_chunk, ctx->tile_spec.p, tile_shift,
+                entry_bits, ctx->pair_keys.p, ctx->pair_vals.p, (unsigned long long)cap, ctx->dev_counters.p);
         else
-            gate_rows_kernel<<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(
-                v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_count.p, ctx->tile_spec.p, tile_shift, entry_bits, ctx->pair_keys.p,
-                ctx->pair_vals.p, (unsigned long long)cap, ctx->dev_counters.p);
+            gate_rows_kernel<<<(unsigned)gate_blocks, PROBE_THREADS, 0, ctx->stream>>>(
+                v, p_begin, seg_cap, ctx->live_rows.p, ctx->live_prefix.p, (int)blocks, ctx->tile_spec.p, tile_shift, entry_bits,
+                ctx->pair_keys.p, ctx->pair_vals.p, (unsigned long long)cap, ctx->dev_counters.p);
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
         // sort pairs by (spectrum, entry): only the populated key bits are radix-sorted, sentinels end up last

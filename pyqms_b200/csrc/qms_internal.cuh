@@ -115,7 +115,7 @@ struct qms_ctx {
     DBuf<int32_t> pair_flag;
     DBuf<int64_t> pair_win_off, pair_best;
     DBuf<int64_t> blk_hits, blk_wins;
-    DBuf<uint32_t> live_rows, live_count;   // K5a -> K5b: per-block segments of surviving peak rows
+    DBuf<uint32_t> live_rows, live_count, live_prefix;   // K5a -> K5b: per-block segments of surviving peak rows (+ prefix sums)
     DBuf<int32_t> o_spec, o_entry;
     DBuf<double> o_score, o_scaling, o_mmz, o_mi;
     DBuf<int64_t> o_win_off, o_peak;
