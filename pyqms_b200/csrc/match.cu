@@ -832,8 +832,15 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
     if (p < n_pairs && keys[p] != ~0ull)          // n_pairs = list capacity; all-ones = unused slot
         score_pair(v, p, keys, vals, entry_bits, p_begin, max_nc, scr_first, scr_cur, scr_best, pair_best, pair_score, pair_scaling,
                    pair_flag, counters, heavy_list, heavy_min, combos, windows);
-    if (combos) atomicAdd(&s_combos, combos);
-    if (windows) atomicAdd(&s_windows, (unsigned long long)windows);
+    unsigned long long w = (unsigned long long)windows;
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        combos += __shfl_xor_sync(0xffffffffu, combos, sft);
+        w += __shfl_xor_sync(0xffffffffu, w, sft);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (combos) atomicAdd(&s_combos, combos);
+        if (w) atomicAdd(&s_windows, w);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_combos) atomicAdd(&counters[C_COMBOS], s_combos);
