@@ -4,11 +4,13 @@
 // The reference walks every match bin for every spectrum, re-hashes the spectrum per bin and
 // intersects Python sets.  Here the work is driven by the spectrum peaks instead:
 //
-//  K5a spectrum_probe     flat, coalesced stream over all peaks of the batch (one LDG.128 per
-//      (m/z, intensity) row).  tmz = rint(mz*P); a two-level cover bitmap rejects rows whose 1/P-Da
-//      bucket no library window contains (the HBM-bound regime of small libraries); surviving rows are
-//      compacted (warp ballot + shared-memory cursor) into per-block segments.
-//  K5b gate_rows            one thread per surviving row: spectrum lookup, bucket dedupe, the lo-sorted
+//  K5a spectrum_probe     flat, coalesced stream over all (m/z, intensity) rows of the batch (only the m/z
+//      half of a row is needed here, DRAM moves the whole 32-byte sectors).  tmz = rint(mz*P); a two-level
+//      cover bitmap rejects rows whose 1/P-Da bucket no library window contains (the HBM-bound regime of
+//      small libraries); surviving rows are compacted (warp ballot + shared-memory cursor) into per-block
+//      segments, a prefix sum over the segment sizes gives K5b a dense numbering of the survivors.
+//  K5b gate_rows            one thread (sparse libraries) or one warp (dense libraries) per surviving row:
+//      spectrum lookup, bucket dedupe, the lo-sorted
 //      window list through the direct-address cell table; for every (bucket, window) incidence the
 //      owning index entry is gated exactly like IL:1968-1976:
 //      |distinct spectrum buckets inside the entry's windows| >= MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES
