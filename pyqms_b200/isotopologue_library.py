@@ -66,6 +66,48 @@ class _LazyEnvelopes(dict):
         return [(lp, self[lp]) for lp in self.keys()]
 
 
+AMOUNT_FIELDS = ("max I in window", "max I in window (rt)", "max I in window (score)", "sum I in window", "auc in window")
+_amount_ctx = None
+
+
+def calc_amounts_of_profiles(profiles, windows=None, ctx=None):
+    """One device pass (``qms_calc_amounts``) over many elution profiles.
+
+    ``profiles[n]`` is a list of ``match`` tuples in acquisition order, ``windows[n] = (start_min, stop_min)`` or
+    NaNs for the whole profile; returns one amount dict (``AMOUNT_FIELDS``) or ``None`` per profile, with the
+    semantics of results.py:1238-1262 + adaptors.py:509-569 (retention times in minutes, the scan stops at the
+    first match beyond the window).  ``ctx`` defaults to a module-wide context on the current device."""
+    global _amount_ctx
+    if ctx is None:
+        if _amount_ctx is None:
+            _amount_ctx = Context()
+        ctx = _amount_ctx
+    seg_off = np.zeros(len(profiles) + 1, dtype=np.int64)
+    rts, intensities, scores = [], [], []
+    for n, profile in enumerate(profiles):
+        for entry in profile:
+            try:                                        # results.py:1240-1246
+                rt = entry.rt[0] / 60 if entry.rt[1] == "second" else entry.rt[0]
+            except TypeError:
+                rt = entry.rt
+            rts.append(rt)
+            intensities.append(entry.scaling_factor)
+            scores.append(entry.score)
+        seg_off[n + 1] = len(rts)
+    rt = np.array(rts, dtype=np.float64)
+    inten = np.array(intensities, dtype=np.float64)
+    score = np.array(scores, dtype=np.float64)
+    start = stop = None
+    if windows is not None:
+        start = np.array([w[0] for w in windows], dtype=np.float64)
+        stop = np.array([w[1] for w in windows], dtype=np.float64)
+    out = np.zeros((len(profiles), 5), dtype=np.float64)
+    count = np.zeros(len(profiles), dtype=np.int32)
+    ctx.call("qms_calc_amounts", len(profiles), ptr(seg_off), ptr(rt), ptr(inten), ptr(score), ptr(start), ptr(stop),
+             ptr(out), ptr(count))
+    return [dict(zip(AMOUNT_FIELDS, out[n].tolist())) if count[n] else None for n in range(len(profiles))]
+
+
 class IsotopologueLibrary(dict):
     """Isotopologue library built and matched on one B200.
 
@@ -777,31 +819,10 @@ class IsotopologueLibrary(dict):
         (adaptors.py:509-569) driven by ``Results.calc_amounts_from_rt_info_file`` (results.py:1238-1262);
         ``None`` for a key without a match in its window.  Computed by ``qms_calc_amounts`` (one thread per key)."""
         keys = list(results.keys())
-        seg_off = np.zeros(len(keys) + 1, dtype=np.int64)
-        rts, intensities, scores = [], [], []
-        for n, key in enumerate(keys):
-            for entry in results[key]["data"]:
-                try:                                        # results.py:1240-1246
-                    rt = entry.rt[0] / 60 if entry.rt[1] == "second" else entry.rt[0]
-                except TypeError:
-                    rt = entry.rt
-                rts.append(rt)
-                intensities.append(entry.scaling_factor)
-                scores.append(entry.score)
-            seg_off[n + 1] = len(rts)
-        rt = np.array(rts, dtype=np.float64)
-        inten = np.array(intensities, dtype=np.float64)
-        score = np.array(scores, dtype=np.float64)
-        start = stop = None
+        windows = None
         if rt_windows is not None:
-            start = np.array([rt_windows.get(k, (_NAN, _NAN))[0] for k in keys], dtype=np.float64)
-            stop = np.array([rt_windows.get(k, (_NAN, _NAN))[1] for k in keys], dtype=np.float64)
-        out = np.zeros((len(keys), 5), dtype=np.float64)
-        count = np.zeros(len(keys), dtype=np.int32)
-        self._ctx.call("qms_calc_amounts", len(keys), ptr(seg_off), ptr(rt), ptr(inten), ptr(score), ptr(start), ptr(stop),
-                       ptr(out), ptr(count))
-        names = ("max I in window", "max I in window (rt)", "max I in window (score)", "sum I in window", "auc in window")
-        return {key: (dict(zip(names, out[n].tolist())) if count[n] else None) for n, key in enumerate(keys)}
+            windows = [rt_windows.get(key, (_NAN, _NAN)) for key in keys]
+        return dict(zip(keys, calc_amounts_of_profiles([results[key]["data"] for key in keys], windows, ctx=self._ctx)))
 
     def score_matches(self, matched_peaks, mz_score_percentile):
         """mScore and scaling factor of one list of (mmz, mi, ri, cmz, ci) tuples (IL:2441-2498), on the device."""

@@ -6,6 +6,11 @@ keyed by ``m_key(file_name, formula, charge, label_percentiles)`` whose values h
 Reporting (csv/xlsx/mzTab writers, RT-window curation, plots; results.py:205-2064) is out of scope
 of this build and works on top of this structure unchanged.
 """
+import ast
+import codecs
+import copy
+import csv
+import sys
 from collections import namedtuple
 
 m_key = namedtuple("m_key", ["file_name", "formula", "charge", "label_percentiles"])
@@ -228,3 +233,194 @@ class Results(dict):
         at = obj_for_calc_amount["i"].index(top)
         return {"max I in window": top, "max I in window (rt)": obj_for_calc_amount["rt"][at],
                 "max I in window (score)": obj_for_calc_amount["scores"][at]}
+
+    # ---- RT windows from identification evidence ----------------------------------------
+    def _determine_rt_windows_from_evidence(self, rt_border_tolerance=None):
+        """``(rt_border_lookup, molecule_lookup)`` per formula of ``lookup["formula to evidences"]``
+        (results.py:1283-1300)."""
+        tolerance = 0 if rt_border_tolerance is None else rt_border_tolerance
+        borders, molecules = {}, {}
+        for formula, evidence_dict in (self.lookup or {}).get("formula to evidences", {}).items():
+            if evidence_dict is None:
+                continue
+            molecules[formula] = evidence_dict.keys()
+            borders[formula] = self.curate_rt_windows(evidence_dict, rt_tolerance=tolerance)
+        return borders, molecules
+
+    def curate_rt_windows(self, evidence_dict, rt_tolerance):
+        """Identification RT span ``[min, max]`` of every molecule that shares a formula, with the borders
+        between neighbouring spans settled by ``window_curator`` (results.py:1937-1967)."""
+        spans = []
+        for molecule, info in evidence_dict.items():
+            times = [evidence["RT"] for evidence in info["evidences"]]
+            spans.append(([min(times), max(times)], molecule))
+        if len(spans) > 1:
+            return self.window_curator(spans, rt_tolerance=rt_tolerance)
+        return {spans[0][1]: {"rt_window": spans[0][0]}}
+
+    def window_curator(self, window_sort_list, rt_tolerance=None, win_key=None):
+        """Walk the RT spans in ascending order; where two neighbours come closer than twice the tolerance,
+        either split the gap (or overlap) half-way -- ``upper_window_border`` of the earlier one and
+        ``lower_window_border`` of the later one, negative for an overlap -- or flag both as
+        ``window_is_unseparable`` when the split point would fall outside one of them or one span encloses
+        the other (results.py:1969-2064)."""
+        window_sort_list.sort()
+        out = {}
+
+        def border(name, which):
+            return out[name].get(which, rt_tolerance)
+
+        for position, (span, name) in enumerate(window_sort_list):
+            out[name] = {"rt_window": span}
+            if position == 0:
+                continue
+            earlier_span, earlier = window_sort_list[position - 1]
+            if not span[0] - rt_tolerance <= earlier_span[-1] + rt_tolerance:
+                continue
+            half_gap = (span[0] - earlier_span[-1]) / 2.0
+            if span[0] - half_gap > span[1] + border(name, "upper_window_border"):
+                clash = True
+            elif earlier_span[-1] - half_gap < earlier_span[0] - border(earlier, "lower_window_border"):
+                clash = True
+            elif earlier_span[0] - border(earlier, "lower_window_border") < span[0] - border(name, "lower_window_border"):
+                clash = earlier_span[-1] + border(earlier, "upper_window_border") > span[-1] + border(name, "upper_window_border")
+            else:
+                clash = False
+            if clash:
+                for member in (name, earlier):
+                    out[member].setdefault("window_is_unseparable", []).append(win_key)
+                    out[member].pop("lower_window_border", None)
+                    out[member].pop("upper_window_border", None)
+            else:
+                out[name]["lower_window_border"] = half_gap
+                out[earlier]["upper_window_border"] = half_gap
+        return out
+
+    # ---- quant summary / RT info file (results.py:1138-1281, 1302-1527) -------------------------------------
+    def write_rt_info_file(self, output_file=None, list_of_csvdicts=None, trivial_name_lookup=None,
+                           rt_border_tolerance=None, update=True, buffer_only=False):
+        """One line per (result key, molecule) with the RT window derived from the identification evidence
+        (``rt_window`` widened by the curated borders or the tolerance), the evidence list ``score@rt;...`` and
+        the trivial names; columns ``RT_INFO_FIELDS``.  Returns the lines; writes ``.csv`` unless ``buffer_only``.
+        Mirrors ``pyqms.Results.write_rt_info_file`` (csv only: openpyxl is not a dependency here)."""
+        assert output_file is not None, "You need to specify an output file"
+        tolerance = 0 if rt_border_tolerance is None else rt_border_tolerance
+        if list_of_csvdicts is None:
+            list_of_csvdicts = [key._asdict() for key in sorted(self.keys())]
+        names_of_formula = {} if trivial_name_lookup is None else trivial_name_lookup
+        borders_of_formula, molecules_of_formula = self._determine_rt_windows_from_evidence(rt_border_tolerance=tolerance)
+        lines = []
+        for line in list_of_csvdicts:
+            if not update:
+                lines.append(copy.deepcopy(line))
+                continue
+            formula = line["formula"]
+            extra_names = ", ".join(names_of_formula.get(formula, []))
+            if line.get("trivial_name(s)", None) is None:
+                line["trivial_name(s)"] = extra_names
+            elif line["trivial_name(s)"] != "":
+                line["trivial_name(s)"] += extra_names
+            borders = borders_of_formula.get(formula, {})
+            evidence = self.lookup["formula to evidences"].get(formula, None) if len(borders) > 0 else None
+            if evidence is not None:
+                molecules = molecules_of_formula[formula]
+            else:
+                molecules = self.lookup.get("formula to molecule", {}).get(formula, [])
+            for molecule in molecules:
+                line["molecule"] = molecule
+                if evidence is not None:
+                    listed = []
+                    for item in evidence[molecule]["evidences"]:
+                        if "RT" not in item:
+                            continue
+                        text = "{0}@{1}".format(item["score"], item["RT"]) if item["score"] != "None" else "{0}".format(item["RT"])
+                        listed.append((item["RT"], text))
+                    window = borders[molecule]
+                    line["start (min)"] = window["rt_window"][0] - window.get("lower_window_border", tolerance)
+                    line["stop (min)"] = window["rt_window"][1] + window.get("upper_window_border", tolerance)
+                    line["evidences (min)"] = ";".join(text for _, text in sorted(listed))
+                    if len(evidence[molecule]["trivial_names"]) > 0:
+                        line["trivial_name(s)"] = ";".join(sorted(set(evidence[molecule]["trivial_names"])))
+                lines.append(copy.deepcopy(line))
+        if not buffer_only:
+            if not str(output_file).endswith(".csv"):
+                raise ValueError("Extension: {0} of file {1} not recognized (csv only)".format(
+                    str(output_file).split(".")[-1], output_file))
+            with codecs.open(str(output_file), mode="w", encoding="utf-8") as handle:
+                writer = csv.DictWriter(handle, RT_INFO_FIELDS, extrasaction="ignore",
+                                        lineterminator="\n" if sys.platform == "win32" else "\r\n")
+                writer.writeheader()
+                for line in lines:
+                    writer.writerow(line)
+        return lines
+
+    def calc_amounts_from_rt_info_file(self, rt_info_file=None, rt_border_tolerance=None, calc_amount_function=None,
+                                       evidence_score_field="PEP", buffer_only=False, buffered_csv_dicts=None,
+                                       on_device=False):
+        """Amounts of every line of a quant summary that carries ``start (min)`` / ``stop (min)``: the matches of
+        the line's key inside the window (retention time in minutes; the scan stops at the first match beyond the
+        window) go to ``calc_amount_function`` -- default ``determine_max_itensity`` -- and its result is merged
+        into the line.  Mirrors ``pyqms.Results.calc_amounts_from_rt_info_file``.
+
+        ``on_device=True`` (additive) computes all five amount fields of all lines in ONE pass of
+        ``qms_calc_amounts`` instead of calling a Python function per line."""
+        if rt_info_file is not None:
+            if not str(rt_info_file).endswith(".csv"):
+                raise ValueError("Extension: {0} of file {1} not recognized (csv only)".format(
+                    str(rt_info_file).split(".")[-1], rt_info_file))
+            with codecs.open(str(rt_info_file), mode="r", encoding="utf-8") as handle:
+                given = list(csv.DictReader(handle))
+        elif buffered_csv_dicts is not None:
+            given = buffered_csv_dicts
+        else:
+            raise ValueError("No RT info file or buffered csv lines were provided")
+        jobs = []       # (line, profile of the key, (start, stop))
+        for line in given:
+            try:
+                line["start (min)"] = float(line.get("start (min)", None))
+                line["stop (min)"] = float(line.get("stop (min)", None))
+            except (TypeError, ValueError):
+                continue
+            percentiles = line["label_percentiles"]
+            if isinstance(percentiles, str):
+                percentiles = ast.literal_eval(percentiles)
+            key = self._m_key_class(line["file_name"], line["formula"], int(line["charge"]), percentiles)
+            jobs.append((line, self[key]["data"], (line["start (min)"], line["stop (min)"])))
+        if on_device:
+            from .isotopologue_library import calc_amounts_of_profiles
+            amounts = calc_amounts_of_profiles([job[1] for job in jobs], [job[2] for job in jobs])
+        else:
+            function = self.determine_max_itensity if calc_amount_function is None else calc_amount_function
+            amounts = [function(_profile_in_window(profile, *window)) for _, profile, window in jobs]
+        for (line, _, _), amount in zip(jobs, amounts):
+            if amount is not None:
+                line.update(amount)
+        if buffer_only is False:
+            self.write_rt_info_file(output_file=rt_info_file, list_of_csvdicts=list(given),
+                                    rt_border_tolerance=rt_border_tolerance, update=False, buffer_only=buffer_only)
+        return list(given)
+
+
+RT_INFO_FIELDS = ["file_name", "formula", "molecule", "trivial_name(s)", "label_percentiles", "charge", "start (min)",
+                  "stop (min)", "max I in window", "max I in window (rt)", "max I in window (score)", "auc in window",
+                  "sum I in window", "evidences (min)"]
+
+
+def _profile_in_window(profile, start, stop):
+    """``obj_for_calc_amount`` of one key: the matches with start <= rt <= stop, scanning stops at the first
+    rt > stop (results.py:1238-1262)."""
+    obj = {"rt": [], "i": [], "scores": [], "spec_ids": []}
+    for entry in profile:
+        try:
+            rt = entry.rt[0] / 60 if entry.rt[1] == "second" else entry.rt[0]
+        except TypeError:
+            rt = entry.rt
+        if rt < start:
+            continue
+        if rt > stop:
+            break
+        obj["rt"].append(rt)
+        obj["i"].append(entry.scaling_factor)
+        obj["scores"].append(entry.score)
+        obj["spec_ids"].append(entry.spec_id)
+    return obj

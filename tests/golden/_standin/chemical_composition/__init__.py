@@ -48,7 +48,10 @@ class ChemicalComposition(dict):
     def __init__(self, sequence=None, formula=None, aa_compositions=None, isotopic_distributions=None,
                  unimod_file_list=None, add_default_files=True, **kw):
         super().__init__()
-        self.aa_compositions = aa_compositions if aa_compositions is not None else {}
+        if aa_compositions is None:      # the real package ships its own residue table; the reference's is the same chemistry
+            import pyqms.knowledge_base as _kb
+            aa_compositions = _kb.aa_compositions
+        self.aa_compositions = aa_compositions
         self.isotopic_distributions = isotopic_distributions if isotopic_distributions is not None else {}
         files = [str(f) for f in (unimod_file_list or [])]
         if add_default_files and str(_DEFAULT_UNIMOD) not in files:
