@@ -6,10 +6,10 @@
 
 Exports mirror pyqms/__init__.py:38-42 of the reference.
 """
-from . import knowledge_base
+from . import adaptors, knowledge_base
 from .params import params
 from .results import Results, match, m_key
 from .isotopologue_library import IsotopologueLibrary
 
 __version__ = "0.1.0"
-__all__ = ["IsotopologueLibrary", "Results", "match", "m_key", "params", "knowledge_base"]
+__all__ = ["IsotopologueLibrary", "Results", "match", "m_key", "params", "knowledge_base", "adaptors"]

@@ -12,6 +12,7 @@ results)`` and the ``Results`` / ``match`` structures follow the reference
   envelope convolution, per-charge m/z + ppm windows, index sort + probe tables, spectrum probe,
   candidate assembly, mScore and hit compaction.  There is no CPU fallback.
 """
+import contextvars
 import copy
 import ctypes as C
 import operator
@@ -64,6 +65,27 @@ class _LazyEnvelopes(dict):
 
     def items(self):
         return [(lp, self[lp]) for lp in self.keys()]
+
+
+_restore_device = contextvars.ContextVar("qms_restore_device", default=None)
+
+
+def _restore_library(state, compositions):
+    library = IsotopologueLibrary.__new__(IsotopologueLibrary)
+    dict.__init__(library)
+    library.__dict__.update(state)
+    for formula, composition in compositions:
+        dict.__setitem__(library, formula, {"env": _LazyEnvelopes(library, formula, library.labled_percentiles),
+                                            "cc": composition})
+    library._ctx = Context(_restore_device.get())      # raises without the CUDA library / a GPU: no fallback
+    library._views = {}
+    library._push_params()
+    verbose, library.verbose = library.verbose, False
+    try:
+        library._build_on_device(distributed=False)
+    finally:
+        library.verbose = verbose
+    return library
 
 
 AMOUNT_FIELDS = ("max I in window", "max I in window (rt)", "max I in window (score)", "sum I in window", "auc in window")
@@ -182,6 +204,35 @@ class IsotopologueLibrary(dict):
                 raise SystemExit(1)          # IL:941-949
             print("> Created {0} match sets, total mz range [{1:10.5f} .. {2:10.5f}]".format(
                 self._n_bins(), *self.match_set_mz_range))
+
+    # ------------------------------------------------------------------ save / load
+    _DEVICE_STATE = ("_ctx", "_views", "_entry_static", "_ent_env", "_ent_z", "_ent_lower", "_ent_upper", "_ent_win_off",
+                     "_win_lo", "_win_hi", "_win_cmz", "_win_ri", "_win_ci")
+
+    def __reduce__(self):
+        """Pickling keeps the host plan (knowledge base, lookups, isotope pools, envelope terms) and drops everything
+        that lives on or was exported from the device; unpickling creates a context on the current device and runs
+        the device build again (milliseconds), skipping all molecule-string work."""
+        state = {k: v for k, v in self.__dict__.items() if k not in self._DEVICE_STATE}
+        compositions = [(formula, dict.__getitem__(self, formula)["cc"]) for formula in dict.keys(self)]
+        return (_restore_library, (state, compositions))
+
+    def save(self, path):
+        """Write the library plan to ``path`` (pickle); ``IsotopologueLibrary.load`` rebuilds it on a GPU."""
+        import pickle
+        with open(path, "wb") as handle:
+            pickle.dump(self, handle, protocol=pickle.HIGHEST_PROTOCOL)
+
+    @staticmethod
+    def load(path, device=None):
+        """Library saved with ``save``; ``device`` as in the constructor (default: ``LOCAL_RANK`` or 0)."""
+        import pickle
+        token = _restore_device.set(device)
+        try:
+            with open(path, "rb") as handle:
+                return pickle.load(handle)
+        finally:
+            _restore_device.reset(token)
 
     # ------------------------------------------------------------------ parameters -> device
     def _push_params(self):
@@ -770,9 +821,29 @@ class IsotopologueLibrary(dict):
             results.flush_queue()                          # spectra queued by earlier match_all calls come first
         out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
         if lazy and hasattr(results, "defer"):
-            results.defer(out, lambda target: self._emit(out, target, file_name, spec_ids, spec_rts, kind == 1))
+            results.defer(out, lambda target: self._emit(out, target, file_name, spec_ids, spec_rts, kind == 1),
+                          table=lambda: self._hit_columns(out, file_name, spec_ids, spec_rts))
             return results
         return self._emit(out, results, file_name, spec_ids, spec_rts, kind == 1)
+
+    def _hit_columns(self, out, file_names, spec_ids, spec_rts):
+        """Columns of ``Results.format_all_results`` (all but ``peaks``) of one packed batch, by array indexing only."""
+        entry, spec = out["entry"], out["spec"]
+        n_lp = len(self.labled_percentiles)
+        env = self._ent_env[entry]
+        formulas = np.array(self._formulas, dtype=object)
+        percentiles = np.empty(n_lp, dtype=object)
+        percentiles[:] = list(self.labled_percentiles)
+        as_object = lambda values: np.array(list(values) + [None], dtype=object)[:-1]   # keeps tuples as cells
+        names = as_object(file_names)[spec] if isinstance(file_names, list) else np.full(len(spec), file_names, dtype=object)
+        matched = np.zeros(len(spec), dtype=np.int64)
+        if out["n_windows"]:
+            hit_of_window = np.repeat(np.arange(len(spec)), np.diff(out["win_off"]))
+            np.add.at(matched, hit_of_window, out["peak"] >= 0)
+        return {"file_name": names, "formula": formulas[env // n_lp], "charge": np.asarray(self.charges)[self._ent_z[entry]],
+                "label_percentiles": percentiles[env % n_lp], "spec_id": as_object(spec_ids)[spec],
+                "rt": as_object(spec_rts)[spec], "score": out["score"], "scaling_factor": out["scaling"],
+                "n_peaks": np.diff(out["win_off"]), "n_matched_peaks": matched}
 
     def match_packed(self, peaks, offsets, mz_score_percentile=None, input_kind=0):
         """Device pass without Python object creation: returns the packed hit arrays of ``qms_match_batch``

@@ -61,6 +61,7 @@ class Results(dict):
         self._silac_pairs = None
         self._pending = []          # thunks of packed batches not yet turned into match tuples
         self._packed = []           # every packed batch ever handed over (kept for array consumers)
+        self._tables = []           # per packed batch: callable giving its hits as columns
         self._queue = []            # spectra handed to match_all and not yet matched
         self._queue_peaks = 0
         self._queue_library = None
@@ -68,10 +69,24 @@ class Results(dict):
         self.index = _FlushingIndex(self, self.index)
 
     # ---- deferred materialisation of packed batches -------------------------------------------------
-    def defer(self, packed, thunk):
-        """Register a packed batch; ``thunk(self)`` must ``add`` its hits in (spectrum, entry) order."""
+    def defer(self, packed, thunk, table=None):
+        """Register a packed batch; ``thunk(self)`` must ``add`` its hits in (spectrum, entry) order;
+        ``table()`` returns the batch as columns for ``packed_table``."""
         self._pending.append(thunk)
         self._packed.append(packed)
+        self._tables.append(table)
+
+    def packed_table(self):
+        """The hits of all batched calls (``match_many``) as a pandas DataFrame with the columns of
+        ``format_all_results`` except ``peaks`` (plus ``n_peaks`` / ``n_matched_peaks``), built from the packed
+        arrays without creating a Python object per hit; rows in (batch, spectrum, index entry) order.
+        Hits added one by one (eager ``match_all``, ``add``) are not part of it."""
+        import pandas as pd
+        frames = [pd.DataFrame(table()) for table in self._tables if table is not None]
+        if not frames:
+            return pd.DataFrame(columns=list(m_key._fields) + ["spec_id", "rt", "score", "scaling_factor", "n_peaks",
+                                                               "n_matched_peaks"])
+        return pd.concat(frames, ignore_index=True)
 
     def packed_batches(self):
         """The packed hit arrays of every batched call so far (see ``IsotopologueLibrary.match_packed``)."""
@@ -147,6 +162,7 @@ class Results(dict):
     def __reduce_ex__(self, protocol):
         self._flush()
         self._packed = []           # arrays are redundant once materialised; keep pickles reference-sized
+        self._tables = []
         self._queue_library = None  # the device context is not picklable
         return dict.__reduce_ex__(self, protocol)
 

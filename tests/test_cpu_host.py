@@ -44,6 +44,25 @@ def test_no_gpu_means_loud_failure():
         pyqms_b200.IsotopologueLibrary(molecules=["PEPTIDE"], charges=[2], verbose=False)
 
 
+def test_saved_library_holds_the_plan_and_needs_a_gpu_to_load(tmp_path):
+    import pickle
+    import torch
+    import pyqms_b200
+    from pyqms_b200._capi import QmsError
+    lib = pyqms_b200.IsotopologueLibrary(molecules=["PEPTIDEK", "DDSPDLPK#Oxidation:1"], charges=[1, 2], verbose=False,
+                                         _plan_only=True)
+    lib.save(tmp_path / "plan.qmslib")
+    blob = (tmp_path / "plan.qmslib").read_bytes()
+    restore, (state, compositions) = lib.__reduce__()
+    assert "_ctx" not in state and "_views" not in state and "_terms" in state and "_pool_tables" in state
+    assert [formula for formula, _ in compositions] == list(lib.keys())
+    if not torch.cuda.is_available():
+        with pytest.raises(QmsError, match="no CPU fallback"):
+            pickle.loads(blob)
+        with pytest.raises(QmsError, match="no CPU fallback"):
+            pyqms_b200.adaptors.calc_amount_function({"rt": [1.0], "i": [2.0], "scores": [0.5]})
+
+
 def test_product_never_imports_the_oracle():
     for path in (ROOT / "pyqms_b200").rglob("*.py"):
         assert "oracle" not in path.read_text(), path

@@ -11,6 +11,8 @@ import sys
 import numpy as np
 import pytest
 
+import pyqms_b200
+
 pytestmark = pytest.mark.gpu
 
 from tests.golden.cases import CASES, PEPTIDE_SEQUENCE_KATS, QUICK_START_EXPECT, QUICK_START_PEAKS  # noqa: E402
@@ -375,6 +377,39 @@ def test_mzml_to_results_end_to_end(pyqms, tmp_path):
     assert len(res) > 0
 
 
+def test_evidence_to_quant_summary_end_to_end(tmp_path):
+    """N4 + N3 + P1 + P2 + N2: identification table -> library -> mzML run -> quant summary with amounts inside the
+    curated evidence RT windows (examples/quantify_mzml.py --evidence)."""
+    import csv
+    from pyqms_b200.mzml import write_mzml
+    from pyqms_b200.synthetic import synth_run
+    evidence = GOLDEN / "evidence" / "ids_run1.csv"
+    cam = {"C": [{"element_composition": {"O": 1, "H": 3, "14N": 1, "C": 2}, "evidence_mod_name": "Carbamidomethyl"}]}
+    labels, lookup, molecules = pyqms_b200.adaptors.parse_evidence(fixed_labels=cam, evidence_files=[str(evidence)])
+    probe = pyqms_b200.IsotopologueLibrary(molecules=molecules, charges=[2, 3], fixed_labels=labels, evidences=lookup, verbose=False)
+    n = 500                          # 0.1 min per spectrum: the run covers the evidence times (15 - 41 min)
+    peaks, offsets = synth_run(*probe.entry_peaks(), n_spectra=n, seed=11, mean_peaks=300, elution_sigma=120.0)
+    path = tmp_path / "run1.mzML"
+    write_mzml(path, [peaks[offsets[s]:offsets[s + 1]] for s in range(n)], rts_minutes=[0.1 * s for s in range(n)])
+    sys.path.insert(0, str(GOLDEN.parent.parent / "examples"))
+    import quantify_mzml
+    summary = tmp_path / "summary.csv"
+    results = quantify_mzml.main(str(path), [], evidence=str(evidence), summary=str(summary), rt_tolerance=1.0, charges=(2, 3))
+    rows = list(csv.DictReader(open(summary)))
+    assert len(rows) >= len(results)            # one line per (key, molecule of the key's formula)
+    quantified = [row for row in rows if row["max I in window"] != ""]
+    assert len(quantified) >= 5
+    for row in quantified:
+        assert float(row["start (min)"]) <= float(row["max I in window (rt)"]) <= float(row["stop (min)"])
+        assert float(row["sum I in window"]) >= float(row["max I in window"]) > 0 and row["evidences (min)"] != ""
+    # the device amounts equal the reference's per-line Python function on the same summary
+    host = results.calc_amounts_from_rt_info_file(rt_info_file=str(summary), buffer_only=True)
+    for row, line in zip(rows, host):
+        assert (row["max I in window"] != "") == (line["max I in window"] != "")
+        if row["max I in window"] != "":
+            assert float(row["max I in window"]) == float(line["max I in window"])
+
+
 def test_c_abi_demo_runs(tmp_path):
     """Plain C driver of the C ABI reproduces the docs' quick-start answer (examples/c_abi_demo.c)."""
     import subprocess
@@ -382,3 +417,57 @@ def test_c_abi_demo_runs(tmp_path):
     done = subprocess.run([str(build_c_demo(tmp_path))], capture_output=True, text=True, timeout=120)
     assert done.returncode == 0 and done.stdout.strip().endswith("OK"), done.stdout + done.stderr
     assert "mScore 0.96066097" in done.stdout
+
+
+def test_library_pickle_and_save_load_rebuild_on_device(tmp_path):
+    """A pickled / saved library carries only the host plan; loading rebuilds the device state (N4)."""
+    import pickle
+    from pyqms_b200.synthetic import BSA_MOLECULES, CAM_FIXED_LABEL
+    lib = pyqms_b200.IsotopologueLibrary(molecules=BSA_MOLECULES, charges=[1, 2, 3], metabolic_labels={"15N": [0, 0.99]},
+                                         fixed_labels=CAM_FIXED_LABEL, verbose=False)
+    clone = pickle.loads(pickle.dumps(lib))
+    path = tmp_path / "bsa.qmslib"
+    lib.save(path)
+    loaded = pyqms_b200.IsotopologueLibrary.load(path, device=0)
+    assert path.stat().st_size < 2_000_000
+    rng = np.random.default_rng(3)
+    for other in (clone, loaded):
+        assert other.formulas_sorted_by_mz == lib.formulas_sorted_by_mz
+        assert other.match_set_mz_range == lib.match_set_mz_range
+        assert list(other.keys()) == list(lib.keys()) and other.lookup == lib.lookup
+        formula = next(iter(lib.keys()))
+        lp = lib.labled_percentiles[0]
+        assert other[formula]["env"][lp]["abun"] == lib[formula]["env"][lp]["abun"]
+    _, _, charge, lp, formula = lib.formulas_sorted_by_mz[len(lib.formulas_sorted_by_mz) // 2]
+    envelope = lib[formula]["env"][lp]
+    peaks = [(mz, 1000.0 * ri) for mz, ri in zip(envelope[charge]["mz"], envelope["relabun"])]
+    peaks = sorted(peaks + [(300.0 + 900.0 * rng.random(), 50.0) for _ in range(200)])
+    want = results_to_rows(lib.match_all(mz_i_list=peaks, file_name="f", spec_id=1, spec_rt=1.0, results=None))
+    assert len(want) >= 1
+    for other in (clone, loaded):
+        got = results_to_rows(other.match_all(mz_i_list=peaks, file_name="f", spec_id=1, spec_rt=1.0, results=None))
+        assert_results_equal(got, want)
+
+
+def test_packed_table_equals_format_all_results():
+    """N1: the array-built hit table has the rows of format_all_results (minus the peaks column)."""
+    from pyqms_b200.synthetic import BSA_MOLECULES, CAM_FIXED_LABEL, synth_run
+    lib = pyqms_b200.IsotopologueLibrary(molecules=BSA_MOLECULES, charges=[1, 2, 3, 4], metabolic_labels={"15N": [0, 0.99]},
+                                         fixed_labels=CAM_FIXED_LABEL, verbose=False)
+    peaks, offsets = synth_run(*lib.entry_peaks(), n_spectra=300, seed=5, elution_sigma=40.0)
+    ids = list(range(1000, 1300))
+    rts = [(0.1 * i, "minute") for i in range(300)]
+    results = lib.match_many(peaks, file_name="run.mzML", spec_ids=ids, spec_rts=rts, offsets=offsets)
+    table = results.packed_table()
+    assert len(table) == results.packed_batches()[0]["n_hits"] > 50
+    full = results.format_all_results()
+    assert len(full) == len(table)
+    columns = ["file_name", "formula", "charge", "label_percentiles", "spec_id", "rt", "score", "scaling_factor"]
+    key = ["spec_id", "formula", "charge", "label_percentiles"]
+    a = table[columns].sort_values(key).reset_index(drop=True)
+    b = full[columns].sort_values(key).reset_index(drop=True)
+    for column in columns:
+        assert a[column].tolist() == b[column].tolist(), column
+    n_matched = {(r.spec_id, r.formula, r.charge, r.label_percentiles): sum(p[0] is not None for p in r.peaks) for r in full.itertuples()}
+    for r in table.itertuples():
+        assert n_matched[(r.spec_id, r.formula, r.charge, r.label_percentiles)] == r.n_matched_peaks <= r.n_peaks
