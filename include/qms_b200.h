@@ -214,6 +214,27 @@ int qms_score_matches(qms_ctx* ctx, int32_t n, const double* mmz, const double* 
                       const double* cmz, const double* ci, double mz_score_percentile, double* score,
                       double* scaling);
 
+/* ---- host-side planner (no GPU work, ctx-free) ----------------------------------------------------
+ * Replaces the per-molecule string loop in front of the build (IL:314-347: one chemical_composition call per
+ * molecule) for plain formulas ("+C104H175N29O33S1", "+C(-6)13C(6)") and unmodified peptides ("PEPTIDEK",
+ * "PEPTIDEK+PO3").  text/str_off: n packed molecule strings.  symbols_blob/symbol_off: the n_symbols (<= 127)
+ * element symbols incl. isotope prefixes.  residue_blob/residue_off: the n_residues residue names (letter +
+ * optional fixed-label index: "A", "C", "C0", "K1"), residue_counts[n_residues x n_symbols],
+ * residue_order[n_residues x n_symbols] (symbol ids in the order the residue's composition lists them,
+ * -1 terminated).  Outputs per molecule: counts[n_symbols], first_seen[n_symbols] (rank at
+ * which the symbol entered the composition, -1 = absent: the element order of IL:546-646), status (0 parsed,
+ * 1 = left to the host parser: modifications, unknown symbols/residues, other syntax). */
+int qms_parse_molecules(const char* text, const int64_t* str_off, int64_t n, int32_t n_symbols,
+                        const char* symbols_blob, const int32_t* symbol_off, int32_t n_residues,
+                        const char* residue_blob, const int32_t* residue_off, const int32_t* residue_counts,
+                        const int8_t* residue_order, int32_t* counts, int16_t* first_seen, uint8_t* status);
+
+/* Hill-notation keys "C(34)H(53)N(7)O(15)" of n count rows: C, H, then the other symbols in string order, as
+ * ChemicalComposition.hill_notation_unimod writes them (IL:343).  out may be NULL to query *needed;
+ * QMS_E_CAPACITY if out_cap is too small.  out_off[n+1] are byte offsets into out. */
+int qms_hill_formulas(const int32_t* counts, int64_t n, int32_t n_symbols, const char* symbols_blob,
+                      const int32_t* symbol_off, char* out, int64_t out_cap, int64_t* out_off, int64_t* needed);
+
 /* ---- next row N2: amounts of matched isotope chromatograms -----------------------------------
  * Replaces pyqms.adaptors.calc_amount_function (adaptors.py:509-569) inside the retention-time window
  * walk of Results.calc_amounts_from_rt_info_file (results.py:1238-1262).  Key k owns the profile

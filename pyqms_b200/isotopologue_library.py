@@ -21,7 +21,7 @@ import sys
 
 import numpy as np
 
-from . import knowledge_base
+from . import knowledge_base, planner
 from .params import params as _default_params
 from ._capi import Context, QmsHits, QmsIndexInfo, QmsParams, ptr
 from .chemistry import ChemicalComposition
@@ -70,13 +70,11 @@ class _LazyEnvelopes(dict):
 _restore_device = contextvars.ContextVar("qms_restore_device", default=None)
 
 
-def _restore_library(state, compositions):
+def _restore_library(state, formulas):
     library = IsotopologueLibrary.__new__(IsotopologueLibrary)
     dict.__init__(library)
     library.__dict__.update(state)
-    for formula, composition in compositions:
-        dict.__setitem__(library, formula, {"env": _LazyEnvelopes(library, formula, library.labled_percentiles),
-                                            "cc": composition})
+    dict.update(library, ((formula, _FormulaRecord(library, k, formula)) for k, formula in enumerate(formulas)))
     library._ctx = Context(_restore_device.get())      # raises without the CUDA library / a GPU: no fallback
     library._views = {}
     library._push_params()
@@ -86,6 +84,57 @@ def _restore_library(state, compositions):
     finally:
         library.verbose = verbose
     return library
+
+
+class _FormulaRecord(dict):
+    """``lib[formula]``: ``{"env": label tuple -> envelope, "cc": composition}``, both built on first access (a
+    library of 10^6 formulas does not create 2*10^6 dictionaries nobody reads)."""
+    _FIELDS = ("env", "cc")
+    __slots__ = ("_library", "_row", "_formula")
+
+    def __init__(self, library, row, formula):          # dict.__new__ already made the (empty) mapping
+        self._library = library
+        self._row = row
+        self._formula = formula
+
+    def __missing__(self, key):
+        if key == "env":
+            value = _LazyEnvelopes(self._library, self._formula, self._library.labled_percentiles)
+        elif key == "cc":
+            value = self._library._composition_of_formula(self._row)
+        else:
+            raise KeyError(key)
+        dict.__setitem__(self, key, value)
+        return value
+
+    def _fill(self):
+        for key in self._FIELDS:
+            self[key]
+        return self
+
+    def __contains__(self, key):
+        return key in self._FIELDS or dict.__contains__(self, key)
+
+    def __iter__(self):
+        return iter(self._fill().keys())
+
+    def __len__(self):
+        return dict.__len__(self._fill())
+
+    def keys(self):
+        return dict.keys(self._fill())
+
+    def values(self):
+        return dict.values(self._fill())
+
+    def items(self):
+        return dict.items(self._fill())
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __reduce__(self):
+        return (dict, (dict(self._fill()),))
 
 
 AMOUNT_FIELDS = ("max I in window", "max I in window (rt)", "max I in window (score)", "sum I in window", "auc in window")
@@ -142,7 +191,7 @@ class IsotopologueLibrary(dict):
 
     def __init__(self, molecules=None, charges=None, metabolic_labels=None, fixed_labels=None, params=None,
                  trivial_names=None, verbose=True, evidences=None, unimod_files=None, add_default_files=True, *,
-                 device=None, distributed=None, defer_matching=True, _plan_only=False):
+                 device=None, distributed=None, defer_matching=True, _plan_only=False, _native_planner=True):
         super().__init__()
         assert molecules is not None, "require list of molecules"
         assert charges is not None, "require list of charges"
@@ -155,6 +204,7 @@ class IsotopologueLibrary(dict):
             metabolic_labels = {"15N": [0.0]}
         self.build_isotoplogues = True
         self.defer_matching = defer_matching
+        self._native_planner = _native_planner
         self.verbose = verbose
         self.metabolic_labels = metabolic_labels
         self.fixed_labels = {} if fixed_labels is None else fixed_labels
@@ -214,8 +264,7 @@ class IsotopologueLibrary(dict):
         that lives on or was exported from the device; unpickling creates a context on the current device and runs
         the device build again (milliseconds), skipping all molecule-string work."""
         state = {k: v for k, v in self.__dict__.items() if k not in self._DEVICE_STATE}
-        compositions = [(formula, dict.__getitem__(self, formula)["cc"]) for formula in dict.keys(self)]
-        return (_restore_library, (state, compositions))
+        return (_restore_library, (state, list(dict.keys(self))))
 
     def save(self, path):
         """Write the library plan to ``path`` (pickle); ``IsotopologueLibrary.load`` rebuilds it on a GPU."""
@@ -340,20 +389,20 @@ class IsotopologueLibrary(dict):
             assert len({len(self.fixed_labels[aa]) for aa in locked}) == 1, \
                 "Length of fixed_labels for aas that ought to be locked into same experiment dont show same number of labels ..."
         expanded = set()
+        letters = "".join(re.escape(k) for k in self.aa_compositions if len(k) == 1)
+        not_a_residue = re.compile("[^%s]" % letters) if letters else re.compile(".", re.S)
+        labelled_residue = re.compile("|".join(re.escape(k) for k in self.fixed_labels)) if self.fixed_labels else None
         for full_molecule in molecules:
-            cut = len(full_molecule)
-            for position, letter in enumerate(full_molecule):
-                if letter not in self.aa_compositions:
-                    cut = position
-                    break
+            stop = not_a_residue.search(full_molecule)      # the sequence ends at the first non-residue character
+            cut = stop.start() if stop else len(full_molecule)
             sequence, addon = full_molecule[:cut], full_molecule[cut:]
+            if labelled_residue is None or labelled_residue.search(sequence) is None:
+                expanded.add(full_molecule)
+                continue
             sites = []
             for amino_acid in self.fixed_labels:
                 for hit in re.finditer(amino_acid, sequence):
                     sites.append(("{0}{1}".format(hit.start(), amino_acid), len(self.fixed_labels[amino_acid])))
-            if not sites:
-                expanded.add(sequence + addon)
-                continue
             for combination in self._create_combinations(sorted(sites, reverse=True)):
                 exchange = sorted(((int(token[:-1]), token[-1], state) for token, state in combination), reverse=True)
                 labelled = sequence
@@ -375,71 +424,101 @@ class IsotopologueLibrary(dict):
 
     # ------------------------------------------------------------------ molecules -> formulas (IL:312-497)
     def _register_molecules(self, molecules, trivial_names, add_default_files):
+        """Molecule strings -> formulas, lookups, per-formula count rows.  Plain formulas and unmodified peptides are
+        parsed in bulk by the native planner; the rest goes through ``ChemicalComposition`` one by one."""
         self._highest_element_count = {}
         self._range_for_elements_with_two_isotopes = [None, None]
         factory = ChemicalComposition(aa_compositions=self.aa_compositions,
                                       isotopic_distributions=self.isotopic_distributions,
                                       unimod_file_list=self.unimod_files, add_default_files=add_default_files)
+        self._add_default_files = add_default_files
         levels = self.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"]
-        two_iso = self._range_for_elements_with_two_isotopes
+        known = self.isotopic_distributions
         # the reference iterates set(molecules) (hash order); sorted() makes the envelope order identical in
         # every process, which the sharded multi-GPU build relies on
-        known = self.isotopic_distributions
-        highest = self._highest_element_count
-        two_isotopes = {}                                   # element -> has a 2-isotope table (IL:448-460)
-        hill_order = {}                                     # element tuple -> Hill order (C, H, then sorted)
-        to_formula = self.lookup["molecule to formula"]
-        to_molecule = self.lookup["formula to molecule"]
-        for molecule in sorted(set(molecules)):
+        ordered = sorted(set(molecules))
+        symbols = list(known)
+        if self._native_planner:
+            counts, seen, status = planner.parse_molecules(ordered, symbols, self.aa_compositions)
+        else:                                              # unit tests: every molecule through the host parser
+            counts = np.zeros((len(ordered), len(symbols)), dtype=np.int32)
+            seen = np.full((len(ordered), len(symbols)), planner.ABSENT, dtype=np.int16)
+            status = np.ones(len(ordered), dtype=np.uint8)
+        parsed_on_host = {}
+        for i in np.flatnonzero(status).tolist():
+            molecule = ordered[i]
             if molecule.count("#") > 1:
                 raise ValueError(f"{molecule} contains too many '#' {molecule.count('#') + 1} only one allowed")
-            composition = factory.composition_of(molecule)
-            elements = tuple(composition)
-            order = hill_order.get(elements)
-            if order is None:
-                order = hill_order[elements] = [e for e in ("C", "H") if e in composition] + \
-                    sorted(e for e in elements if e not in ("C", "H"))
-            formula = "".join(["%s(%d)" % (e, composition[e]) for e in order])
-            if trivial_names is not None:
+            composition = parsed_on_host[i] = factory.composition_of(molecule)
+            for element in composition:
+                if element in known:
+                    continue
+                # isotope-labelled element introduced by a modification (e.g. 13C of a SILAC/TMT unimod), IL:378-436
+                found = _ISOTOPE_ELEMENT.match(element)
+                try:
+                    enriched = int(round(float(found.group("isotope"))))
+                except Exception:
+                    print("Failed on", element)
+                    print("Maybe element is not in pyqms.knowledge_base.py ?")
+                    raise SystemExit(1)
+                template = found.group("element")
+                target = levels.get("{0}{1}".format(enriched, template)) or 0.994
+                if self.verbose:
+                    print("> Extending isotopic distribution that are within the modifications for "
+                          "element {0}{1}, enrichment levels set to {2}".format(enriched, template, target))
+                known[element] = {self.zero_labeled_percentile: self._recalc_isotopic_distribution(
+                    element=template, target_percentile=target, enriched_isotope=enriched)}
+        # columns for symbols the host parser introduced and for the bare elements fixed-label isotopes fold into
+        for symbol in list(known) + [level_symbol[-1] for level_symbol in levels]:
+            if symbol not in symbols and symbol in known:
+                symbols.append(symbol)
+        if len(symbols) > counts.shape[1]:
+            grow = len(symbols) - counts.shape[1]
+            counts = np.hstack([counts, np.zeros((len(ordered), grow), dtype=np.int32)])
+            seen = np.hstack([seen, np.full((len(ordered), grow), planner.ABSENT, dtype=np.int16)])
+        column = {symbol: k for k, symbol in enumerate(symbols)}
+        for i, composition in parsed_on_host.items():
+            for position, (element, count) in enumerate(composition.items()):
+                counts[i, column[element]] = count
+                seen[i, column[element]] = position
+        # keep the columns some molecule uses (+ the fold targets): the knowledge base lists ~60 elements, a library uses ~6
+        bare = {level_symbol[-1] for level_symbol in levels}
+        keep = [k for k in range(len(symbols)) if symbols[k] in bare or bool((seen[:, k] >= 0).any())]
+        symbols = [symbols[k] for k in keep]
+        counts, seen = np.ascontiguousarray(counts[:, keep]), np.ascontiguousarray(seen[:, keep])
+        formulas = planner.hill_formulas(counts, symbols)
+        self.lookup["molecule to formula"].update(zip(ordered, formulas))
+        to_molecule = self.lookup["formula to molecule"]
+        for molecule, formula in zip(ordered, formulas):
+            to_molecule.setdefault(formula, []).append(molecule)
+        if trivial_names is not None:
+            for molecule, formula in zip(ordered, formulas):
                 name = trivial_names.get(molecule, None)
                 if name is not None:
                     self.lookup["formula to trivial name"].setdefault(formula, []).append(name)
                 else:
                     print("No trivial name for molecule", molecule)
-            to_formula[molecule] = formula
-            to_molecule.setdefault(formula, []).append(molecule)
-            if formula not in self:
-                self[formula] = {"env": _LazyEnvelopes(self, formula, self.labled_percentiles), "cc": composition}
-            for element, count in composition.items():
-                if element not in known:
-                    # isotope-labelled element introduced by a modification (e.g. 13C of a SILAC/TMT unimod), IL:378-436
-                    found = _ISOTOPE_ELEMENT.match(element)
-                    try:
-                        enriched = int(round(float(found.group("isotope"))))
-                    except Exception:
-                        print("Failed on", element)
-                        print("Maybe element is not in pyqms.knowledge_base.py ?")
-                        raise SystemExit(1)
-                    template = found.group("element")
-                    target = levels.get("{0}{1}".format(enriched, template)) or 0.994
-                    if self.verbose:
-                        print("> Extending isotopic distribution that are within the modifications for "
-                              "element {0}{1}, enrichment levels set to {2}".format(enriched, template, target))
-                    known[element] = {self.zero_labeled_percentile: self._recalc_isotopic_distribution(
-                        element=template, target_percentile=target, enriched_isotope=enriched)}
-            for element, count in composition.items():
-                if element not in highest:
-                    highest[element] = 0
-                if highest[element] < count:
-                    highest[element] = count
-                has_two = two_isotopes.get(element)
-                if has_two is None:
-                    has_two = two_isotopes[element] = any(len(table) == 2 for table in known[element].values())
-                if has_two:
-                    if two_iso[0] is None or count < two_iso[0]:
-                        two_iso[0] = count
-                    if two_iso[1] is None or count > two_iso[1]:
-                        two_iso[1] = count
+        # one record per formula, taken from the first molecule (in sorted order) that has it
+        first_molecule = dict(zip(reversed(formulas), range(len(formulas) - 1, -1, -1)))
+        new = sorted((i, formula) for formula, i in first_molecule.items() if formula not in self)
+        rows = np.array([i for i, _ in new], dtype=np.int64)
+        self._symbols = symbols
+        self._cc_counts = np.ascontiguousarray(counts[rows]) if len(rows) else np.zeros((0, len(symbols)), dtype=np.int32)
+        self._cc_seen = np.ascontiguousarray(seen[rows]) if len(rows) else np.zeros((0, len(symbols)), dtype=np.int16)
+        dict.update(self, ((formula, _FormulaRecord(self, k, formula)) for k, (_, formula) in enumerate(new)))
+        # highest atom count per element (insertion order = first molecule, then position inside it) and the count range
+        # of the elements with two-isotope tables (IL:438-466)
+        present = seen >= 0
+        touched = np.flatnonzero(present.any(axis=0))
+        first_row = present[:, touched].argmax(axis=0)
+        appearance = sorted(zip(first_row.tolist(), seen[first_row, touched].tolist(), touched.tolist()))
+        two_iso = self._range_for_elements_with_two_isotopes
+        for _, _, k in appearance:
+            element, held = symbols[k], counts[present[:, k], k]
+            self._highest_element_count[element] = max(0, int(held.max()))
+            if any(len(table) == 2 for table in known[element].values()):
+                two_iso[0] = int(held.min()) if two_iso[0] is None else min(two_iso[0], int(held.min()))
+                two_iso[1] = int(held.max()) if two_iso[1] is None else max(two_iso[1], int(held.max()))
         # fold the isotope-labelled counts into their template element (IL:467-497)
         for element in list(self._highest_element_count):
             if element.isalpha():
@@ -450,6 +529,15 @@ class IsotopologueLibrary(dict):
             for table in self.isotopic_distributions[template].values():
                 if len(table) == 2 and self._highest_element_count[template] > two_iso[1]:
                     two_iso[1] = self._highest_element_count[template]
+
+    def _composition_of_formula(self, k):
+        """``lib[formula]["cc"]``: the formula's elements in the order they entered the first molecule's composition."""
+        composition = ChemicalComposition(aa_compositions=self.aa_compositions, isotopic_distributions=self.isotopic_distributions,
+                                          unimod_file_list=self.unimod_files, add_default_files=self._add_default_files)
+        row, seen = self._cc_counts[k], self._cc_seen[k]
+        for column in np.argsort(np.where(seen >= 0, seen, 32767), kind="stable")[:int((seen >= 0).sum())].tolist():
+            composition[self._symbols[column]] = int(row[column])
+        return composition
 
     # ------------------------------------------------------------------ host tables for the device build
     def _plan_device_tables(self):
@@ -478,40 +566,28 @@ class IsotopologueLibrary(dict):
                              np.array(iso_abun, dtype=np.float64), np.array(iso_q, dtype=np.int32),
                              np.array(max_level, dtype=np.int32))
         levels = self.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"]
-        labelled = self.metabolically_labeled_elements
+        symbols = self._symbols
+        column = {symbol: k for k, symbol in enumerate(symbols)}
         n_lp = len(self.labled_percentiles)
         self._formulas = list(self.keys())
         self._formula_index = {f: i for i, f in enumerate(self._formulas)}
         self._lp_index = {lp: i for i, lp in enumerate(self.labled_percentiles)}
-        term_off, term_pool, term_level = [0], [], []
-        pool_ids, default_label = self._pool_ids, self._default_label
-        for formula in self._formulas:
-            composition = self[formula]["cc"]
-            for lp in self.labled_percentiles:
-                merged = {}
-                for element, count in composition.items():
-                    target = element
-                    if element in levels:
-                        bare = element[-1]
-                        for lp_element, lp_label in lp:
-                            if lp_element == bare and lp_label == self._fmt(levels[element]):
-                                target = bare               # fixed-label isotope folds into the labelled pool (Q6)
-                    merged[target] = merged.get(target, 0) + count
-                for element, level in merged.items():
-                    if element in labelled:
-                        continue
-                    term_pool.append(pool_ids[(element, default_label[element])])
-                    term_level.append(level)
-                for element, label in lp:
-                    level = merged.get(element, 0)
-                    if level == 0:
-                        continue
-                    term_pool.append(pool_ids[(element, label)])
-                    term_level.append(level)
-                term_off.append(len(term_pool))
+        pool_of_default = np.array([self._pool_ids.get((s, self._default_label.get(s)), 0) for s in symbols], dtype=np.int32)
+        labelled = np.array([s in self.metabolically_labeled_elements for s in symbols], dtype=bool)
+        fold_target, pool_of_label = [], []
+        for lp in self.labled_percentiles:
+            target = list(range(len(symbols)))
+            for k, symbol in enumerate(symbols):
+                if symbol in levels:
+                    bare = symbol[-1]
+                    for lp_element, lp_label in lp:
+                        if lp_element == bare and lp_label == self._fmt(levels[symbol]) and bare in column:
+                            target[k] = column[bare]   # fixed-label isotope folds into the labelled pool (Q6)
+            fold_target.append(target)
+            pool_of_label.append([(column.get(element), self._pool_ids.get((element, label), 0)) for element, label in lp])
         self._n_env = len(self._formulas) * n_lp
-        self._terms = (np.array(term_off, dtype=np.int64), np.array(term_pool, dtype=np.int32),
-                       np.array(term_level, dtype=np.int32))
+        self._terms = planner.envelope_terms(self._cc_counts, self._cc_seen, symbols, self.labled_percentiles, fold_target,
+                                             labelled, pool_of_default, pool_of_label)
 
     # ------------------------------------------------------------------ device build
     def _build_on_device(self, distributed):

@@ -53,9 +53,9 @@ def test_saved_library_holds_the_plan_and_needs_a_gpu_to_load(tmp_path):
                                          _plan_only=True)
     lib.save(tmp_path / "plan.qmslib")
     blob = (tmp_path / "plan.qmslib").read_bytes()
-    restore, (state, compositions) = lib.__reduce__()
+    restore, (state, formulas) = lib.__reduce__()
     assert "_ctx" not in state and "_views" not in state and "_terms" in state and "_pool_tables" in state
-    assert [formula for formula, _ in compositions] == list(lib.keys())
+    assert formulas == list(lib.keys()) and len(state["_cc_counts"]) == len(formulas)
     if not torch.cuda.is_available():
         with pytest.raises(QmsError, match="no CPU fallback"):
             pickle.loads(blob)

@@ -1,0 +1,134 @@
+"""Native host planner (qms_parse_molecules / qms_hill_formulas) and the array-built term tables against the
+one-molecule-at-a-time host parser and a direct restatement of the reference's term loop (IL:546-646)."""
+import random
+
+import numpy as np
+import pytest
+
+import pyqms_b200
+from pyqms_b200 import knowledge_base, planner
+from pyqms_b200.chemistry import ChemicalComposition
+from pyqms_b200.synthetic import averagine_formulas, random_tryptic_peptides
+from tests.golden.cases import CASES
+
+SYMBOLS = list(knowledge_base.isotopic_distributions)
+
+
+def host_composition(molecule):
+    factory = ChemicalComposition(aa_compositions=knowledge_base.aa_compositions)
+    return factory.composition_of(molecule)
+
+
+def native_rows(molecules):
+    counts, seen, status = planner.parse_molecules(molecules, SYMBOLS, knowledge_base.aa_compositions)
+    rows = []
+    for i in range(len(molecules)):
+        order = [k for k in np.argsort(np.where(seen[i] >= 0, seen[i], 32767), kind="stable") if seen[i, k] >= 0]
+        rows.append([(SYMBOLS[k], int(counts[i, k])) for k in order])
+    return rows, status, counts
+
+
+HANDLED = ["+H2O", "+C104H175N29O33S1", "+C(2)H(3)N(1)O(1)", "+C13C6", "+C2 H6 O", "+C(12)H(-2)O(3)H(2)", "+H2OH(-2)O(-1)C",
+           "PEPTIDEK", "PEPTIDEK+PO3", "A", "CCTESLVNR", "ACDEFGHIKLMNPQRSTVWY", "+Se2C3", "+NaCl"]
+LEFT_TO_HOST = ["PEPTIDEK#Oxidation:3", "PEPTIDEK0", "pEPTIDE", "PEPTIDE+H2O+H2O", "+C(-6)13C(6)", "+Xx2", "+C(2", "+c2", "",
+                "PEPTIDEB", "PEP TIDE", "+C6H12O6+", "+(2)"]
+
+
+def test_native_parser_equals_host_parser_on_handled_syntax():
+    rows, status, counts = native_rows(HANDLED)
+    assert status.tolist() == [0] * len(HANDLED)
+    for molecule, row in zip(HANDLED, rows):
+        assert row == list(host_composition(molecule).items()), molecule
+    formulas = planner.hill_formulas(counts, SYMBOLS)
+    assert formulas == [host_composition(m).hill_notation_unimod() for m in HANDLED]
+
+
+def test_native_parser_hands_everything_else_to_the_host():
+    rows, status, counts = native_rows(LEFT_TO_HOST)
+    assert status.tolist() == [1] * len(LEFT_TO_HOST)
+    assert not counts.any() and all(row == [] for row in rows)
+
+
+def test_native_parser_on_random_molecules():
+    rng = random.Random(5)
+    molecules = averagine_formulas(3000)[::3] + random_tryptic_peptides(1500, seed=3)
+    elements = ["C", "H", "N", "O", "S", "P", "Se", "Na", "Cl", "Fe"]
+    for _ in range(1500):           # shuffled element order, repeated elements, bracketed and negative counts
+        parts = []
+        for element in rng.choices(elements, k=rng.randint(1, 7)):
+            n = rng.randint(-3, 40)
+            parts.append("%s(%d)" % (element, n) if rng.random() < 0.5 or n < 1 else "%s%s" % (element, n if n > 1 else ""))
+        molecules.append("+" + "".join(parts))
+    rows, status, counts = native_rows(molecules)
+    assert not status.any()
+    for molecule, row in zip(molecules, rows):
+        assert row == list(host_composition(molecule).items()), molecule
+    assert planner.hill_formulas(counts, SYMBOLS) == [host_composition(m).hill_notation_unimod() for m in molecules]
+
+
+def reference_term_loop(lib):
+    """The per-formula, per-label-tuple loop the array code replaces (IL:546-646), on lib[formula]["cc"]."""
+    levels = lib.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"]
+    off, pool, level = [0], [], []
+    for formula in lib._formulas:
+        composition = lib[formula]["cc"]
+        for lp in lib.labled_percentiles:
+            merged = {}
+            for element, count in composition.items():
+                target = element
+                if element in levels:
+                    bare = element[-1]
+                    for lp_element, lp_label in lp:
+                        if lp_element == bare and lp_label == lib._fmt(levels[element]):
+                            target = bare
+                merged[target] = merged.get(target, 0) + count
+            for element, n in merged.items():
+                if element in lib.metabolically_labeled_elements:
+                    continue
+                pool.append(lib._pool_ids[(element, lib._default_label[element])])
+                level.append(n)
+            for element, label in lp:
+                n = merged.get(element, 0)
+                if n == 0:
+                    continue
+                pool.append(lib._pool_ids[(element, label)])
+                level.append(n)
+            off.append(len(pool))
+    return off, pool, level
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_bulk_planning_equals_one_by_one_planning(name):
+    kwargs = dict(CASES[name]["lib"])
+    native = pyqms_b200.IsotopologueLibrary(verbose=False, _plan_only=True, **kwargs)
+    by_hand = pyqms_b200.IsotopologueLibrary(verbose=False, _plan_only=True, _native_planner=False, **kwargs)
+    assert native._formulas == by_hand._formulas and native._symbols == by_hand._symbols
+    assert native.lookup == by_hand.lookup
+    assert list(native._highest_element_count.items()) == list(by_hand._highest_element_count.items())
+    assert native._range_for_elements_with_two_isotopes == by_hand._range_for_elements_with_two_isotopes
+    assert native._pools == by_hand._pools
+    for a, b in zip(native._pool_tables + native._terms, by_hand._pool_tables + by_hand._terms):
+        assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+    for formula in native._formulas:
+        assert list(native[formula]["cc"].items()) == list(by_hand[formula]["cc"].items())
+        assert set(native[formula]) == {"env", "cc"} and "cc" in native[formula] and len(native[formula]) == 2
+    off, pool, level = reference_term_loop(native)
+    assert native._terms[0].tolist() == off and native._terms[1].tolist() == pool and native._terms[2].tolist() == level
+    assert native._n_env == len(off) - 1
+
+
+def test_term_tables_of_a_mixed_library_with_folding():
+    """Fixed-label isotopes that fold into a labelled element (Q6), modifications, formulas and peptides together."""
+    molecules = random_tryptic_peptides(300, seed=9) + averagine_formulas(300)[::5] + [
+        "PEPTIDEK#Oxidation:1", "CCTESLVNR#Carbamidomethyl:1;Carbamidomethyl:2", "+C(-6)13C(6)H(12)O(6)", "ELVISLIVESK#Label:13C(6)15N(2):11",
+        "+C(5)15N(2)N(1)H(9)O(2)"]
+    kwargs = dict(molecules=molecules, charges=[2], metabolic_labels={"15N": [0, 0.5, 0.994], "13C": [0, 0.994]},
+                  fixed_labels={"C": ["C(2)H(3)14N(1)O(1)"]}, verbose=False, _plan_only=True)
+    native = pyqms_b200.IsotopologueLibrary(**kwargs)
+    by_hand = pyqms_b200.IsotopologueLibrary(_native_planner=False, **kwargs)
+    assert native._formulas == by_hand._formulas
+    for a, b in zip(native._pool_tables + native._terms, by_hand._pool_tables + by_hand._terms):
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+    off, pool, level = reference_term_loop(native)
+    assert native._terms[0].tolist() == off and native._terms[1].tolist() == pool and native._terms[2].tolist() == level
+    assert len(native.labled_percentiles) == 6 and native._n_env == 6 * len(native._formulas)
