@@ -612,9 +612,13 @@ class IsotopologueLibrary(dict):
             ctx.call("qms_build_envelopes", 0, self._n_env)
         # ranks of (label tuple, formula) under Python ordering: tie-break of the index sort (IL:836-867)
         n_lp = len(self.labled_percentiles)
-        order = sorted(range(self._n_env), key=lambda e: (self.labled_percentiles[e % n_lp], self._formulas[e // n_lp]))
-        rank = np.empty(self._n_env, dtype=np.int64)
-        rank[np.array(order, dtype=np.int64)] = np.arange(self._n_env, dtype=np.int64)
+        n_formulas = len(self._formulas)
+        formula_rank = np.empty(n_formulas, dtype=np.int64)
+        formula_rank[sorted(range(n_formulas), key=self._formulas.__getitem__)] = np.arange(n_formulas, dtype=np.int64)
+        lp_rank = np.empty(n_lp, dtype=np.int64)
+        lp_rank[sorted(range(n_lp), key=self.labled_percentiles.__getitem__)] = np.arange(n_lp, dtype=np.int64)
+        # envelope e = formula * n_lp + label tuple; both key parts are unique, so the pair order is lexicographic
+        rank = (lp_rank[None, :] * n_formulas + formula_rank[:, None]).reshape(-1)
         charges = np.array(self.charges, dtype=np.int32)
         ctx.call("qms_finalize_index", len(charges), ptr(charges), ptr(rank))
         info = QmsIndexInfo()
