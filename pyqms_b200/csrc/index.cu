@@ -209,6 +209,7 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
     ctx->n_charges = n_charges;
     ctx->h_charges.assign(charges, charges + n_charges);
     ctx->have_index = false;
+    qms_trace(ctx, "index: enter");
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     QMS_TRY(qms_upload(ctx, ctx->charges, charges, (size_t)n_charges));
     const size_t plane = (size_t)n_slots * n_charges + 1;
@@ -221,6 +222,7 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
             P.rel_mz_range, P.internal_precision, ctx->pl_mz.p, ctx->pl_lo.p, ctx->pl_hi.p);
         ctx->cnt.kernel_launches++;
     }
+    qms_trace(ctx, "index: charge planes");
     // ---- admission + sort of (envelope, charge) candidates ----
     const int64_t n_cand = n_env * n_charges;
     const size_t nc1 = (size_t)n_cand + 1;
@@ -248,6 +250,7 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         n_entries = (int64_t)ctx->h_pinned[0];
     }
+    qms_trace(ctx, "index: admission + 3-key sort");
     if (n_entries > 0x7fffffffll)
         return qms_fail(ctx, QMS_E_LIMIT, "%lld index entries exceed the int32 entry id space", (long long)n_entries);
     ctx->n_entries = n_entries;
@@ -302,6 +305,7 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
                                                                                   ctx->bin_upper.p);
         ctx->cnt.kernel_launches++;
     }
+    qms_trace(ctx, "index: entry rows, window offsets, bins");
     // ---- entry-major windows + probe tables ----
     const int64_t n_win = ctx->n_windows;
     const size_t nw1 = (size_t)n_win + 1;
@@ -330,6 +334,7 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         QMS_CUDA(ctx, cudaMemcpyAsync(h_stats, stats.b.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         QMS_CUDA(ctx, cudaMemcpyAsync(&first_lo, lo_sorted.b.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        qms_trace(ctx, "index: windows + probe records");
         ctx->t_min = first_lo;
         ctx->t_max = h_stats[0];
         ctx->max_width = h_stats[1];
@@ -355,6 +360,7 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->window_density = ctx->h_pinned[0] ? (double)width_sum / (double)ctx->h_pinned[0] : 0.0;
     }
+    qms_trace(ctx, "index: cell table + cover bitmaps");
     QMS_CUDA(ctx, cudaGetLastError());
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

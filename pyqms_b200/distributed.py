@@ -8,14 +8,16 @@
   data-path collective; rank 0 may gather the packed hits in rank order = spectrum order.
 """
 import ctypes as C
+import sys
 
 import numpy as np
 
 
 def _dist():
-    try:
-        import torch.distributed as dist
-    except Exception:       # torch missing: single process
+    # a process group can only exist if the caller imported torch.distributed; importing torch here would add
+    # seconds to a single-process library build for nothing
+    dist = sys.modules.get("torch.distributed")
+    if dist is None:
         return None
     return dist if dist.is_available() and dist.is_initialized() else None
 
