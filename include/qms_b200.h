@@ -214,6 +214,12 @@ int qms_score_matches(qms_ctx* ctx, int32_t n, const double* mmz, const double* 
                       const double* cmz, const double* ci, double mz_score_percentile, double* score,
                       double* scaling);
 
+/* FP64 roofline of the device the context is bound to, measured with dependency-chain kernels at full
+ * occupancy: fused = DFMA chains (2 flop per instruction), unfused = the DMUL+DADD pairs the envelope
+ * arithmetic is restricted to (no FMA, for parity with IL:518-775).  TFLOP/s; the denominators for the
+ * envelope kernel's roofline fraction. */
+int qms_measure_fp64_peak(qms_ctx* ctx, double* fused_tflops, double* unfused_tflops);
+
 /* ---- host-side planner (no GPU work, ctx-free) ----------------------------------------------------
  * Replaces the per-molecule string loop in front of the build (IL:314-347: one chemical_composition call per
  * molecule) for plain formulas ("+C104H175N29O33S1", "+C(-6)13C(6)") and unmodified peptides ("PEPTIDEK",

@@ -80,6 +80,7 @@ EXPORTS = {  # name -> (restype, argtypes); must list every symbol of include/qm
                                   C.POINTER(QmsHits), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "qms_transform_mz": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qms_calc_amounts": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 8),
+    "qms_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qms_parse_molecules": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.c_char_p, C.c_void_p, C.c_int32,
                                       C.c_char_p] + [C.c_void_p] * 6),
     "qms_hill_formulas": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64,

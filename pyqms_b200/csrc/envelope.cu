@@ -317,3 +317,49 @@ extern "C" int qms_export_envelopes(qms_ctx* ctx, double* mass, double* relabun,
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return QMS_OK;
 }
+
+// ---- FP64 roofline of this box: the denominator for the envelope kernel ----------------
+// Eight independent dependency chains per thread, full occupancy: FUSED issues DFMA (2 flop per instruction), the
+// other variant the DMUL + DADD pair the envelope arithmetic is restricted to (-fmad=false for parity).
+template <bool FUSED>
+__global__ void __launch_bounds__(256) fp64_chain_kernel(double* __restrict__ out, int iterations, double x, double y) {
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 1.0 + 1e-3 * (double)(threadIdx.x + k);
+    for (int i = 0; i < iterations; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = FUSED ? fma(acc[k], x, y) : __dadd_rn(__dmul_rn(acc[k], x), y);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += acc[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+extern "C" int qms_measure_fp64_peak(qms_ctx* ctx, double* fused_tflops, double* unfused_tflops) {
+    if (!ctx || !fused_tflops || !unfused_tflops) return qms_fail(ctx, QMS_E_ARG, "qms_measure_fp64_peak: NULL argument");
+    QMS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iterations = 4096;
+    TmpBuf<double> sink(ctx);
+    QMS_TRY(qms_reserve(ctx, sink.b, (size_t)blocks * threads));
+    const double flops = (double)blocks * threads * iterations * 8.0 * 2.0;
+    double* results[2] = {fused_tflops, unfused_tflops};
+    for (int variant = 0; variant < 2; ++variant) {
+        float best = 0.f;
+        for (int run = 0; run < 4; ++run) {       // first run warms up, best of the next three
+            QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+            if (variant == 0)
+                fp64_chain_kernel<true><<<blocks, threads, 0, ctx->stream>>>(sink.b.p, iterations, 1.0000001, 1e-9);
+            else
+                fp64_chain_kernel<false><<<blocks, threads, 0, ctx->stream>>>(sink.b.p, iterations, 1.0000001, 1e-9);
+            QMS_CUDA(ctx, cudaGetLastError());
+            QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+            QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+            if (run > 0 && (best == 0.f || ms < best)) best = ms;
+        }
+        *results[variant] = flops / (best * 1e-3) / 1e12;
+    }
+    return QMS_OK;
+}
