@@ -111,14 +111,42 @@ __device__ __forceinline__ int64_t spectrum_of(const int64_t* __restrict__ offse
     return a;
 }
 
-// Is bucket t inside any window of the entry?  Windows normally ascend with the isotope position
-// (monotone = true: advance a cursor), otherwise all windows are scanned.
-__device__ __forceinline__ bool in_any_window(const int32_t* __restrict__ wlo, const int32_t* __restrict__ whi, int nc, int32_t t,
-                                              bool monotone, int& cursor) {
-    if (monotone) {
-        while (cursor < nc && __ldg(&whi[cursor]) < t) ++cursor;
-        return cursor < nc && __ldg(&wlo[cursor]) <= t;
+// Window of an entry under a cursor, bounds kept in registers.  Windows normally ascend with the isotope position
+// (lo and hi both non-decreasing: "monotone"); then a bucket sequence that ascends (descends) is tested against the
+// union of the windows by a cursor that only moves up (down): the first window with hi >= t has the smallest lo of
+// all windows that can still hold t (the last window with lo <= t the largest hi).
+struct WindowCursor {
+    int m;
+    int32_t lo, hi;
+    __device__ __forceinline__ void load_up(const int32_t* __restrict__ wlo, const int32_t* __restrict__ whi, int nc) {
+        const bool inside = m < nc;
+        lo = inside ? __ldg(&wlo[m]) : INT32_MAX;        // past the last window: nothing matches, the cursor stops
+        hi = inside ? __ldg(&whi[m]) : INT32_MAX;
     }
+    __device__ __forceinline__ void load_down(const int32_t* __restrict__ wlo, const int32_t* __restrict__ whi) {
+        const bool inside = m >= 0;
+        lo = inside ? __ldg(&wlo[m]) : INT32_MIN;
+        hi = inside ? __ldg(&whi[m]) : INT32_MIN;
+    }
+    // buckets arrive in ascending order
+    __device__ __forceinline__ bool holds_ascending(const int32_t* __restrict__ wlo, const int32_t* __restrict__ whi, int nc, int32_t t) {
+        while (hi < t) {
+            ++m;
+            load_up(wlo, whi, nc);
+        }
+        return lo <= t;
+    }
+    // buckets arrive in descending order
+    __device__ __forceinline__ bool holds_descending(const int32_t* __restrict__ wlo, const int32_t* __restrict__ whi, int32_t t) {
+        while (lo > t) {
+            --m;
+            load_down(wlo, whi);
+        }
+        return t <= hi;
+    }
+};
+
+__device__ __forceinline__ bool in_any_window_scan(const int32_t* __restrict__ wlo, const int32_t* __restrict__ whi, int nc, int32_t t) {
     for (int m = 0; m < nc; ++m)
         if (__ldg(&wlo[m]) <= t && t <= __ldg(&whi[m])) return true;
     return false;
@@ -130,17 +158,19 @@ __device__ __forceinline__ bool in_any_window(const int32_t* __restrict__ wlo, c
 //
 // An entry's windows span a few Da while a spectrum holds ~0.5 rows per Da, so instead of searching
 // the spectrum once per window the rows next to row i are walked (adjacent 16-byte rows, same cache
-// lines) and each is tested against the entry's window list (two short contiguous int arrays).
+// lines, the next row's load issued before the current one is tested) and merged with the window list.
 __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64_t i, int32_t t, int32_t x, int32_t k) {
     int64_t ca, cb;
     entry_clamp(v, sb, se, x, ca, cb);
     if (i < ca || i >= cb) return false;
-    const int32_t t_before = i > ca ? tmz_at(v.peaks, i - 1, v.precision) : INT32_MIN;
-    if (t_before == t) return false;                      // not the first row of its bucket (IL:2014)
+    double x_back = i > ca ? __ldg(&v.peaks[i - 1].x) : 0.0;
+    double x_next = i + 1 < cb ? __ldg(&v.peaks[i + 1].x) : 0.0;
     const int64_t w0 = __ldg(&v.ent_win_off[x]);
     const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
     const int32_t* wlo = v.win_lo + w0;
     const int32_t* whi = v.win_hi + w0;
+    const int32_t t_before = i > ca ? qms_tmz(x_back, v.precision) : INT32_MIN;
+    if (t_before == t) return false;                      // not the first row of its bucket (IL:2014)
     int32_t lo_min = INT32_MAX, hi_max = INT32_MIN, prev_lo = INT32_MIN, prev_hi = INT32_MIN;
     bool monotone = true;
     for (int m = 0; m < nc; ++m) {
@@ -155,29 +185,35 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
     // no earlier bucket may lie inside the union of the windows
     {
         int32_t last = t;
+        WindowCursor down{nc - 1, 0, 0};
+        down.load_down(wlo, whi);
         for (int64_t j = i - 1; j >= ca; --j) {
-            const int32_t tj = tmz_at(v.peaks, j, v.precision);
+            const int32_t tj = qms_tmz(x_back, v.precision);
+            if (j > ca) x_back = __ldg(&v.peaks[j - 1].x);
             if (tj < lo_min) break;
             if (tj == last) continue;
             last = tj;
-            int cursor = 0;
-            if (in_any_window(wlo, whi, nc, tj, monotone, cursor)) return false;
+            if (monotone ? down.holds_descending(wlo, whi, tj) : in_any_window_scan(wlo, whi, nc, tj)) return false;
         }
     }
-    // distinct buckets inside the union of the windows (Q10), walking forward from row i
+    // distinct buckets inside the union of the windows (Q10), walking forward from row i.  The pair passes with
+    // `need` buckets: the smallest count c with c >= min_match and not (c / n_c < required overlap), IL:1973-1976
+    int need = v.min_match > 1 ? v.min_match : 1;
+    while ((double)need / (double)nc < v.req_overlap) ++need;
     int cnt = 1;
-    if (cnt >= v.min_match && !((double)cnt / (double)nc < v.req_overlap)) return true;
+    if (cnt >= need) return true;
     int32_t last = t;
-    int cursor = k;
-    if (!monotone) cursor = 0;
+    WindowCursor up{monotone ? k : 0, 0, 0};
+    up.load_up(wlo, whi, nc);
     for (int64_t j = i + 1; j < cb; ++j) {
-        const int32_t tj = tmz_at(v.peaks, j, v.precision);
+        const int32_t tj = qms_tmz(x_next, v.precision);
+        if (j + 1 < cb) x_next = __ldg(&v.peaks[j + 1].x);
         if (tj > hi_max) break;
         if (tj == last) continue;
         last = tj;
-        if (in_any_window(wlo, whi, nc, tj, monotone, cursor)) {
+        if (monotone ? up.holds_ascending(wlo, whi, nc, tj) : in_any_window_scan(wlo, whi, nc, tj)) {
             ++cnt;
-            if (cnt >= v.min_match && !((double)cnt / (double)nc < v.req_overlap)) return true;   // IL:1973-1976
+            if (cnt >= need) return true;
         }
     }
     return false;
