@@ -665,23 +665,40 @@ __device__ void score_pair(const MatchView& v, int64_t p, const unsigned long lo
     int64_t* best = nc <= K6_LOCAL ? l_best : scr_best + p * max_nc;
     const int32_t* wlo = v.win_lo + w0;
     const int32_t* whi = v.win_hi + w0;
-    int32_t hi_max = INT32_MIN;
+    int32_t hi_max = INT32_MIN, prev_lo = INT32_MIN, prev_hi = INT32_MIN;
+    bool monotone = true;
     for (int m = 0; m < nc; ++m) {
         first[m] = -1;
-        const int32_t hi = __ldg(&whi[m]);
+        const int32_t lo = __ldg(&wlo[m]), hi = __ldg(&whi[m]);
+        monotone = monotone && lo >= prev_lo && hi >= prev_hi;
+        prev_lo = lo;
+        prev_hi = hi;
         hi_max = hi > hi_max ? hi : hi_max;
     }
     // candidates of window m = distinct buckets in [lo, hi] (IL:2001-2002): walk the rows from the canonical
-    // row (no bucket of any window lies before it) and record the first row of every window
+    // row (no bucket of any window lies before it) and record the first row of every window.  With ascending
+    // windows the ones that hold a bucket are the run starting at the first window with hi >= bucket.
     {
         int32_t last = INT32_MIN;
+        WindowCursor up{0, 0, 0};
+        up.load_up(wlo, whi, nc);
+        double x_next = row0 < cb ? __ldg(&v.peaks[row0].x) : 0.0;
         for (int64_t j = row0; j < cb; ++j) {
-            const int32_t tj = tmz_at(v.peaks, j, v.precision);
+            const int32_t tj = qms_tmz(x_next, v.precision);
+            if (j + 1 < cb) x_next = __ldg(&v.peaks[j + 1].x);
             if (tj > hi_max) break;
             if (tj == last) continue;
             last = tj;
-            for (int m = 0; m < nc; ++m)
-                if (first[m] < 0 && __ldg(&wlo[m]) <= tj && tj <= __ldg(&whi[m])) first[m] = j;
+            if (monotone) {
+                if (!up.holds_ascending(wlo, whi, nc, tj)) continue;
+                for (int m = up.m; m < nc; ++m) {
+                    if (m > up.m && __ldg(&wlo[m]) > tj) break;
+                    if (first[m] < 0) first[m] = j;
+                }
+            } else {
+                for (int m = 0; m < nc; ++m)
+                    if (first[m] < 0 && __ldg(&wlo[m]) <= tj && tj <= __ldg(&whi[m])) first[m] = j;
+            }
         }
     }
     int n_matched = 0;
@@ -856,14 +873,8 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
                                                              double* __restrict__ pair_score, double* __restrict__ pair_scaling,
                                                              int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters,
                                                              int64_t* __restrict__ heavy_list, int heavy_min) {
-    // statistics go through shared memory: one global atomic per CTA instead of one per pair (12 M same-address
-    // atomics cost more than the scoring itself on the dense libraries)
-    __shared__ unsigned long long s_combos, s_windows;
-    if (threadIdx.x == 0) {
-        s_combos = 0;
-        s_windows = 0;
-    }
-    __syncthreads();
+    // statistics: one global atomic per warp (one per pair cost more than the scoring itself on the dense libraries;
+    // a per-CTA sum needs a barrier, and finished warps parked at it were 23 % of the kernel's stall samples)
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long combos = 0;
     int windows = 0;
@@ -876,13 +887,8 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
         w += __shfl_xor_sync(0xffffffffu, w, sft);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (combos) atomicAdd(&s_combos, combos);
-        if (w) atomicAdd(&s_windows, w);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_combos) atomicAdd(&counters[C_COMBOS], s_combos);
-        if (s_windows) atomicAdd(&counters[C_PAIR_WINDOWS], s_windows);
+        if (combos) atomicAdd(&counters[C_COMBOS], combos);
+        if (w) atomicAdd(&counters[C_PAIR_WINDOWS], w);
     }
 }
 
