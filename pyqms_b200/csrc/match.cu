@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
 struct HeavyTables {
     int64_t row[K6_LOCAL][K6B_CANDS];
     double mmz[K6_LOCAL][K6B_CANDS], mi[K6_LOCAL][K6B_CANDS], p[K6_LOCAL][K6B_CANDS], mz_term[K6_LOCAL][K6B_CANDS];
-    double ri[K6_LOCAL], ci[K6_LOCAL];
+    double ri[K6_LOCAL], ci[K6_LOCAL], span[K6_LOCAL];     // span = (1 + REL_I_RANGE) - ri, the intensity tolerance of a window
     int count[K6_LOCAL];
 };
 
@@ -953,6 +953,7 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
             const double ri = __ldg(&v.win_ri[w0 + m]), cmz = __ldg(&v.win_cmz[w0 + m]);
             T.ri[m] = ri;
             T.ci[m] = (double)__ldg(&v.win_ci[w0 + m]);
+            T.span[m] = __dsub_rn(one_plus_reli, ri);
             int count = 0;
             int32_t last = INT32_MIN;
             for (int64_t j = row0; j < cb && count < K6B_CANDS; ++j) {
@@ -997,14 +998,29 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
         double b_score = 0.0, b_scaling = 0.0;
         unsigned long long b_digits = 0;
         bool have = false;
-        for (unsigned long long k = lane; k < total; k += 32) {
-            unsigned long long rest = k, digits = 0;
-            for (int m = nc - 1; m >= 0; --m) {            // last window fastest
+        // combination k in mixed radix, one 4-bit digit per window (last window fastest, like the odometer of K6).
+        // A lane visits k = lane, lane + 32, ...: the digits of its first k come from divisions, every further k
+        // from adding the digits of 32 with carry (a 64-bit division per window and combination was 21 % of the
+        // kernel's instructions).
+        unsigned long long digits = 0, stride = 0;
+        auto to_digits = [&](auto value) {                  // mixed-radix digits of `value` (32-bit arithmetic when it fits)
+            unsigned long long packed = 0;
+            for (int m = nc - 1; m >= 0; --m) {
                 const int c = T.count[m];
                 if (c <= 0) continue;
-                digits |= (rest % (unsigned long long)c) << (4 * m);
-                rest /= (unsigned long long)c;
+                packed |= (unsigned long long)(value % (decltype(value))c) << (4 * m);
+                value /= (decltype(value))c;
             }
+            return packed;
+        };
+        if (total <= 0xffffffffull) {
+            digits = to_digits((unsigned int)lane);
+            if (total > 32) stride = to_digits(32u);
+        } else {
+            digits = to_digits((unsigned long long)lane);
+            stride = to_digits(32ull);
+        }
+        for (unsigned long long k = lane; k < total; k += 32) {
             double measured = 0.0;
             for (int m = 0; m < nc; ++m)
                 if (T.count[m] > 0) measured = __dadd_rn(measured, T.p[m][(digits >> (4 * m)) & 15ull]);
@@ -1017,7 +1033,7 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
                 const double si = __dmul_rn(T.ci[m], scaling);
                 if (si > QMS_DBL_EPS) {
                     const double err = __ddiv_rn(fabs(__dsub_rn(T.mi[m][d], si)), si);
-                    const double span = __dsub_rn(one_plus_reli, T.ri[m]);
+                    const double span = T.span[m];
                     const double local = err > span ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, span));
                     term = __dmul_rn(local, T.ri[m]);
                 }
@@ -1032,6 +1048,19 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
                 b_score = score;
                 b_scaling = scaling;
                 b_digits = digits;
+            }
+            if (k + 32 < total) {                            // digits += stride, least significant (last) window first
+                unsigned long long next = 0;
+                int carry = 0;
+                for (int m = nc - 1; m >= 0; --m) {
+                    const int c = T.count[m];
+                    if (c <= 0) continue;
+                    int d = (int)((digits >> (4 * m)) & 15ull) + (int)((stride >> (4 * m)) & 15ull) + carry;
+                    carry = d >= c;
+                    if (carry) d -= c;
+                    next |= (unsigned long long)d << (4 * m);
+                }
+                digits = next;
             }
         }
         // best across the warp (lanes without a combination carry have = false)
