@@ -119,7 +119,7 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     REL(win_lo); REL(win_hi); REL(win_ci); REL(win_cmz); REL(win_ri); REL(probe); REL(cell_start); REL(cover);
     REL(d_peaks); REL(d_offsets); REL(pair_keys); REL(pair_keys_alt); REL(cub_tmp); REL(dev_counters);
     REL(pair_score); REL(pair_scaling); REL(pair_flag); REL(pair_win_off); REL(pair_best);
-    REL(blk_hits); REL(blk_wins); REL(live_rows); REL(live_count); REL(live_prefix); REL(pair_vals); REL(pair_vals_alt);
+    REL(blk_hits); REL(blk_wins); REL(live_rows); REL(live_count); REL(live_prefix); REL(need_of_nc); REL(pair_vals); REL(pair_vals_alt);
     REL(pair_nc); REL(scr_first); REL(scr_cur); REL(scr_best); REL(heavy_list); REL(tile_spec);
     REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak);
 #undef REL
@@ -146,6 +146,7 @@ int qms_set_params(qms_ctx* ctx, const qms_params* p) {
     if (p->max_molecules_per_bin < 1) return qms_fail(ctx, QMS_E_PARAM, "MAX_MOLECULES_PER_MATCH_BIN must be >= 1");
     ctx->prm = *p;
     ctx->have_params = true;
+    ctx->need_dirty = true;
     return QMS_OK;
 }
 

@@ -294,6 +294,7 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         QMS_CUDA(ctx, cudaMemcpyAsync(&h_max_nc, d_max_nc.b.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->max_nc = (int32_t)h_max_nc;
+        ctx->need_dirty = true;
         ctx->n_windows = (int64_t)ctx->h_pinned[0];
         ctx->mz_min = range[0];   // entries are sorted by lower m/z (IL:923-931)
         ctx->mz_max = range[1];   // IL:932-939

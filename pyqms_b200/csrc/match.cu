@@ -55,6 +55,7 @@ struct MatchView {
     int only_entry;        // >= 0: match_isotopologue mode (one entry, no score thresholds)
     double precision, mz_min, mz_max;
     int min_match;
+    const int32_t* need_of_nc;   // buckets an entry with n_c windows needs inside them to pass both overlap gates
     double req_overlap, min_rel, rel_mz, rel_i, xi, score_thr;
 };
 
@@ -173,6 +174,7 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
     if (t_before == t) return false;                      // not the first row of its bucket (IL:2014)
     int32_t lo_min = INT32_MAX, hi_max = INT32_MIN, prev_lo = INT32_MIN, prev_hi = INT32_MIN;
     bool monotone = true;
+    WindowCursor down{-1, INT32_MIN, INT32_MIN};          // ends up on the last window that starts at or below t
     for (int m = 0; m < nc; ++m) {
         const int32_t lo = __ldg(&wlo[m]), hi = __ldg(&whi[m]);
         if (m < k && lo <= t && t <= hi) return false;    // a lower window also holds t: that incidence owns the pair
@@ -181,12 +183,11 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
         prev_hi = hi;
         lo_min = lo < lo_min ? lo : lo_min;
         hi_max = hi > hi_max ? hi : hi_max;
+        if (lo <= t) down = WindowCursor{m, lo, hi};
     }
     // no earlier bucket may lie inside the union of the windows
     {
         int32_t last = t;
-        WindowCursor down{nc - 1, 0, 0};
-        down.load_down(wlo, whi);
         for (int64_t j = i - 1; j >= ca; --j) {
             const int32_t tj = qms_tmz(x_back, v.precision);
             if (j > ca) x_back = __ldg(&v.peaks[j - 1].x);
@@ -198,8 +199,8 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
     }
     // distinct buckets inside the union of the windows (Q10), walking forward from row i.  The pair passes with
     // `need` buckets: the smallest count c with c >= min_match and not (c / n_c < required overlap), IL:1973-1976
-    int need = v.min_match > 1 ? v.min_match : 1;
-    while ((double)need / (double)nc < v.req_overlap) ++need;
+    // (a function of n_c only, tabulated per library)
+    const int need = __ldg(&v.need_of_nc[nc]);
     int cnt = 1;
     if (cnt >= need) return true;
     int32_t last = t;
@@ -1220,6 +1221,32 @@ static float elapsed(qms_ctx* ctx, int a, int b) {
     return ms;
 }
 
+// need_of_nc[n_c]: smallest bucket count c >= max(1, MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES) for which
+// c / n_c < REQUIRED_PERCENTILE_PEAK_OVERLAP is false, with the reference's double division (IL:1973-1976).
+static int overlap_need_table(qms_ctx* ctx) {
+    const qms_params& P = ctx->prm;
+    const int top = ctx->max_nc > 0 ? ctx->max_nc : 1;
+    if (!ctx->need_dirty && (int)ctx->h_need.size() == top + 1) return QMS_OK;
+    ctx->h_need.assign((size_t)top + 1, 1);
+    const int floor_need = P.min_matched_isotopologues > 1 ? P.min_matched_isotopologues : 1;
+    for (int nc = 1; nc <= top; ++nc) {
+        const double real_need = P.required_peak_overlap * (double)nc;
+        int need = floor_need;
+        if (real_need >= 2.0e9) {
+            need = INT32_MAX;                              // no spectrum holds that many buckets
+        } else {
+            if (real_need - 2.0 > (double)need) need = (int)(real_need - 2.0);     // the predicate is certainly false below
+            while ((double)need / (double)nc < P.required_peak_overlap) ++need;
+        }
+        ctx->h_need[nc] = need;
+    }
+    ctx->h_need[0] = floor_need;
+    QMS_TRY(qms_upload(ctx, ctx->need_of_nc, ctx->h_need.data(), ctx->h_need.size()));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->need_dirty = false;
+    return QMS_OK;
+}
+
 static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra, int32_t input_kind,
                       double mz_score_percentile, int32_t only_entry, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
     if (!ctx || !offsets || n_spectra < 0 || !n_hits || !n_hit_windows)
@@ -1305,6 +1332,8 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     v.mz_min = ctx->mz_min;
     v.mz_max = ctx->mz_max;
     v.min_match = P.min_matched_isotopologues;
+    QMS_TRY(overlap_need_table(ctx));
+    v.need_of_nc = ctx->need_of_nc.p;
     v.req_overlap = P.required_peak_overlap;
     v.min_rel = P.min_rel_peak_intensity;
     v.rel_mz = P.rel_mz_range;

@@ -106,6 +106,9 @@ struct qms_ctx {
     DBuf<int64_t> pair_nc, scr_first, scr_cur, scr_best, heavy_list;
     DBuf<int32_t> tile_spec;
     int32_t max_nc = 0;            // most c-peak windows of any index entry
+    DBuf<int32_t> need_of_nc;      // per window count: buckets needed to pass the overlap gates (params x library)
+    std::vector<int32_t> h_need;
+    bool need_dirty = true;
     double window_density = 0.0;   // sum of window widths / covered grid cells = windows over an average covered cell
     int64_t pair_cap_hint = 0;     // capacity of the pair list, learned from the previous batch (+25 %)
     int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
