@@ -471,3 +471,29 @@ def test_packed_table_equals_format_all_results():
     n_matched = {(r.spec_id, r.formula, r.charge, r.label_percentiles): sum(p[0] is not None for p in r.peaks) for r in full.itertuples()}
     for r in table.itertuples():
         assert n_matched[(r.spec_id, r.formula, r.charge, r.label_percentiles)] == r.n_matched_peaks <= r.n_peaks
+
+
+@pytest.mark.parametrize("min_matched,overlap", [(1, 0.0), (1, 1.0), (2, 0.5), (3, 0.34), (4, 0.75), (2, 1.5), (7, 0.1)])
+def test_overlap_gates_follow_the_params(pyqms, min_matched, overlap):
+    """MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES x REQUIRED_PERCENTILE_PEAK_OVERLAP (IL:1968-1976): the tabulated
+    per-window-count thresholds of the gate give the oracle's hit sets for loose, strict and unreachable settings."""
+    sys.setrecursionlimit(20000)
+    from oracle.qms_oracle import OracleLibrary
+    from pyqms_b200.synthetic import random_tryptic_peptides, synth_run
+    from tests.golden.spectra import entry_peaks
+    params = {"MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES": min_matched, "REQUIRED_PERCENTILE_PEAK_OVERLAP": overlap,
+              "M_SCORE_THRESHOLD": 0.3}
+    kwargs = dict(molecules=random_tryptic_peptides(40, seed=5), charges=[1, 2, 3], params=params)
+    ora = OracleLibrary(**kwargs)
+    lib = pyqms.IsotopologueLibrary(verbose=False, **kwargs)
+    mzs, cis = entry_peaks(ora)
+    peaks, offsets = synth_run(mzs, cis, n_spectra=20, seed=99, mean_peaks=300, elution_sigma=2.0, entry_fraction=0.4, dropout=0.35)
+    want = {}
+    for s in range(len(offsets) - 1):
+        ora.match_all(peaks[offsets[s]:offsets[s + 1]], "r", s, float(s), want)
+    got = lib.match_many(peaks, file_name="r", spec_ids=list(range(20)), spec_rts=[float(s) for s in range(20)], offsets=offsets)
+    assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN)
+    if overlap > 1.0:
+        assert len(want) == 0
+    if (min_matched, overlap) == (1, 0.0):
+        assert sum(len(v["data"]) if isinstance(v, dict) else len(v) for v in want.values()) > 20
