@@ -1167,9 +1167,15 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_emit_kernel(
     const double* __restrict__ pair_scaling, const int64_t* __restrict__ blk_hits, const int64_t* __restrict__ blk_wins,
     int32_t* __restrict__ o_spec, int32_t* __restrict__ o_entry, double* __restrict__ o_score, double* __restrict__ o_scaling,
     int64_t* __restrict__ o_win_off, double* __restrict__ o_mmz, double* __restrict__ o_mi, int64_t* __restrict__ o_peak,
-    int64_t peak_base, int entry_bits) {
+    int64_t peak_base, int entry_bits, const unsigned long long* __restrict__ counters, int64_t cap_hits, int64_t cap_windows,
+    unsigned long long pair_cap) {
     __shared__ int64_t s_h[CMP_THREADS / 32], s_w[CMP_THREADS / 32];
+    // The kernel is launched before the host knows the hit count: it emits only if the hits fit the buffers it was
+    // given and the pair list did not overflow (the host reads the same counters afterwards and emits again if not).
+    const int64_t n_hits = (int64_t)counters[40], n_windows = (int64_t)counters[41];
+    if (n_hits > cap_hits || n_windows > cap_windows || counters[C_PAIRS] > pair_cap) return;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) o_win_off[n_hits] = n_windows;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nc = p < n_pairs ? pair_flag[p] : 0;
     const bool flag = nc > 0;
@@ -1219,6 +1225,41 @@ static float elapsed(qms_ctx* ctx, int a, int b) {
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
     return ms;
+}
+
+// Where K7b writes: the caller's buffers if all of them are device memory (no staging copy), else the retained
+// buffers of the context with whatever capacity earlier batches left them.
+struct EmitTarget {
+    int32_t *spec, *entry;
+    double *score, *scaling;
+    int64_t* win_off;
+    double *mmz, *mi;
+    int64_t* peak;
+    int64_t cap_hits, cap_windows;     // -1: no room at all (not even the closing win_off element)
+    bool callers;
+};
+
+static EmitTarget emit_target(qms_ctx* ctx, const qms_hits* out) {
+    EmitTarget t;
+    const bool callers = out && out->hit_spec && out->hit_entry && out->hit_score && out->hit_scaling && out->hit_win_off &&
+                         out->hit_mmz && out->hit_mi && out->hit_peak && qms_is_device_ptr(out->hit_spec) &&
+                         qms_is_device_ptr(out->hit_entry) && qms_is_device_ptr(out->hit_score) && qms_is_device_ptr(out->hit_scaling) &&
+                         qms_is_device_ptr(out->hit_win_off) && qms_is_device_ptr(out->hit_mmz) && qms_is_device_ptr(out->hit_mi) &&
+                         qms_is_device_ptr(out->hit_peak);
+    if (callers) {
+        t = EmitTarget{(int32_t*)out->hit_spec, (int32_t*)out->hit_entry, (double*)out->hit_score, (double*)out->hit_scaling,
+                       (int64_t*)out->hit_win_off, (double*)out->hit_mmz, (double*)out->hit_mi, (int64_t*)out->hit_peak,
+                       out->cap_hits, out->cap_windows, true};
+    } else {
+        size_t hits = ctx->o_spec.cap;
+        for (size_t c : {ctx->o_entry.cap, ctx->o_score.cap, ctx->o_scaling.cap}) hits = c < hits ? c : hits;
+        if (ctx->o_win_off.cap < hits + 1) hits = ctx->o_win_off.cap ? ctx->o_win_off.cap - 1 : 0;
+        size_t windows = ctx->o_mmz.cap;
+        for (size_t c : {ctx->o_mi.cap, ctx->o_peak.cap}) windows = c < windows ? c : windows;
+        t = EmitTarget{ctx->o_spec.p, ctx->o_entry.p, ctx->o_score.p, ctx->o_scaling.p, ctx->o_win_off.p, ctx->o_mmz.p, ctx->o_mi.p,
+                       ctx->o_peak.p, (int64_t)hits - 1, (int64_t)windows - 1, false};
+    }
+    return t;
 }
 
 // need_of_nc[n_c]: smallest bucket count c >= max(1, MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES) for which
@@ -1401,6 +1442,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     const unsigned long long* keys = nullptr;
     const unsigned long long* vals = nullptr;
     int64_t cblocks = 0;
+    EmitTarget target{};
     for (int attempt = 0;; ++attempt) {
         QMS_TRY(qms_reserve(ctx, ctx->pair_keys, (size_t)cap));
         QMS_TRY(qms_reserve(ctx, ctx->pair_vals, (size_t)cap));
@@ -1477,8 +1519,15 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         compact_count_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(cap, ctx->pair_flag.p, ctx->blk_hits.p,
                                                                                 ctx->blk_wins.p);
         compact_scan_kernel<<<1, 32, 0, ctx->stream>>>(cblocks, ctx->blk_hits.p, ctx->blk_wins.p, ctx->dev_counters.p + 40);
+        // K7b, launched without waiting for the counts: into the caller's device buffers if it passed any, else into
+        // the retained buffers as far as the previous batches grew them (guarded on the device, checked below)
+        target = emit_target(ctx, out);
+        compact_emit_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(
+            v, cap, keys, ctx->pair_flag.p, max_nc, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->blk_hits.p,
+            ctx->blk_wins.p, target.spec, target.entry, target.score, target.scaling, target.win_off, target.mmz, target.mi,
+            target.peak, 0, entry_bits, ctx->dev_counters.p, target.cap_hits, target.cap_windows, (unsigned long long)cap);
         QMS_CUDA(ctx, cudaGetLastError());
-        ctx->cnt.kernel_launches += 10;
+        ctx->cnt.kernel_launches += 11;
         QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                       ctx->stream));
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
@@ -1516,36 +1565,35 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         }
         return QMS_OK;
     }
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    QMS_TRY(qms_reserve(ctx, ctx->o_spec, (size_t)nh + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->o_entry, (size_t)nh + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->o_score, (size_t)nh + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->o_scaling, (size_t)nh + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->o_win_off, (size_t)nh + 2));
-    QMS_TRY(qms_reserve(ctx, ctx->o_mmz, (size_t)nw + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->o_mi, (size_t)nw + 1));
-    QMS_TRY(qms_reserve(ctx, ctx->o_peak, (size_t)nw + 1));
     const bool fits = out && nh <= out->cap_hits && nw <= out->cap_windows;
+    const bool emitted = nh <= target.cap_hits && nw <= target.cap_windows;
     // caller buffers in device memory are written by the emit kernel itself (no staging copy); the hits then are
     // not retained for qms_fetch_hits
-    const bool direct = fits && out->hit_spec && out->hit_entry && out->hit_score && out->hit_scaling && out->hit_win_off &&
-                        out->hit_mmz && out->hit_mi && out->hit_peak && qms_is_device_ptr(out->hit_spec) &&
-                        qms_is_device_ptr(out->hit_entry) && qms_is_device_ptr(out->hit_score) && qms_is_device_ptr(out->hit_scaling) &&
-                        qms_is_device_ptr(out->hit_win_off) && qms_is_device_ptr(out->hit_mmz) && qms_is_device_ptr(out->hit_mi) &&
-                        qms_is_device_ptr(out->hit_peak);
-    int64_t* t_win_off = direct ? out->hit_win_off : ctx->o_win_off.p;
-    compact_emit_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(
-        v, cap, keys, ctx->pair_flag.p, max_nc, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->blk_hits.p,
-        ctx->blk_wins.p, direct ? out->hit_spec : ctx->o_spec.p, direct ? out->hit_entry : ctx->o_entry.p,
-        direct ? out->hit_score : ctx->o_score.p, direct ? out->hit_scaling : ctx->o_scaling.p, t_win_off,
-        direct ? out->hit_mmz : ctx->o_mmz.p, direct ? out->hit_mi : ctx->o_mi.p, direct ? out->hit_peak : ctx->o_peak.p, 0, entry_bits);
-    QMS_CUDA(ctx, cudaGetLastError());
-    QMS_CUDA(ctx, cudaMemcpyAsync(t_win_off + nh, &ctx->h_pinned[41], sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    ctx->cnt.kernel_launches++;
+    const bool direct = target.callers && emitted;
     ctx->last_hits = direct ? 0 : nh;            // retained in the o_* buffers for qms_fetch_hits
     ctx->last_windows = direct ? 0 : nw;
-    if (fits && !direct) {
+    ctx->cnt.hits += nh;
+    ctx->cnt.hit_windows += nw;
+    if (direct) return QMS_OK;                   // nothing left to do on the device: one synchronisation per batch
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (!emitted) {                              // first batches / a batch with more hits than any before it
+        QMS_TRY(qms_reserve(ctx, ctx->o_spec, (size_t)nh + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->o_entry, (size_t)nh + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->o_score, (size_t)nh + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->o_scaling, (size_t)nh + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->o_win_off, (size_t)nh + 2));
+        QMS_TRY(qms_reserve(ctx, ctx->o_mmz, (size_t)nw + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->o_mi, (size_t)nw + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->o_peak, (size_t)nw + 1));
+        compact_emit_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(
+            v, cap, keys, ctx->pair_flag.p, max_nc, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->blk_hits.p,
+            ctx->blk_wins.p, ctx->o_spec.p, ctx->o_entry.p, ctx->o_score.p, ctx->o_scaling.p, ctx->o_win_off.p, ctx->o_mmz.p,
+            ctx->o_mi.p, ctx->o_peak.p, 0, entry_bits, ctx->dev_counters.p, nh, nw, (unsigned long long)cap);
+        QMS_CUDA(ctx, cudaGetLastError());
+        ctx->cnt.kernel_launches++;
+    }
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (fits) {
         QMS_TRY(copy_out(ctx, out->hit_spec, ctx->o_spec.p, (size_t)nh));
         QMS_TRY(copy_out(ctx, out->hit_entry, ctx->o_entry.p, (size_t)nh));
         QMS_TRY(copy_out(ctx, out->hit_score, ctx->o_score.p, (size_t)nh));
@@ -1559,8 +1607,6 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->cnt.ms_compact += elapsed(ctx, 2, 3);
     ctx->cnt.ms_d2h += elapsed(ctx, 3, 4);
-    ctx->cnt.hits += nh;
-    ctx->cnt.hit_windows += nw;
     if (out && !fits)
         return qms_fail(ctx, QMS_E_CAPACITY,
                         "hit buffers too small: need %lld hits / %lld windows, have %lld / %lld (results retained: qms_fetch_hits)",
