@@ -1527,7 +1527,8 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
             ctx->blk_wins.p, target.spec, target.entry, target.score, target.scaling, target.win_off, target.mmz, target.mi,
             target.peak, 0, entry_bits, ctx->dev_counters.p, target.cap_hits, target.cap_windows, (unsigned long long)cap);
         QMS_CUDA(ctx, cudaGetLastError());
-        ctx->cnt.kernel_launches += 11;
+        // probe, tiling, gate, score, count, scan, emit + the radix sort's histogram, prefix and one pass per 8 key bits
+        ctx->cnt.kernel_launches += 7 + 2 + (key_bits + 7) / 8;
         QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                       ctx->stream));
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
