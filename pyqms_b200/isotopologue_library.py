@@ -796,11 +796,23 @@ class IsotopologueLibrary(dict):
         """Packed hits -> ``results.add`` in (spectrum, entry) order (IL:1872-1882).  The matched (m/z,
         intensity) come back from the device: numpy scalars for numpy input, Python floats for list input,
         like the objects the reference hands back (IL:2014-2017, 2594-2600)."""
-        win_off, mmz, mi = out["win_off"], out["mmz"], out["mi"]
+        n_hits = out["n_hits"]
+        if n_hits == 0:
+            return results
+        # whole-array conversions once per batch; the per-hit loop then only indexes Python lists
+        spec, entry, win_off = out["spec"].tolist(), out["entry"].tolist(), out["win_off"].tolist()
+        if python_floats:
+            mmz, mi, score, scaling = out["mmz"].tolist(), out["mi"].tolist(), out["score"].tolist(), out["scaling"].tolist()
+        else:
+            mmz, mi, score, scaling = list(out["mmz"]), list(out["mi"]), list(out["score"]), list(out["scaling"])
         statics = self._entry_static
         one_name = not isinstance(file_names, list)
-        for h in range(out["n_hits"]):
-            s, x = int(out["spec"][h]), int(out["entry"][h])
+        append = getattr(results, "_append_match", None)     # pyqms_b200.Results: skips per-hit key / index-set work
+        if append is not None:
+            results._flush()                                  # older deferred batches come first
+            new_key, new_match, keys = results._m_key_class, results._match_class, {}
+        for h in range(n_hits):
+            s, x = spec[h], entry[h]
             static = statics.get(x)
             if static is None:
                 lo, hi, charge, lp, formula = self._entry_tuple(x)
@@ -808,17 +820,17 @@ class IsotopologueLibrary(dict):
                 static = statics[x] = (formula, charge, lp, self._win_ri[a:b].tolist(), self._win_cmz[a:b].tolist(),
                                        self._win_ci[a:b].tolist())
             formula, charge, lp, ri, cmz, ci = static
-            a, b = int(win_off[h]), int(win_off[h + 1])
-            if python_floats:
-                pairs = zip(mmz[a:b].tolist(), mi[a:b].tolist())
-                score, scaling = float(out["score"][h]), float(out["scaling"][h])
-            else:
-                pairs = zip(mmz[a:b], mi[a:b])
-                score, scaling = out["score"][h], out["scaling"][h]
-            peaks = tuple((None, None, ri[m], cmz[m], ci[m]) if x_mz != x_mz else (x_mz, x_i, ri[m], cmz[m], ci[m])
-                          for m, (x_mz, x_i) in enumerate(pairs))
-            results.add((file_names if one_name else file_names[s], formula, charge, lp),
-                        (spec_ids[s], spec_rts[s], score, scaling, peaks))
+            a = win_off[h]
+            peaks = tuple([(None, None, ri[m], cmz[m], ci[m]) if mmz[a + m] != mmz[a + m] else (mmz[a + m], mi[a + m], ri[m], cmz[m], ci[m])
+                           for m in range(win_off[h + 1] - a)])
+            name = file_names if one_name else file_names[s]
+            if append is None:
+                results.add((name, formula, charge, lp), (spec_ids[s], spec_rts[s], score[h], scaling[h], peaks))
+                continue
+            key = keys.get((name, x))
+            if key is None:
+                key = keys[(name, x)] = new_key(name, formula, charge, lp)
+            append(key, new_match(spec_ids[s], spec_rts[s], score[h], scaling[h], peaks))
         return results
 
     # spectra handed to match_all are queued on the Results object and matched in one device pass when the

@@ -191,6 +191,24 @@ class Results(dict):
         dict.__getitem__(index, "label_percentiles").add(key.label_percentiles)
         return key
 
+    def _append_match(self, key, entry):
+        """``add`` for emitters that hand over ready ``m_key`` / ``match`` objects in order (no flush, no re-wrapping;
+        the index sets only change when a key is new)."""
+        slot = dict.get(self, key)
+        if slot is None:
+            slot = {"data": [], "max_score": -1, "max_score_index": -1, "len_data": 0}
+            dict.__setitem__(self, key, slot)
+            index = self.index
+            dict.__getitem__(index, "files").add(key.file_name)
+            dict.__getitem__(index, "charges").add(key.charge)
+            dict.__getitem__(index, "formulas").add(key.formula)
+            dict.__getitem__(index, "label_percentiles").add(key.label_percentiles)
+        if slot["max_score"] < entry.score:
+            slot["max_score"] = entry.score
+            slot["max_score_index"] = len(slot["data"])
+        slot["len_data"] += 1
+        slot["data"].append(entry)
+
     def _translate_molecules_to_formulas(self, molecules, formulas):
         """Formulas of ``molecules`` (via ``lookup["molecule to formula"]``) added to ``formulas`` (results.py:343-358)."""
         formulas = set(formulas) if formulas is not None else set()
