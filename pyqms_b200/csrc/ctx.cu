@@ -3,6 +3,8 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <thread>
+#include <vector>
 
 #include "qms_internal.cuh"
 
@@ -44,6 +46,94 @@ bool qms_is_device_ptr(const void* p) {
         return false;
     }
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// ---- host <-> device copies of large pageable buffers ---------------------------------------------------------
+static const size_t STAGE_CHUNK = 16u << 20;      // per slot
+static const size_t STAGE_MIN = 8u << 20;         // below this the driver's own pageable path is as good
+
+static bool is_pageable_host(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+static int stage_threads() {
+    static int n = 0;
+    if (n == 0) {
+        const char* e = getenv("QMS_COPY_THREADS");
+        n = e ? atoi(e) : (int)(std::thread::hardware_concurrency() / 2);
+        if (n < 1) n = 1;
+        if (n > 8) n = 8;
+    }
+    return n;
+}
+
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const int threads = stage_threads();
+    const size_t share = ((bytes + threads - 1) / threads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+        const size_t a = share * t;
+        if (a >= bytes) break;
+        const size_t n = bytes - a < share ? bytes - a : share;
+        pool.emplace_back([=] { memcpy((char*)dst + a, (const char*)src + a, n); });
+    }
+    memcpy(dst, src, bytes < share ? bytes : share);
+    for (auto& t : pool) t.join();
+}
+
+static int stage_ready(qms_ctx* ctx) {
+    for (int k = 0; k < 2; ++k) {
+        if (!ctx->stage_slot[k]) QMS_CUDA(ctx, cudaHostAlloc(&ctx->stage_slot[k], STAGE_CHUNK, cudaHostAllocDefault));
+        if (!ctx->stage_ev[k]) QMS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+    }
+    return QMS_OK;
+}
+
+int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    if (!bytes) return QMS_OK;
+    if (bytes < STAGE_MIN || !is_pageable_host(host)) {
+        QMS_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return QMS_OK;                             // stream-ordered; the caller synchronises once for all its copies
+    }
+    QMS_TRY(stage_ready(ctx));
+    const size_t chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    for (size_t k = 0; k <= chunks; ++k) {
+        if (k < chunks) {                          // DMA of chunk k into its slot (free: chunk k-2 was drained at step k-1)
+            const size_t off = k * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+            QMS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_slot[k & 1], (const char*)dev + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+            QMS_CUDA(ctx, cudaEventRecord(ctx->stage_ev[k & 1], ctx->stream));
+        }
+        if (k > 0) {                               // meanwhile the host drains chunk k-1
+            const size_t off = (k - 1) * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+            QMS_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[(k - 1) & 1]));
+            parallel_memcpy((char*)host + off, ctx->stage_slot[(k - 1) & 1], n);
+        }
+    }
+    return QMS_OK;
+}
+
+int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    if (!bytes) return QMS_OK;
+    if (bytes < STAGE_MIN || !is_pageable_host(host)) {
+        QMS_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return QMS_OK;                             // stream-ordered like every other upload
+    }
+    QMS_TRY(stage_ready(ctx));
+    const size_t chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    for (size_t k = 0; k < chunks; ++k) {
+        const size_t off = k * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
+        if (k >= 2) QMS_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[k & 1]));    // the slot's previous DMA has finished
+        parallel_memcpy(ctx->stage_slot[k & 1], (const char*)host + off, n);
+        QMS_CUDA(ctx, cudaMemcpyAsync((char*)dev + off, ctx->stage_slot[k & 1], n, cudaMemcpyHostToDevice, ctx->stream));
+        QMS_CUDA(ctx, cudaEventRecord(ctx->stage_ev[k & 1], ctx->stream));
+    }
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the slots are reused by the next copy
+    return QMS_OK;
 }
 
 int qms_reserve_bytes(qms_ctx* ctx, void** p, size_t* cap_elems, size_t elems, size_t elem_size, bool keep) {
@@ -125,6 +215,10 @@ void qms_ctx_destroy(qms_ctx* ctx) {
 #undef REL
     for (int i = 0; i < 12; ++i) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->stage_slot[k]) cudaFreeHost(ctx->stage_slot[k]);
+        if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -1216,8 +1216,8 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_emit_kernel(
 template <class T>
 static int copy_out(qms_ctx* ctx, T* dst, const T* src, size_t n) {
     if (!dst || !n) return QMS_OK;
-    const cudaMemcpyKind kind = qms_is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    QMS_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(T), kind, ctx->stream));
+    if (!qms_is_device_ptr(dst)) return qms_copy_to_host(ctx, dst, src, n * sizeof(T));
+    QMS_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
     return QMS_OK;
 }
 
@@ -1325,8 +1325,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     // the device copy mirrors the caller's row numbering, so reported peak rows need no rebasing
     if (n_peaks > 0 && !qms_is_device_ptr(peaks)) {
         QMS_TRY(qms_reserve(ctx, ctx->d_peaks, (size_t)p_end * 2));
-        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->d_peaks.p + 2 * p_begin, peaks + 2 * p_begin, (size_t)n_peaks * 2 * sizeof(double),
-                                      cudaMemcpyHostToDevice, ctx->stream));
+        QMS_TRY(qms_copy_to_device(ctx, ctx->d_peaks.p + 2 * p_begin, peaks + 2 * p_begin, (size_t)n_peaks * 2 * sizeof(double)));
         d_peaks = reinterpret_cast<const double2*>(ctx->d_peaks.p);
     }
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));

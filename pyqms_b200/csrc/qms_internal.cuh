@@ -107,6 +107,8 @@ struct qms_ctx {
     DBuf<int32_t> tile_spec;
     int32_t max_nc = 0;            // most c-peak windows of any index entry
     DBuf<int32_t> need_of_nc;      // per window count: buckets needed to pass the overlap gates (params x library)
+    void* stage_slot[2] = {nullptr, nullptr};   // pinned staging slots for large pageable host buffers
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     std::vector<int32_t> h_need;
     bool need_dirty = true;
     double window_density = 0.0;   // sum of window widths / covered grid cells = windows over an average covered cell
@@ -161,6 +163,12 @@ inline int qms_download(qms_ctx* ctx, T* host, const T* dev, size_t n) {
     return QMS_OK;
 }
 bool qms_is_device_ptr(const void* p);
+// Copies between device memory and a HOST buffer of any kind.  Pinned memory goes straight to the copy engine; large
+// pageable buffers are staged through two pinned slots of the context, the DMA of one chunk overlapping the (multi-
+// threaded, first-touch parallel) host copy of the other.  Small or pinned copies stay stream-ordered (the caller
+// synchronises), staged ones have completed on return.
+int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes);
+int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes);
 
 static inline int qms_blocks(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
