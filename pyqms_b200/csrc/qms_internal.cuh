@@ -151,6 +151,13 @@ struct TmpBuf {  // scratch device buffer released on scope exit
     TmpBuf(const TmpBuf&) = delete;
     TmpBuf& operator=(const TmpBuf&) = delete;
 };
+// Copies between device memory and a HOST buffer of any kind.  Pinned memory goes straight to the copy engine; large
+// pageable buffers are staged through two pinned slots of the context, the DMA of one chunk overlapping the (multi-
+// threaded, first-touch parallel) host copy of the other.  Small or pinned copies stay stream-ordered (the caller
+// synchronises), staged ones have completed on return.
+int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes);
+int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes);
+
 template <class T>
 inline int qms_upload(qms_ctx* ctx, DBuf<T>& b, const T* host, size_t n) {
     QMS_TRY(qms_reserve(ctx, b, n ? n : 1));
@@ -159,16 +166,11 @@ inline int qms_upload(qms_ctx* ctx, DBuf<T>& b, const T* host, size_t n) {
 }
 template <class T>
 inline int qms_download(qms_ctx* ctx, T* host, const T* dev, size_t n) {
-    if (n && host) QMS_CUDA(ctx, cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && host) return qms_copy_to_host(ctx, host, dev, n * sizeof(T));
     return QMS_OK;
 }
 bool qms_is_device_ptr(const void* p);
-// Copies between device memory and a HOST buffer of any kind.  Pinned memory goes straight to the copy engine; large
-// pageable buffers are staged through two pinned slots of the context, the DMA of one chunk overlapping the (multi-
-// threaded, first-touch parallel) host copy of the other.  Small or pinned copies stay stream-ordered (the caller
-// synchronises), staged ones have completed on return.
-int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes);
-int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes);
+
 
 static inline int qms_blocks(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
