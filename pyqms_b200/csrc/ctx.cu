@@ -65,9 +65,9 @@ static int stage_threads() {
     static int n = 0;
     if (n == 0) {
         const char* e = getenv("QMS_COPY_THREADS");
-        n = e ? atoi(e) : (int)(std::thread::hardware_concurrency() / 2);
+        n = e ? atoi(e) : (int)(std::thread::hardware_concurrency() / 2);   // half the cores: one process per GPU shares the host
         if (n < 1) n = 1;
-        if (n > 8) n = 8;
+        if (n > (e ? 32 : 8)) n = e ? 32 : 8;
     }
     return n;
 }
