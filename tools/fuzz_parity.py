@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Randomised differential run: CUDA path vs the CPU oracle over random libraries, params and spectra (both input kinds).
+
+    python tools/fuzz_parity.py [n_configs] [first_seed]
+
+Prints one line per configuration and exits non-zero at the first mismatch.  (Test infrastructure: imports oracle/.)
+"""
+import random
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.setrecursionlimit(20000)
+import pyqms_b200  # noqa: E402
+from oracle.qms_oracle import OracleLibrary  # noqa: E402
+from pyqms_b200.synthetic import averagine_formulas, random_tryptic_peptides, synth_run  # noqa: E402
+from tests.golden.spectra import entry_peaks  # noqa: E402
+from tests.helpers import assert_results_equal, results_to_rows  # noqa: E402
+
+
+def random_config(seed):
+    rng = random.Random(seed)
+    molecules = random_tryptic_peptides(rng.randint(5, 60), seed=seed)
+    if rng.random() < 0.5:
+        molecules += averagine_formulas(rng.randint(3, 20), seed=seed, min_mass=200.0, max_mass=rng.choice([2000.0, 6000.0]))
+    if rng.random() < 0.4:
+        molecules += [m + "#Oxidation:1" for m in molecules[:5] if m[0] != "+"]
+    charges = sorted(rng.sample([1, 2, 3, 4, 5], rng.randint(1, 4)))
+    labels = rng.choice([None, {"15N": [0, 0.99]}, {"15N": [0, 0.5, 0.994]}, {"13C": [0, 0.98], "15N": [0, 0.99]}])
+    fixed = rng.choice([None, {"C": ["C(2)H(3)14N(1)O(1)"]}])
+    params = {"M_SCORE_THRESHOLD": rng.choice([0.3, 0.5, 0.7]), "REL_MZ_RANGE": rng.choice([5e-6, 1e-5, 5e-5]),
+              "REL_I_RANGE": rng.choice([0.2, 0.5]), "MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES": rng.choice([1, 2, 3]),
+              "REQUIRED_PERCENTILE_PEAK_OVERLAP": rng.choice([0.2, 0.5, 0.8]), "MZ_SCORE_PERCENTILE": rng.choice([0.2, 0.4, 0.9]),
+              "MAX_MOLECULES_PER_MATCH_BIN": rng.choice([1, 7, 20]), "MACHINE_OFFSET_IN_PPM": rng.choice([0.0, -2.0, 4.0]),
+              "INTERNAL_PRECISION": rng.choice([1000, 1000, 10000])}
+    run = dict(n_spectra=rng.randint(4, 16), seed=seed + 1, mean_peaks=rng.choice([80, 300, 1200]), elution_sigma=rng.choice([1.0, 3.0]),
+               entry_fraction=rng.choice([0.2, 0.6, 1.0]), ppm_sd=rng.choice([1.0, 3.0]), dropout=rng.choice([0.0, 0.2, 0.4]))
+    return dict(molecules=molecules, charges=charges, metabolic_labels=labels, fixed_labels=fixed, params=params), run, rng.random() < 0.5
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    for seed in range(first, first + n):
+        kwargs, run, as_lists = random_config(seed)
+        t0 = time.time()
+        oracle = OracleLibrary(**kwargs)
+        if len(oracle.formulas_sorted_by_mz) == 0:
+            print("seed %d: empty library, skipped" % seed)
+            continue
+        lib = pyqms_b200.IsotopologueLibrary(verbose=False, **kwargs)
+        peaks, offsets = synth_run(*entry_peaks(oracle), **run)
+        want, got = {}, None
+        spectra = [peaks[offsets[s]:offsets[s + 1]] for s in range(len(offsets) - 1)]
+        if as_lists:
+            spectra = [[(float(a), float(b)) for a, b in spec] for spec in spectra]
+        for s, spec in enumerate(spectra):
+            oracle.match_all(spec, "f", s, float(s), want)
+            got = lib.match_all(mz_i_list=spec, file_name="f", spec_id=s, spec_rt=float(s), results=got)
+        tie_prone = any(len(v) > 2 for v in (kwargs["metabolic_labels"] or {}).values()) or len(kwargs["metabolic_labels"] or {}) > 1
+        assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=1e-6, cmz_rel=1e-12, ri_rel=1e-9, key_order=not tie_prone)
+        hits = sum(len(v) for v in want.values())
+        print("seed %d: ok  entries %d, %d spectra (%s), %d keys, %d hits, %.1f s" % (
+            seed, len(oracle.formulas_sorted_by_mz), len(spectra), "lists" if as_lists else "numpy", len(want), hits, time.time() - t0), flush=True)
+
+
+if __name__ == "__main__":
+    main()
