@@ -1,11 +1,15 @@
 #!/usr/bin/env python
 """Randomised differential run: CUDA path vs the CPU oracle over random libraries, params and spectra (both input kinds).
 
-    python tools/fuzz_parity.py [n_configs] [first_seed]
+    python tools/fuzz_parity.py [n_configs] [first_seed] [seconds_per_config=20]
 
 Prints one line per configuration and exits non-zero at the first mismatch.  (Test infrastructure: imports oracle/.)
+The oracle enumerates candidate combinations like the reference and can take minutes on a dense spectrum with wide
+windows: every configuration runs under an alarm and is skipped when the oracle exceeds its time limit -- do not
+hold a GPU box with an unbounded run.
 """
 import random
+import signal
 import sys
 import time
 from pathlib import Path
@@ -37,35 +41,57 @@ def random_config(seed):
               "REQUIRED_PERCENTILE_PEAK_OVERLAP": rng.choice([0.2, 0.5, 0.8]), "MZ_SCORE_PERCENTILE": rng.choice([0.2, 0.4, 0.9]),
               "MAX_MOLECULES_PER_MATCH_BIN": rng.choice([1, 7, 20]), "MACHINE_OFFSET_IN_PPM": rng.choice([0.0, -2.0, 4.0]),
               "INTERNAL_PRECISION": rng.choice([1000, 1000, 10000])}
-    run = dict(n_spectra=rng.randint(4, 16), seed=seed + 1, mean_peaks=rng.choice([80, 300, 1200]), elution_sigma=rng.choice([1.0, 3.0]),
+    wide = params["REL_MZ_RANGE"] >= 5e-5              # wide windows x dense spectra = combinatorial candidates for the oracle
+    run = dict(n_spectra=rng.randint(4, 16), seed=seed + 1, mean_peaks=rng.choice([80, 300] if wide else [80, 300, 1200]),
+               elution_sigma=rng.choice([1.0, 3.0]),
                entry_fraction=rng.choice([0.2, 0.6, 1.0]), ppm_sd=rng.choice([1.0, 3.0]), dropout=rng.choice([0.0, 0.2, 0.4]))
     return dict(molecules=molecules, charges=charges, metabolic_labels=labels, fixed_labels=fixed, params=params), run, rng.random() < 0.5
+
+
+class TooSlow(Exception):
+    pass
+
+
+def _alarm(signum, frame):
+    raise TooSlow()
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    limit = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    signal.signal(signal.SIGALRM, _alarm)
     for seed in range(first, first + n):
-        kwargs, run, as_lists = random_config(seed)
-        t0 = time.time()
-        oracle = OracleLibrary(**kwargs)
-        if len(oracle.formulas_sorted_by_mz) == 0:
-            print("seed %d: empty library, skipped" % seed)
-            continue
-        lib = pyqms_b200.IsotopologueLibrary(verbose=False, **kwargs)
-        peaks, offsets = synth_run(*entry_peaks(oracle), **run)
-        want, got = {}, None
-        spectra = [peaks[offsets[s]:offsets[s + 1]] for s in range(len(offsets) - 1)]
-        if as_lists:
-            spectra = [[(float(a), float(b)) for a, b in spec] for spec in spectra]
-        for s, spec in enumerate(spectra):
-            oracle.match_all(spec, "f", s, float(s), want)
-            got = lib.match_all(mz_i_list=spec, file_name="f", spec_id=s, spec_rt=float(s), results=got)
-        tie_prone = any(len(v) > 2 for v in (kwargs["metabolic_labels"] or {}).values()) or len(kwargs["metabolic_labels"] or {}) > 1
-        assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=1e-6, cmz_rel=1e-12, ri_rel=1e-9, key_order=not tie_prone)
-        hits = sum(len(v) for v in want.values())
-        print("seed %d: ok  entries %d, %d spectra (%s), %d keys, %d hits, %.1f s" % (
-            seed, len(oracle.formulas_sorted_by_mz), len(spectra), "lists" if as_lists else "numpy", len(want), hits, time.time() - t0), flush=True)
+        signal.alarm(limit)
+        try:
+            check(seed)
+        except TooSlow:
+            print("seed %d: skipped, the oracle needs more than %d s" % (seed, limit), flush=True)
+        finally:
+            signal.alarm(0)
+
+
+def check(seed):
+    kwargs, run, as_lists = random_config(seed)
+    t0 = time.time()
+    oracle = OracleLibrary(**kwargs)
+    if len(oracle.formulas_sorted_by_mz) == 0:
+        print("seed %d: empty library, skipped" % seed)
+        return
+    lib = pyqms_b200.IsotopologueLibrary(verbose=False, **kwargs)
+    peaks, offsets = synth_run(*entry_peaks(oracle), **run)
+    want, got = {}, None
+    spectra = [peaks[offsets[s]:offsets[s + 1]] for s in range(len(offsets) - 1)]
+    if as_lists:
+        spectra = [[(float(a), float(b)) for a, b in spec] for spec in spectra]
+    for s, spec in enumerate(spectra):
+        oracle.match_all(spec, "f", s, float(s), want)
+        got = lib.match_all(mz_i_list=spec, file_name="f", spec_id=s, spec_rt=float(s), results=got)
+    tie_prone = any(len(v) > 2 for v in (kwargs["metabolic_labels"] or {}).values()) or len(kwargs["metabolic_labels"] or {}) > 1
+    assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=1e-6, cmz_rel=1e-12, ri_rel=1e-9, key_order=not tie_prone)
+    hits = sum(len(v) for v in want.values())
+    print("seed %d: ok  entries %d, %d spectra (%s), %d keys, %d hits, %.1f s" % (
+        seed, len(oracle.formulas_sorted_by_mz), len(spectra), "lists" if as_lists else "numpy", len(want), hits, time.time() - t0), flush=True)
 
 
 if __name__ == "__main__":
