@@ -132,3 +132,43 @@ def test_term_tables_of_a_mixed_library_with_folding():
     off, pool, level = reference_term_loop(native)
     assert native._terms[0].tolist() == off and native._terms[1].tolist() == pool and native._terms[2].tolist() == level
     assert len(native.labled_percentiles) == 6 and native._n_env == 6 * len(native._formulas)
+
+
+def test_envelope_terms_do_not_depend_on_the_block_size():
+    """planner.envelope_terms works through the formulas in blocks (bounded memory); any block size gives the same tables."""
+    kwargs = dict(molecules=random_tryptic_peptides(500, seed=21) + averagine_formulas(200), charges=[2],
+                  metabolic_labels={"15N": [0, 0.3, 0.99]}, fixed_labels={"C": ["C(2)H(3)14N(1)O(1)"]}, verbose=False, _plan_only=True)
+    lib = pyqms_b200.IsotopologueLibrary(**kwargs)
+    levels = lib.params["FIXED_LABEL_ISOTOPE_ENRICHMENT_LEVELS"]
+    column = {symbol: k for k, symbol in enumerate(lib._symbols)}
+    pool_of_default = np.array([lib._pool_ids.get((s, lib._default_label.get(s)), 0) for s in lib._symbols], dtype=np.int32)
+    labelled = np.array([s in lib.metabolically_labeled_elements for s in lib._symbols], dtype=bool)
+    fold_target, pool_of_label = [], []
+    for lp in lib.labled_percentiles:
+        target = list(range(len(lib._symbols)))
+        for k, symbol in enumerate(lib._symbols):
+            if symbol in levels:
+                for element, label in lp:
+                    if element == symbol[-1] and label == lib._fmt(levels[symbol]) and symbol[-1] in column:
+                        target[k] = column[symbol[-1]]
+        fold_target.append(target)
+        pool_of_label.append([(column.get(element), lib._pool_ids.get((element, label), 0)) for element, label in lp])
+    for rows_per_block in (1, 7, 64, 1 << 16):
+        off, pool, level = planner.envelope_terms(lib._cc_counts, lib._cc_seen, lib._symbols, lib.labled_percentiles, fold_target,
+                                                  labelled, pool_of_default, pool_of_label, rows_per_block=rows_per_block)
+        assert np.array_equal(off, lib._terms[0]) and np.array_equal(pool, lib._terms[1]) and np.array_equal(level, lib._terms[2])
+
+
+def test_formula_records_behave_like_the_reference_dicts():
+    lib = pyqms_b200.IsotopologueLibrary(molecules=["PEPTIDEK", "+C6H12O6"], charges=[1], verbose=False, _plan_only=True)
+    formula = lib.lookup["molecule to formula"]["+C6H12O6"]
+    record = lib[formula]
+    assert "cc" in record and "env" in record and "other" not in record and record.get("other", 5) == 5
+    assert sorted(record) == ["cc", "env"] and len(record) == 2 and sorted(record.keys()) == ["cc", "env"]
+    assert dict(record["cc"]) == {"C": 6, "H": 12, "O": 6} and list(record["cc"]) == ["C", "H", "O"]
+    assert record["cc"] is record["cc"]                                 # built once
+    assert [key for key, _ in record.items()] == list(record.keys()) and len(list(record.values())) == 2
+    with pytest.raises(KeyError):
+        record["nothing"]
+    peptide = lib[lib.lookup["molecule to formula"]["PEPTIDEK"]]["cc"]
+    assert list(peptide.items()) == list(host_composition("PEPTIDEK").items())
