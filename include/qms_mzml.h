@@ -1,0 +1,47 @@
+/* libqms_mzml.so -- native mzML ingest for the matching path.
+ *
+ * Replaces the per-spectrum Python loop of the reference's scripts (example_scripts/quantify_mzml.py:59-73:
+ * pymzml.run.Reader -> spectrum.centroidedPeaks -> match_all) by one pass that goes from the file to the packed
+ * layout qms_match_batch consumes: an (N, 2) float64 array of (m/z, intensity) rows + row offsets.  Host-only
+ * code (no CUDA): the file is memory-mapped and indexed by a tag scanner, the binary arrays (base64, optional
+ * zlib, 32/64-bit floats; mzML 1.1 accessions MS:1000514/515/521/523/574/576) are decoded by a pool of threads
+ * straight into their slots of the packed array.
+ *
+ * Every call returns 0 or a negative code; qms_mzml_last_error() gives the message of the calling thread.
+ * QMS_MZML_E_UNSUPPORTED (numpress / integer arrays / external data) tells the caller to use another reader. */
+#ifndef QMS_MZML_H
+#define QMS_MZML_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMS_MZML_OK 0
+#define QMS_MZML_E_IO (-1)
+#define QMS_MZML_E_FORMAT (-2)
+#define QMS_MZML_E_UNSUPPORTED (-3)
+#define QMS_MZML_E_ARG (-4)
+
+typedef struct qms_mzml qms_mzml;
+
+/* Map `path` and index its <spectrum> elements (ms level, scan start time, array encodings and byte ranges). */
+int qms_mzml_open(const char* path, qms_mzml** out);
+void qms_mzml_close(qms_mzml* file);
+const char* qms_mzml_last_error(void);
+
+/* Spectra of `ms_level` (0 = every level) and the number of (m/z, intensity) rows they hold. */
+int qms_mzml_count(qms_mzml* file, int32_t ms_level, int64_t* n_spectra, int64_t* n_peaks);
+
+/* Decode the selected spectra with `n_threads` threads (<= 0: half the cores, at most 16).
+ * peaks[n_peaks x 2], offsets[n_spectra + 1]; per spectrum: ids (scan number of the native id, else ordinal + 1),
+ * rt (value as written), rt_unit (0 none, 1 minute, 2 second), levels (-1 if the file gives none).
+ * sort_peaks != 0: spectra whose m/z are not ascending are stably reordered by m/z. */
+int qms_mzml_read(qms_mzml* file, int32_t ms_level, int32_t sort_peaks, int32_t n_threads, double* peaks, int64_t* offsets,
+                  int64_t* ids, double* rt, uint8_t* rt_unit, int32_t* levels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,513 @@
+// Native mzML ingest (include/qms_mzml.h): memory-mapped file, one tag scan to index the spectra, parallel decode of
+// the binary arrays into the packed (N, 2) layout.  Host-only; built as libqms_mzml.so next to libqms_b200.so.
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/qms_mzml.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+struct Span {
+    const char* a = nullptr;
+    const char* b = nullptr;
+    bool empty() const { return a == b; }
+    size_t size() const { return (size_t)(b - a); }
+    bool equals(const char* s) const { return size() == strlen(s) && memcmp(a, s, size()) == 0; }
+    std::string str() const { return std::string(a, b); }
+};
+
+struct ArrayInfo {
+    Span text;            // base64 payload
+    bool present = false, f32 = false, zlib = false;
+    int64_t length = -1;  // arrayLength attribute, if given
+};
+
+struct Param {            // one cvParam that matters (accession + value + unitName)
+    Span accession, value, unit;
+};
+
+struct SpectrumInfo {
+    int64_t ordinal = 0;          // position among all <spectrum> elements of the file
+    Span native_id;
+    int32_t level = -1;
+    bool has_rt = false, rt_seconds = false;
+    double rt = 0.0;
+    int64_t default_length = -1;
+    ArrayInfo mz, intensity;
+    bool unsupported = false;
+};
+
+enum ArrayKind { KIND_NONE, KIND_MZ, KIND_INTENSITY };
+
+}  // namespace
+
+struct qms_mzml {
+    int fd = -1;
+    const char* data = nullptr;
+    size_t size = 0;
+    std::vector<SpectrumInfo> spectra;
+};
+
+namespace {
+
+// value of attribute `name` inside the tag text [a, b) (after the tag name); empty span if absent
+Span attribute(const char* a, const char* b, const char* name) {
+    const size_t n = strlen(name);
+    for (const char* p = a; p + n + 2 < b; ++p) {
+        if ((p == a || p[-1] == ' ' || p[-1] == '\t' || p[-1] == '\n' || p[-1] == '\r') && memcmp(p, name, n) == 0) {
+            const char* q = p + n;
+            while (q < b && (*q == ' ' || *q == '\t' || *q == '\n' || *q == '\r')) ++q;
+            if (q >= b || *q != '=') continue;
+            ++q;
+            while (q < b && (*q == ' ' || *q == '\t' || *q == '\n' || *q == '\r')) ++q;
+            if (q >= b || (*q != '"' && *q != '\'')) continue;
+            const char quote = *q++;
+            const char* e = (const char*)memchr(q, quote, (size_t)(b - q));
+            if (!e) return Span{};
+            return Span{q, e};
+        }
+    }
+    return Span{};
+}
+
+int64_t to_int(Span s, int64_t fallback) {
+    if (s.empty()) return fallback;
+    char buf[32];
+    const size_t n = std::min(s.size(), sizeof(buf) - 1);
+    memcpy(buf, s.a, n);
+    buf[n] = 0;
+    char* end = nullptr;
+    const long long v = strtoll(buf, &end, 10);
+    return end == buf ? fallback : (int64_t)v;
+}
+
+bool to_double(Span s, double& out) {
+    if (s.empty()) return false;
+    char buf[64];
+    const size_t n = std::min(s.size(), sizeof(buf) - 1);
+    memcpy(buf, s.a, n);
+    buf[n] = 0;
+    char* end = nullptr;
+    out = strtod(buf, &end);
+    return end != buf;
+}
+
+// what one cvParam means for the spectrum / the binary array that is open
+void apply_param(const Param& p, SpectrumInfo& s, ArrayInfo* array, ArrayKind* kind) {
+    const Span& acc = p.accession;
+    if (acc.equals("MS:1000511")) {
+        s.level = (int32_t)to_int(p.value, -1);
+    } else if (acc.equals("MS:1000016")) {
+        if (!s.has_rt) {
+            double v;
+            if (to_double(p.value, v)) {
+                s.has_rt = true;
+                s.rt = v;
+                // unitName 'second' / 'minute' (missing: minute), compared case-insensitively on its first three letters
+                s.rt_seconds = p.unit.size() >= 3 && (p.unit.a[0] | 32) == 's' && (p.unit.a[1] | 32) == 'e' && (p.unit.a[2] | 32) == 'c';
+            }
+        }
+    } else if (array) {
+        if (acc.equals("MS:1000514")) *kind = KIND_MZ;
+        else if (acc.equals("MS:1000515")) *kind = KIND_INTENSITY;
+        else if (acc.equals("MS:1000521")) array->f32 = true;
+        else if (acc.equals("MS:1000523")) array->f32 = false;
+        else if (acc.equals("MS:1000574")) array->zlib = true;
+        else if (acc.equals("MS:1000576")) array->zlib = false;
+        else if (acc.equals("MS:1000519") || acc.equals("MS:1000522") ||                              // integer arrays
+                 acc.equals("MS:1002312") || acc.equals("MS:1002313") || acc.equals("MS:1002314") ||  // numpress
+                 acc.equals("MS:1002746") || acc.equals("MS:1002747") || acc.equals("MS:1002748"))
+            s.unsupported = true;
+    }
+}
+
+int build_index(qms_mzml* f) {
+    const char* p = f->data;
+    const char* end = f->data + f->size;
+    std::unordered_map<std::string, std::vector<Param>> groups;
+    std::vector<Param>* open_group = nullptr;
+    SpectrumInfo* spectrum = nullptr;
+    ArrayInfo array;
+    ArrayKind kind = KIND_NONE;
+    bool in_array = false;
+    int64_t ordinal = 0;
+    while (p < end) {
+        const char* lt = (const char*)memchr(p, '<', (size_t)(end - p));
+        if (!lt || lt + 1 >= end) break;
+        const char* name = lt + 1;
+        if (*name == '!' || *name == '?') {                // comments, declarations, processing instructions
+            const char* gt = (const char*)memchr(name, '>', (size_t)(end - name));
+            if (!gt) break;
+            p = gt + 1;
+            continue;
+        }
+        const bool closing = *name == '/';
+        if (closing) ++name;
+        const char* q = name;
+        while (q < end && *q != ' ' && *q != '>' && *q != '/' && *q != '\t' && *q != '\n' && *q != '\r') ++q;
+        // end of the tag, quotes respected ('>' may stand inside an attribute value)
+        const char* gt = q;
+        char quote = 0;
+        while (gt < end && (quote || *gt != '>')) {
+            if (quote) {
+                if (*gt == quote) quote = 0;
+            } else if (*gt == '"' || *gt == '\'') {
+                quote = *gt;
+            }
+            ++gt;
+        }
+        if (gt >= end) break;
+        Span tag{name, q};
+        const char* colon = (const char*)memchr(tag.a, ':', tag.size());     // namespace prefix
+        if (colon) tag.a = colon + 1;
+        const bool self_closing = gt > lt && gt[-1] == '/';
+        if (!closing) {
+            if (tag.equals("cvParam")) {
+                Param param{attribute(q, gt, "accession"), attribute(q, gt, "value"), attribute(q, gt, "unitName")};
+                if (open_group) open_group->push_back(param);
+                else if (spectrum) apply_param(param, *spectrum, in_array ? &array : nullptr, &kind);
+            } else if (tag.equals("referenceableParamGroupRef")) {
+                if (spectrum) {
+                    auto it = groups.find(attribute(q, gt, "ref").str());
+                    if (it != groups.end())
+                        for (const Param& param : it->second) apply_param(param, *spectrum, in_array ? &array : nullptr, &kind);
+                }
+            } else if (tag.equals("referenceableParamGroup")) {
+                open_group = self_closing ? nullptr : &groups[attribute(q, gt, "id").str()];
+            } else if (tag.equals("spectrum")) {
+                f->spectra.emplace_back();
+                spectrum = &f->spectra.back();
+                spectrum->ordinal = ordinal++;
+                spectrum->native_id = attribute(q, gt, "id");
+                spectrum->default_length = to_int(attribute(q, gt, "defaultArrayLength"), -1);
+                if (self_closing) spectrum = nullptr;
+            } else if (tag.equals("binaryDataArray") && spectrum) {
+                array = ArrayInfo{};
+                array.length = to_int(attribute(q, gt, "arrayLength"), -1);
+                kind = KIND_NONE;
+                in_array = !self_closing;
+            } else if (tag.equals("binary") && spectrum && in_array) {
+                array.present = true;
+                if (self_closing) {
+                    array.text = Span{gt, gt};
+                } else {
+                    const char* close = (const char*)memmem(gt + 1, (size_t)(end - gt - 1), "</", 2);
+                    if (!close) return fail(QMS_MZML_E_FORMAT, "unterminated <binary> element");
+                    array.text = Span{gt + 1, close};
+                    p = close;
+                    continue;
+                }
+            }
+        } else {
+            if (tag.equals("binaryDataArray") && spectrum && in_array) {
+                if (kind == KIND_MZ) spectrum->mz = array;
+                else if (kind == KIND_INTENSITY) spectrum->intensity = array;
+                in_array = false;
+            } else if (tag.equals("spectrum")) {
+                spectrum = nullptr;
+                in_array = false;
+            } else if (tag.equals("referenceableParamGroup")) {
+                open_group = nullptr;
+            }
+        }
+        p = gt + 1;
+    }
+    return QMS_MZML_OK;
+}
+
+// ---- decoding --------------------------------------------------------------------------------------------------
+struct Base64Table {
+    int8_t value[256];
+    Base64Table() {
+        memset(value, -1, sizeof(value));
+        const char* alphabet = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+        for (int i = 0; i < 64; ++i) value[(unsigned char)alphabet[i]] = (int8_t)i;
+    }
+};
+const Base64Table g_base64;
+
+// characters outside the alphabet (white space, padding) are skipped, like Python's base64.b64decode
+void base64_decode(Span text, std::vector<unsigned char>& out) {
+    out.resize(text.size() / 4 * 3 + 3);
+    unsigned char* o = out.data();
+    const unsigned char* p = (const unsigned char*)text.a;
+    const unsigned char* end = (const unsigned char*)text.b;
+    uint32_t acc = 0;
+    int bits = 0;
+    while (p < end) {
+        // fast path: whole quartets of alphabet characters (the usual payload has no white space inside)
+        if (bits == 0) {
+            while (p + 4 <= end) {
+                const int a = g_base64.value[p[0]], b = g_base64.value[p[1]], c = g_base64.value[p[2]], d = g_base64.value[p[3]];
+                if ((a | b | c | d) < 0) break;
+                const uint32_t v = ((uint32_t)a << 18) | ((uint32_t)b << 12) | ((uint32_t)c << 6) | (uint32_t)d;
+                o[0] = (unsigned char)(v >> 16);
+                o[1] = (unsigned char)(v >> 8);
+                o[2] = (unsigned char)v;
+                o += 3;
+                p += 4;
+            }
+            if (p >= end) break;
+        }
+        const int v = g_base64.value[*p++];
+        if (v < 0) continue;
+        acc = (acc << 6) | (uint32_t)v;
+        bits += 6;
+        if (bits >= 8) {
+            bits -= 8;
+            *o++ = (unsigned char)(acc >> bits);
+        }
+    }
+    out.resize((size_t)(o - out.data()));
+}
+
+struct Inflater {               // one zlib stream per thread, reset between arrays
+    z_stream z;
+    bool ready = false;
+    ~Inflater() {
+        if (ready) inflateEnd(&z);
+    }
+    bool run(const std::vector<unsigned char>& in, std::vector<unsigned char>& out, size_t expected) {
+        if (in.empty()) {
+            out.clear();
+            return true;
+        }
+        if (!ready) {
+            memset(&z, 0, sizeof(z));
+            if (inflateInit(&z) != Z_OK) return false;
+            ready = true;
+        } else if (inflateReset(&z) != Z_OK) {
+            return false;
+        }
+        out.resize(std::max<size_t>(expected, in.size() * 4) + 64);
+        z.next_in = const_cast<unsigned char*>(in.data());
+        z.avail_in = (uInt)in.size();
+        for (;;) {
+            z.next_out = out.data() + z.total_out;
+            z.avail_out = (uInt)(out.size() - z.total_out);
+            const int rc = inflate(&z, Z_NO_FLUSH);
+            if (rc == Z_STREAM_END) break;
+            if (rc != Z_OK && rc != Z_BUF_ERROR) return false;
+            if (z.avail_out == 0) out.resize(out.size() * 2);
+            else if (z.avail_in == 0) return false;        // truncated stream
+        }
+        out.resize(z.total_out);
+        return true;
+    }
+};
+
+struct Scratch {
+    Inflater inflater;
+    std::vector<unsigned char> raw, plain;
+    std::vector<double> mz, intensity;
+    std::vector<int64_t> order;
+};
+
+// one binary array -> doubles; false on a broken payload
+bool decode_array(const ArrayInfo& a, int64_t expected, Scratch& s, std::vector<double>& out) {
+    out.clear();
+    if (!a.present) return true;
+    base64_decode(a.text, s.raw);
+    const std::vector<unsigned char>* bytes = &s.raw;
+    if (a.zlib) {
+        const size_t guess = expected > 0 ? (size_t)expected * (a.f32 ? 4 : 8) : 0;
+        if (!s.inflater.run(s.raw, s.plain, guess)) return false;
+        bytes = &s.plain;
+    }
+    const size_t width = a.f32 ? 4 : 8;
+    const size_t n = bytes->size() / width;
+    out.resize(n);
+    if (a.f32) {
+        for (size_t i = 0; i < n; ++i) {
+            float v;
+            memcpy(&v, bytes->data() + 4 * i, 4);
+            out[i] = (double)v;
+        }
+    } else if (n) {
+        memcpy(out.data(), bytes->data(), 8 * n);
+    }
+    return true;
+}
+
+int64_t expected_length(const SpectrumInfo& s, const ArrayInfo& a) { return a.length >= 0 ? a.length : s.default_length; }
+
+// rows of a spectrum before decoding: exact for uncompressed arrays, the declared length for compressed ones
+int64_t planned_rows(const SpectrumInfo& s) {
+    if (!s.mz.present) return 0;
+    if (!s.mz.zlib) {
+        size_t symbols = 0;
+        for (const char* p = s.mz.text.a; p < s.mz.text.b; ++p) symbols += g_base64.value[(unsigned char)*p] >= 0;
+        return (int64_t)(symbols * 6 / 8 / (s.mz.f32 ? 4 : 8));
+    }
+    const int64_t n = expected_length(s, s.mz);
+    return n < 0 ? 0 : n;
+}
+
+// pymzml-style id: the number behind the first "scan=", "index=" or "spectrum=" of the native id, else ordinal + 1
+int64_t spectrum_id(const SpectrumInfo& s) {
+    static const char* keys[3] = {"scan=", "index=", "spectrum="};
+    for (const char* p = s.native_id.a; p < s.native_id.b; ++p) {
+        for (const char* key : keys) {
+            const size_t n = strlen(key);
+            if ((size_t)(s.native_id.b - p) > n && memcmp(p, key, n) == 0 && p[n] >= '0' && p[n] <= '9') {
+                int64_t v = 0;
+                for (const char* d = p + n; d < s.native_id.b && *d >= '0' && *d <= '9'; ++d) v = v * 10 + (*d - '0');
+                return v;
+            }
+        }
+    }
+    return s.ordinal + 1;
+}
+
+bool selected(const SpectrumInfo& s, int32_t ms_level) { return ms_level <= 0 || s.level == ms_level; }
+
+}  // namespace
+
+extern "C" {
+
+const char* qms_mzml_last_error(void) { return g_error.c_str(); }
+
+int qms_mzml_open(const char* path, qms_mzml** out) {
+    if (!path || !out) return fail(QMS_MZML_E_ARG, "qms_mzml_open: NULL argument");
+    *out = nullptr;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(QMS_MZML_E_IO, "cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) {
+        close(fd);
+        return fail(QMS_MZML_E_IO, "cannot stat %s (or the file is empty)", path);
+    }
+    void* map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (map == MAP_FAILED) {
+        close(fd);
+        return fail(QMS_MZML_E_IO, "cannot map %s", path);
+    }
+    madvise(map, (size_t)st.st_size, MADV_SEQUENTIAL);
+    qms_mzml* f = new qms_mzml();
+    f->fd = fd;
+    f->data = (const char*)map;
+    f->size = (size_t)st.st_size;
+    const int rc = build_index(f);
+    if (rc != QMS_MZML_OK) {
+        qms_mzml_close(f);
+        return rc;
+    }
+    *out = f;
+    return QMS_MZML_OK;
+}
+
+void qms_mzml_close(qms_mzml* f) {
+    if (!f) return;
+    if (f->data) munmap((void*)f->data, f->size);
+    if (f->fd >= 0) close(f->fd);
+    delete f;
+}
+
+int qms_mzml_count(qms_mzml* f, int32_t ms_level, int64_t* n_spectra, int64_t* n_peaks) {
+    if (!f || !n_spectra || !n_peaks) return fail(QMS_MZML_E_ARG, "qms_mzml_count: NULL argument");
+    int64_t spectra = 0, peaks = 0;
+    for (const SpectrumInfo& s : f->spectra) {
+        if (!selected(s, ms_level)) continue;
+        if (s.unsupported) return fail(QMS_MZML_E_UNSUPPORTED, "spectrum %lld uses an array encoding this reader does not decode", (long long)s.ordinal);
+        if (!s.mz.present || !s.intensity.present)
+            return fail(QMS_MZML_E_FORMAT, "spectrum %lld: m/z and intensity arrays missing", (long long)s.ordinal);
+        ++spectra;
+        peaks += planned_rows(s);
+    }
+    *n_spectra = spectra;
+    *n_peaks = peaks;
+    return QMS_MZML_OK;
+}
+
+int qms_mzml_read(qms_mzml* f, int32_t ms_level, int32_t sort_peaks, int32_t n_threads, double* peaks, int64_t* offsets, int64_t* ids,
+                  double* rt, uint8_t* rt_unit, int32_t* levels) {
+    if (!f || !offsets) return fail(QMS_MZML_E_ARG, "qms_mzml_read: NULL argument");
+    std::vector<const SpectrumInfo*> chosen;
+    for (const SpectrumInfo& s : f->spectra)
+        if (selected(s, ms_level)) chosen.push_back(&s);
+    offsets[0] = 0;
+    for (size_t i = 0; i < chosen.size(); ++i) {
+        offsets[i + 1] = offsets[i] + planned_rows(*chosen[i]);
+        if (ids) ids[i] = spectrum_id(*chosen[i]);
+        if (rt) rt[i] = chosen[i]->has_rt ? chosen[i]->rt : 0.0;
+        if (rt_unit) rt_unit[i] = chosen[i]->has_rt ? (chosen[i]->rt_seconds ? 2 : 1) : 0;
+        if (levels) levels[i] = chosen[i]->level;
+    }
+    if (chosen.empty()) return QMS_MZML_OK;
+    if (!peaks && offsets[chosen.size()] > 0) return fail(QMS_MZML_E_ARG, "qms_mzml_read: peaks is NULL");
+    int threads = n_threads > 0 ? n_threads : (int)(std::thread::hardware_concurrency() / 2);
+    threads = std::max(1, std::min(threads, 16));
+    threads = (int)std::min<size_t>((size_t)threads, chosen.size());
+    std::atomic<size_t> next{0};
+    std::atomic<int> status{QMS_MZML_OK};
+    std::atomic<long long> broken{-1};
+    auto worker = [&]() {
+        Scratch s;
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= chosen.size() || status.load() != QMS_MZML_OK) return;
+            const SpectrumInfo& sp = *chosen[i];
+            const int64_t rows = offsets[i + 1] - offsets[i];
+            if (!decode_array(sp.mz, expected_length(sp, sp.mz), s, s.mz) ||
+                !decode_array(sp.intensity, expected_length(sp, sp.intensity), s, s.intensity) ||
+                (int64_t)s.mz.size() != rows || s.intensity.size() != s.mz.size()) {
+                broken.store((long long)sp.ordinal);
+                status.store(QMS_MZML_E_FORMAT);
+                return;
+            }
+            double* out = peaks + 2 * offsets[i];
+            bool ascending = true;
+            for (int64_t k = 1; k < rows && ascending; ++k) ascending = !(s.mz[k] < s.mz[k - 1]);
+            if (sort_peaks && !ascending) {
+                s.order.resize((size_t)rows);
+                std::iota(s.order.begin(), s.order.end(), (int64_t)0);
+                std::stable_sort(s.order.begin(), s.order.end(), [&](int64_t a, int64_t b) { return s.mz[a] < s.mz[b]; });
+                for (int64_t k = 0; k < rows; ++k) {
+                    out[2 * k] = s.mz[s.order[k]];
+                    out[2 * k + 1] = s.intensity[s.order[k]];
+                }
+            } else {
+                for (int64_t k = 0; k < rows; ++k) {
+                    out[2 * k] = s.mz[k];
+                    out[2 * k + 1] = s.intensity[k];
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    if (status.load() != QMS_MZML_OK)
+        return fail(status.load(), "spectrum %lld: binary arrays are broken or do not have the declared length", broken.load());
+    return QMS_MZML_OK;
+}
+
+}  // extern "C"

@@ -10,10 +10,12 @@ m/z array, MS:1000515 intensity array, MS:1000521/523 32/64-bit float, MS:100057
     results = lib.match_many(run.peaks, file_name=run.name, spec_ids=run.spec_ids, spec_rts=run.rts, offsets=run.offsets)
 """
 import base64
+import ctypes as C
 import os
 import re
 import zlib
 from collections import namedtuple
+from pathlib import Path
 import xml.etree.ElementTree as ET
 
 import numpy as np
@@ -58,11 +60,77 @@ def spectrum_id(native_id, index):
     return int(found.group(1)) if found else index + 1
 
 
-def read_mzml(path, ms_level=1, sort_peaks=True):
+_NATIVE = None
+_NATIVE_PATH = Path(__file__).resolve().parent / "libqms_mzml.so"
+
+
+def _native():
+    """ctypes handle of libqms_mzml.so (include/qms_mzml.h), or None if it has not been built."""
+    global _NATIVE
+    if _NATIVE is None:
+        if not _NATIVE_PATH.exists():
+            _NATIVE = False
+        else:
+            lib = C.CDLL(str(_NATIVE_PATH))
+            lib.qms_mzml_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+            lib.qms_mzml_close.argtypes = [C.c_void_p]
+            lib.qms_mzml_close.restype = None
+            lib.qms_mzml_last_error.restype = C.c_char_p
+            lib.qms_mzml_count.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+            lib.qms_mzml_read.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
+            _NATIVE = lib
+    return _NATIVE or None
+
+
+def _read_native(lib, path, ms_level, sort_peaks, threads):
+    """The packed run through libqms_mzml.so; None when the file needs a decoder the native reader lacks."""
+    handle = C.c_void_p()
+    rc = lib.qms_mzml_open(os.fsencode(str(path)), C.byref(handle))
+    if rc != 0:
+        raise OSError("%s: %s" % (path, lib.qms_mzml_last_error().decode()))
+    try:
+        n_spectra, n_peaks = C.c_int64(), C.c_int64()
+        level = 0 if ms_level is None else int(ms_level)
+        rc = lib.qms_mzml_count(handle, level, C.byref(n_spectra), C.byref(n_peaks))
+        if rc == -3:
+            return None
+        if rc != 0:
+            raise ValueError(lib.qms_mzml_last_error().decode())
+        n = n_spectra.value
+        peaks = np.empty((n_peaks.value, 2), dtype=np.float64)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        ids, rt = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.float64)
+        unit, levels = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.int32)
+        rc = lib.qms_mzml_read(handle, level, 1 if sort_peaks else 0, int(threads or 0), peaks.ctypes.data, offsets.ctypes.data,
+                               ids.ctypes.data, rt.ctypes.data, unit.ctypes.data, levels.ctypes.data)
+        if rc != 0:
+            raise ValueError(lib.qms_mzml_last_error().decode())
+    finally:
+        lib.qms_mzml_close(handle)
+    names = (None, "minute", "second")
+    rts = [None if u == 0 else (value, names[u]) for value, u in zip(rt.tolist(), unit.tolist())]
+    return Run(os.path.basename(str(path)), peaks, offsets, ids.tolist(), rts, [None if v < 0 else v for v in levels.tolist()])
+
+
+def read_mzml(path, ms_level=1, sort_peaks=True, native=None, threads=None):
     """Read every spectrum of ``ms_level`` (None = all) into a packed ``Run``.
 
     ``rts`` holds ``(value, unit)`` tuples like pymzml's ``scan_time`` (unit 'minute' or 'second'), which is
-    what ``Results``/``calc_amounts`` understand (results.py:1240-1246)."""
+    what ``Results``/``calc_amounts`` understand (results.py:1240-1246).
+
+    ``native``: None (default) uses libqms_mzml.so when it is built -- the file is memory-mapped, indexed by a tag
+    scanner and decoded by ``threads`` threads -- and falls back to the ElementTree reader below for encodings it
+    does not decode (numpress, integer arrays); True insists on the native reader, False on the ElementTree one."""
+    if native is not False:
+        lib = _native()
+        if lib is None and native:
+            raise ImportError("%s not found: build it with `make -C pyqms_b200/csrc`" % _NATIVE_PATH)
+        if lib is not None:
+            run = _read_native(lib, path, ms_level, sort_peaks, threads)
+            if run is not None:
+                return run
+            if native:
+                raise ValueError("%s uses an array encoding the native reader does not decode" % path)
     mz_parts, int_parts, lengths, ids, rts, levels = [], [], [], [], [], []
     index = -1
     for _, element in ET.iterparse(str(path), events=("end",)):

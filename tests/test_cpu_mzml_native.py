@@ -1,0 +1,141 @@
+"""libqms_mzml.so (include/qms_mzml.h): the native mzML reader must return exactly what the ElementTree reader returns
+(N3), for every encoding the writer produces and for hand-written files with the variations converters produce."""
+import base64
+import ctypes
+import re
+import struct
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from pyqms_b200 import mzml
+from pyqms_b200.mzml import read_mzml, write_mzml
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built_library():
+    if not (ROOT / "pyqms_b200" / "libqms_mzml.so").exists():     # fresh checkout: make builds it with the CUDA library
+        import sys
+        sys.path.insert(0, str(ROOT))
+        import __graft_entry__
+        __graft_entry__.build()
+        mzml._NATIVE = None
+
+
+def same_run(a, b):
+    return (np.array_equal(a.peaks, b.peaks) and np.array_equal(a.offsets, b.offsets) and a.spec_ids == b.spec_ids and
+            a.rts == b.rts and a.ms_levels == b.ms_levels and a.name == b.name)
+
+
+def test_native_library_exports_the_declared_symbols():
+    header = (ROOT / "include" / "qms_mzml.h").read_text()
+    declared = sorted(set(re.findall(r"\b(qms_mzml_[a-z_]+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S))))
+    assert len(declared) == 5
+    lib = ctypes.CDLL(str(ROOT / "pyqms_b200" / "libqms_mzml.so"))
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+@pytest.mark.parametrize("precision,compress", [(64, True), (64, False), (32, True), (32, False)])
+def test_native_reader_equals_elementtree_reader(tmp_path, precision, compress):
+    rng = np.random.default_rng(precision + compress)
+    spectra, levels = [], []
+    for s in range(40):
+        k = int(rng.integers(0, 400)) if s != 5 else 0          # an empty spectrum, too
+        mz, inten = np.sort(rng.uniform(100, 2000, k)), 10 ** rng.uniform(2, 7, k)
+        if s % 6 == 0 and k > 3:                                  # unsorted peaks: both readers reorder stably
+            mz[[0, -1]] = mz[[-1, 0]]
+            mz[k // 2] = mz[k // 2 - 1]
+        spectra.append(np.stack([mz, inten], axis=1))
+        levels.append(2 if s % 4 == 3 else 1)
+    path = tmp_path / "run.mzML"
+    write_mzml(path, spectra, rts_minutes=[0.25 * s for s in range(40)], ms_levels=levels, precision=precision, compress=compress)
+    for level in (1, 2, None):
+        for sort_peaks in (True, False):
+            slow = read_mzml(path, ms_level=level, sort_peaks=sort_peaks, native=False)
+            for threads in (1, 3):
+                fast = read_mzml(path, ms_level=level, sort_peaks=sort_peaks, native=True, threads=threads)
+                assert same_run(slow, fast), (level, sort_peaks, threads)
+    assert len(read_mzml(path, ms_level=1).spec_ids) == 30 and same_run(read_mzml(path), read_mzml(path, native=False))
+
+
+def _array(values, accession, dtype="<f8", compressed=False, wrap=False, group=None):
+    raw = np.asarray(values, dtype=dtype).tobytes()
+    if compressed:
+        raw = zlib.compress(raw)
+    text = base64.b64encode(raw).decode()
+    if wrap:                                                     # line breaks inside the payload
+        text = "\n".join(text[i:i + 60] for i in range(0, len(text), 60)) + "\n"
+    width = "MS:1000523" if dtype == "<f8" else "MS:1000521"
+    packing = "MS:1000574" if compressed else "MS:1000576"
+    params = ('<referenceableParamGroupRef ref="%s"/>' % group) if group else (
+        '<cvParam cvRef="MS" accession="%s" name="float"/><cvParam cvRef="MS" accession="%s" name="packing"/>' % (width, packing))
+    return ('<binaryDataArray encodedLength="%d">%s<cvParam cvRef="MS" accession="%s" name="array"/><binary>%s</binary>'
+            '</binaryDataArray>' % (len(text), params, accession, text))
+
+
+def _spectrum(index, native_id, level_xml, rt_xml, mz, inten, **kw):
+    return ('<spectrum index="%d" id="%s" defaultArrayLength="%d">%s<scanList count="1"><scan>%s</scan></scanList>'
+            '<binaryDataArrayList count="2">%s%s</binaryDataArrayList></spectrum>' % (
+                index, native_id, len(mz), level_xml, rt_xml, _array(mz, "MS:1000514", **kw), _array(inten, "MS:1000515", **kw)))
+
+
+def test_converter_style_variations(tmp_path):
+    """Param groups, namespace prefixes, comments, '>' inside attribute values, wrapped base64, seconds, missing times."""
+    level1 = '<cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="1"/>'
+    body = "".join([
+        _spectrum(0, "controllerType=0 controllerNumber=1 scan=17", level1,
+                  '<cvParam cvRef="MS" accession="MS:1000016" name="scan start time" value="93.5" unitName="second"/>',
+                  [400.5, 300.25, 500.125], [10.0, 20.0, 30.0], wrap=True),
+        "<!-- a comment with <spectrum> inside -->",
+        _spectrum(1, "index=7", '<referenceableParamGroupRef ref="ms1"/>',
+                  '<userParam name="filter" value="FTMS + p NSI Full ms [300.00-2000.00] a>b"/>'
+                  '<cvParam cvRef="MS" accession="MS:1000016" name="scan start time" value="1.75" unitName="minute"/>',
+                  [200.0, 201.0], [5.0, 6.0], compressed=True, group="zlib64"),
+        _spectrum(2, "no number here", level1, "", [100.0], [1.0], dtype="<f4"),
+        _spectrum(3, "scan=9", '<cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="2"/>', "", [50.0, 60.0], [1.0, 2.0]),
+    ])
+    text = ('<?xml version="1.0" encoding="utf-8"?>\n<mzML xmlns="http://psi.hupo.org/ms/mzml"><referenceableParamGroupList count="2">'
+            '<referenceableParamGroup id="ms1"><cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="1"/>'
+            '</referenceableParamGroup><referenceableParamGroup id="zlib64"><cvParam cvRef="MS" accession="MS:1000523" name="64-bit float"/>'
+            '<cvParam cvRef="MS" accession="MS:1000574" name="zlib compression"/></referenceableParamGroup></referenceableParamGroupList>'
+            '<run id="r"><spectrumList count="4">%s</spectrumList><chromatogramList count="1"><chromatogram index="0" id="TIC" '
+            'defaultArrayLength="2"><binaryDataArrayList count="1">%s</binaryDataArrayList></chromatogram></chromatogramList></run></mzML>'
+            % (body, _array([1.0, 2.0], "MS:1000595")))
+    path = tmp_path / "variations.mzML"
+    path.write_text(text)
+    run = read_mzml(path, ms_level=1, native=True)
+    assert run.spec_ids == [17, 7, 3] and run.ms_levels == [1, 1, 1]
+    assert run.rts == [(93.5, "second"), (1.75, "minute"), None]
+    assert run.offsets.tolist() == [0, 3, 5, 6]
+    assert run.peaks.tolist() == [[300.25, 20.0], [400.5, 10.0], [500.125, 30.0], [200.0, 5.0], [201.0, 6.0], [100.0, 1.0]]
+    everything = read_mzml(path, ms_level=None, native=True)
+    assert everything.spec_ids == [17, 7, 3, 9] and everything.ms_levels == [1, 1, 1, 2] and len(everything.peaks) == 8
+    # the ElementTree reader does not resolve param groups; on the spectra that do not use them both agree
+    slow = read_mzml(path, ms_level=2, native=False)
+    assert same_run(slow, read_mzml(path, ms_level=2, native=True))
+
+
+def test_unsupported_encodings_fall_back_and_broken_files_raise(tmp_path):
+    level1 = '<cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="1"/>'
+    numpress = _spectrum(0, "scan=1", level1, "", [100.0, 200.0], [1.0, 2.0]).replace(
+        '<cvParam cvRef="MS" accession="MS:1000514"', '<cvParam cvRef="MS" accession="MS:1002312" name="numpress"/><cvParam cvRef="MS" accession="MS:1000514"')
+    path = tmp_path / "numpress.mzML"
+    path.write_text("<mzML><run><spectrumList>%s</spectrumList></run></mzML>" % numpress)
+    with pytest.raises(ValueError, match="does not decode"):
+        read_mzml(path, native=True)
+    fallback = read_mzml(path)                                   # default: quietly handled by the ElementTree reader
+    assert fallback.offsets.tolist() == [0, 2]
+    broken = _spectrum(0, "scan=1", level1, "", [100.0, 200.0, 300.0], [1.0, 2.0, 3.0], compressed=True)
+    payload = re.search(r"<binary>([^<]+)</binary>", broken).group(1)
+    path = tmp_path / "broken.mzML"
+    path.write_text("<mzML><run><spectrumList>%s</spectrumList></run></mzML>" % broken.replace(payload, payload[:12], 1))
+    with pytest.raises(ValueError, match="broken"):
+        read_mzml(path, native=True)
+    with pytest.raises(OSError):
+        read_mzml(tmp_path / "missing.mzML", native=True)
+    assert struct.calcsize("d") == 8 and mzml._native() is not None
