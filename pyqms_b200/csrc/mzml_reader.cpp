@@ -148,24 +148,31 @@ void apply_param(const Param& p, SpectrumInfo& s, ArrayInfo* array, ArrayKind* k
     }
 }
 
-int build_index(qms_mzml* f) {
-    const char* p = f->data;
-    const char* end = f->data + f->size;
-    std::unordered_map<std::string, std::vector<Param>> groups;
+typedef std::unordered_map<std::string, std::vector<Param>> ParamGroups;
+
+// Tag scan of [begin, end).  Spectra found are appended to `out` with ordinals from `first_ordinal`; param-group
+// definitions go to `define` (head of the file) and are looked up in `groups`.  With `stop_at_spectrum` the scan
+// ends at the first <spectrum> tag and reports its position.
+int scan_range(const char* begin, const char* end, const ParamGroups& groups, ParamGroups* define, int64_t first_ordinal,
+               std::vector<SpectrumInfo>& out, bool stop_at_spectrum, const char** stopped_at) {
+    const char* p = begin;
     std::vector<Param>* open_group = nullptr;
-    SpectrumInfo* spectrum = nullptr;
+    bool in_spectrum = false;           // `out.back()` is open
     ArrayInfo array;
     ArrayKind kind = KIND_NONE;
     bool in_array = false;
-    int64_t ordinal = 0;
+    int64_t ordinal = first_ordinal;
+    if (stopped_at) *stopped_at = nullptr;
     while (p < end) {
         const char* lt = (const char*)memchr(p, '<', (size_t)(end - p));
         if (!lt || lt + 1 >= end) break;
         const char* name = lt + 1;
         if (*name == '!' || *name == '?') {                // comments, declarations, processing instructions
-            const char* gt = (const char*)memchr(name, '>', (size_t)(end - name));
+            const char* gt = name[0] == '!' && name + 2 < end && name[1] == '-' && name[2] == '-'
+                                 ? (const char*)memmem(name, (size_t)(end - name), "-->", 3)
+                                 : (const char*)memchr(name, '>', (size_t)(end - name));
             if (!gt) break;
-            p = gt + 1;
+            p = gt + (*gt == '-' ? 3 : 1);
             continue;
         }
         const bool closing = *name == '/';
@@ -188,6 +195,7 @@ int build_index(qms_mzml* f) {
         const char* colon = (const char*)memchr(tag.a, ':', tag.size());     // namespace prefix
         if (colon) tag.a = colon + 1;
         const bool self_closing = gt > lt && gt[-1] == '/';
+        SpectrumInfo* spectrum = in_spectrum ? &out.back() : nullptr;
         if (!closing) {
             if (tag.equals("cvParam")) {
                 Param param{attribute(q, gt, "accession"), attribute(q, gt, "value"), attribute(q, gt, "unitName")};
@@ -200,14 +208,18 @@ int build_index(qms_mzml* f) {
                         for (const Param& param : it->second) apply_param(param, *spectrum, in_array ? &array : nullptr, &kind);
                 }
             } else if (tag.equals("referenceableParamGroup")) {
-                open_group = self_closing ? nullptr : &groups[attribute(q, gt, "id").str()];
+                open_group = (self_closing || !define) ? nullptr : &(*define)[attribute(q, gt, "id").str()];
             } else if (tag.equals("spectrum")) {
-                f->spectra.emplace_back();
-                spectrum = &f->spectra.back();
+                if (stop_at_spectrum) {
+                    if (stopped_at) *stopped_at = lt;
+                    return QMS_MZML_OK;
+                }
+                out.emplace_back();
+                spectrum = &out.back();
                 spectrum->ordinal = ordinal++;
                 spectrum->native_id = attribute(q, gt, "id");
                 spectrum->default_length = to_int(attribute(q, gt, "defaultArrayLength"), -1);
-                if (self_closing) spectrum = nullptr;
+                in_spectrum = !self_closing;
             } else if (tag.equals("binaryDataArray") && spectrum) {
                 array = ArrayInfo{};
                 array.length = to_int(attribute(q, gt, "arrayLength"), -1);
@@ -231,7 +243,7 @@ int build_index(qms_mzml* f) {
                 else if (kind == KIND_INTENSITY) spectrum->intensity = array;
                 in_array = false;
             } else if (tag.equals("spectrum")) {
-                spectrum = nullptr;
+                in_spectrum = false;
                 in_array = false;
             } else if (tag.equals("referenceableParamGroup")) {
                 open_group = nullptr;
@@ -239,6 +251,95 @@ int build_index(qms_mzml* f) {
         }
         p = gt + 1;
     }
+    return QMS_MZML_OK;
+}
+
+// byte offsets of the <spectrum> elements from the index of an indexedmzML file; empty if there is no usable index
+std::vector<size_t> indexed_offsets(const qms_mzml* f) {
+    std::vector<size_t> offsets;
+    const size_t tail = std::min<size_t>(f->size, 4096);
+    const char* tag = (const char*)memmem(f->data + f->size - tail, tail, "<indexListOffset>", 17);
+    if (!tag) return offsets;
+    const int64_t list_at = to_int(Span{tag + 17, std::min(tag + 17 + 24, f->data + f->size)}, -1);
+    if (list_at <= 0 || (size_t)list_at >= f->size || memcmp(f->data + list_at, "<indexList", 10) != 0) return offsets;
+    const char* p = f->data + list_at;
+    const char* end = f->data + f->size;
+    const char* index = (const char*)memmem(p, (size_t)(end - p), "<index name=\"spectrum\"", 23);
+    if (!index) return offsets;
+    const char* index_end = (const char*)memmem(index, (size_t)(end - index), "</index>", 8);
+    if (!index_end) return offsets;
+    for (const char* o = index; (o = (const char*)memmem(o, (size_t)(index_end - o), "<offset", 7)) != nullptr;) {
+        const char* gt = (const char*)memchr(o, '>', (size_t)(index_end - o));
+        if (!gt) break;
+        const int64_t at = to_int(Span{gt + 1, std::min(gt + 1 + 24, index_end)}, -1);
+        // every offset must point at a <spectrum> tag in ascending order, or the index is not trusted at all
+        if (at <= 0 || (size_t)at + 10 >= (size_t)list_at || memcmp(f->data + at, "<spectrum", 9) != 0 ||
+            (!offsets.empty() && (size_t)at <= offsets.back()))
+            return std::vector<size_t>();
+        offsets.push_back((size_t)at);
+        o = gt;
+    }
+    return offsets;
+}
+
+int build_index(qms_mzml* f, int n_threads) {
+    const char* begin = f->data;
+    const char* end = f->data + f->size;
+    ParamGroups groups;
+    const std::vector<size_t> offsets = indexed_offsets(f);
+    int threads = n_threads > 0 ? n_threads : (int)(std::thread::hardware_concurrency() / 2);
+    threads = std::max(1, std::min(threads, 16));
+    if (offsets.size() < 64 || threads < 2) {               // no (trusted) index or nothing to gain: one sequential scan
+        const ParamGroups none;
+        std::vector<SpectrumInfo> head;
+        const char* first = nullptr;
+        int rc = scan_range(begin, end, none, &groups, 0, head, true, &first);
+        if (rc != QMS_MZML_OK || !first) return rc;
+        return scan_range(first, end, groups, nullptr, 0, f->spectra, false, nullptr);
+    }
+    // indexed file: the head (param groups) sequentially, then the spectra in contiguous blocks, one per thread
+    {
+        const ParamGroups none;
+        std::vector<SpectrumInfo> head;
+        int rc = scan_range(begin, begin + offsets[0], none, &groups, 0, head, true, nullptr);
+        if (rc != QMS_MZML_OK) return rc;
+    }
+    const char* list_end = (const char*)memmem(begin + offsets.back(), (size_t)(end - begin) - offsets.back(), "</spectrumList", 14);
+    const char* region_end = list_end ? list_end : end;
+    threads = (int)std::min<size_t>((size_t)threads, offsets.size() / 32);
+    std::vector<std::vector<SpectrumInfo>> parts((size_t)threads);
+    std::vector<int> status((size_t)threads, QMS_MZML_OK);
+    std::vector<std::string> messages((size_t)threads);
+    auto work = [&](int t) {
+        const size_t a = offsets.size() * (size_t)t / (size_t)threads, b = offsets.size() * (size_t)(t + 1) / (size_t)threads;
+        const char* stop = b < offsets.size() ? begin + offsets[b] : region_end;
+        status[t] = scan_range(begin + offsets[a], stop, groups, nullptr, (int64_t)a, parts[t], false, nullptr);
+        if (status[t] != QMS_MZML_OK) messages[t] = g_error;
+        if (status[t] == QMS_MZML_OK && parts[t].size() != b - a) {
+            status[t] = QMS_MZML_E_FORMAT;
+            messages[t] = "the spectrum index of the file does not match its content";
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& t : pool) t.join();
+    for (int t = 0; t < threads; ++t)
+        if (status[t] != QMS_MZML_OK) {
+            if (status[t] == QMS_MZML_E_FORMAT && messages[t].find("index of the file") != std::string::npos) {
+                // a wrong index is not an error of the data: fall back to the sequential scan
+                f->spectra.clear();
+                const ParamGroups none;
+                ParamGroups again;
+                std::vector<SpectrumInfo> head;
+                const char* first = nullptr;
+                int rc = scan_range(begin, end, none, &again, 0, head, true, &first);
+                if (rc != QMS_MZML_OK || !first) return rc;
+                return scan_range(first, end, again, nullptr, 0, f->spectra, false, nullptr);
+            }
+            return fail(status[t], "%s", messages[t].c_str());
+        }
+    for (auto& part : parts) f->spectra.insert(f->spectra.end(), part.begin(), part.end());
     return QMS_MZML_OK;
 }
 
@@ -414,7 +515,7 @@ int qms_mzml_open(const char* path, qms_mzml** out) {
     f->fd = fd;
     f->data = (const char*)map;
     f->size = (size_t)st.st_size;
-    const int rc = build_index(f);
+    const int rc = build_index(f, 0);
     if (rc != QMS_MZML_OK) {
         qms_mzml_close(f);
         return rc;

@@ -178,8 +178,9 @@ def read_mzml(path, ms_level=1, sort_peaks=True, native=None, threads=None):
     return Run(os.path.basename(str(path)), peaks, offsets, ids, rts, levels)
 
 
-def write_mzml(path, spectra, rts_minutes=None, ms_levels=None, precision=64, compress=True):
-    """Minimal mzML 1.1 writer (test fixtures and synthetic runs): ``spectra`` = list of (n, 2) arrays."""
+def write_mzml(path, spectra, rts_minutes=None, ms_levels=None, precision=64, compress=True, indexed=False):
+    """Minimal mzML 1.1 writer (test fixtures and synthetic runs): ``spectra`` = list of (n, 2) arrays.
+    ``indexed``: wrap the document in ``<indexedmzML>`` with the byte offset of every spectrum, as converters do."""
     dtype = np.dtype("<f8" if precision == 64 else "<f4")
 
     def binary(values, accession, name):
@@ -193,18 +194,34 @@ def write_mzml(path, spectra, rts_minutes=None, ms_levels=None, precision=64, co
                     len(text), _F64 if precision == 64 else _F32, precision, _ZLIB if compress else "MS:1000576",
                     "zlib compression" if compress else "no compression", accession, name, text)
 
-    with open(path, "w") as out:
-        out.write('<?xml version="1.0" encoding="utf-8"?>\n<mzML xmlns="http://psi.hupo.org/ms/mzml" version="1.1.0">\n'
-                  '<run id="synthetic"><spectrumList count="%d">\n' % len(spectra))
+    with open(path, "w", newline="") as out:
+        written, offsets = 0, []
+
+        def emit(text):
+            nonlocal written
+            out.write(text)
+            written += len(text)             # the document is pure ASCII: characters = bytes
+
+        emit('<?xml version="1.0" encoding="utf-8"?>\n')
+        if indexed:
+            emit('<indexedmzML xmlns="http://psi.hupo.org/ms/mzml">\n')
+        emit('<mzML xmlns="http://psi.hupo.org/ms/mzml" version="1.1.0">\n<run id="synthetic"><spectrumList count="%d">\n' % len(spectra))
         for n, spectrum in enumerate(spectra):
             spectrum = np.asarray(spectrum, dtype=np.float64).reshape(-1, 2)
             level = 1 if ms_levels is None else ms_levels[n]
             rt = 0.01 * n if rts_minutes is None else rts_minutes[n]
-            out.write('<spectrum index="%d" id="controllerType=0 controllerNumber=1 scan=%d" defaultArrayLength="%d">'
-                      '<cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="%d"/>'
-                      '<scanList count="1"><scan><cvParam cvRef="MS" accession="MS:1000016" name="scan start time" '
-                      'value="%r" unitName="minute"/></scan></scanList><binaryDataArrayList count="2">%s%s'
-                      "</binaryDataArrayList></spectrum>\n" % (
-                          n, n + 1, len(spectrum), level, rt, binary(spectrum[:, 0], _MZ, "m/z array"),
-                          binary(spectrum[:, 1], _INTENSITY, "intensity array")))
-        out.write("</spectrumList></run></mzML>\n")
+            offsets.append(written)
+            emit('<spectrum index="%d" id="controllerType=0 controllerNumber=1 scan=%d" defaultArrayLength="%d">'
+                 '<cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="%d"/>'
+                 '<scanList count="1"><scan><cvParam cvRef="MS" accession="MS:1000016" name="scan start time" '
+                 'value="%r" unitName="minute"/></scan></scanList><binaryDataArrayList count="2">%s%s'
+                 "</binaryDataArrayList></spectrum>\n" % (
+                     n, n + 1, len(spectrum), level, rt, binary(spectrum[:, 0], _MZ, "m/z array"),
+                     binary(spectrum[:, 1], _INTENSITY, "intensity array")))
+        emit("</spectrumList></run></mzML>\n")
+        if indexed:
+            list_at = written
+            emit('<indexList count="1">\n<index name="spectrum">\n')
+            for n, at in enumerate(offsets):
+                emit('<offset idRef="controllerType=0 controllerNumber=1 scan=%d">%d</offset>\n' % (n + 1, at))
+            emit("</index>\n</indexList>\n<indexListOffset>%d</indexListOffset>\n</indexedmzML>\n" % list_at)

@@ -139,3 +139,38 @@ def test_unsupported_encodings_fall_back_and_broken_files_raise(tmp_path):
     with pytest.raises(OSError):
         read_mzml(tmp_path / "missing.mzML", native=True)
     assert struct.calcsize("d") == 8 and mzml._native() is not None
+
+
+def test_indexed_files_are_scanned_in_parallel_blocks(tmp_path):
+    """indexedmzML: the spectrum offsets of the file's index split the tag scan over the threads; a wrong index is ignored."""
+    rng = np.random.default_rng(8)
+    spectra = [np.stack([np.sort(rng.uniform(100, 2000, k)), 10 ** rng.uniform(2, 7, k)], axis=1)
+               for k in rng.integers(1, 60, size=300)]
+    levels = [1 if s % 5 else 2 for s in range(300)]
+    path = tmp_path / "indexed.mzML"
+    write_mzml(path, spectra, ms_levels=levels, indexed=True)
+    plain = tmp_path / "plain.mzML"
+    write_mzml(plain, spectra, ms_levels=levels, indexed=False)
+    want = read_mzml(plain, ms_level=None, native=False)
+    for threads in (1, 2, 5, 16):
+        lib = mzml._native()
+        handle = ctypes.c_void_p()
+        assert lib.qms_mzml_open(str(path).encode(), ctypes.byref(handle)) == 0
+        lib.qms_mzml_close(handle)
+        got = read_mzml(path, ms_level=None, native=True, threads=threads)
+        assert np.array_equal(got.peaks, want.peaks) and np.array_equal(got.offsets, want.offsets)
+        assert got.spec_ids == want.spec_ids and got.rts == want.rts and got.ms_levels == want.ms_levels
+    assert same_run(read_mzml(path, ms_level=1, native=False)._replace(name="x"), read_mzml(path, ms_level=1, native=True)._replace(name="x"))
+    # an index whose offsets do not point at <spectrum> tags (file edited after indexing) is not used
+    text = path.read_text()
+    shifted = re.sub(r"<offset ([^>]*)>(\\d+)</offset>", lambda m: "<offset %s>%d</offset>" % (m.group(1), int(m.group(2)) + 3), text)
+    bad = tmp_path / "bad_index.mzML"
+    bad.write_text(shifted)
+    got = read_mzml(bad, ms_level=None, native=True)
+    assert np.array_equal(got.peaks, want.peaks) and got.spec_ids == want.spec_ids
+    # an index that lists fewer spectra than the file holds (count mismatch inside a block) falls back as well
+    fewer = re.sub(r'<offset idRef="[^"]*scan=(?:7|8|9)">\\d+</offset>\\n', "", text)
+    short = tmp_path / "short_index.mzML"
+    short.write_text(fewer)
+    got = read_mzml(short, ms_level=None, native=True)
+    assert np.array_equal(got.peaks, want.peaks) and got.spec_ids == want.spec_ids
