@@ -26,7 +26,8 @@ extern "C" {
 
 typedef struct qms_mzml qms_mzml;
 
-/* Map `path` and index its <spectrum> elements (ms level, scan start time, array encodings and byte ranges). */
+/* Map `path` (a gzip-compressed file is inflated into memory first) and index its <spectrum> elements (ms level,
+ * scan start time, array encodings and byte ranges); the scan is split over threads for indexedmzML files. */
 int qms_mzml_open(const char* path, qms_mzml** out);
 void qms_mzml_close(qms_mzml* file);
 const char* qms_mzml_last_error(void);

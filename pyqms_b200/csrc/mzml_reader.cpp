@@ -70,8 +70,10 @@ enum ArrayKind { KIND_NONE, KIND_MZ, KIND_INTENSITY };
 
 struct qms_mzml {
     int fd = -1;
-    const char* data = nullptr;
+    const char* data = nullptr;       // the mapped file, or `inflated` for a gzip-compressed one
     size_t size = 0;
+    bool mapped = false;
+    std::vector<char> inflated;
     std::vector<SpectrumInfo> spectra;
 };
 
@@ -515,6 +517,45 @@ int qms_mzml_open(const char* path, qms_mzml** out) {
     f->fd = fd;
     f->data = (const char*)map;
     f->size = (size_t)st.st_size;
+    f->mapped = true;
+    if (f->size > 2 && (unsigned char)f->data[0] == 0x1f && (unsigned char)f->data[1] == 0x8b) {
+        // gzip-compressed file (.mzML.gz): inflate it into memory once, index and decode from there
+        z_stream z;
+        memset(&z, 0, sizeof(z));
+        if (inflateInit2(&z, 16 + MAX_WBITS) != Z_OK) {
+            qms_mzml_close(f);
+            return fail(QMS_MZML_E_IO, "zlib initialisation failed");
+        }
+        f->inflated.resize(f->size * 4 + (1u << 20));
+        z.next_in = (Bytef*)f->data;
+        size_t fed = 0;
+        int zrc = Z_OK;
+        while (zrc != Z_STREAM_END) {
+            if (z.avail_in == 0 && fed < f->size) {
+                const size_t n = std::min<size_t>(f->size - fed, 1u << 30);
+                z.next_in = (Bytef*)(f->data + fed);
+                z.avail_in = (uInt)n;
+                fed += n;
+            }
+            if (z.total_out == f->inflated.size()) f->inflated.resize(f->inflated.size() * 2);
+            z.next_out = (Bytef*)f->inflated.data() + z.total_out;
+            z.avail_out = (uInt)std::min<size_t>(f->inflated.size() - z.total_out, 1u << 30);
+            zrc = inflate(&z, Z_NO_FLUSH);
+            if (zrc != Z_OK && zrc != Z_STREAM_END && zrc != Z_BUF_ERROR) break;
+            if (zrc == Z_BUF_ERROR && z.avail_in == 0 && fed >= f->size) break;      // truncated
+        }
+        const size_t total = z.total_out;
+        inflateEnd(&z);
+        if (zrc != Z_STREAM_END) {
+            qms_mzml_close(f);
+            return fail(QMS_MZML_E_FORMAT, "%s: broken gzip stream", path);
+        }
+        f->inflated.resize(total);
+        munmap((void*)f->data, f->size);
+        f->mapped = false;
+        f->data = f->inflated.data();
+        f->size = total;
+    }
     const int rc = build_index(f, 0);
     if (rc != QMS_MZML_OK) {
         qms_mzml_close(f);
@@ -526,7 +567,7 @@ int qms_mzml_open(const char* path, qms_mzml** out) {
 
 void qms_mzml_close(qms_mzml* f) {
     if (!f) return;
-    if (f->data) munmap((void*)f->data, f->size);
+    if (f->data && f->mapped) munmap((void*)f->data, f->size);
     if (f->fd >= 0) close(f->fd);
     delete f;
 }

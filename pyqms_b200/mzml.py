@@ -3,7 +3,7 @@
 The reference's scripts loop ``pymzml.run.Reader`` and hand every MS1 spectrum's ``centroidedPeaks`` to
 ``match_all`` (example_scripts/quantify_mzml.py:59-73).  This reader goes from the file straight to the packed
 layout the batched matcher consumes -- one (N, 2) float64 array of (m/z, intensity) rows plus row offsets --
-without a Python object per peak: binary arrays are base64/zlib-decoded into numpy buffers (mzML 1.1: MS:1000514
+without a Python object per peak (plain or gzip-compressed files): binary arrays are base64/zlib-decoded into numpy buffers (mzML 1.1: MS:1000514
 m/z array, MS:1000515 intensity array, MS:1000521/523 32/64-bit float, MS:1000574 zlib, MS:1000576 none).
 
     run = read_mzml("BSA1.mzML", ms_level=1)
@@ -11,6 +11,7 @@ m/z array, MS:1000515 intensity array, MS:1000521/523 32/64-bit float, MS:100057
 """
 import base64
 import ctypes as C
+import gzip
 import os
 import re
 import zlib
@@ -133,7 +134,8 @@ def read_mzml(path, ms_level=1, sort_peaks=True, native=None, threads=None):
                 raise ValueError("%s uses an array encoding the native reader does not decode" % path)
     mz_parts, int_parts, lengths, ids, rts, levels = [], [], [], [], [], []
     index = -1
-    for _, element in ET.iterparse(str(path), events=("end",)):
+    source = gzip.open(str(path), "rb") if str(path).lower().endswith(".gz") else str(path)
+    for _, element in ET.iterparse(source, events=("end",)):
         if _local(element.tag) != "spectrum":
             continue
         index += 1

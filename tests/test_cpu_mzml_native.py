@@ -174,3 +174,22 @@ def test_indexed_files_are_scanned_in_parallel_blocks(tmp_path):
     short.write_text(fewer)
     got = read_mzml(short, ms_level=None, native=True)
     assert np.array_equal(got.peaks, want.peaks) and got.spec_ids == want.spec_ids
+
+
+def test_gzip_compressed_files(tmp_path):
+    import gzip
+    rng = np.random.default_rng(3)
+    spectra = [np.stack([np.sort(rng.uniform(100, 2000, k)), 10 ** rng.uniform(2, 7, k)], axis=1) for k in rng.integers(0, 200, size=80)]
+    plain = tmp_path / "run.mzML"
+    write_mzml(plain, spectra, indexed=True)
+    packed = tmp_path / "run.mzML.gz"
+    packed.write_bytes(gzip.compress(plain.read_bytes()))
+    want = read_mzml(plain, native=False)
+    for native in (True, False):
+        got = read_mzml(packed, native=native)
+        assert np.array_equal(got.peaks, want.peaks) and np.array_equal(got.offsets, want.offsets)
+        assert got.spec_ids == want.spec_ids and got.rts == want.rts and got.name == "run.mzML.gz"
+    broken = tmp_path / "cut.mzML.gz"
+    broken.write_bytes(packed.read_bytes()[:2000])
+    with pytest.raises(OSError):
+        read_mzml(broken, native=True)
