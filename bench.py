@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the matching hot path (spectra/s through match_all) on B200 -- see DESIGN.md section 6.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bsa|bsa_pct|proteome]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload proteome|bsa|bsa_pct]
 
-One *step* = one pass of the matcher over one synthetic LC-MS run (the `bsa` workload: BASELINE.json
-configs[1], 19 BSA molecules, 14N+15N, charges 1-4, carbamidomethyl fixed label, 30 000 spectra).
-Prints ONE JSON line (rank 0).  `value` = spectra/s with the run resident in HBM, device-timed (CUDA events
-on the library's stream, max over ranks); `e2e` = the same through the public host API with pinned HOST
-buffers (H2D of the spectra and D2H of the packed hits inside the timed region); `roofline` = the probe
-kernel against the measured HBM peak; `cpu_baseline` = the CPU oracle port (the reference's algorithm,
-pure Python like the reference) on a bounded sample of the same run on this box's host cores.
-`--impl reference` times that CPU path alone, on all host cores (one process per core over spectrum shards).
+Default workload = BASELINE.json configs[3], the north-star configuration: a 500 000-peptide tryptic proteome
+library (charges 1-5, carbamidomethyl fixed label; 1.59 M index entries, 10.3 M windows) against the 200 000-spectrum
+synthetic run, which is made of 8 shards of 25 000 spectra (seed 20260104 + shard).  One *step* = one pass of the
+matcher over ONE shard per GPU: N=1 matches shard 0, N GPUs match shards 0..N-1 (rank r owns shard r, library
+replicated, no data-path collective; N=8 is the whole named run) -- weak scaling.
+Prints ONE JSON line (rank 0).  `value` = spectra/s with the shard resident in HBM, device-timed (CUDA events on the
+library's stream, max over ranks); `e2e` = the same through the public host API (`match_many`) with pinned HOST
+buffers, H2D of the spectra and D2H of the packed hits inside the timed region and, for N>1, the hits of all ranks
+gathered on rank 0 in spectrum order; `roofline` = the kernel that dominates the step against the measured HBM peak
+with the algorithmic bytes of SURVEY.md 8d; `cpu_baseline` = the reference's CPU path on a bounded sample.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, pure Python) on all host cores, one process per core
+over disjoint spectra of the same shard, against a 5 000-peptide sample of the same library (the reference needs
+~20 min and ~40 GB per process to build the full one) and extrapolates by its measured per-bin cost.
 """
 import argparse
 import json
@@ -29,25 +34,64 @@ sys.path.insert(0, str(ROOT))
 from pyqms_b200.synthetic import BSA_MOLECULES, CAM_FIXED_LABEL, random_tryptic_peptides, synth_run  # noqa: E402
 
 WORKLOADS = {
-    # BASELINE.json configs[1] / SURVEY.md 8d "C2"
+    # BASELINE.json configs[3] / SURVEY.md 8d "C4": the north-star configuration
+    "proteome": dict(lib=dict(charges=[1, 2, 3, 4, 5], fixed_labels=CAM_FIXED_LABEL),
+                     run=dict(n_spectra=25000, seed=20260104, entry_fraction=0.02), shards=8,
+                     name="human-scale tryptic proteome (500k peptides x z1-5, CAM) vs the 200k-spectrum run, one 25k-spectrum shard per GPU"),
+    # configs[1] "C2"
     "bsa": dict(lib=dict(molecules=BSA_MOLECULES, charges=[1, 2, 3, 4], metabolic_labels={"15N": [0, 0.99]},
                          fixed_labels=CAM_FIXED_LABEL),
-                run=dict(n_spectra=30000, seed=20260101), name="BSA 19 molecules 14N+15N z1-4 CAM vs 30k-spectrum synthetic run"),
+                run=dict(n_spectra=30000, seed=20260101), shards=1, name="BSA 19 molecules 14N+15N z1-4 CAM vs 30k-spectrum synthetic run"),
     # configs[2] "C3"
     "bsa_pct": dict(lib=dict(molecules=BSA_MOLECULES, charges=[1, 2, 3, 4], fixed_labels=CAM_FIXED_LABEL,
                              metabolic_labels={"15N": [round(0.01 * i, 2) for i in range(100)]}),
-                    run=dict(n_spectra=30000, seed=20260101), name="BSA x 100 15N percentiles vs 30k-spectrum run"),
-    # configs[3] "C4" scaled by --proteome-size (default 500k peptides is the named size)
-    "proteome": dict(lib=dict(charges=[1, 2, 3, 4, 5], fixed_labels=CAM_FIXED_LABEL),
-                     run=dict(n_spectra=25000, seed=20260104, entry_fraction=0.02),
-                     name="random tryptic proteome z1-5 CAM vs 25k spectra per GPU"),
+                    run=dict(n_spectra=30000, seed=20260101), shards=1, name="BSA x 100 15N percentiles vs 30k-spectrum run"),
 }
+REFERENCE_SAMPLE_PEPTIDES = 5000       # library sample the CPU arms can build
+FIXTURE = ROOT / "bench_data" / "proteome500k_shard0_planted.npz"
 
 
-def make_run(entry_mz, entry_ci, run, rank):
-    kw = dict(run)
-    kw["seed"] = kw["seed"] + rank
-    return synth_run(entry_mz, entry_ci, **kw)
+def static_config(args):
+    """`config` of the JSON line: a function of the command line only, so both arms print the same dict."""
+    wl = WORKLOADS[args.workload]
+    cfg = {"workload": wl["name"], "spectra_per_gpu": wl["run"]["n_spectra"], "run_seed": wl["run"]["seed"],
+           "input_kind": "numpy (N,2) float64", "l2_policy": "inputs (hundreds of MB of peaks per step) larger than L2"}
+    if args.workload == "proteome":
+        cfg["library_peptides"] = args.proteome_size
+    return cfg
+
+
+def library_kwargs(args, n_peptides=None):
+    kw = dict(WORKLOADS[args.workload]["lib"])
+    if args.workload == "proteome":
+        peptides = random_tryptic_peptides(args.proteome_size, seed=20260104)
+        kw["molecules"] = peptides if n_peptides is None else peptides[:n_peptides]
+    return kw
+
+
+def load_fixture(args):
+    """c-peak table of the entries planted into shard 0 (written by tools/make_bench_fixture.py from the full library):
+    lets a process without the library (the reference arm) draw the identical spectra."""
+    if args.workload != "proteome" or args.proteome_size != 500000 or not FIXTURE.exists():
+        return None
+    z = np.load(FIXTURE)
+    return {"n_entries": int(z["n_entries"]), "lens": z["lens"].astype(np.int64), "mz": z["mz"], "ci": z["ci"].astype(np.float64)}
+
+
+def make_shard(args, shard, entry_peaks=None):
+    """(peaks, offsets, how) of one shard of the run.  Shard 0 comes from the committed planted table when it matches
+    the library; other shards (and other workloads) plant from the library's own entries."""
+    run = dict(WORKLOADS[args.workload]["run"])
+    run["seed"] = run["seed"] + shard
+    table = load_fixture(args) if shard == 0 else None
+    if table is not None and (entry_peaks is None or table["n_entries"] == entry_peaks[2]):
+        peaks, offsets = synth_run(None, None, planted=table, **run)
+        return peaks, offsets, "planted table bench_data/%s" % FIXTURE.name
+    if entry_peaks is None:
+        return None, None, "no planted table"
+    mz, ci = entry_peaks[0]()
+    peaks, offsets = synth_run(mz, ci, **run)
+    return peaks, offsets, "planted from the library's entries"
 
 
 class ClockSampler:
@@ -98,88 +142,118 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------- CPU legs (oracle)
-def _oracle_library(workload, proteome_size):
-    from oracle.qms_oracle import OracleLibrary
+# ------------------------------------------------------------------------------------- CPU legs
+def cpu_library(args, n_peptides):
+    """(library, kind): the unmodified reference from baseline/_ref when it is there, else the oracle port."""
     sys.setrecursionlimit(20000)
-    kw = dict(WORKLOADS[workload]["lib"])
-    if workload == "proteome":
-        kw["molecules"] = random_tryptic_peptides(proteome_size, seed=20260104)
-    return OracleLibrary(**kw)
+    kw = library_kwargs(args, n_peptides)
+    ref_dir = ROOT / "baseline" / "_ref"
+    if (ref_dir / "pyqms" / "__init__.py").exists() and not args.cpu_port:
+        import warnings
+        warnings.filterwarnings("ignore")
+        if str(ref_dir) not in sys.path:
+            sys.path.insert(0, str(ref_dir))
+        import pyqms                                       # the reference itself (+ the parser stand-in, SURVEY.md 8c)
+        return pyqms.IsotopologueLibrary(verbose=False, **kw), "reference"
+    from oracle.qms_oracle import OracleLibrary
+    return OracleLibrary(**kw), "port"
 
 
-def _oracle_entry_peaks(lib):
-    mzs, cis = [], []
-    for lo, hi, z, lp, formula in lib.formulas_sorted_by_mz:
-        env = lib[formula]["env"][lp]
-        keep = [n for n, p in enumerate(env["c_peak_pos"]) if p is not None]
-        mzs.append(np.array([env[z]["mz"][n] for n in keep]))
-        cis.append(np.array([env["abun"][n] for n in keep], dtype=np.float64))
-    return mzs, cis
+def cpu_match(lib, kind, spectrum, spec_id, results):
+    if kind == "reference":
+        return lib.match_all(mz_i_list=spectrum, file_name="run", spec_id=spec_id, spec_rt=spec_id * 0.2, results=results)
+    return lib.match_all(spectrum, "run", spec_id, spec_id * 0.2, results)
+
+
+def n_bins(lib, kind):
+    return len(lib.match_sets)
+
+
+def full_library_bins(args, entries_full=None):
+    """Match bins of the full library (entries / MAX_MOLECULES_PER_MATCH_BIN): the reference's per-spectrum cost is
+    linear in them (it re-slices and re-hashes the spectrum per bin, IL:1835-1839)."""
+    if entries_full is None:
+        table = load_fixture(args)
+        entries_full = table["n_entries"] if table is not None else None
+    return None if entries_full is None else (entries_full + 19) // 20
 
 
 _WORKER = {}
 
 
-def _cpu_worker_init(workload, proteome_size):
-    _WORKER["lib"] = _oracle_library(workload, proteome_size)
-
-
 def _cpu_worker_run(spectra):
-    lib = _WORKER["lib"]
+    lib, kind = _WORKER["lib"], _WORKER["kind"]
     t0 = time.perf_counter()
-    res = {}
-    for s, spec in enumerate(spectra):
-        lib.match_all(spec, "run", s, s * 0.2, res)
-    return time.perf_counter() - t0, sum(len(v) for v in res.values())
+    res = None if kind == "reference" else {}
+    for s, spec in spectra:
+        res = cpu_match(lib, kind, spec, s, res)
+    hits = sum(len(v["data"]) if kind == "reference" else len(v) for v in res.values()) if res is not None else 0
+    return time.perf_counter() - t0, hits
 
 
-def cpu_time_sample(lib, peaks, offsets, budget_s, max_spectra):
-    """Time the oracle on leading spectra of the run until ~budget_s elapsed (single core)."""
-    res, n, t0 = {}, 0, time.perf_counter()
+def cpu_time_sample(lib, kind, peaks, offsets, budget_s, max_spectra):
+    """Time the CPU path on leading spectra of the shard until ~budget_s elapsed (single core)."""
+    res, n, t0 = (None if kind == "reference" else {}), 0, time.perf_counter()
     while n < min(max_spectra, len(offsets) - 1):
-        lib.match_all(peaks[offsets[n]:offsets[n + 1]], "run", n, n * 0.2, res)
+        res = cpu_match(lib, kind, peaks[offsets[n]:offsets[n + 1]], n, res)
         n += 1
         if n >= 20 and time.perf_counter() - t0 > budget_s:
             break
-    return n, time.perf_counter() - t0, sum(len(v) for v in res.values())
+    hits = sum(len(v["data"]) if kind == "reference" else len(v) for v in res.values()) if res is not None else 0
+    return n, time.perf_counter() - t0, hits
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and cannot
-    travel to the GPU box) on all host cores, one process per core over disjoint spectrum shards."""
+    """--impl reference: the reference's own CPU code on all host cores, one process per core over disjoint spectra."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = max(1, (os.cpu_count() or 1))
-    cores = min(cores, 64)
-    lib = _oracle_library(args.workload, args.proteome_size)
-    mzs, cis = _oracle_entry_peaks(lib)
-    per_proc = args.ref_spectra_per_core
-    run = dict(WORKLOADS[args.workload]["run"])
-    run["n_spectra"] = min(run["n_spectra"], per_proc * cores)
-    peaks, offsets = make_run(mzs, cis, run, 0)
-    n = len(offsets) - 1
-    shards = [[peaks[offsets[s]:offsets[s + 1]] for s in range(i, n, cores)] for i in range(cores)]
+    cores = min(max(1, (os.cpu_count() or 1)), 64)
+    sample = REFERENCE_SAMPLE_PEPTIDES if args.workload == "proteome" else None
+    t0 = time.perf_counter()
+    lib, kind = cpu_library(args, sample)
+    build_s = time.perf_counter() - t0
+    peaks, offsets, how = make_shard(args, 0)
+    if peaks is None:                                     # no planted table: plant from the sample library's own entries
+        from tests.golden.spectra import entry_peaks as ref_entry_peaks
+        mz, ci = ref_entry_peaks(lib)
+        run = dict(WORKLOADS[args.workload]["run"])
+        run["n_spectra"] = min(run["n_spectra"], args.ref_spectra_per_core * cores)
+        peaks, offsets = synth_run(mz, ci, **run)
+        how = "planted from the sample library's entries (no planted table for this configuration)"
+    n = min(len(offsets) - 1, args.ref_spectra_per_core * cores)
+    shards = [[(s, peaks[offsets[s]:offsets[s + 1]]) for s in range(i, n, cores)] for i in range(cores)]
+    _WORKER["lib"], _WORKER["kind"] = lib, kind           # inherited by the forked workers (no rebuild per process)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(args.workload, args.proteome_size)) as pool:
+    with ctx.Pool(cores) as pool:
         times = []
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_cpu_worker_run, shards)
+            pool.map(_cpu_worker_run, shards, chunksize=1)
             dt = time.perf_counter() - t0
             if step >= args.warmup:
                 times.append(dt)
     total = sum(times)
-    value = n * len(times) / total
+    measured = n * len(times) / total
+    bins_sample = n_bins(lib, kind)
+    bins_full = full_library_bins(args) if sample is not None else bins_sample
+    scale = bins_sample / bins_full if bins_full else 1.0
+    value = measured * scale
     line = {
         "impl": "reference", "metric": "spectra/sec through match_all", "value": value, "unit": "spectra/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]["name"], "library_entries": len(lib.formulas_sorted_by_mz)},
-        "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": cores, "kind": "port",
-                         "sample": "%d spectra of the run per step, %d processes x %d spectra" % (n, cores, len(shards[0]))},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": static_config(args),
+        "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": cores, "kind": kind,
+                         "sample": "%d spectra of shard 0 per step (%s), %d processes x %d spectra, against %s; measured %.1f spectra/s "
+                                   "on %d match bins%s" % (
+                                       n, how, cores, len(shards[0]),
+                                       "the first %d peptides of the library" % sample if sample else "the full library",
+                                       measured, bins_sample,
+                                       ", scaled by %d/%d bins to the full library (the reference's cost per spectrum is linear in "
+                                       "the bins, BASELINE.md section 3)" % (bins_sample, bins_full) if scale != 1.0 else ""),
+                         "measured_on_sample": measured, "bins_sample": bins_sample, "bins_full": bins_full,
+                         "library_build_s": build_s},
         "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,6 +261,43 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------- our arm
+def device_buffers(torch, QmsHits, cap_h, cap_w):
+    dev = {"spec": torch.empty(cap_h, dtype=torch.int32, device="cuda"), "entry": torch.empty(cap_h, dtype=torch.int32, device="cuda"),
+           "score": torch.empty(cap_h, dtype=torch.float64, device="cuda"), "scaling": torch.empty(cap_h, dtype=torch.float64, device="cuda"),
+           "win_off": torch.empty(cap_h + 1, dtype=torch.int64, device="cuda"), "mmz": torch.empty(cap_w, dtype=torch.float64, device="cuda"),
+           "mi": torch.empty(cap_w, dtype=torch.float64, device="cuda"), "peak": torch.empty(cap_w, dtype=torch.int64, device="cuda")}
+    return dev, QmsHits(cap_h, cap_w, *[dev[k].data_ptr() for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
+
+
+def sparse_probe_figure(pyqms_b200, torch, local, peak_gbs, n_spectra=10000, steps=10):
+    """The HBM-bound regime (configs[1], BSA library: 99 % of the peaks are rejected by the cover bitmap): roofline of the
+    streaming probe kernel, reported beside the headline as `roofline_sparse`."""
+    import ctypes as C
+    from pyqms_b200._capi import QmsHits
+    wl = WORKLOADS["bsa"]
+    lib = pyqms_b200.IsotopologueLibrary(verbose=False, device=local, distributed=False, **wl["lib"])
+    mz, ci = lib.entry_peaks()
+    peaks, offsets = synth_run(mz, ci, n_spectra=n_spectra, seed=wl["run"]["seed"])
+    ctx, xi = lib._ctx, lib.params["MZ_SCORE_PERCENTILE"]
+    d_peaks = torch.from_numpy(peaks).cuda()
+    dev, hits = device_buffers(torch, QmsHits, 1 << 16, 1 << 19)
+    nh, nw = C.c_int64(), C.c_int64()
+    for it in range(3 + steps):
+        if it == 3:
+            ctx.reset_counters()
+        ctx.check(ctx.lib.qms_match_batch(ctx.handle, d_peaks.data_ptr(), offsets.ctypes.data, len(offsets) - 1, 0, xi, C.byref(hits),
+                                          C.byref(nh), C.byref(nw)))
+    c = ctx.counters()
+    alg = 16.0 * c["peaks"] / steps
+    ms = c["ms_probe"] / steps
+    achieved = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    step_ms = (c["ms_probe"] + c["ms_gate"] + c["ms_score"] + c["ms_compact"]) / steps
+    return {"workload": "%s, first %d spectra" % (wl["name"], n_spectra), "bound": "hbm", "kernel": "spectrum_probe_warp_kernel",
+            "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            "algorithmic_bytes_per_launch": alg, "kernel_ms": ms, "kernels_ms_per_step": step_ms,
+            "spectra_per_s_device_kernels": (len(offsets) - 1) / (step_ms * 1e-3) if step_ms > 0 else None}
+
+
 def run_ours(args):
     import ctypes as C
     import torch
@@ -199,20 +310,19 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     from pyqms_b200.distributed import bind_to_gpu_numa_node
-    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None    # before any pinned allocation
+    numa_node = bind_to_gpu_numa_node(local)               # before any pinned allocation
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
     wl = WORKLOADS[args.workload]
-    kw = dict(wl["lib"])
-    if args.workload == "proteome":
-        kw["molecules"] = random_tryptic_peptides(args.proteome_size, seed=20260104)
     t0 = time.perf_counter()
-    lib = pyqms_b200.IsotopologueLibrary(verbose=False, device=local, **kw)     # sharded build + all-gather when world > 1
+    lib = pyqms_b200.IsotopologueLibrary(verbose=False, device=local, **library_kwargs(args))     # sharded build + all-gather when world > 1
     build_s = time.perf_counter() - t0
     build_counters = lib.device_counters()
-    entry_mz, entry_ci = lib.entry_peaks()
-    peaks, offsets = make_run(entry_mz, entry_ci, wl["run"], rank)
+    shard = rank % wl["shards"]
+    t0 = time.perf_counter()
+    peaks, offsets, run_how = make_shard(args, shard, (lib.entry_peaks, None, int(lib._n_entries)))
+    synth_s = time.perf_counter() - t0
     n_spec = len(offsets) - 1
     ctx = lib._ctx
     xi = lib.params["MZ_SCORE_PERCENTILE"]
@@ -220,25 +330,21 @@ def run_ours(args):
 
     # ---- resident inputs + device output buffers
     d_peaks = torch.from_numpy(peaks).cuda()
-    d_offsets = torch.from_numpy(offsets).cuda()
     cap_h, cap_w = 1 << 16, 1 << 19
     while True:
-        dev = {"spec": torch.empty(cap_h, dtype=torch.int32, device="cuda"), "entry": torch.empty(cap_h, dtype=torch.int32, device="cuda"),
-               "score": torch.empty(cap_h, dtype=torch.float64, device="cuda"), "scaling": torch.empty(cap_h, dtype=torch.float64, device="cuda"),
-               "win_off": torch.empty(cap_h + 1, dtype=torch.int64, device="cuda"), "mmz": torch.empty(cap_w, dtype=torch.float64, device="cuda"),
-               "mi": torch.empty(cap_w, dtype=torch.float64, device="cuda"), "peak": torch.empty(cap_w, dtype=torch.int64, device="cuda")}
-        hits = QmsHits(cap_h, cap_w, *[dev[k].data_ptr() for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
+        dev, hits = device_buffers(torch, QmsHits, cap_h, cap_w)
         nh, nw = C.c_int64(), C.c_int64()
         rc = ctx.lib.qms_match_batch(ctx.handle, d_peaks.data_ptr(), offsets.ctypes.data, n_spec, 0, xi, C.byref(hits), C.byref(nh),
                                      C.byref(nw))
         if rc == -3:
             cap_h, cap_w = nh.value + 1024, nw.value + 8192
+            del dev
             continue
         ctx.check(rc)
         break
 
     def device_step():
-        # peaks resident in HBM; the 240 KB of row offsets stay a host array (the library needs the row count on the host)
+        # peaks resident in HBM; the row offsets stay a host array (the library needs the row count on the host)
         ctx.check(ctx.lib.qms_match_batch(ctx.handle, d_peaks.data_ptr(), offsets.ctypes.data, n_spec, 0, xi, C.byref(hits),
                                           C.byref(nh), C.byref(nw)))
 
@@ -271,19 +377,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * n_spec * args.steps / (ms_max / 1e3)
+    device_hits = int(nh.value)
+    del dev, d_peaks
+    torch.cuda.empty_cache()
 
-    # ---- e2e through the public host API: pinned host spectra -> packed hits on the host
+    # ---- e2e through the public host API: pinned host spectra -> packed hits on the host (rank 0 holds all ranks' hits)
     pin_peaks = torch.from_numpy(peaks).pin_memory()
     pin_offsets = torch.from_numpy(offsets).pin_memory()
     h_peaks, h_offsets = pin_peaks.numpy(), pin_offsets.numpy()
     spec_ids = list(range(n_spec))
+    gather_stats = {}
 
     def e2e_step():
         # the call a user makes for a whole run: host (N,2) array in, pyqms Results out (hits stay packed until read)
         res = lib.match_many(h_peaks, file_name="run", spec_ids=spec_ids, spec_rts=spec_ids, offsets=h_offsets)
-        return res.packed_batches()[-1]
+        out = res.packed_batches()[-1]
+        if world > 1:
+            from pyqms_b200.distributed import gather_hits_to_rank0
+            out = gather_hits_to_rank0(out, spectrum_begin=rank * n_spec, stats=gather_stats)
+        return out
 
-    for _ in range(max(1, args.warmup)):
+    for _ in range(max(1, min(args.warmup, 3))):
         out = e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -296,107 +410,141 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n_spec * args.steps / float(t.item())
     h2d = int(peaks.nbytes + offsets.nbytes)
-    d2h = int(out["n_hits"] * (4 + 4 + 8 + 8 + 8) + 8 + out["n_windows"] * 8)   # spec, entry, score, scaling, win_off + peak rows
+    own = out if world == 1 else gather_stats.get("own", out)
+    d2h = int(sum(np.asarray(own[k]).nbytes for k in ("spec", "entry", "score", "scaling", "win_off", "peak")))
+    e2e_counters = ctx.counters()
 
-    # ---- roofline of the dominant kernel (spectrum_probe_gate): SURVEY.md 8d algorithmic bytes
-    launches_per_step = counters["kernel_launches"] / max(steps_counted, 1)
-    probe_ms = counters["ms_probe"] / max(steps_counted, 1)
-    # the probe kernel streams every (m/z, intensity) row once: 16 B per peak (first term); the
-    # candidate and hit terms belong to the gate / score / compaction kernels and are reported with the step
-    alg_bytes = 16.0 * counters["peaks"] / max(steps_counted, 1)
-    step_alg_bytes = (16.0 * counters["peaks"] + 16.0 * counters["candidates"] + 28.0 * counters["candidate_windows"]
-                      + 24.0 * counters["hits"] + 16.0 * counters["hit_windows"]) / max(steps_counted, 1)
+    # ---- roofline of the kernel that dominates the step (SURVEY.md 8d algorithmic bytes)
     peaks_json = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak_gbs = float(peaks_json.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes / (probe_ms * 1e-3) / 1e9 if probe_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "spectrum_probe_warp_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+    per_step = {k: counters[k] / max(steps_counted, 1) for k in counters}
+    launches_per_step = per_step["kernel_launches"]
+    dense = counters["dense_batches"] > 0
+    step_alg_bytes = (16.0 * per_step["peaks"] + 16.0 * per_step["candidates"] + 28.0 * per_step["candidate_windows"]
+                      + 24.0 * per_step["hits"] + 16.0 * per_step["hit_windows"])
+    if dense:
+        # match_spectrum_kernel reads every peak row once, every candidate's entry header and window rows
+        kernel, kernel_ms = "match_spectrum_kernel", per_step["ms_gate"]
+        alg_bytes = 16.0 * per_step["peaks"] + 16.0 * per_step["candidates"] + 28.0 * per_step["candidate_windows"]
+    else:
+        kernel, kernel_ms = "spectrum_probe_warp_kernel", per_step["ms_probe"]
+        alg_bytes = 16.0 * per_step["peaks"]
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks_json else "fallback",
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": probe_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / (ms_max / args.steps),
                 "step_algorithmic_bytes": step_alg_bytes, "step_achieved_gbs": step_alg_bytes / (ms_max / args.steps * 1e-3) / 1e9,
-                "step_ms_breakdown": {k: counters[k] / max(steps_counted, 1) for k in ("ms_probe", "ms_gate", "ms_score", "ms_compact", "ms_d2h", "ms_h2d")}}
-    traffic_file = ROOT / "profiles" / "probe_traffic.json"
-    if traffic_file.exists():
+                "step_ms_breakdown": {k: per_step[k] for k in ("ms_probe", "ms_gate", "ms_score", "ms_compact", "ms_d2h", "ms_h2d")},
+                "note": ("not HBM-bound: the kernel gates ~100 (peak, window) incidences per peak row from L2-resident library tables "
+                         "and shared-memory spectrum tables; see the ncu figures" if dense else None)}
+    ncu_file = ROOT / "profiles" / "kernel_ncu.json"
+    if ncu_file.exists():
         try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get(args.workload)
+            facts = json.loads(ncu_file.read_text()).get(kernel)
+            if facts:
+                roofline["traffic"] = facts.get("dram_bytes_per_launch")
+                roofline["ncu"] = facts
         except Exception:
             pass
 
-    # ---- second half of the metric: isotopologue envelopes built per second (BASELINE.json configs[4] shape, bounded)
-    build_metric = None
-    if rank == 0 and not args.no_build_metric:
-        from pyqms_b200.synthetic import averagine_formulas
-        formulas = averagine_formulas(args.build_formulas, seed=20260105)
-        # one untimed warm-up build (first-touch allocations of the 60 kDa cell table, lazy module loading), then timed builds
-        walls, runs, sweep = [], [], None
-        for _ in range(1 + max(1, args.build_repeats)):
-            del sweep
-            t0 = time.perf_counter()
-            sweep = pyqms_b200.IsotopologueLibrary(molecules=formulas, charges=[1], verbose=False, device=local, distributed=False,
-                                                   params={"UPPER_MZ_LIMIT": 60000, "LOWER_MZ_LIMIT": 50})
-            walls.append(time.perf_counter() - t0)
-            runs.append((walls[-1], sweep.device_counters()))
-        wall, c = sorted(runs[1:], key=lambda r: r[0])[(len(runs) - 1) // 2]      # the median build and its stage times
-        build_metric = {"metric": "isotopologue envelopes built/sec", "workload": "%d averagine formulas 100 Da - 50 kDa, natural abundance" % args.build_formulas,
-                        "envelopes": int(c["envelopes"]), "value_device": c["envelopes"] / (c["ms_envelopes"] * 1e-3),
-                        "value_e2e_host_strings_to_index": c["envelopes"] / wall, "unit": "envelopes/s", "ms_envelope_kernel": c["ms_envelopes"],
-                        "ms_trees": c["ms_trees"], "ms_index": c["ms_index"], "fp64_gflops": c["envelope_flops"] / (c["ms_envelopes"] * 1e-3) / 1e9,
-                        "wall_s": wall, "wall_s_all": walls, "timing": "median of %d builds after 1 warm-up build" % (len(walls) - 1)}
-        # FP64 roofline of the envelope kernel: DFMA-chain and DMUL+DADD-chain peaks measured on this GPU
-        import ctypes
-        fused, unfused = ctypes.c_double(), ctypes.c_double()
-        sweep._ctx.call("qms_measure_fp64_peak", ctypes.byref(fused), ctypes.byref(unfused))
-        achieved = build_metric["fp64_gflops"] / 1e3
-        build_metric["roofline"] = {"bound": "fp64", "kernel": "envelope_convolve_kernel", "achieved": achieved, "unit": "TFLOP/s",
-                                    "peak": unfused.value, "frac": achieved / unfused.value if unfused.value else None,
-                                    "peak_fused_dfma": fused.value, "frac_of_fused": achieved / fused.value if fused.value else None,
-                                    "peak_source": "qms_measure_fp64_peak: dependency-chain kernels on this GPU; the kernel may not fuse (parity)"}
-        if not args.no_cpu_baseline:
-            from oracle.qms_oracle import OracleLibrary
-            sys.setrecursionlimit(20000)
-            # the reference's build is O(N^2) big-int work in the largest atom count (552 s for one 50 kDa formula,
-            # SURVEY.md section 6): the CPU sample is bounded to formulas below ~3 kDa (<= 130 carbons)
-            small = [f for f in formulas[:20000] if int(f[2:].split("H")[0]) <= 130][:args.build_cpu_formulas]
-            t0 = time.perf_counter()
-            ora = OracleLibrary(molecules=small, charges=[1], params={"UPPER_MZ_LIMIT": 60000, "LOWER_MZ_LIMIT": 50})
-            secs = time.perf_counter() - t0
-            build_metric["cpu_baseline"] = {"value": len(ora) / secs, "unit": "envelopes/s", "cores": 1, "kind": "port",
-                                            "sample": "first %d formulas <= 130 C (~3 kDa) of the same sweep (%.1f s)" % (len(small), secs)}
-        del sweep
-
     line = None
     if rank == 0:
-        # ---- CPU baseline: oracle port on a bounded sample of the same run, one core
+        extras = {}
+        if not args.no_extras:
+            try:
+                extras["roofline_sparse"] = sparse_probe_figure(pyqms_b200, torch, local, peak_gbs)
+            except Exception as exc:                       # the headline must not die with an extra
+                extras["roofline_sparse"] = {"error": repr(exc)}
+            extras["build"] = build_metric(args, pyqms_b200, local)
+        # ---- CPU baseline: the reference (or the port) on a bounded sample of the same shard, one core
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            ora = _oracle_library(args.workload, min(args.proteome_size, 5000))
-            n, secs, nhits = cpu_time_sample(ora, peaks, offsets, args.cpu_budget, 20000)
-            cpu = {"value": n / secs, "unit": "spectra/s", "cores": 1, "kind": "port",
-                   "sample": "first %d spectra of the same run (%.1f s, %d hits), oracle/qms_oracle.py single process" % (n, secs, nhits)}
+            sample = REFERENCE_SAMPLE_PEPTIDES if args.workload == "proteome" else None
+            t0 = time.perf_counter()
+            cpu_lib, kind = cpu_library(args, sample)
+            cpu_build = time.perf_counter() - t0
+            n, secs, nhits = cpu_time_sample(cpu_lib, kind, peaks, offsets, args.cpu_budget, 20000)
+            bins_sample = n_bins(cpu_lib, kind)
+            bins_full = (int(lib._n_entries) + 19) // 20
+            scale = bins_sample / bins_full if sample else 1.0
+            cpu = {"value": n / secs * scale, "unit": "spectra/s", "cores": 1, "kind": kind,
+                   "sample": "first %d spectra of the same shard in %.1f s (%d hits) against %s: %.2f spectra/s on %d match bins%s" % (
+                       n, secs, nhits, "the first %d peptides of the library" % sample if sample else "the full library", n / secs,
+                       bins_sample, ", scaled by %d/%d bins to the full library (cost per spectrum linear in the bins, "
+                       "BASELINE.md section 3)" % (bins_sample, bins_full) if sample else ""),
+                   "measured_on_sample": n / secs, "library_build_s": cpu_build}
         line = {
             "metric": "spectra/sec through match_all", "value": value, "unit": "spectra/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "spectra_per_gpu": n_spec, "peaks_per_gpu": int(len(peaks)),
-                       "library_entries": int(lib._n_entries), "library_windows": int(lib._n_windows),
-                       "l2_policy": "inputs (%d MB of peaks per step) larger than L2" % (peaks.nbytes >> 20),
-                       "input_kind": "numpy (N,2) float64", "hits_per_step": int(nh.value), "numa_node_rank0": numa_node},
-            "e2e": {"value": e2e_value, "unit": "spectra/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "dtype": "f64", "data": "synthetic", "config": static_config(args),
+            "e2e": {"value": e2e_value, "unit": "spectra/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * float(t.item()) / args.steps, "gather": gather_stats.get("summary"),
+                    "ms_h2d_per_step": (e2e_counters["ms_h2d"] - counters["ms_h2d"]) / max(args.steps + min(args.warmup, 3), 1),
+                    "ms_d2h_per_step": (e2e_counters["ms_d2h"] - counters["ms_d2h"]) / max(args.steps + min(args.warmup, 3), 1)},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
+            "workload_stats": {"shard": shard, "spectra": n_spec, "peaks": int(len(peaks)), "run_source": run_how, "synth_s": synth_s,
+                               "library_entries": int(lib._n_entries), "library_windows": int(lib._n_windows),
+                               "hits_per_step": device_hits, "numa_node_rank0": numa_node, "matcher": "spectrum-resident" if dense else "row-streaming"},
             "library_build": {"seconds_wall": build_s, "envelopes": int(build_counters["envelopes"]),
                               "ms_trees": build_counters["ms_trees"], "ms_envelopes": build_counters["ms_envelopes"],
                               "ms_index": build_counters["ms_index"],
                               "envelopes_per_s_device": (build_counters["envelopes"] / (build_counters["ms_envelopes"] * 1e-3)
-                                                         if build_counters["ms_envelopes"] > 0 else None)},
-            "build": build_metric,
-            "counters_per_step": {k: counters[k] / max(steps_counted, 1) for k in
-                                  ("peaks", "live_peaks", "incidences", "candidates", "combinations", "hits")},
+                                                         if build_counters["ms_envelopes"] > 0 else None),
+                              "envelopes_per_s_wall": build_counters["envelopes"] / build_s,
+                              "distributed": getattr(lib, "_build_stats", None)},
+            "counters_per_step": {k: per_step[k] for k in ("peaks", "live_peaks", "incidences", "candidates", "candidate_windows",
+                                                            "combinations", "hits", "hit_windows")},
         }
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def build_metric(args, pyqms_b200, local):
+    """Second half of the metric: isotopologue envelopes built per second (BASELINE.json configs[4] shape, bounded)."""
+    from pyqms_b200.synthetic import averagine_formulas
+    formulas = averagine_formulas(args.build_formulas, seed=20260105)
+    # one untimed warm-up build (first-touch allocations of the 60 kDa cell table, lazy module loading), then timed builds
+    walls, runs, sweep = [], [], None
+    for _ in range(1 + max(1, args.build_repeats)):
+        del sweep
+        t0 = time.perf_counter()
+        sweep = pyqms_b200.IsotopologueLibrary(molecules=formulas, charges=[1], verbose=False, device=local, distributed=False,
+                                               params={"UPPER_MZ_LIMIT": 60000, "LOWER_MZ_LIMIT": 50})
+        walls.append(time.perf_counter() - t0)
+        runs.append((walls[-1], sweep.device_counters()))
+    wall, c = sorted(runs[1:], key=lambda r: r[0])[(len(runs) - 1) // 2]      # the median build and its stage times
+    out = {"metric": "isotopologue envelopes built/sec", "workload": "%d averagine formulas 100 Da - 50 kDa, natural abundance" % args.build_formulas,
+           "envelopes": int(c["envelopes"]), "value_device": c["envelopes"] / (c["ms_envelopes"] * 1e-3),
+           "value_e2e_host_strings_to_index": c["envelopes"] / wall, "unit": "envelopes/s", "ms_envelope_kernel": c["ms_envelopes"],
+           "ms_trees": c["ms_trees"], "ms_index": c["ms_index"], "fp64_gflops": c["envelope_flops"] / (c["ms_envelopes"] * 1e-3) / 1e9,
+           "wall_s": wall, "wall_s_all": walls, "timing": "median of %d builds after 1 warm-up build" % (len(walls) - 1)}
+    # FP64 roofline of the envelope kernel: DFMA-chain and DMUL+DADD-chain peaks measured on this GPU
+    import ctypes
+    fused, unfused = ctypes.c_double(), ctypes.c_double()
+    sweep._ctx.call("qms_measure_fp64_peak", ctypes.byref(fused), ctypes.byref(unfused))
+    achieved = out["fp64_gflops"] / 1e3
+    out["roofline"] = {"bound": "fp64", "kernel": "envelope_convolve_kernel", "achieved": achieved, "unit": "TFLOP/s",
+                       "peak": unfused.value, "frac": achieved / unfused.value if unfused.value else None,
+                       "peak_fused_dfma": fused.value, "frac_of_fused": achieved / fused.value if fused.value else None,
+                       "peak_source": "qms_measure_fp64_peak: dependency-chain kernels on this GPU; the kernel may not fuse (parity)"}
+    if not args.no_cpu_baseline:
+        from oracle.qms_oracle import OracleLibrary
+        sys.setrecursionlimit(20000)
+        # the reference's build is O(N^2) big-int work in the largest atom count (552 s for one 50 kDa formula,
+        # SURVEY.md section 6): the CPU sample is bounded to formulas below ~3 kDa (<= 130 carbons)
+        small = [f for f in formulas[:20000] if int(f[2:].split("H")[0]) <= 130][:args.build_cpu_formulas]
+        t0 = time.perf_counter()
+        ora = OracleLibrary(molecules=small, charges=[1], params={"UPPER_MZ_LIMIT": 60000, "LOWER_MZ_LIMIT": 50})
+        secs = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(ora) / secs, "unit": "envelopes/s", "cores": 1, "kind": "port",
+                               "sample": "first %d formulas <= 130 C (~3 kDa) of the same sweep (%.1f s)" % (len(small), secs)}
+    del sweep
+    return out
 
 
 def main():
@@ -407,15 +555,16 @@ def main():
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="bsa", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="proteome", choices=list(WORKLOADS))
     ap.add_argument("--proteome-size", type=int, default=500000)
-    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU oracle time for cpu_baseline")
-    ap.add_argument("--ref-spectra-per-core", type=int, default=250)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU matching time for cpu_baseline")
+    ap.add_argument("--cpu-port", action="store_true", help="CPU legs with the oracle port even if baseline/_ref is there")
+    ap.add_argument("--ref-spectra-per-core", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-build-metric", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sparse-library probe figure and the build metric")
     ap.add_argument("--build-formulas", type=int, default=100000)
     ap.add_argument("--build-repeats", type=int, default=3)
     ap.add_argument("--build-cpu-formulas", type=int, default=2000)

@@ -73,6 +73,8 @@ typedef struct qms_counters {
     double ms_index;            /* device ms in mz_windows + index/probe-table build             */
     int64_t envelopes;          /* envelopes built by this context                               */
     int64_t envelope_flops;     /* FP64 operations of the convolutions (2 mul + 2 add per pair and array) */
+    int64_t dense_batches;      /* batches matched by the spectrum-resident kernels (match_spectrum.cu)  */
+    int64_t gated_incidences;   /* ... incidences that survived its zone-mask bound and were gated window by window */
 } qms_counters;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -85,6 +87,11 @@ int qms_synchronize(qms_ctx* ctx);
 int qms_get_counters(qms_ctx* ctx, qms_counters* out);
 int qms_reset_counters(qms_ctx* ctx);
 int qms_device_bytes(qms_ctx* ctx, int64_t* out);    /* device memory currently owned by the context */
+/* Implementation switches that never change a result, only which kernels produce it (tests run both paths):
+ *   "dense_mode"  0 = always the row-streaming matcher, 1 = the spectrum-resident matcher whenever its tables allow it,
+ *                 2 = by library density (default; QMS_DENSE_MODE overrides the default)
+ *   "dense_ctas"  resident CTAs per SM of the spectrum-resident kernel (default 4; QMS_DENSE_CTAS) */
+int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value);
 
 /* ---- P1 prologue: enriched isotope tables ----------------------------------------------------
  * Replaces _recalc_isotopic_distribution IL:2109-2165: the isotope whose rounded mass equals

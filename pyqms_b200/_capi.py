@@ -31,7 +31,7 @@ class QmsCounters(C.Structure):
         "spectra", "peaks", "live_peaks", "incidences", "candidates", "candidate_windows", "combinations", "hits",
         "hit_windows", "kernel_launches")] + [(n, C.c_double) for n in (
             "ms_probe", "ms_gate", "ms_score", "ms_compact", "ms_h2d", "ms_d2h", "ms_trees", "ms_envelopes", "ms_index")] + [
-        ("envelopes", C.c_int64), ("envelope_flops", C.c_int64)]
+        ("envelopes", C.c_int64), ("envelope_flops", C.c_int64), ("dense_batches", C.c_int64), ("gated_incidences", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -58,6 +58,7 @@ EXPORTS = {  # name -> (restype, argtypes); must list every symbol of include/qm
     "qms_get_counters": (C.c_int, [C.c_void_p, C.POINTER(QmsCounters)]),
     "qms_reset_counters": (C.c_int, [C.c_void_p]),
     "qms_device_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "qms_set_tuning": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "qms_recalc_distribution": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "qms_build_element_trees": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int32]),
@@ -156,6 +157,9 @@ class Context:
 
     def reset_counters(self):
         self.call("qms_reset_counters")
+
+    def set_tuning(self, key, value):
+        self.call("qms_set_tuning", key.encode(), int(value))
 
     def stream(self):
         return self.lib.qms_stream(self.handle)

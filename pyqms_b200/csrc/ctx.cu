@@ -191,7 +191,23 @@ int qms_ctx_create(int device, qms_ctx** out) {
     for (int i = 0; i < 12; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaHostAlloc((void**)&ctx->h_pinned, 64 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (const char* e = getenv("QMS_DENSE_MODE")) ctx->dense_mode = atoi(e);
+    if (const char* e = getenv("QMS_DENSE_CTAS")) ctx->dense_ctas = atoi(e);
     *out = ctx;
+    return QMS_OK;
+}
+
+int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value) {
+    if (!ctx || !key) return qms_fail(ctx, QMS_E_ARG, "qms_set_tuning: NULL argument");
+    if (!strcmp(key, "dense_mode")) {
+        if (value < 0 || value > 2) return qms_fail(ctx, QMS_E_ARG, "dense_mode must be 0, 1 or 2");
+        ctx->dense_mode = value;
+    } else if (!strcmp(key, "dense_ctas")) {
+        if (value < 1 || value > 32) return qms_fail(ctx, QMS_E_ARG, "dense_ctas must be in [1, 32]");
+        ctx->dense_ctas = value;
+    } else {
+        return qms_fail(ctx, QMS_E_ARG, "unknown tuning key '%s'", key);
+    }
     return QMS_OK;
 }
 
@@ -211,6 +227,9 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     REL(pair_score); REL(pair_scaling); REL(pair_flag); REL(pair_win_off); REL(pair_best);
     REL(blk_hits); REL(blk_wins); REL(live_rows); REL(live_count); REL(live_prefix); REL(need_of_nc); REL(pair_vals); REL(pair_vals_alt);
     REL(pair_nc); REL(scr_first); REL(scr_cur); REL(scr_best); REL(heavy_list); REL(tile_spec);
+    REL(probe2); REL(cell_range); REL(win_lohi); REL(win_entry); REL(zone_tab);
+    REL(st_key); REL(st_key_alt); REL(st_score); REL(st_scaling); REL(st_woff); REL(st_nc); REL(st_rows); REL(st_order); REL(st_order_alt);
+    REL(spec_buckets); REL(spec_rows); REL(st_nc_sorted);
     REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak);
 #undef REL
     for (int i = 0; i < 12; ++i) cudaEventDestroy(ctx->ev[i]);

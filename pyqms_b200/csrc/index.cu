@@ -187,6 +187,99 @@ __global__ void cover_popcount_kernel(int64_t n_words, const uint32_t* __restric
     if ((threadIdx.x & 31) == 0 && bits) atomicAdd(total, bits);
 }
 
+// ---- tables of the spectrum-resident matcher (match_spectrum.cu) --------------------------------------------
+#define ZONE_BANDS 32        // m/z bands of the zone table (window widths grow with m/z)
+#define ZONE_GROUPS 16       // entry groups (= charge index); group 15 = entry without zones
+#define ZONE_OFFSETS 32      // window-ordinal differences -16 .. +15
+
+__global__ void probe2_kernel(int64_t n_windows, const ProbeRec* __restrict__ probe, const int64_t* __restrict__ ent_win_off,
+                              const int32_t* __restrict__ ent_z, int n_groups, int4* __restrict__ probe2, int32_t t_min,
+                              int32_t* __restrict__ first_cover) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_windows) return;
+    const ProbeRec r = probe[i];
+    const int64_t w0 = ent_win_off[r.entry];
+    const int nc = (int)(ent_win_off[r.entry + 1] - w0);
+    const int g = (n_groups > 0 && nc <= 16) ? ent_z[r.entry] : 15;
+    probe2[i] = make_int4(r.lo, r.hi, (int32_t)w0, r.k | (g << 12) | (nc << 16));
+    for (int32_t c = r.lo; c <= r.hi; ++c) atomicMin(&first_cover[c - t_min], (int32_t)i);
+}
+
+// Zone table of the spectrum-resident matcher: for a spectrum bucket t inside window k of an entry of group g, window
+// m = k + d of the same entry lies inside [t + zone.x, t + zone.y], zone = table[band(t)][g][d + 16]: the extreme
+// (lo_m - hi_k, hi_m - lo_k) over all entries of the group whose window k touches the band.  Data-driven, so the
+// containment holds for any library; tight for peptides because the isotope spacing hardly depends on the composition.
+__global__ void zone_table_kernel(int64_t n_entries, const int64_t* __restrict__ ent_win_off, const int32_t* __restrict__ ent_z,
+                                  const int32_t* __restrict__ win_lo, const int32_t* __restrict__ win_hi, int32_t t_min,
+                                  int band_shift, int n_groups, int2* __restrict__ zone_tab) {
+    extern __shared__ int s_zone[];                           // [bands][n_groups][32] lo, then hi
+    const int cells = ZONE_BANDS * n_groups * ZONE_OFFSETS;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+        s_zone[c] = INT32_MAX;
+        s_zone[cells + c] = INT32_MIN;
+    }
+    __syncthreads();
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_entries; x += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w0 = ent_win_off[x];
+        const int nc = (int)(ent_win_off[x + 1] - w0);
+        if (nc > 16) continue;
+        const int g = ent_z[x];
+        for (int k = 0; k < nc; ++k) {
+            const int32_t lo_k = win_lo[w0 + k], hi_k = win_hi[w0 + k];
+            int b0 = (lo_k - t_min) >> band_shift, b1 = (hi_k - t_min) >> band_shift;
+            b0 = b0 < ZONE_BANDS - 1 ? b0 : ZONE_BANDS - 1;
+            b1 = b1 < ZONE_BANDS - 1 ? b1 : ZONE_BANDS - 1;
+            for (int b = b0; b <= b1; ++b)
+                for (int m = 0; m < nc; ++m) {
+                    const int cell = (b * n_groups + g) * ZONE_OFFSETS + (m - k + 16);
+                    atomicMin(&s_zone[cell], win_lo[w0 + m] - hi_k);
+                    atomicMax(&s_zone[cells + cell], win_hi[w0 + m] - lo_k);
+                }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+        const int b = c / (n_groups * ZONE_OFFSETS), g = (c / ZONE_OFFSETS) % n_groups, d = c % ZONE_OFFSETS;
+        int* cell = reinterpret_cast<int*>(&zone_tab[(b * ZONE_GROUPS + g) * ZONE_OFFSETS + d]);
+        if (s_zone[c] != INT32_MAX) atomicMin(cell, s_zone[c]);
+        if (s_zone[cells + c] != INT32_MIN) atomicMax(cell + 1, s_zone[cells + c]);
+    }
+}
+
+__global__ void zone_init_kernel(int n, int2* __restrict__ zone_tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) zone_tab[i] = make_int2(INT32_MAX, INT32_MIN);
+}
+
+__global__ void cell_range_kernel(int64_t span, const int32_t* __restrict__ cell_start, const int32_t* __restrict__ first_cover,
+                                  int2* __restrict__ cell_range) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= span) return;
+    const int32_t end = cell_start[c + 1];                 // first record with lo > cell
+    const int32_t first = first_cover[c];
+    cell_range[c] = make_int2(first < end ? first : end, end);
+}
+
+__global__ void win_lohi_kernel(int64_t n_windows, const int32_t* __restrict__ win_lo, const int32_t* __restrict__ win_hi,
+                                int2* __restrict__ win_lohi) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n_windows) win_lohi[w] = make_int2(win_lo[w], win_hi[w]);
+}
+
+// flags[0] |= 1 if some entry's windows touch, overlap or descend; flags[0] |= 2 if a window count does not fit 12 bits
+__global__ void window_shape_kernel(int64_t n_entries, const int64_t* __restrict__ ent_win_off, const int32_t* __restrict__ win_lo,
+                                    const int32_t* __restrict__ win_hi, int32_t* __restrict__ flags) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_entries) return;
+    const int64_t a = ent_win_off[x], b = ent_win_off[x + 1];
+    int bad = (b - a) > 4095 ? 2 : 0;
+    for (int64_t w = a; w < b; ++w) {
+        if (win_lo[w] > win_hi[w]) bad |= 1;
+        if (w > a && win_lo[w] <= win_hi[w - 1]) bad |= 1;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
 template <class K, class V>
 static int sort_pairs(qms_ctx* ctx, K* k_in, K* k_out, V* v_in, V* v_out, int64_t n) {
     size_t bytes = 0;
@@ -314,21 +407,22 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
     QMS_TRY(qms_reserve(ctx, ctx->win_cmz, nw1)); QMS_TRY(qms_reserve(ctx, ctx->win_ri, nw1));
     QMS_TRY(qms_reserve(ctx, ctx->win_ci, nw1)); QMS_TRY(qms_reserve(ctx, ctx->probe, nw1));
     if (n_win > 0) {
-        TmpBuf<int32_t> win_entry(ctx), lo_sorted(ctx);
+        TmpBuf<int32_t> lo_sorted(ctx);
+        DBuf<int32_t>& win_entry_b = ctx->win_entry;
         TmpBuf<int64_t> w_ids(ctx), w_sorted(ctx);
         TmpBuf<int> stats(ctx);
-        QMS_TRY(qms_reserve(ctx, win_entry.b, nw1)); QMS_TRY(qms_reserve(ctx, lo_sorted.b, nw1));
+        QMS_TRY(qms_reserve(ctx, win_entry_b, nw1)); QMS_TRY(qms_reserve(ctx, lo_sorted.b, nw1));
         QMS_TRY(qms_reserve(ctx, w_ids.b, nw1)); QMS_TRY(qms_reserve(ctx, w_sorted.b, nw1));
         QMS_TRY(qms_reserve(ctx, stats.b, 4));
         QMS_CUDA(ctx, cudaMemsetAsync(stats.b.p, 0, 4 * sizeof(int), ctx->stream));
         entry_windows_kernel<<<qms_blocks(n_entries, threads), threads, 0, ctx->stream>>>(
             n_entries, n_slots, ctx->ent_env.p, ctx->ent_z.p, ctx->ent_win_off.p, ctx->slot_off.p, ctx->env_len.p, ctx->env_cflag.p,
             ctx->env_relabun.p, ctx->env_abun.p, ctx->pl_mz.p, ctx->pl_lo.p, ctx->pl_hi.p, ctx->win_lo.p, ctx->win_hi.p,
-            ctx->win_cmz.p, ctx->win_ri.p, ctx->win_ci.p, win_entry.b.p);
+            ctx->win_cmz.p, ctx->win_ri.p, ctx->win_ci.p, win_entry_b.p);
         iota_i64_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, w_ids.b.p);
         QMS_TRY(sort_pairs(ctx, ctx->win_lo.p, lo_sorted.b.p, w_ids.b.p, w_sorted.b.p, n_win));  // stable: ties keep (entry,k)
         probe_records_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(
-            n_win, w_sorted.b.p, ctx->win_lo.p, ctx->win_hi.p, win_entry.b.p, ctx->ent_win_off.p, ctx->probe.p, stats.b.p);
+            n_win, w_sorted.b.p, ctx->win_lo.p, ctx->win_hi.p, win_entry_b.p, ctx->ent_win_off.p, ctx->probe.p, stats.b.p);
         ctx->cnt.kernel_launches += 3;
         int h_stats[4] = {0, 0, 0, 0};
         int32_t first_lo = 0;
@@ -360,6 +454,48 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->window_density = ctx->h_pinned[0] ? (double)width_sum / (double)ctx->h_pinned[0] : 0.0;
+        // tables of the spectrum-resident matcher
+        ctx->dense_tables = false;
+        ctx->windows_disjoint = false;
+        if (n_win < 0x7fffffffll) {
+            TmpBuf<int32_t> first_cover(ctx), flags(ctx);
+            QMS_TRY(qms_reserve(ctx, first_cover.b, (size_t)span + 1));
+            QMS_TRY(qms_reserve(ctx, flags.b, 1));
+            QMS_TRY(qms_reserve(ctx, ctx->probe2, nw1));
+            QMS_TRY(qms_reserve(ctx, ctx->win_lohi, nw1));
+            QMS_TRY(qms_reserve(ctx, ctx->cell_range, (size_t)span + 1));
+            fill_i32_kernel<<<qms_blocks(span + 1, threads), threads, 0, ctx->stream>>>(span + 1, INT32_MAX, first_cover.b.p);
+            QMS_CUDA(ctx, cudaMemsetAsync(flags.b.p, 0, sizeof(int32_t), ctx->stream));
+            window_shape_kernel<<<qms_blocks(n_entries, threads), threads, 0, ctx->stream>>>(n_entries, ctx->ent_win_off.p, ctx->win_lo.p,
+                                                                                           ctx->win_hi.p, flags.b.p);
+            // zone table: groups = charge indices (entries of one charge share the isotope spacing)
+            ctx->zone_groups = n_charges <= 8 ? n_charges : 0;
+            ctx->zone_band_shift = 0;
+            while ((span >> ctx->zone_band_shift) >= ZONE_BANDS) ++ctx->zone_band_shift;
+            const int zone_cells = ZONE_BANDS * ZONE_GROUPS * ZONE_OFFSETS;
+            QMS_TRY(qms_reserve(ctx, ctx->zone_tab, (size_t)zone_cells));
+            zone_init_kernel<<<qms_blocks(zone_cells, threads), threads, 0, ctx->stream>>>(zone_cells, ctx->zone_tab.p);
+            if (ctx->zone_groups > 0) {
+                const size_t zone_smem = (size_t)2 * ZONE_BANDS * ctx->zone_groups * ZONE_OFFSETS * sizeof(int);
+                QMS_CUDA(ctx, cudaFuncSetAttribute(zone_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zone_smem));
+                zone_table_kernel<<<ctx->sm_count * 2, threads, zone_smem, ctx->stream>>>(
+                    n_entries, ctx->ent_win_off.p, ctx->ent_z.p, ctx->win_lo.p, ctx->win_hi.p, ctx->t_min, ctx->zone_band_shift,
+                    ctx->zone_groups, ctx->zone_tab.p);
+            }
+            probe2_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->probe.p, ctx->ent_win_off.p, ctx->ent_z.p,
+                                                                                  ctx->zone_groups, ctx->probe2.p, ctx->t_min,
+                                                                                  first_cover.b.p);
+            cell_range_kernel<<<qms_blocks(span, threads), threads, 0, ctx->stream>>>(span, ctx->cell_start.p, first_cover.b.p,
+                                                                                     ctx->cell_range.p);
+            win_lohi_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->win_lo.p, ctx->win_hi.p, ctx->win_lohi.p);
+            ctx->cnt.kernel_launches += 7;
+            int32_t h_flags = 0;
+            QMS_CUDA(ctx, cudaMemcpyAsync(&h_flags, flags.b.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            QMS_CUDA(ctx, cudaGetLastError());
+            QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->dense_tables = !(h_flags & 2);
+            ctx->windows_disjoint = !(h_flags & 1);
+        }
     }
     qms_trace(ctx, "index: cell table + cover bitmaps");
     QMS_CUDA(ctx, cudaGetLastError());

@@ -25,43 +25,11 @@
 //      into the hit arrays.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
-#include "qms_internal.cuh"
-
-#define QMS_DBL_EPS 2.220446049250313e-16
-
-enum { C_LIVE = 0, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_HEAVY, C_PAIR_WINDOWS, C_GATE_TICKET, C_N };   // slots of the device counter block
-
-struct MatchView {
-    const double2* peaks;
-    const int64_t* offsets;
-    int64_t n_spectra;
-    const ProbeRec* probe;
-    const int32_t* cell_start;
-    const uint32_t* cover;
-    const uint32_t* cover2;
-    int32_t t_min, t_max, max_width;
-    const int64_t* ent_win_off;
-    const int32_t* win_lo;
-    const int32_t* win_hi;
-    const double* win_cmz;
-    const double* win_ri;
-    const int32_t* win_ci;
-    const double* ent_lower;
-    const double* bin_upper;
-    int per_bin;
-    int input_kind;
-    int only_entry;        // >= 0: match_isotopologue mode (one entry, no score thresholds)
-    double precision, mz_min, mz_max;
-    int min_match;
-    const int32_t* need_of_nc;   // buckets an entry with n_c windows needs inside them to pass both overlap gates
-    double req_overlap, min_rel, rel_mz, rel_i, xi, score_thr;
-};
-
-__device__ __forceinline__ int32_t tmz_at(const double2* __restrict__ peaks, int64_t i, double precision) {
-    return qms_tmz(__ldg(&peaks[i].x), precision);
-}
+#include "match_shared.cuh"
 
 // bisect.bisect_right of the tuple (mz, inten) in a list of (mz, intensity) tuples (IL:2511-2516)
 __device__ __forceinline__ int64_t bisect_right_tuple(const double2* __restrict__ peaks, int64_t a, int64_t b, double mz, double inten) {
@@ -576,44 +544,6 @@ __global__ void __launch_bounds__(PROBE_THREADS) gate_rows_warp_kernel(MatchView
         if (n_live) atomicAdd(&counters[C_LIVE], n_live);
         if (n_inc) atomicAdd(&counters[C_INCID], n_inc);
     }
-}
-
-// ---- scoring (IL:2441-2498), sequential FP64, no FMA ------------------------------------------------
-template <class Rows>  // Rows: n(), matched(m), mmz(m), mi(m), ri(m), cmz(m), ci(m)
-__device__ void score_rows(const Rows& r, double min_rel, double rel_mz, double rel_i, double xi, double& score, double& scaling) {
-    double measured = 0.0, calculated = 0.0, ri_sum = 0.0;
-    const int n = r.n();
-    for (int m = 0; m < n; ++m) {
-        const double ri = r.ri(m);
-        if (ri < min_rel) continue;
-        if (r.matched(m)) {
-            calculated = __dadd_rn(calculated, __dmul_rn(r.ci(m), ri));
-            measured = __dadd_rn(measured, __dmul_rn(r.mi(m), ri));
-        }
-        ri_sum = __dadd_rn(ri_sum, ri);
-    }
-    scaling = __ddiv_rn(measured, calculated);
-    double mz_score = 0.0, i_score = 0.0;
-    for (int m = 0; m < n; ++m) {
-        const double ri = r.ri(m);
-        if (ri < min_rel || !r.matched(m)) continue;
-        const double si = __dmul_rn(r.ci(m), scaling);
-        const double cmz = r.cmz(m);
-        if (cmz > QMS_DBL_EPS) {
-            const double err = __ddiv_rn(fabs(__dsub_rn(r.mmz(m), cmz)), cmz);
-            const double local = err > rel_mz ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, rel_mz));
-            mz_score = __dadd_rn(mz_score, __dmul_rn(local, ri));
-        }
-        if (si > QMS_DBL_EPS) {
-            const double err = __ddiv_rn(fabs(__dsub_rn(r.mi(m), si)), si);
-            const double span = __dsub_rn(__dadd_rn(1.0, rel_i), ri);
-            const double local = err > span ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, span));
-            i_score = __dadd_rn(i_score, __dmul_rn(local, ri));
-        }
-    }
-    mz_score = __ddiv_rn(mz_score, ri_sum);
-    i_score = __ddiv_rn(i_score, ri_sum);
-    score = __dadd_rn(__dmul_rn(mz_score, xi), __dmul_rn(i_score, __dsub_rn(1.0, xi)));
 }
 
 struct PairRows {  // rows of one (spectrum, entry) pair under the current candidate choice
@@ -1288,6 +1218,50 @@ static int overlap_need_table(qms_ctx* ctx) {
     return QMS_OK;
 }
 
+int qms_score_pair_list(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, const unsigned long long* keys, const unsigned long long* vals,
+                        int entry_bits, int64_t p_begin, int heavy_min) {
+    if (n_pairs <= 0) return QMS_OK;
+    const int max_nc = ctx->max_nc > 0 ? ctx->max_nc : 1;
+    const size_t scratch = max_nc > K6_LOCAL ? (size_t)n_pairs * (size_t)max_nc + 1 : 1;
+    QMS_TRY(qms_reserve(ctx, ctx->scr_first, scratch));
+    QMS_TRY(qms_reserve(ctx, ctx->scr_cur, scratch));
+    QMS_TRY(qms_reserve(ctx, ctx->scr_best, scratch));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_best, (size_t)n_pairs * (size_t)max_nc + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_score, (size_t)n_pairs));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)n_pairs));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)n_pairs));
+    QMS_TRY(qms_reserve(ctx, ctx->heavy_list, (size_t)n_pairs + 1));
+    QMS_CUDA(ctx, cudaMemsetAsync(ctx->pair_flag.p, 0, (size_t)n_pairs * sizeof(int32_t), ctx->stream));
+    assemble_score_kernel<<<qms_blocks(n_pairs, 128), 128, 0, ctx->stream>>>(
+        v, n_pairs, keys, vals, entry_bits, p_begin, max_nc, ctx->scr_first.p, ctx->scr_cur.p, ctx->scr_best.p, ctx->pair_best.p,
+        ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p, heavy_min > 0 ? ctx->heavy_list.p : nullptr,
+        heavy_min);
+    QMS_CUDA(ctx, cudaGetLastError());
+    ctx->cnt.kernel_launches++;
+    if (heavy_min > 0) {
+        int64_t hblocks = (n_pairs + K6B_WARPS - 1) / K6B_WARPS;
+        const int64_t hmax = (int64_t)ctx->sm_count * 8;
+        if (hblocks > hmax) hblocks = hmax;
+        score_heavy_kernel<<<(unsigned)hblocks, 32 * K6B_WARPS, 0, ctx->stream>>>(
+            v, keys, vals, entry_bits, p_begin, max_nc, ctx->heavy_list.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p,
+            ctx->pair_flag.p, ctx->dev_counters.p);
+        QMS_CUDA(ctx, cudaGetLastError());
+        ctx->cnt.kernel_launches++;
+    }
+    return QMS_OK;
+}
+
+// caller buffers the emit kernels can write directly: all in device memory (the matched values are optional)
+static bool callers_on_device(const qms_hits* out) {
+    if (!out || !out->hit_spec || !out->hit_entry || !out->hit_score || !out->hit_scaling || !out->hit_win_off || !out->hit_peak)
+        return false;
+    if ((out->hit_mmz == nullptr) != (out->hit_mi == nullptr)) return false;
+    for (const void* p : {(const void*)out->hit_spec, (const void*)out->hit_entry, (const void*)out->hit_score, (const void*)out->hit_scaling,
+                          (const void*)out->hit_win_off, (const void*)out->hit_peak})
+        if (!qms_is_device_ptr(p)) return false;
+    return !out->hit_mmz || (qms_is_device_ptr(out->hit_mmz) && qms_is_device_ptr(out->hit_mi));
+}
+
 static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra, int32_t input_kind,
                       double mz_score_percentile, int32_t only_entry, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
     if (!ctx || !offsets || n_spectra < 0 || !n_hits || !n_hit_windows)
@@ -1303,18 +1277,20 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     // ---- inputs -> device ----
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     const bool off_dev = qms_is_device_ptr(offsets);
-    int64_t p_begin = 0, p_end = 0;
+    int64_t p_begin = 0, p_end = 0, longest = 0;
     const int64_t* d_off = offsets;
     if (off_dev) {
-        int64_t ends[2] = {0, 0};
-        QMS_CUDA(ctx, cudaMemcpyAsync(&ends[0], offsets, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        QMS_CUDA(ctx, cudaMemcpyAsync(&ends[1], offsets + n_spectra, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->h_offsets.resize((size_t)n_spectra + 1);
+        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_offsets.data(), offsets, ((size_t)n_spectra + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        p_begin = ends[0];
-        p_end = ends[1];
+        p_begin = ctx->h_offsets[0];
+        p_end = ctx->h_offsets[n_spectra];
+        for (int64_t s = 0; s < n_spectra; ++s) longest = std::max(longest, ctx->h_offsets[s + 1] - ctx->h_offsets[s]);
     } else {
         p_begin = offsets[0];
         p_end = offsets[n_spectra];
+        for (int64_t s = 0; s < n_spectra; ++s) longest = std::max(longest, offsets[s + 1] - offsets[s]);
         QMS_TRY(qms_upload(ctx, ctx->d_offsets, offsets, (size_t)n_spectra + 1));
         d_off = ctx->d_offsets.p;
     }
@@ -1390,6 +1366,54 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     int entry_bits = 1, spec_bits = 1;
     while ((1ll << entry_bits) < ctx->n_entries) ++entry_bits;
     while ((1ll << spec_bits) < n_spectra) ++spec_bits;
+    if (qms_dense_eligible(ctx, input_kind, only_entry, longest)) {
+        // dense library: the spectrum-resident matcher (match_spectrum.cu)
+        const bool want_values = !out || (out->hit_mmz && out->hit_mi);
+        const bool on_device = callers_on_device(out);
+        int64_t nh = 0, nw = 0;
+        bool wrote_callers = false;
+        QMS_TRY(qms_match_dense(ctx, v, p_begin, p_end, entry_bits, spec_bits, on_device ? out : nullptr, want_values, &nh, &nw,
+                                &wrote_callers));
+        ctx->cnt.ms_h2d += elapsed(ctx, 0, 1);
+        ctx->cnt.dense_batches++;
+        *n_hits = nh;
+        *n_hit_windows = nw;
+        ctx->cnt.hits += nh;
+        ctx->cnt.hit_windows += nw;
+        ctx->last_hits = wrote_callers ? 0 : nh;
+        ctx->last_windows = wrote_callers ? 0 : nw;
+        ctx->last_values = want_values;
+        if (nh == 0) {
+            if (out && out->hit_win_off && out->cap_hits >= 0) {
+                const int64_t zero = 0;
+                QMS_CUDA(ctx, cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t),
+                                         qms_is_device_ptr(out->hit_win_off) ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+            }
+            return QMS_OK;
+        }
+        if (wrote_callers) return QMS_OK;
+        if (!out) return QMS_OK;                       // size query: the hits stay on the device for qms_fetch_hits
+        if (nh > out->cap_hits || nw > out->cap_windows)
+            return qms_fail(ctx, QMS_E_CAPACITY,
+                            "hit buffers too small: need %lld hits / %lld windows, have %lld / %lld (results retained: qms_fetch_hits)",
+                            (long long)nh, (long long)nw, (long long)out->cap_hits, (long long)out->cap_windows);
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+        QMS_TRY(copy_out(ctx, out->hit_spec, ctx->o_spec.p, (size_t)nh));
+        QMS_TRY(copy_out(ctx, out->hit_entry, ctx->o_entry.p, (size_t)nh));
+        QMS_TRY(copy_out(ctx, out->hit_score, ctx->o_score.p, (size_t)nh));
+        QMS_TRY(copy_out(ctx, out->hit_scaling, ctx->o_scaling.p, (size_t)nh));
+        QMS_TRY(copy_out(ctx, out->hit_win_off, ctx->o_win_off.p, (size_t)nh + 1));
+        if (want_values) {
+            QMS_TRY(copy_out(ctx, out->hit_mmz, ctx->o_mmz.p, (size_t)nw));
+            QMS_TRY(copy_out(ctx, out->hit_mi, ctx->o_mi.p, (size_t)nw));
+        }
+        QMS_TRY(copy_out(ctx, out->hit_peak, ctx->o_peak.p, (size_t)nw));
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->cnt.ms_d2h += elapsed(ctx, 3, 4);
+        return QMS_OK;
+    }
+    ctx->last_values = true;
     static int variant = -1;   // QMS_PROBE_VARIANT: tuning switch for profiling runs (default = best measured)
     if (variant < 0) {
         const char* e = getenv("QMS_PROBE_VARIANT");
@@ -1622,6 +1646,8 @@ extern "C" int qms_fetch_hits(qms_ctx* ctx, qms_hits* out, int64_t* n_hits, int6
     if (n_hit_windows) *n_hit_windows = nw;
     if (nh > out->cap_hits || nw > out->cap_windows)
         return qms_fail(ctx, QMS_E_CAPACITY, "hit buffers too small: need %lld hits / %lld windows", (long long)nh, (long long)nw);
+    if ((out->hit_mmz || out->hit_mi) && !ctx->last_values && nw > 0)
+        return qms_fail(ctx, QMS_E_ARG, "the last match was asked not to keep the matched values (hit_mmz / hit_mi were NULL)");
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     if (nh == 0) {
         const int64_t zero = 0;

@@ -95,6 +95,15 @@ struct qms_ctx {
     DBuf<ProbeRec> probe;         // windows sorted by lo
     DBuf<int32_t> cell_start;     // S[c - t_min] = first probe index with lo >= c ; size span+2
     DBuf<uint32_t> cover;         // 1 bit per grid cell: covered by >= 1 window
+    // tables of the spectrum-resident matcher (match_spectrum.cu), derived from the ones above
+    DBuf<int4> probe2;            // probe record as {lo, hi, first window of the entry, k | group << 12 | n_c << 16}
+    DBuf<int2> cell_range;        // per grid cell: [first probe record that covers it, first record with lo > cell)
+    DBuf<int2> win_lohi;          // (lo, hi) of every window, entry-major: one 8-byte load per window
+    DBuf<int32_t> win_entry;      // index entry of every window
+    DBuf<int2> zone_tab;          // [32 m/z bands][16 groups][32 window-ordinal differences]: where the other windows of an entry lie
+    int zone_groups = 0, zone_band_shift = 0;
+    bool dense_tables = false;    // the four tables exist (window ids fit 31 bits, k and n_c fit 16)
+    bool windows_disjoint = false;   // every entry's windows ascend without touching (lo[m+1] > hi[m])
     int32_t t_min = 0, t_max = -1, max_width = 0;
     double mz_min = 0, mz_max = 0;
     bool have_index = false;
@@ -110,10 +119,14 @@ struct qms_ctx {
     void* stage_slot[2] = {nullptr, nullptr};   // pinned staging slots for large pageable host buffers
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     std::vector<int32_t> h_need;
+    std::vector<int64_t> h_offsets;      // host copy of device-resident row offsets
     bool need_dirty = true;
     double window_density = 0.0;   // sum of window widths / covered grid cells = windows over an average covered cell
     int64_t pair_cap_hint = 0;     // capacity of the pair list, learned from the previous batch (+25 %)
     int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
+    int dense_mode = 2;            // spectrum-resident matcher: 0 never, 1 whenever its tables allow it, 2 by library density
+    int dense_ctas = 4;            // its resident CTAs per SM
+    bool last_values = true;                   // ... including the matched (m/z, intensity) values
     DBuf<uint8_t> cub_tmp;
     DBuf<unsigned long long> dev_counters;   // see match.cu
     DBuf<double> pair_score, pair_scaling;
@@ -125,6 +138,12 @@ struct qms_ctx {
     DBuf<double> o_score, o_scaling, o_mmz, o_mi;
     DBuf<int64_t> o_win_off, o_peak;
     unsigned long long* h_pinned = nullptr;  // small pinned mailbox for counters
+    // staging of the spectrum-resident matcher: hits in discovery order, sorted by (spectrum, entry) afterwards
+    DBuf<unsigned long long> st_key, st_key_alt;
+    DBuf<double> st_score, st_scaling;
+    DBuf<uint32_t> st_woff, st_nc, st_rows, st_order, st_order_alt, spec_buckets, spec_rows;
+    DBuf<int64_t> st_nc_sorted;
+    int64_t stage_hits_hint = 0, stage_windows_hint = 0, multi_cap_hint = 0;
 };
 
 // allocation helpers (ctx.cu)

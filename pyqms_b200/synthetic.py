@@ -68,7 +68,7 @@ def averagine_formulas(n, seed=20260105, min_mass=100.0, max_mass=50000.0):
 
 def synth_run(entry_mz, entry_ci, n_spectra, seed, mean_peaks=800, sigma_peaks=0.5, min_peaks=100,
               max_peaks=5000, entry_fraction=1.0, elution_sigma=15.0, mz_lo=150.0, mz_hi=2000.0,
-              ppm_sd=1.5, intensity_sd=0.08, dropout=0.10):
+              ppm_sd=1.5, intensity_sd=0.08, dropout=0.10, planted=None, return_planted=False):
     """Synthetic run: uniform background + Gaussian-eluting library entries.
 
     entry_mz / entry_ci: per library index entry, 1-D arrays of the theoretical c-peak m/z and the
@@ -76,6 +76,10 @@ def synth_run(entry_mz, entry_ci, n_spectra, seed, mean_peaks=800, sigma_peaks=0
     once (apex uniform over the run, sd ``elution_sigma`` spectra, on for +-3 sd); while on, each
     c-peak is planted at mz*(1+N(0, ppm_sd ppm)) with intensity ci*amount*(1+N(0, intensity_sd)),
     ``dropout`` of them missing.  Returns (peaks (n,2) float64, offsets (n_spectra+1) int64).
+
+    ``planted``: the c-peak table of the chosen entries from an earlier call with ``return_planted=True``
+    (dict n_entries, lens, mz, ci); with it the identical run is drawn without a library (entry_mz / entry_ci
+    may be None) -- bench.py's reference arm reproduces the GPU arm's spectra from a committed table this way.
     """
     rng = np.random.default_rng(seed)
     n_bg = np.clip(np.rint(rng.lognormal(np.log(mean_peaks), sigma_peaks, size=n_spectra)), min_peaks,
@@ -84,7 +88,7 @@ def synth_run(entry_mz, entry_ci, n_spectra, seed, mean_peaks=800, sigma_peaks=0
     bg_mz = rng.uniform(mz_lo, mz_hi, size=bg_spec.size)
     bg_i = 10.0 ** rng.uniform(3.0, 6.0, size=bg_spec.size)
 
-    n_entries = len(entry_mz)
+    n_entries = int(planted["n_entries"]) if planted is not None else len(entry_mz)
     chosen = np.arange(n_entries)
     if entry_fraction < 1.0:
         chosen = np.sort(rng.choice(n_entries, size=max(1, int(round(n_entries * entry_fraction))),
@@ -94,9 +98,16 @@ def synth_run(entry_mz, entry_ci, n_spectra, seed, mean_peaks=800, sigma_peaks=0
         apex = rng.uniform(0, n_spectra, size=len(chosen))
         amount = 10.0 ** rng.uniform(1.0, 3.0, size=len(chosen))
         half = int(np.ceil(3 * elution_sigma))
-        lens = np.array([len(entry_mz[e]) for e in chosen], dtype=np.int64)
-        flat_mz = np.concatenate([np.asarray(entry_mz[e], dtype=np.float64) for e in chosen])
-        flat_ci = np.concatenate([np.asarray(entry_ci[e], dtype=np.float64) for e in chosen])
+        if planted is not None:
+            lens = np.asarray(planted["lens"], dtype=np.int64)
+            flat_mz = np.asarray(planted["mz"], dtype=np.float64)
+            flat_ci = np.asarray(planted["ci"], dtype=np.float64)
+            assert len(lens) == len(chosen), "planted table does not belong to this (seed, n_spectra, entry_fraction)"
+        else:
+            lens = np.array([len(entry_mz[e]) for e in chosen], dtype=np.int64)
+            flat_mz = np.concatenate([np.asarray(entry_mz[e], dtype=np.float64) for e in chosen])
+            flat_ci = np.concatenate([np.asarray(entry_ci[e], dtype=np.float64) for e in chosen])
+        table = {"n_entries": n_entries, "lens": lens, "mz": flat_mz, "ci": flat_ci}
         owner = np.repeat(np.arange(len(chosen)), lens)           # per c-peak: which chosen entry
         shifts = np.arange(-half, half + 1)
         # (c-peak, shift) grid
@@ -119,6 +130,8 @@ def synth_run(entry_mz, entry_ci, n_spectra, seed, mean_peaks=800, sigma_peaks=0
     peaks[:, 1] = inten[order]
     offsets = np.zeros(n_spectra + 1, dtype=np.int64)
     np.cumsum(np.bincount(spec, minlength=n_spectra), out=offsets[1:])
+    if return_planted:
+        return peaks, offsets, (table if len(chosen) else {"n_entries": n_entries, "lens": [], "mz": [], "ci": []})
     return peaks, offsets
 
 

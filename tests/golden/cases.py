@@ -107,4 +107,19 @@ CASES = {
     "big_formula": dict(
         lib=dict(molecules=["+C222H349N61O66S2", "+C444H698N122O133S4", "+C130H210N30O45S1"], charges=[3, 5, 8]),
         run=dict(n_spectra=10, mean_peaks=150, seed=22, elution_sigma=3.0)),
+    # averagine at 20 kDa and 50 kDa: the range where the reference's 2-isotope levels use exact big-int binomials
+    # (IL:1121-1140, 1216-1324) and the kernels FP64 pow x iterated C(n,k).  heavy: the reference needs 13 s / ~10 min
+    # and several GB for these, so the CPU suite does not rebuild them with the oracle (QMS_HEAVY_ORACLE=1 does); the
+    # fixtures carry minPos/maxPos of every tree level instead of the full trees.
+    "avg_20kda": dict(
+        lib=dict(molecules=["+C889H1396N244O266S8"], charges=[11, 14, 18]),
+        run=dict(n_spectra=8, mean_peaks=150, seed=25, elution_sigma=3.0), skip_trees=True, tree_bounds=True, heavy=True),
+    "avg_50kda": dict(
+        lib=dict(molecules=["+C2222H3491N611O665S19"], charges=[26, 32]),
+        run=dict(n_spectra=8, mean_peaks=150, seed=26, elution_sigma=3.0), skip_trees=True, tree_bounds=True, heavy=True),
+    # BASELINE.json configs[2] at its full shape: all 19 BSA molecules x 100 label percentiles, charges 1-4
+    "bsa_pct_full": dict(
+        lib=dict(molecules=BSA_MOLECULES, charges=[1, 2, 3, 4], fixed_labels=CAM_FIXED_LABEL,
+                 metabolic_labels={"15N": [round(0.01 * i, 2) for i in range(100)]}),
+        run=dict(n_spectra=30, mean_peaks=300, seed=27, elution_sigma=2.0, entry_fraction=0.05), skip_trees=True, heavy=True),
 }

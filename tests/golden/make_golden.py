@@ -35,7 +35,7 @@ def f(x):
     return None if x is None else float(x)
 
 
-def dump_library(lib, skip_trees=False):
+def dump_library(lib, skip_trees=False, tree_bounds=False):
     formulas = list(lib.keys())
     lps = list(lib.labled_percentiles)
     env = {}
@@ -64,7 +64,13 @@ def dump_library(lib, skip_trees=False):
                 out[str(n)] = [lo, hi, [f(node["env"][p]["abun"]) for p in span],
                                [f(node["env"][p]["mass"]) for p in span]]
             trees[el][label] = out
+    bounds = {}
+    if tree_bounds:      # minPos / maxPos of every level (what the pruning threshold decides), without the envelopes
+        for el, by_label in lib.element_trees.items():
+            bounds[el] = {label: {str(n): [node["minPos"], node["maxPos"]] for n, node in levels.items()}
+                          for label, levels in by_label.items()}
     return {
+        "tree_bounds": bounds,
         "formulas": formulas, "cc": {k: dict(lib[k]["cc"]) for k in formulas},
         "labled_percentiles": [[list(p) for p in lp] for lp in lps],
         "molecule_to_formula": lib.lookup["molecule to formula"],
@@ -108,7 +114,7 @@ def main():
             continue
         lib = pyqms.IsotopologueLibrary(verbose=False, **case["lib"])
         peaks, offsets = draw_case_spectra(lib, case["run"], name)
-        blob = {"library": dump_library(lib, case.get("skip_trees", False)),
+        blob = {"library": dump_library(lib, case.get("skip_trees", False), case.get("tree_bounds", False)),
                 "results_numpy": dump_results(run_matches(lib, peaks, offsets, False)),
                 "results_list": dump_results(run_matches(lib, peaks, offsets, True))}
         with gzip.open(HERE / (name + ".json.gz"), "wt") as fh:

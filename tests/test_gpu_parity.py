@@ -130,6 +130,45 @@ def test_match_many_equals_match_all_loop(case):
                          key_order=not TIE_PRONE[name])
 
 
+def test_spectrum_resident_matcher_matches_reference(case):
+    """The dense-library kernels (match_spectrum.cu), forced on for every library whose windows allow them."""
+    name, blob, peaks, offsets, lib = case
+    n = len(offsets) - 1
+    lib._ctx.set_tuning("dense_mode", 1)
+    try:
+        before = lib.device_counters()["dense_batches"]
+        res = lib.match_many(peaks, file_name="run", spec_ids=list(range(n)), spec_rts=[s * 0.2 for s in range(n)], offsets=offsets)
+        used = lib.device_counters()["dense_batches"] - before
+    finally:
+        lib._ctx.set_tuning("dense_mode", 2)
+    assert_results_equal(results_to_rows(res), blob["results_numpy"], score_tol=SCORE_TOL, cmz_rel=REL_MASS, ri_rel=REL_ABUN,
+                         key_order=not TIE_PRONE[name])
+    assert used == (0 if name == "overlap_windows" else 1)      # overlapping windows: not eligible, same results through match.cu
+
+
+def test_tree_bounds_match_reference(case):
+    """minPos / maxPos of every tree level (the > 1e-3 pruning decision, IL:1216-1324) for the 20 / 50 kDa formulas."""
+    name, blob, _, _, lib = case
+    bounds = blob["library"].get("tree_bounds") or {}
+    if not bounds:
+        pytest.skip("fixture without tree bounds")
+    trees = lib.element_trees
+    checked = 0
+    for el, by_label in bounds.items():
+        for label, levels in by_label.items():
+            top = max(trees[el][label])
+            for n, (lo, hi) in levels.items():
+                if int(n) > top:
+                    continue        # the reference builds one level more than it can use for >2-isotope elements (Q5)
+                if lo is None:
+                    assert int(n) not in trees[el][label]
+                    continue
+                node = trees[el][label][int(n)]
+                assert (node["minPos"], node["maxPos"]) == (lo, hi), (el, label, n)
+                checked += 1
+    assert checked > 1000
+
+
 def test_reference_peptide_sequence_vectors(pyqms, golden_dir):
     for molecule, formula, abun, (lo, hi) in PEPTIDE_SEQUENCE_KATS:
         lib = pyqms.IsotopologueLibrary(molecules=[molecule], charges=[2], verbose=False,

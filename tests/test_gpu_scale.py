@@ -89,6 +89,34 @@ def test_proteome_sublibrary_independence():
     assert np.all(key[1:] > key[:-1])
 
 
+def test_spectrum_resident_matcher_equals_row_streaming_matcher():
+    """The two matchers of the library (match.cu / match_spectrum.cu) on a dense library: identical packed hits,
+    bit for bit, including spectra too large for the shared-memory bucket array (global spill) and empty spectra."""
+    import pyqms_b200
+    peptides = random_tryptic_peptides(20000, seed=20260104)
+    lib = pyqms_b200.IsotopologueLibrary(molecules=peptides, charges=[1, 2, 3, 4, 5], fixed_labels=CAM_FIXED_LABEL, verbose=False)
+    mz, ci = lib.entry_peaks()
+    peaks, offsets = synth_run(mz, ci, n_spectra=600, seed=77, entry_fraction=0.05, elution_sigma=3.0)
+    big, big_off = synth_run(mz, ci, n_spectra=3, seed=78, mean_peaks=9000, sigma_peaks=0.05, max_peaks=12000, entry_fraction=0.01)
+    empty = np.zeros(2, dtype=np.int64)
+    peaks = np.concatenate([peaks, big])
+    offsets = np.concatenate([offsets, offsets[-1] + empty[1:], offsets[-1] + big_off[1:]])      # one empty spectrum in between
+    assert np.diff(offsets).max() > 4096 and np.diff(offsets).min() == 0
+    outs = {}
+    for mode in (0, 1):
+        lib._ctx.set_tuning("dense_mode", mode)
+        before = lib.device_counters()["dense_batches"]
+        outs[mode] = lib.match_packed(peaks, offsets)
+        assert lib.device_counters()["dense_batches"] - before == mode
+    lib._ctx.set_tuning("dense_mode", 2)
+    a, b = outs[0], outs[1]
+    assert a["n_hits"] == b["n_hits"] > 1000 and a["n_windows"] == b["n_windows"]
+    for k in ("spec", "entry", "win_off", "peak"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("score", "scaling", "mmz", "mi"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
 def test_envelope_sweep_against_oracle():
     """configs[4] shape, bounded: averagine formulas 100 Da - 12 kDa, FP64 abundance parity 1e-9 vs the oracle."""
     sys.setrecursionlimit(20000)

@@ -42,7 +42,7 @@ def timed_match(lib, peaks, offsets, reps=3):
     wall = (time.perf_counter() - t0) / reps
     c = lib.device_counters()
     n = len(offsets) - 1
-    per = {k: c[k] / reps for k in ("peaks", "live_peaks", "incidences", "candidates", "candidate_windows", "combinations", "hits",
+    per = {k: c[k] / reps for k in ("peaks", "live_peaks", "incidences", "gated_incidences", "candidates", "candidate_windows", "combinations", "hits",
                                     "ms_probe", "ms_gate", "ms_score", "ms_compact", "ms_h2d", "ms_d2h")}
     device_ms = per["ms_probe"] + per["ms_gate"] + per["ms_score"] + per["ms_compact"]
     return {"spectra": n, "wall_s_e2e_host_buffers": wall, "spectra_per_s_e2e": n / wall, "device_ms": device_ms,
