@@ -93,6 +93,12 @@ int qms_device_bytes(qms_ctx* ctx, int64_t* out);    /* device memory currently 
  *   "dense_ctas"  resident CTAs per SM of the spectrum-resident kernel (default 4; QMS_DENSE_CTAS) */
 int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value);
 
+/* Page-locked host memory for spectrum and hit buffers (cudaHostAlloc, portable): copies to and from such buffers run
+ * at link speed and overlap the kernels (qms_match_batch pipelines sub-batches of a large host-resident run only when
+ * its buffers are page-locked or device memory).  No context needed; error text through qms_last_error(NULL). */
+int qms_host_alloc(void** out, size_t bytes);
+int qms_host_free(void* p);
+
 /* ---- P1 prologue: enriched isotope tables ----------------------------------------------------
  * Replaces _recalc_isotopic_distribution IL:2109-2165: the isotope whose rounded mass equals
  * enriched_isotope gets abundance target_percentile, the others share (natural - target) in

@@ -197,6 +197,22 @@ int qms_ctx_create(int device, qms_ctx** out) {
     return QMS_OK;
 }
 
+int qms_host_alloc(void** out, size_t bytes) {
+    if (!out) return QMS_E_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) return qms_fail(nullptr, QMS_E_CUDA, "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return QMS_OK;
+}
+
+int qms_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        cudaGetLastError();
+        return QMS_E_CUDA;
+    }
+    return QMS_OK;
+}
+
 int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value) {
     if (!ctx || !key) return qms_fail(ctx, QMS_E_ARG, "qms_set_tuning: NULL argument");
     if (!strcmp(key, "dense_mode")) {

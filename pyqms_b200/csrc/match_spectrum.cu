@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
     __shared__ uint32_t s_wcount[MS_WARPS];
     __shared__ int32_t s_need[MS_MAXNC + 1];
     __shared__ long long s_spec;
+    __shared__ uint32_t s_next;          // next bucket of the spectrum nobody has taken yet
+    __shared__ int s_plain;              // 1: every intensity of the spectrum is finite (the score bound may be used)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned below = (1u << lane) - 1u;
     uint32_t* q_i = s_queues + warp * 8 * MS_QUEUE;      // incidences waiting for the window-by-window gate
@@ -134,7 +136,11 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
 
     for (;;) {
         __syncthreads();                                   // the previous spectrum is done before its tables are overwritten
-        if (tid == 0) s_spec = (long long)atomicAdd(&counters[C_SPEC_TICKET], 1ull);
+        if (tid == 0) {
+            s_spec = (long long)atomicAdd(&counters[C_SPEC_TICKET], 1ull);
+            s_next = 0;
+            s_plain = 1;
+        }
         __syncthreads();
         const int64_t s = s_spec;
         if (s >= v.n_spectra) break;
@@ -149,7 +155,9 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
         for (int64_t base = sb; base < se; base += MS_THREADS) {
             const int64_t i = base + tid;
             const bool valid = i < se;
-            const int32_t t = valid ? tmz_at(v.peaks, i, v.precision) : INT32_MAX;
+            const double2 row = valid ? __ldg(&v.peaks[i]) : make_double2(0.0, 0.0);
+            const int32_t t = valid ? qms_tmz(row.x, v.precision) : INT32_MAX;
+            if (!(fabs(row.y) <= 1.7976931348623157e308)) s_plain = 0;      // NaN or infinite intensity (benign race: all write 0)
             int32_t t_prev = __shfl_up_sync(0xffffffffu, t, 1);
             if (lane == 0) t_prev = (valid && i > sb) ? tmz_at(v.peaks, i - 1, v.precision) : INT32_MIN;
             if (valid && t < t_prev) atomicAdd(&counters[C_UNSORTED], 1ull);
@@ -194,6 +202,8 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
 
         // ---- phase B ----
         int q_n = 0, sq_n = 0;                               // warp-uniform
+        // the bound needs a convex score (0 <= xi <= 1), finite intensities and positive calculated intensities
+        const bool bound_ok = s_plain && v.xi >= 0.0 && v.xi <= 1.0 && v.score_thr > 0.0;
         auto first_at_or_above = [&](int32_t value) -> uint32_t {
             uint32_t a = s_table[(uint32_t)(value - v.t_min) >> sh];
             while (B[a] < value) ++a;
@@ -239,12 +249,29 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                     }
                 } else {
                     const InlineRows r{&v, w0, p_begin, nc, rows};
-                    score_rows(r, v.min_rel, v.rel_mz, v.rel_i, v.xi, score, scaling);
                     ++st_combos;
                     st_windows += (unsigned long long)nc;
-                    pass = true;
-                    if (score < v.score_thr) pass = false;            // IL:1860
-                    if (n_matched < v.min_match) pass = false;        // IL:1862-1870
+                    pass = n_matched >= v.min_match;                  // IL:1862-1870
+                    if (pass && bound_ok) {
+                        // Every per-peak term of the mScore is at most ri (IL:2460-2479), so score <= sum of the matched
+                        // ri / sum of all ri whatever the measured values are.  A pair whose bound is clearly below the
+                        // threshold (1e-9 relative, the rounding of the real computation is ~1e-14) needs no scoring.
+                        double ri_all = 0.0, ri_hit = 0.0, calculated = 0.0;
+                        for (int m = 0; m < nc; ++m) {
+                            const double ri = r.ri(m);
+                            if (ri < v.min_rel) continue;
+                            ri_all += ri;
+                            if (rows[m] != MS_NONE) {
+                                ri_hit += ri;
+                                calculated += r.ci(m) * ri;
+                            }
+                        }
+                        if (calculated > 0.0 && ri_hit < v.score_thr * ri_all * (1.0 - 1e-9)) pass = false;
+                    }
+                    if (pass) {
+                        score_rows(r, v.min_rel, v.rel_mz, v.rel_i, v.xi, score, scaling);
+                        if (score < v.score_thr) pass = false;        // IL:1860
+                    }
                 }
             }
             stage_hits(d, counters, pass, key, score, scaling, nc, rows);
@@ -336,7 +363,12 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                 __syncwarp();
             }
         };
-        for (uint32_t i = warp; i < n; i += MS_WARPS) {
+        for (;;) {
+            // buckets differ in cost by an order of magnitude (records per cell, survivors): the warps draw them one by one
+            uint32_t i = 0;
+            if (lane == 0) i = atomicAdd(&s_next, 1u);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= n) break;
             const int32_t t = B[i];
             const int32_t t_before = i ? B[i - 1] : INT32_MIN;
             // zone masks of this bucket: per entry group, 2-bit (saturating) bucket counts of the 32 zones in which the

@@ -42,6 +42,6 @@ for row in csv.reader(text.splitlines()):
 total_samples = sum(v[0] for v in per_line.values()) or 1
 total_executed = sum(v[1] for v in per_line.values()) or 1
 print("samples %d, warp instructions %d" % (total_samples, total_executed))
-for (name, line), v in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
+for (name, line), v in sorted(per_line.items(), key=lambda kv: -kv[1][int(__import__('os').environ.get('NCU_SORT','0'))])[:top]:
     print("%-18s %4d %5.1f%% samples %5.1f%% instr  lanes %4.1f | %s" % (name[:18], line, 100 * v[0] / total_samples,
                                                                          100 * v[1] / total_executed, v[2] / max(1, v[1]), v[3].strip()[:90]))
