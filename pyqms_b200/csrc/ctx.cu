@@ -94,10 +94,11 @@ static int stage_ready(qms_ctx* ctx) {
     return QMS_OK;
 }
 
-int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes) {
+int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t stream) {
     if (!bytes) return QMS_OK;
+    if (!stream) stream = ctx->stream;
     if (bytes < STAGE_MIN || !is_pageable_host(host)) {
-        QMS_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        QMS_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream));
         return QMS_OK;                             // stream-ordered; the caller synchronises once for all its copies
     }
     QMS_TRY(stage_ready(ctx));
@@ -105,8 +106,8 @@ int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes) {
     for (size_t k = 0; k <= chunks; ++k) {
         if (k < chunks) {                          // DMA of chunk k into its slot (free: chunk k-2 was drained at step k-1)
             const size_t off = k * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
-            QMS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_slot[k & 1], (const char*)dev + off, n, cudaMemcpyDeviceToHost, ctx->stream));
-            QMS_CUDA(ctx, cudaEventRecord(ctx->stage_ev[k & 1], ctx->stream));
+            QMS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_slot[k & 1], (const char*)dev + off, n, cudaMemcpyDeviceToHost, stream));
+            QMS_CUDA(ctx, cudaEventRecord(ctx->stage_ev[k & 1], stream));
         }
         if (k > 0) {                               // meanwhile the host drains chunk k-1
             const size_t off = (k - 1) * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
@@ -117,10 +118,11 @@ int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes) {
     return QMS_OK;
 }
 
-int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes) {
+int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes, cudaStream_t stream) {
     if (!bytes) return QMS_OK;
+    if (!stream) stream = ctx->stream;
     if (bytes < STAGE_MIN || !is_pageable_host(host)) {
-        QMS_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        QMS_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream));
         return QMS_OK;                             // stream-ordered like every other upload
     }
     QMS_TRY(stage_ready(ctx));
@@ -129,10 +131,10 @@ int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes) 
         const size_t off = k * STAGE_CHUNK, n = bytes - off < STAGE_CHUNK ? bytes - off : STAGE_CHUNK;
         if (k >= 2) QMS_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[k & 1]));    // the slot's previous DMA has finished
         parallel_memcpy(ctx->stage_slot[k & 1], (const char*)host + off, n);
-        QMS_CUDA(ctx, cudaMemcpyAsync((char*)dev + off, ctx->stage_slot[k & 1], n, cudaMemcpyHostToDevice, ctx->stream));
-        QMS_CUDA(ctx, cudaEventRecord(ctx->stage_ev[k & 1], ctx->stream));
+        QMS_CUDA(ctx, cudaMemcpyAsync((char*)dev + off, ctx->stage_slot[k & 1], n, cudaMemcpyHostToDevice, stream));
+        QMS_CUDA(ctx, cudaEventRecord(ctx->stage_ev[k & 1], stream));
     }
-    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the slots are reused by the next copy
+    QMS_CUDA(ctx, cudaStreamSynchronize(stream));      // the slots are reused by the next copy
     return QMS_OK;
 }
 
@@ -193,6 +195,7 @@ int qms_ctx_create(int device, qms_ctx** out) {
     cudaHostAlloc((void**)&ctx->h_pinned, 64 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (const char* e = getenv("QMS_DENSE_MODE")) ctx->dense_mode = atoi(e);
     if (const char* e = getenv("QMS_DENSE_CTAS")) ctx->dense_ctas = atoi(e);
+    if (const char* e = getenv("QMS_SUB_BATCH_ROWS")) ctx->sub_batch_rows = atoll(e);
     *out = ctx;
     return QMS_OK;
 }
@@ -221,6 +224,9 @@ int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value) {
     } else if (!strcmp(key, "dense_ctas")) {
         if (value < 1 || value > 32) return qms_fail(ctx, QMS_E_ARG, "dense_ctas must be in [1, 32]");
         ctx->dense_ctas = value;
+    } else if (!strcmp(key, "sub_batch_rows")) {
+        if (value < 0) return qms_fail(ctx, QMS_E_ARG, "sub_batch_rows must be >= 0");
+        ctx->sub_batch_rows = value;
     } else {
         return qms_fail(ctx, QMS_E_ARG, "unknown tuning key '%s'", key);
     }
@@ -245,7 +251,7 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     REL(pair_nc); REL(scr_first); REL(scr_cur); REL(scr_best); REL(heavy_list); REL(tile_spec);
     REL(probe2); REL(cell_range); REL(win_lohi); REL(win_entry); REL(zone_tab);
     REL(st_key); REL(st_key_alt); REL(st_score); REL(st_scaling); REL(st_woff); REL(st_nc); REL(st_rows); REL(st_order); REL(st_order_alt);
-    REL(spec_buckets); REL(spec_rows); REL(st_nc_sorted);
+    REL(spec_buckets); REL(spec_rows); REL(st_nc_sorted); REL(st_win_off);
     REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak);
 #undef REL
     for (int i = 0; i < 12; ++i) cudaEventDestroy(ctx->ev[i]);
@@ -254,6 +260,11 @@ void qms_ctx_destroy(qms_ctx* ctx) {
         if (ctx->stage_slot[k]) cudaFreeHost(ctx->stage_slot[k]);
         if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
     }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+    if (ctx->ev_emit) cudaEventDestroy(ctx->ev_emit);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

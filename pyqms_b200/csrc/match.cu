@@ -26,6 +26,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include <cub/cub.cuh>
 
@@ -1262,67 +1263,12 @@ static bool callers_on_device(const qms_hits* out) {
     return !out->hit_mmz || (qms_is_device_ptr(out->hit_mmz) && qms_is_device_ptr(out->hit_mi));
 }
 
-static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra, int32_t input_kind,
-                      double mz_score_percentile, int32_t only_entry, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
-    if (!ctx || !offsets || n_spectra < 0 || !n_hits || !n_hit_windows)
-        return qms_fail(ctx, QMS_E_ARG, "qms_match_batch: bad arguments");
-    if (!ctx->have_index) return qms_fail(ctx, QMS_E_ARG, "library index not built (qms_finalize_index)");
-    if (input_kind != 0 && input_kind != 1) return qms_fail(ctx, QMS_E_ARG, "input_kind must be 0 (numpy) or 1 (list)");
-    if (n_spectra >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 spectra per batch");
-    QMS_CUDA(ctx, cudaSetDevice(ctx->device));
-    *n_hits = 0;
-    *n_hit_windows = 0;
-    ctx->last_hits = ctx->last_windows = 0;
+static int make_view(qms_ctx* ctx, MatchView& v, const double2* d_peaks, const int64_t* d_off, int64_t n_spectra, int32_t input_kind,
+                     int32_t only_entry, double xi) {
     const qms_params& P = ctx->prm;
-    // ---- inputs -> device ----
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    const bool off_dev = qms_is_device_ptr(offsets);
-    int64_t p_begin = 0, p_end = 0, longest = 0;
-    const int64_t* d_off = offsets;
-    if (off_dev) {
-        ctx->h_offsets.resize((size_t)n_spectra + 1);
-        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_offsets.data(), offsets, ((size_t)n_spectra + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                      ctx->stream));
-        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        p_begin = ctx->h_offsets[0];
-        p_end = ctx->h_offsets[n_spectra];
-        for (int64_t s = 0; s < n_spectra; ++s) longest = std::max(longest, ctx->h_offsets[s + 1] - ctx->h_offsets[s]);
-    } else {
-        p_begin = offsets[0];
-        p_end = offsets[n_spectra];
-        for (int64_t s = 0; s < n_spectra; ++s) longest = std::max(longest, offsets[s + 1] - offsets[s]);
-        QMS_TRY(qms_upload(ctx, ctx->d_offsets, offsets, (size_t)n_spectra + 1));
-        d_off = ctx->d_offsets.p;
-    }
-    if (p_begin < 0 || p_end < p_begin) return qms_fail(ctx, QMS_E_ARG, "offsets must be non-decreasing and non-negative");
-    const int64_t n_peaks = p_end - p_begin;
-    if (n_peaks > 0 && !peaks) return qms_fail(ctx, QMS_E_ARG, "peaks is NULL");
-    const double2* d_peaks = reinterpret_cast<const double2*>(peaks);
-    // the device copy mirrors the caller's row numbering, so reported peak rows need no rebasing
-    if (n_peaks > 0 && !qms_is_device_ptr(peaks)) {
-        QMS_TRY(qms_reserve(ctx, ctx->d_peaks, (size_t)p_end * 2));
-        QMS_TRY(qms_copy_to_device(ctx, ctx->d_peaks.p + 2 * p_begin, peaks + 2 * p_begin, (size_t)n_peaks * 2 * sizeof(double)));
-        d_peaks = reinterpret_cast<const double2*>(ctx->d_peaks.p);
-    }
-    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    ctx->cnt.spectra += n_spectra;
-    ctx->cnt.peaks += n_peaks;
-    if (n_peaks == 0 || n_spectra == 0 || ctx->n_windows == 0) {
-        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->cnt.ms_h2d += elapsed(ctx, 0, 1);
-        if (out && out->hit_win_off && out->cap_hits >= 0) {
-            const int64_t zero = 0;
-            if (qms_is_device_ptr(out->hit_win_off))
-                cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t), cudaMemcpyHostToDevice);
-            else
-                out->hit_win_off[0] = 0;
-        }
-        return QMS_OK;
-    }
     const int64_t span = (int64_t)ctx->t_max - ctx->t_min + 1;
     const int64_t cover_words = (span + 31) / 32;
     static_assert(sizeof(ProbeRec) == 16, "ProbeRec must be 16 bytes");
-    MatchView v;
     v.peaks = d_peaks;
     v.offsets = d_off;
     v.n_spectra = n_spectra;
@@ -1354,65 +1300,270 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     v.min_rel = P.min_rel_peak_intensity;
     v.rel_mz = P.rel_mz_range;
     v.rel_i = P.rel_i_range;
-    v.xi = mz_score_percentile;
+    v.xi = xi;
     v.score_thr = P.m_score_threshold;
+    return QMS_OK;
+}
+
+static int write_empty_result(qms_ctx* ctx, qms_hits* out) {
+    if (out && out->hit_win_off && out->cap_hits >= 0) {
+        const int64_t zero = 0;
+        QMS_CUDA(ctx, cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t),
+                                 qms_is_device_ptr(out->hit_win_off) ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+    }
+    return QMS_OK;
+}
+
+// host-or-device output copy on a given stream
+template <class T>
+static int copy_out_on(qms_ctx* ctx, cudaStream_t stream, T* dst, const T* src, size_t n) {
+    if (!dst || !n) return QMS_OK;
+    if (!qms_is_device_ptr(dst)) return qms_copy_to_host(ctx, dst, src, n * sizeof(T), stream);
+    QMS_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+    return QMS_OK;
+}
+
+// retained hit arrays of a whole run: room for `hits` hits and `windows` hit windows, contents kept
+static int reserve_run(qms_ctx* ctx, int64_t hits, int64_t windows, bool values) {
+    if ((int64_t)ctx->o_spec.cap >= hits + 1 && (int64_t)ctx->o_entry.cap >= hits + 1 && (int64_t)ctx->o_score.cap >= hits + 1 &&
+        (int64_t)ctx->o_scaling.cap >= hits + 1 && (int64_t)ctx->o_win_off.cap >= hits + 2 && (int64_t)ctx->o_peak.cap >= windows + 1 &&
+        (!values || ((int64_t)ctx->o_mmz.cap >= windows + 1 && (int64_t)ctx->o_mi.cap >= windows + 1)))
+        return QMS_OK;
+    if (ctx->s_out) QMS_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));     // copies out of the old arrays have finished
+    const size_t h = (size_t)hits + (size_t)hits / 4 + 2, w = (size_t)windows + (size_t)windows / 4 + 2;
+    QMS_TRY(qms_reserve(ctx, ctx->o_spec, h, true));
+    QMS_TRY(qms_reserve(ctx, ctx->o_entry, h, true));
+    QMS_TRY(qms_reserve(ctx, ctx->o_score, h, true));
+    QMS_TRY(qms_reserve(ctx, ctx->o_scaling, h, true));
+    QMS_TRY(qms_reserve(ctx, ctx->o_win_off, h + 1, true));
+    QMS_TRY(qms_reserve(ctx, ctx->o_peak, w, true));
+    if (values) {
+        QMS_TRY(qms_reserve(ctx, ctx->o_mmz, w, true));
+        QMS_TRY(qms_reserve(ctx, ctx->o_mi, w, true));
+    }
+    return QMS_OK;
+}
+
+// The spectrum-resident matcher over a whole batch.  A large host-resident run is cut into sub-batches of spectra:
+// while the kernels of sub-batch b run, the rows of sub-batch b+1 travel to the device and the hits of sub-batch b-1
+// travel to the caller's arrays (copy streams s_in / s_out; page-locked buffers go by DMA, pageable ones through the
+// pinned staging slots, driven from the host thread while it would otherwise wait for the kernel).  Hits of all
+// sub-batches are appended, in spectrum order, to the retained arrays of the context, so qms_fetch_hits works as ever.
+static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, const int64_t* d_off, int64_t n_spectra,
+                     double xi, int entry_bits, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
+    const int64_t p_begin = h_off[0], p_end = h_off[n_spectra], n_peaks = p_end - p_begin;
+    const bool peaks_on_device = qms_is_device_ptr(peaks);
+    const double2* d_peaks = reinterpret_cast<const double2*>(peaks);
+    if (!peaks_on_device) {
+        // the device copy mirrors the caller's row numbering, so reported peak rows need no rebasing
+        QMS_TRY(qms_reserve(ctx, ctx->d_peaks, (size_t)p_end * 2));
+        d_peaks = reinterpret_cast<const double2*>(ctx->d_peaks.p);
+    }
+    if (!ctx->s_in) {
+        QMS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        QMS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) QMS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+    }
+    // sub-batches: cut at spectrum boundaries every ~sub_rows rows (host-resident runs only)
+    std::vector<int64_t> cuts{0};
+    const int64_t sub_rows = ctx->sub_batch_rows > 0 ? ctx->sub_batch_rows : (int64_t)16 << 20;   // measured: 4 Mi rows 147 ms, 8 Mi 138 ms, 16 Mi 135 ms per 39 M-row shard
+    if (!peaks_on_device && n_peaks > sub_rows + sub_rows / 2) {
+        int64_t next = p_begin + sub_rows;
+        for (int64_t s = 1; s < n_spectra; ++s)
+            if (h_off[s] >= next && p_end - h_off[s] > sub_rows / 4) {
+                cuts.push_back(s);
+                next = h_off[s] + sub_rows;
+            }
+    }
+    cuts.push_back(n_spectra);
+    const size_t n_sub = cuts.size() - 1;
+    const bool want_values = !out || (out->hit_mmz && out->hit_mi);
+    const bool direct = n_sub == 1 && callers_on_device(out);     // one batch straight into the caller's device arrays
+    MatchView v;
+    QMS_TRY(make_view(ctx, v, d_peaks, d_off, n_spectra, 0, -1, xi));
+    std::vector<cudaEvent_t> timing;                              // (start, stop) pairs on the copy streams
+    auto stamp = [&](cudaStream_t stream) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        timing.push_back(e);
+    };
+    size_t n_in_events = 0;
+    auto upload = [&](size_t b) -> int {
+        if (peaks_on_device) return QMS_OK;
+        const int64_t r0 = h_off[cuts[b]], r1 = h_off[cuts[b + 1]];
+        stamp(ctx->s_in);
+        QMS_TRY(qms_copy_to_device(ctx, ctx->d_peaks.p + 2 * r0, peaks + 2 * r0, (size_t)(r1 - r0) * 2 * sizeof(double), ctx->s_in));
+        stamp(ctx->s_in);
+        n_in_events += 2;
+        QMS_CUDA(ctx, cudaEventRecord(ctx->ev_in[b & 1], ctx->s_in));
+        return QMS_OK;
+    };
+    struct Part {
+        int64_t h0, nh, w0, nw;
+    };
+    bool fits = out != nullptr;
+    auto download = [&](const Part& part) -> int {                // hits of one sub-batch -> the caller's arrays
+        if (!out || direct || !fits) return QMS_OK;
+        if (part.h0 + part.nh > out->cap_hits || part.w0 + part.nw > out->cap_windows) {
+            fits = false;                                         // keep counting: the call reports the sizes it needs
+            return QMS_OK;
+        }
+        stamp(ctx->s_out);
+        QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_spec ? out->hit_spec + part.h0 : nullptr, ctx->o_spec.p + part.h0, (size_t)part.nh));
+        QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_entry ? out->hit_entry + part.h0 : nullptr, ctx->o_entry.p + part.h0, (size_t)part.nh));
+        QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_score ? out->hit_score + part.h0 : nullptr, ctx->o_score.p + part.h0, (size_t)part.nh));
+        QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_scaling ? out->hit_scaling + part.h0 : nullptr, ctx->o_scaling.p + part.h0,
+                            (size_t)part.nh));
+        QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_win_off ? out->hit_win_off + part.h0 : nullptr, ctx->o_win_off.p + part.h0,
+                            (size_t)part.nh + 1));
+        if (want_values) {
+            QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_mmz + part.w0, ctx->o_mmz.p + part.w0, (size_t)part.nw));
+            QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_mi + part.w0, ctx->o_mi.p + part.w0, (size_t)part.nw));
+        }
+        QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_peak ? out->hit_peak + part.w0 : nullptr, ctx->o_peak.p + part.w0, (size_t)part.nw));
+        stamp(ctx->s_out);
+        return QMS_OK;
+    };
+    if (!direct && ctx->run_hits_hint > 0) QMS_TRY(reserve_run(ctx, ctx->run_hits_hint, ctx->run_windows_hint, want_values));
+    int64_t total_h = 0, total_w = 0;
+    bool have_pending = false, wrote_callers = false;
+    Part pending{0, 0, 0, 0};
+    QMS_TRY(upload(0));
+    for (size_t b = 0; b < n_sub; ++b) {
+        const int64_t r0 = h_off[cuts[b]], r1 = h_off[cuts[b + 1]];
+        if (!peaks_on_device) QMS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b & 1], 0));
+        MatchView vb = v;
+        vb.offsets = d_off + cuts[b];
+        vb.n_spectra = cuts[b + 1] - cuts[b];
+        auto overlap = [&]() -> int {
+            if (b + 1 < n_sub) QMS_TRY(upload(b + 1));
+            if (have_pending) QMS_TRY(download(pending));
+            have_pending = false;
+            return QMS_OK;
+        };
+        int64_t nh = 0, nw = 0;
+        QMS_TRY(qms_dense_stage(ctx, vb, r0, r1, entry_bits, overlap, &nh, &nw));
+        int spec_bits = 1;
+        while ((1ll << spec_bits) < vb.n_spectra) ++spec_bits;
+        qms_hits target;
+        if (direct && nh <= out->cap_hits && nw <= out->cap_windows) {
+            target = *out;
+            wrote_callers = true;
+        } else {
+            if (b == 0 && n_sub > 1 && r1 > r0)                   // first look at the hit density: size the arrays for the whole run
+                QMS_TRY(reserve_run(ctx, (int64_t)((double)nh * (double)n_peaks / (double)(r1 - r0) * 1.1),
+                                    (int64_t)((double)nw * (double)n_peaks / (double)(r1 - r0) * 1.1), want_values));
+            QMS_TRY(reserve_run(ctx, total_h + nh, total_w + nw, want_values));
+            target.cap_hits = nh;
+            target.cap_windows = nw;
+            target.hit_spec = ctx->o_spec.p + total_h;
+            target.hit_entry = ctx->o_entry.p + total_h;
+            target.hit_score = ctx->o_score.p + total_h;
+            target.hit_scaling = ctx->o_scaling.p + total_h;
+            target.hit_win_off = ctx->o_win_off.p + total_h;
+            target.hit_mmz = want_values ? ctx->o_mmz.p + total_w : nullptr;
+            target.hit_mi = want_values ? ctx->o_mi.p + total_w : nullptr;
+            target.hit_peak = ctx->o_peak.p + total_w;
+        }
+        QMS_TRY(qms_dense_emit(ctx, vb, r0, entry_bits, spec_bits, nh, cuts[b], total_w, target));
+        pending = Part{total_h, nh, total_w, nw};
+        have_pending = nh > 0;
+        total_h += nh;
+        total_w += nw;
+    }
+    if (have_pending) QMS_TRY(download(pending));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    for (size_t k = 0; k + 1 < timing.size(); k += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, timing[k], timing[k + 1]);
+        (k < n_in_events ? ctx->cnt.ms_h2d : ctx->cnt.ms_d2h) += ms;
+    }
+    for (cudaEvent_t e : timing) cudaEventDestroy(e);
+    ctx->cnt.dense_batches += (int64_t)n_sub;
+    ctx->cnt.hits += total_h;
+    ctx->cnt.hit_windows += total_w;
+    ctx->run_hits_hint = total_h;
+    ctx->run_windows_hint = total_w;
+    *n_hits = total_h;
+    *n_hit_windows = total_w;
+    ctx->last_hits = wrote_callers ? 0 : total_h;
+    ctx->last_windows = wrote_callers ? 0 : total_w;
+    ctx->last_values = want_values;
+    if (total_h == 0) return write_empty_result(ctx, out);
+    if (wrote_callers || !out) return QMS_OK;                     // out == NULL: size query, the hits stay for qms_fetch_hits
+    if (!fits || total_h > out->cap_hits || total_w > out->cap_windows)
+        return qms_fail(ctx, QMS_E_CAPACITY,
+                        "hit buffers too small: need %lld hits / %lld windows, have %lld / %lld (results retained: qms_fetch_hits)",
+                        (long long)total_h, (long long)total_w, (long long)out->cap_hits, (long long)out->cap_windows);
+    return QMS_OK;
+}
+
+static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra, int32_t input_kind,
+                      double mz_score_percentile, int32_t only_entry, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
+    if (!ctx || !offsets || n_spectra < 0 || !n_hits || !n_hit_windows)
+        return qms_fail(ctx, QMS_E_ARG, "qms_match_batch: bad arguments");
+    if (!ctx->have_index) return qms_fail(ctx, QMS_E_ARG, "library index not built (qms_finalize_index)");
+    if (input_kind != 0 && input_kind != 1) return qms_fail(ctx, QMS_E_ARG, "input_kind must be 0 (numpy) or 1 (list)");
+    if (n_spectra >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 spectra per batch");
+    QMS_CUDA(ctx, cudaSetDevice(ctx->device));
+    *n_hits = 0;
+    *n_hit_windows = 0;
+    ctx->last_hits = ctx->last_windows = 0;
+    // ---- inputs -> device ----
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    const bool off_dev = qms_is_device_ptr(offsets);
+    int64_t p_begin = 0, p_end = 0, longest = 0;
+    const int64_t* d_off = offsets;
+    const int64_t* h_off = offsets;
+    if (off_dev) {
+        ctx->h_offsets.resize((size_t)n_spectra + 1);
+        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_offsets.data(), offsets, ((size_t)n_spectra + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        h_off = ctx->h_offsets.data();
+    } else {
+        QMS_TRY(qms_upload(ctx, ctx->d_offsets, offsets, (size_t)n_spectra + 1));
+        d_off = ctx->d_offsets.p;
+    }
+    p_begin = h_off[0];
+    p_end = h_off[n_spectra];
+    for (int64_t s = 0; s < n_spectra; ++s) {
+        if (h_off[s + 1] < h_off[s]) return qms_fail(ctx, QMS_E_ARG, "offsets must be non-decreasing and non-negative");
+        longest = std::max(longest, h_off[s + 1] - h_off[s]);
+    }
+    if (p_begin < 0 || p_end < p_begin) return qms_fail(ctx, QMS_E_ARG, "offsets must be non-decreasing and non-negative");
+    const int64_t n_peaks = p_end - p_begin;
+    if (n_peaks > 0 && !peaks) return qms_fail(ctx, QMS_E_ARG, "peaks is NULL");
+    if (n_peaks >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 peaks per batch (split the run)");
+    ctx->cnt.spectra += n_spectra;
+    ctx->cnt.peaks += n_peaks;
+    if (n_peaks == 0 || n_spectra == 0 || ctx->n_windows == 0) {
+        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return write_empty_result(ctx, out);
+    }
+    QMS_TRY(qms_reserve(ctx, ctx->dev_counters, 64));
+    int entry_bits = 1, spec_bits = 1;
+    while ((1ll << entry_bits) < ctx->n_entries) ++entry_bits;
+    while ((1ll << spec_bits) < n_spectra) ++spec_bits;
+    if (qms_dense_eligible(ctx, input_kind, only_entry, longest))      // dense library: the spectrum-resident matcher (match_spectrum.cu)
+        return dense_run(ctx, peaks, h_off, d_off, n_spectra, mz_score_percentile, entry_bits, out, n_hits, n_hit_windows);
+    const double2* d_peaks = reinterpret_cast<const double2*>(peaks);
+    // the device copy mirrors the caller's row numbering, so reported peak rows need no rebasing
+    if (!qms_is_device_ptr(peaks)) {
+        QMS_TRY(qms_reserve(ctx, ctx->d_peaks, (size_t)p_end * 2));
+        QMS_TRY(qms_copy_to_device(ctx, ctx->d_peaks.p + 2 * p_begin, peaks + 2 * p_begin, (size_t)n_peaks * 2 * sizeof(double)));
+        d_peaks = reinterpret_cast<const double2*>(ctx->d_peaks.p);
+    }
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    MatchView v;
+    QMS_TRY(make_view(ctx, v, d_peaks, d_off, n_spectra, input_kind, only_entry, mz_score_percentile));
 
     // ---- K5a .. K7a are enqueued back to back; the host looks at the counters once, after the hit count ----
     // The pair list has a capacity learned from the previous batch (its pair count + 25 %); unused slots hold an all-ones
     // sentinel key that sorts behind every real (spectrum, entry) key, so the sort, the window scan and the scoring
     // kernels can be launched over the capacity without knowing the pair count (no host round trip after the gate).
-    if (n_peaks >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 peaks per batch (split the run)");
-    QMS_TRY(qms_reserve(ctx, ctx->dev_counters, 64));
-    int entry_bits = 1, spec_bits = 1;
-    while ((1ll << entry_bits) < ctx->n_entries) ++entry_bits;
-    while ((1ll << spec_bits) < n_spectra) ++spec_bits;
-    if (qms_dense_eligible(ctx, input_kind, only_entry, longest)) {
-        // dense library: the spectrum-resident matcher (match_spectrum.cu)
-        const bool want_values = !out || (out->hit_mmz && out->hit_mi);
-        const bool on_device = callers_on_device(out);
-        int64_t nh = 0, nw = 0;
-        bool wrote_callers = false;
-        QMS_TRY(qms_match_dense(ctx, v, p_begin, p_end, entry_bits, spec_bits, on_device ? out : nullptr, want_values, &nh, &nw,
-                                &wrote_callers));
-        ctx->cnt.ms_h2d += elapsed(ctx, 0, 1);
-        ctx->cnt.dense_batches++;
-        *n_hits = nh;
-        *n_hit_windows = nw;
-        ctx->cnt.hits += nh;
-        ctx->cnt.hit_windows += nw;
-        ctx->last_hits = wrote_callers ? 0 : nh;
-        ctx->last_windows = wrote_callers ? 0 : nw;
-        ctx->last_values = want_values;
-        if (nh == 0) {
-            if (out && out->hit_win_off && out->cap_hits >= 0) {
-                const int64_t zero = 0;
-                QMS_CUDA(ctx, cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t),
-                                         qms_is_device_ptr(out->hit_win_off) ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
-            }
-            return QMS_OK;
-        }
-        if (wrote_callers) return QMS_OK;
-        if (!out) return QMS_OK;                       // size query: the hits stay on the device for qms_fetch_hits
-        if (nh > out->cap_hits || nw > out->cap_windows)
-            return qms_fail(ctx, QMS_E_CAPACITY,
-                            "hit buffers too small: need %lld hits / %lld windows, have %lld / %lld (results retained: qms_fetch_hits)",
-                            (long long)nh, (long long)nw, (long long)out->cap_hits, (long long)out->cap_windows);
-        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-        QMS_TRY(copy_out(ctx, out->hit_spec, ctx->o_spec.p, (size_t)nh));
-        QMS_TRY(copy_out(ctx, out->hit_entry, ctx->o_entry.p, (size_t)nh));
-        QMS_TRY(copy_out(ctx, out->hit_score, ctx->o_score.p, (size_t)nh));
-        QMS_TRY(copy_out(ctx, out->hit_scaling, ctx->o_scaling.p, (size_t)nh));
-        QMS_TRY(copy_out(ctx, out->hit_win_off, ctx->o_win_off.p, (size_t)nh + 1));
-        if (want_values) {
-            QMS_TRY(copy_out(ctx, out->hit_mmz, ctx->o_mmz.p, (size_t)nw));
-            QMS_TRY(copy_out(ctx, out->hit_mi, ctx->o_mi.p, (size_t)nw));
-        }
-        QMS_TRY(copy_out(ctx, out->hit_peak, ctx->o_peak.p, (size_t)nw));
-        QMS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
-        QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->cnt.ms_d2h += elapsed(ctx, 3, 4);
-        return QMS_OK;
-    }
     ctx->last_values = true;
     static int variant = -1;   // QMS_PROBE_VARIANT: tuning switch for profiling runs (default = best measured)
     if (variant < 0) {

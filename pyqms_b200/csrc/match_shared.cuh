@@ -1,5 +1,7 @@
 // Declarations shared by the translation units of the matcher (match.cu, match_spectrum.cu).
 #pragma once
+#include <functional>
+
 #include "qms_internal.cuh"
 
 #define QMS_DBL_EPS 2.220446049250313e-16
@@ -83,5 +85,7 @@ __device__ void score_rows(const Rows& r, double min_rel, double rel_mz, double 
 int qms_score_pair_list(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, const unsigned long long* keys, const unsigned long long* vals,
                         int entry_bits, int64_t p_begin, int heavy_min);
 bool qms_dense_eligible(qms_ctx* ctx, int input_kind, int only_entry, int64_t longest_spectrum);
-int qms_match_dense(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p_end, int entry_bits, int spec_bits,
-                    const qms_hits* device_out, bool emit_values, int64_t* n_hits, int64_t* n_windows, bool* wrote_callers);
+int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p_end, int entry_bits,
+                    const std::function<int()>& while_running, int64_t* n_hits, int64_t* n_windows);
+int qms_dense_emit(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int entry_bits, int spec_bits, int64_t nh, int64_t spec_base,
+                   int64_t win_base, const qms_hits& out);

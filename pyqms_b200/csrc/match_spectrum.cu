@@ -25,6 +25,8 @@
 // ascending windows; everything else runs through match.cu.
 #include <stdlib.h>
 
+#include <functional>
+
 #include <cub/cub.cuh>
 
 #include "match_shared.cuh"
@@ -505,19 +507,27 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(MatchView v, int64_t n
                                                           const double* __restrict__ st_scaling, const uint32_t* __restrict__ st_woff,
                                                           const uint32_t* __restrict__ st_rows, int32_t* __restrict__ o_spec,
                                                           int32_t* __restrict__ o_entry, double* __restrict__ o_score,
-                                                          double* __restrict__ o_scaling, const int64_t* __restrict__ o_win_off,
+                                                          double* __restrict__ o_scaling, int64_t* __restrict__ o_win_off,
                                                           double* __restrict__ o_mmz, double* __restrict__ o_mi,
-                                                          int64_t* __restrict__ o_peak) {
+                                                          int64_t* __restrict__ o_peak, const int64_t* __restrict__ local_win_off,
+                                                          int64_t spec_base, int64_t win_base) {
+    // o_* point at this batch's first hit / first window inside the run's arrays; spectra and window offsets are
+    // rebased to the run (spec_base = spectra before this batch, win_base = hit windows before it)
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_hits) return;
+    if (q > n_hits) return;
+    if (q == n_hits) {
+        o_win_off[q] = win_base + local_win_off[q];          // closes this batch = opens the next one
+        return;
+    }
     const uint32_t h = order[q];
     const unsigned long long key = keys_sorted[q];
-    o_spec[q] = (int32_t)(key >> entry_bits);
+    o_spec[q] = (int32_t)(spec_base + (int64_t)(key >> entry_bits));
     o_entry[q] = (int32_t)(key & ((1ull << entry_bits) - 1ull));
     o_score[q] = st_score[h];
     o_scaling[q] = st_scaling[h];
-    const int64_t w = o_win_off[q];
-    const int nc = (int)(o_win_off[q + 1] - w);
+    const int64_t w = local_win_off[q];
+    const int nc = (int)(local_win_off[q + 1] - w);
+    o_win_off[q] = win_base + w;
     const uint32_t* rows = st_rows + st_woff[h];
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     for (int m = 0; m < nc; ++m) {
@@ -545,11 +555,12 @@ bool qms_dense_eligible(qms_ctx* ctx, int input_kind, int only_entry, int64_t lo
     return mode == 1 || ctx->window_density >= 4.0;
 }
 
-// The spectrum-resident pass over spectra [0, v.n_spectra) whose rows are [p_begin, p_end).  Leaves the hits, sorted by
-// (spectrum, entry), in the context's o_* arrays (or in the caller's device buffers, see qms_match_batch); n_hits /
-// n_windows receive the counts.  `emit_values`: also write the matched (m/z, intensity) values.
-int qms_match_dense(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p_end, int entry_bits, int spec_bits,
-                    const qms_hits* device_out, bool emit_values, int64_t* n_hits, int64_t* n_windows, bool* wrote_callers) {
+// Stage 1 of the spectrum-resident pass over spectra [0, v.n_spectra) whose rows are [p_begin, p_end): kernels + the
+// combination pass over the multi-candidate pairs.  Leaves the hits in the staging area in discovery order and their
+// counts in n_hits / n_windows.  `while_running` (may be empty) is called once, right after the main kernel has been
+// launched and before the host waits for it: copies of neighbouring sub-batches are driven from there.
+int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p_end, int entry_bits,
+                    const std::function<int()>& while_running, int64_t* n_hits, int64_t* n_windows) {
     const int64_t n_peaks = p_end - p_begin, n_spectra = v.n_spectra;
     const int64_t span = (int64_t)ctx->t_max - ctx->t_min + 1;
     int shift = 0;
@@ -587,10 +598,16 @@ int qms_match_dense(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
         heavy_min = e ? atoi(e) : 16;
     }
     const int max_nc = ctx->max_nc > 0 ? ctx->max_nc : 1;
-    int64_t cap_h = ctx->stage_hits_hint > 0 ? ctx->stage_hits_hint : n_peaks / 4 + 4096;
-    int64_t cap_w = ctx->stage_windows_hint > 0 ? ctx->stage_windows_hint : cap_h * 8;
-    int64_t cap_m = ctx->multi_cap_hint > 0 ? ctx->multi_cap_hint : n_peaks / 8 + 4096;
+    // capacities: learned from earlier batches as hits (windows, multi-candidate pairs) per peak row, with head room
+    auto from_rate = [&](double rate, int64_t floor_value) {
+        const int64_t want = (int64_t)(rate * 1.25 * (double)n_peaks) + 4096;
+        return (want > floor_value ? want : floor_value + 4095) / 4096 * 4096;
+    };
+    int64_t cap_h = ctx->rate_hits > 0 ? from_rate(ctx->rate_hits, 0) : n_peaks / 4 + 4096;
+    int64_t cap_w = ctx->rate_windows > 0 ? from_rate(ctx->rate_windows, 0) : cap_h * 8;
+    int64_t cap_m = ctx->rate_multi > 0 ? from_rate(ctx->rate_multi, 0) : n_peaks / 8 + 4096;
     int64_t nh = 0, nw = 0, n_multi = 0;
+    bool overlapped = false;
     for (int attempt = 0;; ++attempt) {
         if (cap_h > 0xfffffff0ll || cap_w > 0xfffffff0ll)
             return qms_fail(ctx, QMS_E_LIMIT, "more than 2^32 hits or hit windows in one batch (split the run)");
@@ -621,6 +638,10 @@ int qms_match_dense(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
         QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                       ctx->stream));
+        if (!overlapped && while_running) {
+            overlapped = true;
+            QMS_TRY(while_running());
+        }
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->cnt.ms_gate += ms_between(ctx, 2, 5);
         if (ctx->h_pinned[C_UNSORTED])
@@ -652,13 +673,16 @@ int qms_match_dense(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
         nh = (int64_t)ctx->h_pinned[C_STAGE_HITS];
         nw = (int64_t)ctx->h_pinned[C_STAGE_WINDOWS];
         overflow = overflow || nh > cap_h || nw > cap_w;
+        int64_t bound_h = nh, bound_w = nw;
         if (multi_overflow) {                                // the combination pass did not run: its hits are still to come
-            nh += n_multi;
-            nw += n_multi * max_nc;
+            bound_h += n_multi;
+            bound_w += n_multi * max_nc;
         }
-        ctx->stage_hits_hint = (nh + nh / 4 + 4095) / 4096 * 4096;
-        ctx->stage_windows_hint = (nw + nw / 4 + 4095) / 4096 * 4096;
-        ctx->multi_cap_hint = (n_multi + n_multi / 4 + 4095) / 4096 * 4096;
+        if (n_peaks > 0) {
+            ctx->rate_hits = (double)bound_h / (double)n_peaks;
+            ctx->rate_windows = (double)bound_w / (double)n_peaks;
+            ctx->rate_multi = (double)n_multi / (double)n_peaks;
+        }
         if (!overflow) {
             ctx->cnt.live_peaks += live;
             ctx->cnt.incidences += inc;
@@ -669,63 +693,46 @@ int qms_match_dense(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
             break;
         }
         if (attempt == 2) return qms_fail(ctx, QMS_E_LIMIT, "hit staging overflow after regrow");
-        cap_h = ctx->stage_hits_hint;                        // first batches / a batch with more hits than any before: run it again
-        cap_w = ctx->stage_windows_hint;
-        cap_m = ctx->multi_cap_hint;
+        cap_h = (bound_h + bound_h / 4 + 4095) / 4096 * 4096;       // a batch with more hits per row than any before: run it again
+        cap_w = (bound_w + bound_w / 4 + 4095) / 4096 * 4096;
+        cap_m = (n_multi + n_multi / 4 + 4095) / 4096 * 4096;
     }
     *n_hits = nh;
     *n_windows = nw;
-    *wrote_callers = false;
+    return QMS_OK;
+}
+
+// Stage 2: sort the staged hits by (spectrum, entry) and write them to `out` (device arrays, already pointing at this
+// batch's first hit / first hit window; hit_mmz / hit_mi may be NULL).  Spectrum numbers are rebased by spec_base,
+// window offsets by win_base; out.hit_win_off receives nh + 1 values.  Synchronises the context's stream.
+int qms_dense_emit(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int entry_bits, int spec_bits, int64_t nh, int64_t spec_base,
+                   int64_t win_base, const qms_hits& out) {
     if (nh == 0) return QMS_OK;
-    // ---- sort the staged hits by (spectrum, entry) and emit ----
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
     QMS_TRY(qms_reserve(ctx, ctx->st_key_alt, (size_t)nh + 1));
     QMS_TRY(qms_reserve(ctx, ctx->st_order, (size_t)nh + 1));
     QMS_TRY(qms_reserve(ctx, ctx->st_order_alt, (size_t)nh + 1));
     QMS_TRY(qms_reserve(ctx, ctx->st_nc_sorted, (size_t)nh + 2));
+    QMS_TRY(qms_reserve(ctx, ctx->st_win_off, (size_t)nh + 2));
     iota_u32_kernel<<<qms_blocks(nh, 256), 256, 0, ctx->stream>>>(nh, ctx->st_order.p);
     size_t sort_bytes = 0, scan_bytes = 0;
     const int key_bits = entry_bits + spec_bits;
     QMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, ctx->st_key.p, ctx->st_key_alt.p, ctx->st_order.p,
                                                   ctx->st_order_alt.p, nh, 0, key_bits, ctx->stream));
-    const bool to_callers = device_out && nh <= device_out->cap_hits && nw <= device_out->cap_windows;
-    int32_t *o_spec, *o_entry;
-    double *o_score, *o_scaling, *o_mmz, *o_mi;
-    int64_t *o_win_off, *o_peak;
-    if (to_callers) {
-        o_spec = device_out->hit_spec; o_entry = device_out->hit_entry; o_score = device_out->hit_score;
-        o_scaling = device_out->hit_scaling; o_win_off = device_out->hit_win_off; o_mmz = device_out->hit_mmz;
-        o_mi = device_out->hit_mi; o_peak = device_out->hit_peak;
-    } else {
-        QMS_TRY(qms_reserve(ctx, ctx->o_spec, (size_t)nh + 1));
-        QMS_TRY(qms_reserve(ctx, ctx->o_entry, (size_t)nh + 1));
-        QMS_TRY(qms_reserve(ctx, ctx->o_score, (size_t)nh + 1));
-        QMS_TRY(qms_reserve(ctx, ctx->o_scaling, (size_t)nh + 1));
-        QMS_TRY(qms_reserve(ctx, ctx->o_win_off, (size_t)nh + 2));
-        QMS_TRY(qms_reserve(ctx, ctx->o_peak, (size_t)nw + 1));
-        if (emit_values) {
-            QMS_TRY(qms_reserve(ctx, ctx->o_mmz, (size_t)nw + 1));
-            QMS_TRY(qms_reserve(ctx, ctx->o_mi, (size_t)nw + 1));
-        }
-        o_spec = ctx->o_spec.p; o_entry = ctx->o_entry.p; o_score = ctx->o_score.p; o_scaling = ctx->o_scaling.p;
-        o_win_off = ctx->o_win_off.p; o_peak = ctx->o_peak.p;
-        o_mmz = emit_values ? ctx->o_mmz.p : nullptr;
-        o_mi = emit_values ? ctx->o_mi.p : nullptr;
-    }
-    QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->st_nc_sorted.p, o_win_off, nh + 1, ctx->stream));
+    QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->st_nc_sorted.p, ctx->st_win_off.p, nh + 1, ctx->stream));
     QMS_TRY(qms_reserve(ctx, ctx->cub_tmp, (sort_bytes > scan_bytes ? sort_bytes : scan_bytes) + 16));
     QMS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, sort_bytes, ctx->st_key.p, ctx->st_key_alt.p, ctx->st_order.p,
                                                   ctx->st_order_alt.p, nh, 0, key_bits, ctx->stream));
     sorted_counts_kernel<<<qms_blocks(nh + 1, 256), 256, 0, ctx->stream>>>(nh, ctx->st_order_alt.p, ctx->st_nc.p, ctx->st_nc_sorted.p);
-    QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, scan_bytes, ctx->st_nc_sorted.p, o_win_off, nh + 1, ctx->stream));
-    emit_sorted_kernel<<<qms_blocks(nh, 256), 256, 0, ctx->stream>>>(v, nh, entry_bits, p_begin, ctx->st_key_alt.p, ctx->st_order_alt.p,
-                                                                    ctx->st_score.p, ctx->st_scaling.p, ctx->st_woff.p, ctx->st_rows.p,
-                                                                    o_spec, o_entry, o_score, o_scaling, o_win_off, o_mmz, o_mi, o_peak);
+    QMS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, scan_bytes, ctx->st_nc_sorted.p, ctx->st_win_off.p, nh + 1, ctx->stream));
+    emit_sorted_kernel<<<qms_blocks(nh + 1, 256), 256, 0, ctx->stream>>>(
+        v, nh, entry_bits, p_begin, ctx->st_key_alt.p, ctx->st_order_alt.p, ctx->st_score.p, ctx->st_scaling.p, ctx->st_woff.p,
+        ctx->st_rows.p, out.hit_spec, out.hit_entry, out.hit_score, out.hit_scaling, out.hit_win_off, out.hit_mmz, out.hit_mi,
+        out.hit_peak, ctx->st_win_off.p, spec_base, win_base);
     QMS_CUDA(ctx, cudaGetLastError());
     ctx->cnt.kernel_launches += 3 + 2 + (key_bits + 7) / 8 + 2;
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->cnt.ms_compact += ms_between(ctx, 6, 8);
-    *wrote_callers = to_callers;
     return QMS_OK;
 }

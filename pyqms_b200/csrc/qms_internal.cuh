@@ -125,6 +125,7 @@ struct qms_ctx {
     int64_t pair_cap_hint = 0;     // capacity of the pair list, learned from the previous batch (+25 %)
     int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
     int dense_mode = 2;            // spectrum-resident matcher: 0 never, 1 whenever its tables allow it, 2 by library density
+    int64_t sub_batch_rows = 0;   // rows per sub-batch of the pipelined run (0: default)
     int dense_ctas = 4;            // its resident CTAs per SM
     bool last_values = true;                   // ... including the matched (m/z, intensity) values
     DBuf<uint8_t> cub_tmp;
@@ -142,8 +143,11 @@ struct qms_ctx {
     DBuf<unsigned long long> st_key, st_key_alt;
     DBuf<double> st_score, st_scaling;
     DBuf<uint32_t> st_woff, st_nc, st_rows, st_order, st_order_alt, spec_buckets, spec_rows;
-    DBuf<int64_t> st_nc_sorted;
-    int64_t stage_hits_hint = 0, stage_windows_hint = 0, multi_cap_hint = 0;
+    DBuf<int64_t> st_nc_sorted, st_win_off;
+    double rate_hits = 0, rate_windows = 0, rate_multi = 0;     // hits / hit windows / multi-candidate pairs per peak row of the last batch
+    int64_t run_hits_hint = 0, run_windows_hint = 0;            // hits of the last whole run (capacity of the o_* arrays)
+    cudaStream_t s_in = nullptr, s_out = nullptr;               // copy streams of the pipelined run (sub-batches)
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_emit = nullptr;
 };
 
 // allocation helpers (ctx.cu)
@@ -174,8 +178,8 @@ struct TmpBuf {  // scratch device buffer released on scope exit
 // pageable buffers are staged through two pinned slots of the context, the DMA of one chunk overlapping the (multi-
 // threaded, first-touch parallel) host copy of the other.  Small or pinned copies stay stream-ordered (the caller
 // synchronises), staged ones have completed on return.
-int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes);
-int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes);
+int qms_copy_to_host(qms_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t stream = nullptr);
+int qms_copy_to_device(qms_ctx* ctx, void* dev, const void* host, size_t bytes, cudaStream_t stream = nullptr);
 
 template <class T>
 inline int qms_upload(qms_ctx* ctx, DBuf<T>& b, const T* host, size_t n) {

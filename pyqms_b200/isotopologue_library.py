@@ -23,7 +23,8 @@ import numpy as np
 
 from . import knowledge_base, planner
 from .params import params as _default_params
-from ._capi import Context, QmsHits, QmsIndexInfo, QmsParams, ptr
+from ._capi import QMS_E_CAPACITY, Context, QmsHits, QmsIndexInfo, QmsParams, ptr
+from ._pinned import PinnedPool
 from .chemistry import ChemicalComposition
 from .results import Results
 
@@ -179,6 +180,32 @@ def calc_amounts_of_profiles(profiles, windows=None, ctx=None):
     return [dict(zip(AMOUNT_FIELDS, out[n].tolist())) if count[n] else None for n in range(len(profiles))]
 
 
+class PackedHits(dict):
+    """Packed hit arrays of one device pass: spec, entry, score, scaling (per hit), win_off (n_hits + 1), peak (row of the
+    matched peak per hit window, -1 = None), n_hits, n_windows -- and ``mmz`` / ``mi``, the matched (m/z, intensity)
+    values (NaN = None).  When the pass did not bring the values back from the device they are gathered from the
+    spectra by ``peak`` row on first access (the spectra array is kept alive for that; do not overwrite it)."""
+
+    def __init__(self, peaks=None):
+        super().__init__()
+        self._peaks = peaks
+
+    def __missing__(self, key):
+        if key not in ("mmz", "mi") or self._peaks is None:
+            raise KeyError(key)
+        row = self["peak"]
+        values = self._peaks[np.maximum(row, 0), 0 if key == "mmz" else 1]
+        values[row < 0] = _NAN
+        self[key] = values
+        return values
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
 class IsotopologueLibrary(dict):
     """Isotopologue library built and matched on one B200.
 
@@ -256,7 +283,10 @@ class IsotopologueLibrary(dict):
                 self._n_bins(), *self.match_set_mz_range))
 
     # ------------------------------------------------------------------ save / load
-    _DEVICE_STATE = ("_ctx", "_views", "_entry_static", "_ent_env", "_ent_z", "_ent_lower", "_ent_upper", "_ent_win_off",
+    _hit_pool = None                     # page-locked result arrays, created with the first match
+    _hit_caps = (4096, 32768)            # (hits, hit windows) the next result arrays are sized for
+
+    _DEVICE_STATE = ("_hit_pool", "_ctx", "_views", "_entry_static", "_ent_env", "_ent_z", "_ent_lower", "_ent_upper", "_ent_win_off",
                      "_win_lo", "_win_hi", "_win_cmz", "_win_ri", "_win_ci")
 
     def __reduce__(self):
@@ -750,25 +780,54 @@ class IsotopologueLibrary(dict):
                        metabolic_labels=self.metabolic_labels, params=self.params)
 
     def _run_matcher(self, peaks, offsets, input_kind, xi, only_entry=None, values=True):
-        """One ``qms_match_batch`` / ``qms_match_entry`` pass with host buffers, then ``qms_fetch_hits`` into
-        exactly sized arrays (size query + fetch: the spectra are matched once).  ``values=False`` skips the
-        copies of the matched (m/z, intensity) values when the caller indexes its own spectra by ``peak`` row."""
+        """One ``qms_match_batch`` / ``qms_match_entry`` pass with host buffers.
+
+        The hits land in page-locked arrays of a reusable pool (``_pinned.PinnedPool``): the library copies every
+        sub-batch of a large run out while the next one is being matched, and a block returns to the pool when the
+        last array viewing it is collected.  The pool arrays are sized from the previous call; a call that needs more
+        gets ``QMS_E_CAPACITY`` with the sizes and fetches the hits the device has kept (``qms_fetch_hits``; no second
+        matching pass).  ``values=False`` leaves the matched (m/z, intensity) values on the host side: ``PackedHits``
+        gathers them from ``peaks`` by ``peak`` row when somebody asks."""
         ctx = self._ctx
         n_spec = len(offsets) - 1
         nh, nw = C.c_int64(), C.c_int64()
+        pool = self._hit_pool
+        if pool is None:
+            pool = self._hit_pool = PinnedPool()
+        cap_h, cap_w = self._hit_caps
+
+        def buffers(h, w):
+            out = PackedHits(peaks if not values else None)
+            out.update({"spec": pool.array(np.int32, h), "entry": pool.array(np.int32, h), "score": pool.array(np.float64, h),
+                        "scaling": pool.array(np.float64, h), "win_off": pool.array(np.int64, h + 1), "peak": pool.array(np.int64, w)})
+            if values:
+                out["mmz"], out["mi"] = pool.array(np.float64, w), pool.array(np.float64, w)
+            hits = QmsHits(h, w, *[out[k].ctypes.data if k in out else None
+                                   for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
+            return out, hits
+
+        out, hits = buffers(cap_h, cap_w)
         if only_entry is None:
-            ctx.check(ctx.lib.qms_match_batch(ctx.handle, ptr(peaks), ptr(offsets), n_spec, input_kind, float(xi), None,
-                                              C.byref(nh), C.byref(nw)))
+            rc = ctx.lib.qms_match_batch(ctx.handle, ptr(peaks), ptr(offsets), n_spec, input_kind, float(xi), C.byref(hits),
+                                         C.byref(nh), C.byref(nw))
         else:
-            ctx.check(ctx.lib.qms_match_entry(ctx.handle, ptr(peaks), len(peaks), input_kind, int(only_entry), float(xi), None,
-                                              C.byref(nh), C.byref(nw)))
+            rc = ctx.lib.qms_match_entry(ctx.handle, ptr(peaks), len(peaks), input_kind, int(only_entry), float(xi), C.byref(hits),
+                                         C.byref(nh), C.byref(nw))
+        if rc == QMS_E_CAPACITY:
+            del out, hits
+            out, hits = buffers(nh.value + nh.value // 8 + 64, nw.value + nw.value // 8 + 512)
+            rc = ctx.lib.qms_fetch_hits(ctx.handle, C.byref(hits), C.byref(nh), C.byref(nw))
+        ctx.check(rc)
         h, w = nh.value, nw.value
-        out = {"spec": np.empty(h, dtype=np.int32), "entry": np.empty(h, dtype=np.int32), "score": np.empty(h),
-               "scaling": np.empty(h), "win_off": np.zeros(h + 1, dtype=np.int64), "peak": np.empty(w, dtype=np.int64),
-               "mmz": np.empty(w) if values else None, "mi": np.empty(w) if values else None}
-        hits = QmsHits(h, w, *[None if out[k] is None else out[k].ctypes.data
-                               for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
-        ctx.check(ctx.lib.qms_fetch_hits(ctx.handle, C.byref(hits), C.byref(nh), C.byref(nw)))
+        self._hit_caps = (max(4096, h + h // 4), max(32768, w + w // 4))     # the next call of a run needs about as much
+        for k in ("spec", "entry", "score", "scaling"):
+            out[k] = out[k][:h]
+        out["win_off"] = out["win_off"][:h + 1]
+        if h == 0:
+            out["win_off"][0] = 0
+        for k in ("peak", "mmz", "mi"):
+            if k in out:
+                out[k] = out[k][:w]
         out["n_hits"], out["n_windows"] = h, w
         return out
 
@@ -911,8 +970,11 @@ class IsotopologueLibrary(dict):
             return results
         if hasattr(results, "flush_queue"):
             results.flush_queue()                          # spectra queued by earlier match_all calls come first
-        out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"])
-        if lazy and hasattr(results, "defer"):
+        deferred = lazy and hasattr(results, "defer")
+        # a lazy result leaves the matched (m/z, intensity) values where they are, in ``peaks``: they are gathered by
+        # peak row if somebody reads them (``peaks`` is kept alive by the result; do not overwrite it meanwhile)
+        out = self._run_matcher(peaks, offsets, kind, results.params["MZ_SCORE_PERCENTILE"], values=not deferred)
+        if deferred:
             results.defer(out, lambda target: self._emit(out, target, file_name, spec_ids, spec_rts, kind == 1),
                           table=lambda: self._hit_columns(out, file_name, spec_ids, spec_rts))
             return results

@@ -11,6 +11,7 @@ import codecs
 import copy
 import csv
 import sys
+import weakref
 from collections import namedtuple
 
 m_key = namedtuple("m_key", ["file_name", "formula", "charge", "label_percentiles"])
@@ -24,15 +25,28 @@ class _FlushingIndex(dict):
 
     def __init__(self, owner, content):
         super().__init__(content)
-        self._owner = owner
+        self._owner = weakref.ref(owner)      # no reference cycle: a dropped Results frees its packed (page-locked) arrays at once
 
     def __getitem__(self, key):
-        if self._owner._queue or self._owner._pending:
-            self._owner._flush()
+        owner = self._owner()
+        if owner is not None and (owner._queue or owner._pending):
+            owner._flush()
         return dict.__getitem__(self, key)
 
     def __reduce__(self):
         return (dict, (dict(self),))          # pickles hold a plain dict, like the reference's Results.index
+
+
+_TRANSIENT_STATE = ("_pending", "_packed", "_tables", "_queue", "_queue_peaks", "_queue_library", "_busy")
+
+
+def _restore_results(cls, state, items):
+    obj = cls.__new__(cls)
+    dict.update(obj, items)
+    obj.__dict__.update(state)
+    obj.__dict__.update(_pending=[], _packed=[], _tables=[], _queue=[], _queue_peaks=0, _queue_library=None, _busy=False)
+    obj.index = _FlushingIndex(obj, dict(obj.index))
+    return obj
 
 
 class Results(dict):
@@ -160,11 +174,11 @@ class Results(dict):
         return dict.get(self, key, default)
 
     def __reduce_ex__(self, protocol):
+        """Pickles and deep copies hold the materialised matches only: the packed arrays are redundant once the match
+        tuples exist and the device context is not picklable.  The live object keeps both."""
         self._flush()
-        self._packed = []           # arrays are redundant once materialised; keep pickles reference-sized
-        self._tables = []
-        self._queue_library = None  # the device context is not picklable
-        return dict.__reduce_ex__(self, protocol)
+        state = {k: v for k, v in self.__dict__.items() if k not in _TRANSIENT_STATE}
+        return (_restore_results, (type(self), state, list(dict.items(self))))
 
     def __repr__(self):
         self._flush()

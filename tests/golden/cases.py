@@ -121,5 +121,5 @@ CASES = {
     "bsa_pct_full": dict(
         lib=dict(molecules=BSA_MOLECULES, charges=[1, 2, 3, 4], fixed_labels=CAM_FIXED_LABEL,
                  metabolic_labels={"15N": [round(0.01 * i, 2) for i in range(100)]}),
-        run=dict(n_spectra=30, mean_peaks=300, seed=27, elution_sigma=2.0, entry_fraction=0.05), skip_trees=True, heavy=True),
+        run=dict(n_spectra=20, mean_peaks=300, seed=27, elution_sigma=1.0, entry_fraction=0.004), skip_trees=True, heavy=True),
 }

@@ -115,6 +115,30 @@ def test_spectrum_resident_matcher_equals_row_streaming_matcher():
         assert np.array_equal(a[k], b[k]), k
     for k in ("score", "scaling", "mmz", "mi"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+    # the pipelined run: sub-batches of ~60 000 rows, copies of neighbouring sub-batches overlapping the kernels;
+    # first with result arrays that are too small (QMS_E_CAPACITY -> qms_fetch_hits), then with room, then lazily
+    lib._ctx.set_tuning("sub_batch_rows", 60000)
+    try:
+        for attempt in range(2):
+            if attempt == 0:
+                lib._hit_caps = (64, 512)
+            before = lib.device_counters()["dense_batches"]
+            c = lib.match_packed(peaks, offsets)
+            assert lib.device_counters()["dense_batches"] - before > 5
+            assert c["n_hits"] == b["n_hits"] and c["n_windows"] == b["n_windows"]
+            for k in ("spec", "entry", "win_off", "peak"):
+                assert np.array_equal(b[k], c[k]), (attempt, k)
+            for k in ("score", "scaling", "mmz", "mi"):
+                assert np.array_equal(b[k], c[k], equal_nan=True), (attempt, k)
+        n = len(offsets) - 1
+        res = lib.match_many(peaks, file_name="run", spec_ids=list(range(n)), spec_rts=list(range(n)), offsets=offsets)
+        lazy = res.packed_batches()[-1]
+        assert "mmz" not in dict.keys(lazy)                  # the values did not cross the bus ...
+        for k in ("spec", "entry", "win_off", "peak", "score", "scaling"):
+            assert np.array_equal(b[k], lazy[k]), k
+        assert np.array_equal(b["mmz"], lazy["mmz"], equal_nan=True) and np.array_equal(b["mi"], lazy["mi"], equal_nan=True)   # ... and are gathered on demand
+    finally:
+        lib._ctx.set_tuning("sub_batch_rows", 0)
 
 
 def test_envelope_sweep_against_oracle():

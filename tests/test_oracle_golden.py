@@ -1,6 +1,7 @@
 """Pin the CPU oracle (oracle/qms_oracle.py) against vectors produced by the unmodified reference
 (tests/golden/make_golden.py) and against the reference's own golden vectors.  Bit-exact."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -15,6 +16,11 @@ sys.setrecursionlimit(20000)
 
 @pytest.fixture(scope="module", params=list(CASES))
 def case(request):
+    if CASES[request.param].get("heavy") and not os.environ.get("QMS_HEAVY_ORACLE"):
+        # 20 / 50 kDa formulas and the 1 900-envelope percentile grid: minutes to hours of pure-Python big-int work.
+        # The GPU tests check the CUDA path against these reference-generated fixtures directly; the oracle was
+        # checked against them once (QMS_HEAVY_ORACLE=1).
+        pytest.skip("heavy fixture: set QMS_HEAVY_ORACLE=1 to rebuild it with the oracle")
     blob, peaks, offsets = load_case(request.param)
     lib = OracleLibrary(**CASES[request.param]["lib"])
     return request.param, blob, peaks, offsets, lib
