@@ -387,14 +387,19 @@ def run_ours(args):
     h_peaks, h_offsets = pin_peaks.numpy(), pin_offsets.numpy()
     spec_ids = list(range(n_spec))
     gather_stats = {}
+    arena = None
+    if world > 1:
+        # hits of every rank land, by DMA, in a page-locked shared-memory segment that rank 0 maps (no data-path collective)
+        from pyqms_b200.distributed import SharedHitArena, gather_hits_to_rank0
+        arena = SharedHitArena()
+        lib.use_hit_arena(arena)
 
     def e2e_step():
         # the call a user makes for a whole run: host (N,2) array in, pyqms Results out (hits stay packed until read)
         res = lib.match_many(h_peaks, file_name="run", spec_ids=spec_ids, spec_rts=spec_ids, offsets=h_offsets)
         out = res.packed_batches()[-1]
         if world > 1:
-            from pyqms_b200.distributed import gather_hits_to_rank0
-            out = gather_hits_to_rank0(out, spectrum_begin=rank * n_spec, stats=gather_stats)
+            out = gather_hits_to_rank0(out, spectrum_begin=rank * n_spec, arena=arena, stats=gather_stats)
         return out
 
     for _ in range(max(1, min(args.warmup, 3))):

@@ -100,6 +100,10 @@ int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value);
  * its buffers are page-locked or device memory).  No context needed; error text through qms_last_error(NULL). */
 int qms_host_alloc(void** out, size_t bytes);
 int qms_host_free(void* p);
+/* Page-lock memory the caller owns (cudaHostRegister), e.g. a shared-memory segment that several processes map: the
+ * hits of every GPU of a box then land, by DMA, in memory that the collecting process already holds. */
+int qms_host_register(void* p, size_t bytes);
+int qms_host_unregister(void* p);
 
 /* ---- P1 prologue: enriched isotope tables ----------------------------------------------------
  * Replaces _recalc_isotopic_distribution IL:2109-2165: the isotope whose rounded mass equals

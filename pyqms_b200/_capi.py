@@ -61,6 +61,8 @@ EXPORTS = {  # name -> (restype, argtypes); must list every symbol of include/qm
     "qms_set_tuning": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "qms_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "qms_host_free": (C.c_int, [C.c_void_p]),
+    "qms_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "qms_host_unregister": (C.c_int, [C.c_void_p]),
     "qms_recalc_distribution": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "qms_build_element_trees": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int32]),

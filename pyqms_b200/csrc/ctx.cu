@@ -216,6 +216,24 @@ int qms_host_free(void* p) {
     return QMS_OK;
 }
 
+int qms_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return QMS_E_ARG;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return qms_fail(nullptr, QMS_E_CUDA, "cudaHostRegister(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return QMS_OK;
+}
+
+int qms_host_unregister(void* p) {
+    if (p && cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return QMS_E_CUDA;
+    }
+    return QMS_OK;
+}
+
 int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value) {
     if (!ctx || !key) return qms_fail(ctx, QMS_E_ARG, "qms_set_tuning: NULL argument");
     if (!strcmp(key, "dense_mode")) {

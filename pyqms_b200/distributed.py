@@ -146,6 +146,187 @@ def allgather_envelopes(ctx, n_env, world):
     return received
 
 
+_HIT_FIELDS = (("spec", np.int32, "h"), ("entry", np.int32, "h"), ("score", np.float64, "h"), ("scaling", np.float64, "h"),
+               ("win_off", np.int64, "h1"), ("peak", np.int64, "w"), ("mmz", np.float64, "w"), ("mi", np.float64, "w"))
+
+
+def _segment_layout(cap_h, cap_w, values):
+    """Byte offsets of the hit arrays inside a segment with room for cap_h hits and cap_w hit windows."""
+    offset, layout = 64, {}
+    for name, dtype, kind in _HIT_FIELDS:
+        if name in ("mmz", "mi") and not values:
+            continue
+        count = {"h": cap_h, "h1": cap_h + 1, "w": cap_w}[kind]
+        layout[name] = (offset, np.dtype(dtype), count)
+        offset = (offset + count * np.dtype(dtype).itemsize + 63) // 64 * 64
+    return layout, offset
+
+
+class SharedHitArena:
+    """Where the hits of this rank land when the ranks of one box match shards of a run: a POSIX shared-memory segment
+    per rank, page-locked in the owning process (the library copies the hits into it by DMA, sub-batch by sub-batch,
+    while it matches) and mapped by rank 0.  After ``collect`` rank 0 holds the hits of all ranks, in rank = spectrum
+    order, as one packed batch per rank -- no pickling, no copy through a pipe, and every GPU uses its own PCIe link
+    (the north star's "results are gathered to host in spectrum order").
+
+        arena = SharedHitArena()
+        lib.use_hit_arena(arena)
+        res = lib.match_many(shard_peaks, offsets=shard_offsets, ...)
+        batches = arena.collect(res.packed_batches()[-1], spectrum_begin)     # rank 0: [PackedHits per rank]; else None
+
+    The arrays of a collected batch are views of the segments: they stay valid until the owning rank matches again."""
+
+    def __init__(self, tag=None, register=True):
+        import os
+        self.rank, self.world = rank(), world_size()
+        self.tag = tag or "qms_%d_%s" % (os.getppid(), os.environ.get("MASTER_PORT", "0"))
+        self.register = register
+        self.generation = 0
+        self._own = None           # (name, mmap, bytes, cap_h, cap_w, values)
+        self._peers = {}           # rank 0: (rank, generation) -> mmap
+        self.stats = {}
+
+    # ---- segment of this rank ------------------------------------------------------------------------------
+    def _name(self, r, generation):
+        return "%s_r%d_g%d" % (self.tag, r, generation)
+
+    def _drop_own(self):
+        import os
+        if self._own is None:
+            return
+        name, mapping, nbytes, *_ = self._own
+        if self.register:
+            from . import _capi
+            address = C.addressof(C.c_char.from_buffer(mapping))
+            _capi.load().qms_host_unregister(address)
+        try:
+            mapping.close()
+        except BufferError:
+            pass                    # arrays handed out earlier still view it; the pages go with them
+        try:
+            os.unlink("/dev/shm/" + name)
+        except OSError:
+            pass
+        self._own = None
+
+    def arrays(self, cap_h, cap_w, values):
+        """numpy views (capacity cap_h hits / cap_w windows) inside this rank's segment, growing it when needed."""
+        import mmap
+        import os
+        own = self._own
+        if own is None or own[3] < cap_h or own[4] < cap_w or own[5] != values:
+            self._drop_own()
+            if own is not None:
+                cap_h, cap_w = max(cap_h, own[3]), max(cap_w, own[4])
+            cap_h, cap_w = cap_h + cap_h // 4 + 64, cap_w + cap_w // 4 + 512
+            layout, nbytes = _segment_layout(cap_h, cap_w, values)
+            self.generation += 1
+            name = self._name(self.rank, self.generation)
+            fd = os.open("/dev/shm/" + name, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            try:
+                os.ftruncate(fd, nbytes)
+                mapping = mmap.mmap(fd, nbytes)
+            finally:
+                os.close(fd)
+            if self.register:
+                from . import _capi
+                lib = _capi.load()
+                address = C.addressof(C.c_char.from_buffer(mapping))
+                rc = lib.qms_host_register(address, nbytes)
+                if rc != _capi.QMS_OK:
+                    raise _capi.QmsError(rc, (lib.qms_last_error(None) or b"").decode())
+            self._own = (name, mapping, nbytes, cap_h, cap_w, values)
+        name, mapping, nbytes, cap_h, cap_w, values = self._own
+        layout, _ = _segment_layout(cap_h, cap_w, values)
+        return {field: np.frombuffer(mapping, dtype=dtype, count=count, offset=offset) for field, (offset, dtype, count) in layout.items()}
+
+    # ---- rank 0: the hits of all ranks ---------------------------------------------------------------------------
+    def collect(self, out, spectrum_begin=0):
+        """All ranks call it after matching their shard; rank 0 gets one packed batch per rank, in rank order
+        (``batch["spec"]`` counts from the first spectrum of the rank's shard, ``batch["spec_base"]`` is that
+        spectrum's number in the run), the other ranks get None."""
+        import mmap
+        import os
+        import time
+        from .isotopologue_library import PackedHits
+        t0 = time.perf_counter()
+        own = self._own
+        in_segment = own is not None and out["n_hits"] > 0 and out["spec"].ctypes.data >= C.addressof(C.c_char.from_buffer(own[1])) and \
+            out["spec"].ctypes.data < C.addressof(C.c_char.from_buffer(own[1])) + own[2]
+        if own is None or not in_segment:                    # matched before the arena was attached, or nothing to show
+            fresh = self.arrays(max(1, out["n_hits"]), max(1, out["n_windows"]), "mmz" in dict.keys(out))
+            for field, array in fresh.items():
+                source = out[field]
+                array[:len(source)] = source
+            own = self._own
+        meta = [out["n_hits"], out["n_windows"], own[3], own[4], self.generation, int(own[5]), int(spectrum_begin)]
+        d = _dist()
+        if d is None or self.world == 1:
+            gathered = [meta]
+        else:
+            import torch
+            on_gpu = d.get_backend() == "nccl"
+            mine = torch.tensor(meta, dtype=torch.int64, device="cuda" if on_gpu else "cpu")
+            pieces = [torch.empty_like(mine) for _ in range(self.world)]
+            d.all_gather(pieces, mine)                       # 56 bytes per rank: the only collective of the matching path
+            gathered = [piece.tolist() for piece in pieces]
+        if self.rank != 0:
+            return None
+        batches = []
+        for r, (n_hits, n_windows, cap_h, cap_w, generation, values, begin) in enumerate(gathered):
+            if r == self.rank:
+                mapping = own[1]
+            else:
+                mapping = self._peers.get((r, generation))
+                if mapping is None:
+                    for key in [k for k in self._peers if k[0] == r]:
+                        try:
+                            self._peers.pop(key).close()
+                        except BufferError:
+                            pass
+                    fd = os.open("/dev/shm/" + self._name(r, generation), os.O_RDWR)
+                    try:
+                        mapping = mmap.mmap(fd, os.fstat(fd).st_size)
+                    finally:
+                        os.close(fd)
+                    self._peers[(r, generation)] = mapping
+            layout, _ = _segment_layout(cap_h, cap_w, bool(values))
+            batch = PackedHits()
+            for field, (offset, dtype, count) in layout.items():
+                used = {"spec": n_hits, "entry": n_hits, "score": n_hits, "scaling": n_hits, "win_off": n_hits + 1}.get(field, n_windows)
+                batch[field] = np.frombuffer(mapping, dtype=dtype, count=used, offset=offset)
+            batch["n_hits"], batch["n_windows"], batch["spec_base"], batch["rank"] = n_hits, n_windows, begin, r
+            batches.append(batch)
+        self.stats = {"collect_ms": 1e3 * (time.perf_counter() - t0), "hits": [int(g[0]) for g in gathered],
+                      "bytes_per_rank": [int(g[0]) * 32 + int(g[1]) * (24 if g[5] else 8) for g in gathered]}
+        return batches
+
+    def close(self):
+        self._drop_own()
+        for mapping in self._peers.values():
+            try:
+                mapping.close()
+            except BufferError:
+                pass
+        self._peers = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gather_hits_to_rank0(out, spectrum_begin, arena, stats=None):
+    """``arena.collect`` plus bookkeeping for bench.py: rank 0 returns the list of per-rank batches."""
+    batches = arena.collect(out, spectrum_begin)
+    if stats is not None:
+        stats["own"] = out
+        if batches is not None:
+            stats["summary"] = dict(arena.stats, ranks=len(batches), total_hits=int(sum(b["n_hits"] for b in batches)))
+    return batches if batches is not None else out
+
+
 def gather_packed_hits(out, spectrum_begin, world):
     """Gather per-rank packed hit dicts on rank 0 in rank (= spectrum) order; other ranks get None.
 

@@ -286,7 +286,13 @@ class IsotopologueLibrary(dict):
     _hit_pool = None                     # page-locked result arrays, created with the first match
     _hit_caps = (4096, 32768)            # (hits, hit windows) the next result arrays are sized for
 
-    _DEVICE_STATE = ("_hit_pool", "_ctx", "_views", "_entry_static", "_ent_env", "_ent_z", "_ent_lower", "_ent_upper", "_ent_win_off",
+    _hit_arena = None                    # distributed.SharedHitArena: result arrays in shared memory instead of the pool
+
+    def use_hit_arena(self, arena):
+        """Let the hits of batched matching land in ``arena`` (``distributed.SharedHitArena``; None = back to the pool)."""
+        self._hit_arena = arena
+
+    _DEVICE_STATE = ("_hit_pool", "_hit_arena", "_ctx", "_views", "_entry_static", "_ent_env", "_ent_z", "_ent_lower", "_ent_upper", "_ent_win_off",
                      "_win_lo", "_win_hi", "_win_cmz", "_win_ri", "_win_ci")
 
     def __reduce__(self):
@@ -798,10 +804,14 @@ class IsotopologueLibrary(dict):
 
         def buffers(h, w):
             out = PackedHits(peaks if not values else None)
-            out.update({"spec": pool.array(np.int32, h), "entry": pool.array(np.int32, h), "score": pool.array(np.float64, h),
-                        "scaling": pool.array(np.float64, h), "win_off": pool.array(np.int64, h + 1), "peak": pool.array(np.int64, w)})
-            if values:
-                out["mmz"], out["mi"] = pool.array(np.float64, w), pool.array(np.float64, w)
+            if self._hit_arena is not None and only_entry is None:
+                out.update(self._hit_arena.arrays(h, w, values))          # shared segment of this rank (distributed.SharedHitArena)
+            else:
+                out.update({"spec": pool.array(np.int32, h), "entry": pool.array(np.int32, h), "score": pool.array(np.float64, h),
+                            "scaling": pool.array(np.float64, h), "win_off": pool.array(np.int64, h + 1),
+                            "peak": pool.array(np.int64, w)})
+                if values:
+                    out["mmz"], out["mi"] = pool.array(np.float64, w), pool.array(np.float64, w)
             hits = QmsHits(h, w, *[out[k].ctypes.data if k in out else None
                                    for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
             return out, hits

@@ -55,6 +55,32 @@ def _worker(rank, world, port, out_dir):
         assert merged["mmz"][6 * (qd.shard_range(n_spec, 1, world)[0])] == 1000.0
     else:
         assert merged is None
+    # --- the same through the shared-memory arena: every rank's hits land in its own segment, rank 0 maps them all
+    # (register=False: no CUDA here; on a GPU box the owning rank page-locks its segment and the library DMAs into it)
+    from pyqms_b200.isotopologue_library import PackedHits
+    arena = qd.SharedHitArena(tag="qmstest_%d" % port, register=False)
+    for step in range(2):                               # the second step reuses the segments (and peers' mappings)
+        target = arena.arrays(nh, 3 * nh, True)
+        out = PackedHits()
+        for field in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi"):
+            target[field][:len(local[field])] = local[field] if field != "score" else local[field] + step
+            out[field] = target[field][:len(local[field])]
+        target["peak"][:3 * nh] = np.arange(3 * nh) + 7 * rank
+        out["peak"] = target["peak"][:3 * nh]
+        out["n_hits"], out["n_windows"] = nh, 3 * nh
+        batches = arena.collect(out, begin)
+        if rank == 0:
+            assert [b["rank"] for b in batches] == list(range(world))
+            assert [b["spec_base"] for b in batches] == [qd.shard_range(n_spec, r, world)[0] for r in range(world)]
+            spectra = np.concatenate([b["spec"] + b["spec_base"] for b in batches])
+            assert list(spectra) == [s for s in range(n_spec) for _ in range(2)]
+            assert batches[1]["mmz"][0] == 1000.0 and batches[1]["peak"][1] == 8 and batches[1]["score"][0] == 0.5 + step
+            assert sum(b["n_hits"] for b in batches) == 2 * n_spec
+        else:
+            assert batches is None
+        dist.barrier()                                  # rank 0 has read the segments before anybody writes them again
+    del batches, out, target
+    arena.close()
     dist.barrier()
     dist.destroy_process_group()
     Path(out_dir, "ok%d" % rank).write_text("ok")
