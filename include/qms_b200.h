@@ -16,6 +16,7 @@
 #ifndef QMS_B200_H
 #define QMS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -151,6 +152,19 @@ int qms_build_envelopes(qms_ctx* ctx, int64_t e_begin, int64_t e_end);
 int qms_envelope_layout(qms_ctx* ctx, int64_t* n_env, int64_t* n_slots, int64_t* slot_off);
 int qms_envelope_buffers(qms_ctx* ctx, void** mass, void** relabun, void** abun, void** pos,
                          void** c_flag, void** len, void** n_c);
+
+/* ---- multi-GPU library build ----------------------------------------------------------
+ * One process per GPU.  Rank 0 draws an id (qms_comm_unique_id, 128 bytes) and hands it to the other ranks by any host
+ * channel; every rank calls qms_comm_init with it, builds its shard of the envelopes -- rank r owns the contiguous block
+ * r of n_env envelopes (sizes differ by at most one, the first n_env % nranks blocks are the larger ones) -- with
+ * qms_build_envelopes and then calls qms_allgather_library: the seven envelope arrays of all shards are packed into
+ * fixed-stride record blocks and assembled with ONE ncclAllGather over NVLink (NCCL is dlopen'ed: libnccl.so.2).
+ * Afterwards every rank holds all envelopes and runs qms_finalize_index redundantly (identical replicas).
+ * bytes_received / ms (may be NULL): payload this rank received and the device time of pack + all-gather + unpack. */
+int qms_comm_unique_id(void* out, size_t capacity);
+int qms_comm_init(qms_ctx* ctx, const void* unique_id, int rank, int nranks);
+int qms_allgather_library(qms_ctx* ctx, int64_t* bytes_received, double* ms);
+int qms_comm_destroy(qms_ctx* ctx);
 
 /* ---- P1c: m/z windows + sorted index ------------------------------------------------------
  * Replaces IL:777-811 + _transform_mz_to_set IL:2533-2552 (per-charge m/z, integer ppm windows),

@@ -32,6 +32,10 @@ int qms_mzml_open(const char* path, qms_mzml** out);
 void qms_mzml_close(qms_mzml* file);
 const char* qms_mzml_last_error(void);
 
+/* Blocks the tag scan of qms_mzml_open was split into at the offsets of the file's own spectrum index (indexedmzML);
+ * 0 = one sequential scan (no index, an index that does not point at <spectrum> tags or miscounts them, a small file). */
+int qms_mzml_scan_blocks(qms_mzml* file);
+
 /* Spectra of `ms_level` (0 = every level) and the number of (m/z, intensity) rows they hold. */
 int qms_mzml_count(qms_mzml* file, int32_t ms_level, int64_t* n_spectra, int64_t* n_peaks);
 

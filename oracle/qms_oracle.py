@@ -616,6 +616,13 @@ class OracleLibrary(dict):
                     match(spec_id, spec_rt, score, scaling, peaks))
         return results
 
+    # IL:1957-1966: match_isotopologue(index=, mz_i_list=): the spectrum is sliced by the entry's own m/z range first
+    def match_isotopologue_of_spectrum(self, index, mz_i_list, xi):
+        lower, upper = self.formulas_sorted_by_mz[index][:2]
+        sliced = self.slice_list(mz_i_list, ((lower, 0), (upper, 0)))
+        keys, lookup = self.transform_spectrum(sliced, mz_range=(lower, upper))
+        return self.match_isotopologue(index, keys, lookup, xi)
+
     # IL:1885-2040 (Q10, Q11)
     def match_isotopologue(self, index, keys, lookup, xi):
         lo, hi, z, lp, formula = self.formulas_sorted_by_mz[index]

@@ -72,6 +72,10 @@ EXPORTS = {  # name -> (restype, argtypes); must list every symbol of include/qm
     "qms_build_envelopes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "qms_envelope_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "qms_envelope_buffers": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 7),
+    "qms_comm_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "qms_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "qms_allgather_library": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "qms_comm_destroy": (C.c_int, [C.c_void_p]),
     "qms_finalize_index": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "qms_index_info_get": (C.c_int, [C.c_void_p, C.POINTER(QmsIndexInfo)]),
     "qms_export_envelopes": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7),

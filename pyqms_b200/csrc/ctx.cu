@@ -255,6 +255,7 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    qms_comm_destroy(ctx);
 #define REL(b) qms_release(ctx, ctx->b)
     REL(iso_off); REL(iso_q); REL(max_level); REL(lvl_base); REL(lvl_min); REL(lvl_max); REL(lvl_f); REL(lvl_l);
     REL(iso_mass); REL(iso_abun); REL(lvl_off); REL(tree_abun); REL(tree_mass);

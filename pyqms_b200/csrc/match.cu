@@ -54,6 +54,22 @@ __device__ __forceinline__ void entry_clamp(const MatchView& v, int64_t b, int64
     ca = b;
     cb = e;
     if (v.input_kind == 0) return;
+    if (v.only_entry >= 0) {
+        // match_isotopologue(index, mz_i_list=list), IL:1957-1966: the spectrum is sliced by the ENTRY's own range,
+        // first around ((lower, 0), (upper, 0)), then -- inside _transform_spectrum -- around ((lower, 0.001), (upper, 0.001))
+        const double lower = __ldg(&v.ent_lower[entry]), upper = __ldg(&v.ent_upper[entry]);
+        int64_t ga = bisect_right_tuple(v.peaks, b, e, lower, 0.0) - 2;
+        int64_t gb = bisect_right_tuple(v.peaks, b, e, upper, 0.0) + 2;
+        if (ga < b) ga = b;
+        if (gb > e) gb = e;
+        if (gb < ga) gb = ga;
+        int64_t la = bisect_right_tuple(v.peaks, ga, gb, lower, 0.001) - 2;
+        int64_t lb = bisect_right_tuple(v.peaks, ga, gb, upper, 0.001) + 2;
+        ca = la < ga ? ga : la;
+        cb = lb > gb ? gb : lb;
+        if (cb < ca) cb = ca;
+        return;
+    }
     int64_t ga = bisect_right_tuple(v.peaks, b, e, v.mz_min, 0.0) - 2;
     int64_t gb = bisect_right_tuple(v.peaks, b, e, v.mz_max, 0.0) + 2;
     if (ga < b) ga = b;
@@ -1286,6 +1302,7 @@ static int make_view(qms_ctx* ctx, MatchView& v, const double2* d_peaks, const i
     v.win_ri = ctx->win_ri.p;
     v.win_ci = ctx->win_ci.p;
     v.ent_lower = ctx->ent_lower.p;
+    v.ent_upper = ctx->ent_upper.p;
     v.bin_upper = ctx->bin_upper.p;
     v.per_bin = P.max_molecules_per_bin;
     v.input_kind = input_kind;

@@ -26,6 +26,7 @@ struct MatchView {
     const double* win_ri;
     const int32_t* win_ci;
     const double* ent_lower;
+    const double* ent_upper;
     const double* bin_upper;
     int per_bin;
     int input_kind;

@@ -22,6 +22,9 @@
 
 namespace {
 
+// memmem with a string literal as the needle (its length without the terminating NUL)
+#define FIND_LIT(hay, n, lit) ((const char*)memmem((hay), (n), (lit), sizeof(lit) - 1))
+
 thread_local std::string g_error;
 
 int fail(int code, const char* fmt, ...) {
@@ -75,6 +78,7 @@ struct qms_mzml {
     bool mapped = false;
     std::vector<char> inflated;
     std::vector<SpectrumInfo> spectra;
+    int scan_blocks = 0;              // blocks the tag scan was split into at the file's own spectrum offsets (0: sequential scan)
 };
 
 namespace {
@@ -171,7 +175,7 @@ int scan_range(const char* begin, const char* end, const ParamGroups& groups, Pa
         const char* name = lt + 1;
         if (*name == '!' || *name == '?') {                // comments, declarations, processing instructions
             const char* gt = name[0] == '!' && name + 2 < end && name[1] == '-' && name[2] == '-'
-                                 ? (const char*)memmem(name, (size_t)(end - name), "-->", 3)
+                                 ? FIND_LIT(name, (size_t)(end - name), "-->")
                                  : (const char*)memchr(name, '>', (size_t)(end - name));
             if (!gt) break;
             p = gt + (*gt == '-' ? 3 : 1);
@@ -232,7 +236,7 @@ int scan_range(const char* begin, const char* end, const ParamGroups& groups, Pa
                 if (self_closing) {
                     array.text = Span{gt, gt};
                 } else {
-                    const char* close = (const char*)memmem(gt + 1, (size_t)(end - gt - 1), "</", 2);
+                    const char* close = FIND_LIT(gt + 1, (size_t)(end - gt - 1), "</");
                     if (!close) return fail(QMS_MZML_E_FORMAT, "unterminated <binary> element");
                     array.text = Span{gt + 1, close};
                     p = close;
@@ -260,17 +264,28 @@ int scan_range(const char* begin, const char* end, const ParamGroups& groups, Pa
 std::vector<size_t> indexed_offsets(const qms_mzml* f) {
     std::vector<size_t> offsets;
     const size_t tail = std::min<size_t>(f->size, 4096);
-    const char* tag = (const char*)memmem(f->data + f->size - tail, tail, "<indexListOffset>", 17);
+    const char* tag = FIND_LIT(f->data + f->size - tail, tail, "<indexListOffset>");
     if (!tag) return offsets;
     const int64_t list_at = to_int(Span{tag + 17, std::min(tag + 17 + 24, f->data + f->size)}, -1);
     if (list_at <= 0 || (size_t)list_at >= f->size || memcmp(f->data + list_at, "<indexList", 10) != 0) return offsets;
     const char* p = f->data + list_at;
     const char* end = f->data + f->size;
-    const char* index = (const char*)memmem(p, (size_t)(end - p), "<index name=\"spectrum\"", 23);
+    // the <index> element whose name attribute is "spectrum" (attribute order and quote character are the writer's choice)
+    const char* index = nullptr;
+    for (const char* q = p; (q = FIND_LIT(q, (size_t)(end - q), "<index")) != nullptr; q += 6) {
+        if (q[6] != ' ' && q[6] != '\t' && q[6] != '\n' && q[6] != '\r') continue;         // <indexList, <indexListOffset
+        const char* gt = (const char*)memchr(q, '>', (size_t)(end - q));
+        if (!gt) break;
+        const Span name = attribute(q + 6, gt, "name");
+        if (name.size() == 8 && memcmp(name.a, "spectrum", 8) == 0) {
+            index = gt;
+            break;
+        }
+    }
     if (!index) return offsets;
-    const char* index_end = (const char*)memmem(index, (size_t)(end - index), "</index>", 8);
+    const char* index_end = FIND_LIT(index, (size_t)(end - index), "</index>");
     if (!index_end) return offsets;
-    for (const char* o = index; (o = (const char*)memmem(o, (size_t)(index_end - o), "<offset", 7)) != nullptr;) {
+    for (const char* o = index; (o = FIND_LIT(o, (size_t)(index_end - o), "<offset")) != nullptr;) {
         const char* gt = (const char*)memchr(o, '>', (size_t)(index_end - o));
         if (!gt) break;
         const int64_t at = to_int(Span{gt + 1, std::min(gt + 1 + 24, index_end)}, -1);
@@ -306,7 +321,7 @@ int build_index(qms_mzml* f, int n_threads) {
         int rc = scan_range(begin, begin + offsets[0], none, &groups, 0, head, true, nullptr);
         if (rc != QMS_MZML_OK) return rc;
     }
-    const char* list_end = (const char*)memmem(begin + offsets.back(), (size_t)(end - begin) - offsets.back(), "</spectrumList", 14);
+    const char* list_end = FIND_LIT(begin + offsets.back(), (size_t)(end - begin) - offsets.back(), "</spectrumList");
     const char* region_end = list_end ? list_end : end;
     threads = (int)std::min<size_t>((size_t)threads, offsets.size() / 32);
     std::vector<std::vector<SpectrumInfo>> parts((size_t)threads);
@@ -342,6 +357,7 @@ int build_index(qms_mzml* f, int n_threads) {
             return fail(status[t], "%s", messages[t].c_str());
         }
     for (auto& part : parts) f->spectra.insert(f->spectra.end(), part.begin(), part.end());
+    f->scan_blocks = threads;
     return QMS_MZML_OK;
 }
 
@@ -541,6 +557,14 @@ int qms_mzml_open(const char* path, qms_mzml** out) {
             z.next_out = (Bytef*)f->inflated.data() + z.total_out;
             z.avail_out = (uInt)std::min<size_t>(f->inflated.size() - z.total_out, 1u << 30);
             zrc = inflate(&z, Z_NO_FLUSH);
+            if (zrc == Z_STREAM_END && (z.avail_in > 0 || fed < f->size)) {
+                // another gzip member follows (bgzip, pigz, concatenated files): gzip.open reads them all, so do we
+                const uLong so_far = z.total_out;
+                if (inflateReset(&z) != Z_OK) break;
+                z.total_out = so_far;
+                zrc = Z_OK;
+                continue;
+            }
             if (zrc != Z_OK && zrc != Z_STREAM_END && zrc != Z_BUF_ERROR) break;
             if (zrc == Z_BUF_ERROR && z.avail_in == 0 && fed >= f->size) break;      // truncated
         }
@@ -571,6 +595,8 @@ void qms_mzml_close(qms_mzml* f) {
     if (f->fd >= 0) close(f->fd);
     delete f;
 }
+
+int qms_mzml_scan_blocks(qms_mzml* file) { return file ? file->scan_blocks : 0; }
 
 int qms_mzml_count(qms_mzml* f, int32_t ms_level, int64_t* n_spectra, int64_t* n_peaks) {
     if (!f || !n_spectra || !n_peaks) return fail(QMS_MZML_E_ARG, "qms_mzml_count: NULL argument");

@@ -146,6 +146,8 @@ struct qms_ctx {
     DBuf<int64_t> st_nc_sorted, st_win_off;
     double rate_hits = 0, rate_windows = 0, rate_multi = 0;     // hits / hit windows / multi-candidate pairs per peak row of the last batch
     int64_t run_hits_hint = 0, run_windows_hint = 0;            // hits of the last whole run (capacity of the o_* arrays)
+    void* nccl_comm = nullptr;                                  // ncclComm_t of the sharded library build (comm.cu)
+    int comm_rank = 0, comm_size = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;               // copy streams of the pipelined run (sub-batches)
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_emit = nullptr;
 };
@@ -193,6 +195,7 @@ inline int qms_download(qms_ctx* ctx, T* host, const T* dev, size_t n) {
     return QMS_OK;
 }
 bool qms_is_device_ptr(const void* p);
+extern "C" int qms_comm_destroy(qms_ctx* ctx);
 
 
 static inline int qms_blocks(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }

@@ -109,31 +109,65 @@ def allgather_ranges(full, ranges):
     return received
 
 
-def allgather_envelopes(ctx, n_env, world):
-    """Assemble the envelope shards of all ranks in place (NCCL all-gather over NVLink).
+SHARD_MIN_ENVELOPES = 4_000_000
 
-    Every rank has written its shard [begin_r, end_r) of envelopes into the shared slot layout; the per-slot
-    arrays (mass, relabun, abun, pos, c_flag) and per-envelope arrays (len, n_c) are gathered one by one."""
+
+def shard_build_by_default(n_env, world):
+    """Whether ``IsotopologueLibrary(distributed=None)`` shards the envelope build over the ranks.
+
+    Measured on B200: the envelope kernel builds ~650 M peptide envelopes per second (0.55 ms for the 365 k envelopes of
+    the 500 k-peptide library), an envelope record is ~400 bytes, i.e. the all-gather moves a shard about as fast as a
+    rank computes it, and a communicator costs a fraction of a second to create -- below a few million envelopes the
+    replicated build is the faster one on every rank (round 1: 1.26 s sharded vs 0.014 s replicated for 38 envelopes)."""
+    return world > 1 and n_env >= SHARD_MIN_ENVELOPES
+
+
+def _same_on_all_ranks(values, device):
+    """Raise if the ranks disagree on ``values`` (the collectives of the build would wait for each other forever)."""
     import torch
+    import torch.distributed as dist
+    mine = torch.tensor(values, dtype=torch.int64, device=device)
+    pieces = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(pieces, mine)
+    if any(not bool(torch.equal(piece, mine)) for piece in pieces):
+        raise RuntimeError("ranks disagree on the envelope layout (different molecule lists / parameters per rank?): %s"
+                           % [piece.tolist() for piece in pieces])
+
+
+def allgather_envelopes(ctx, n_env, world):
+    """Assemble the envelope shards of all ranks in place.  Returns {"bytes_received", "ms", "how"}.
+
+    Under NCCL this is the library's own collective: ``qms_comm_init`` (rank 0's id travels through a 128-byte
+    broadcast) and ``qms_allgather_library`` -- one ``ncclAllGather`` of fixed-stride envelope records over NVLink
+    (csrc/comm.cu).  Other backends (gloo in CPU tests has no device memory to gather) use padded torch all-gathers
+    of the seven arrays."""
+    import torch
+    import torch.distributed as dist
     n_e, n_s = C.c_int64(), C.c_int64()
     ctx.call("qms_envelope_layout", C.byref(n_e), C.byref(n_s), None)
     slot_off = np.zeros(n_e.value + 1, dtype=np.int64)
     ctx.call("qms_envelope_layout", C.byref(n_e), C.byref(n_s), slot_off.ctypes.data_as(C.c_void_p))
+    device = "cuda:%d" % ctx.device
+    digest = [n_e.value, n_s.value, int(np.bitwise_xor.reduce(slot_off * np.arange(1, len(slot_off) + 1)))]
+    if dist.get_backend() == "nccl":
+        _same_on_all_ranks(digest, device)
+        token = torch.zeros(128, dtype=torch.uint8, device=device)
+        if dist.get_rank() == 0:
+            raw = (C.c_ubyte * 128)()
+            ctx.check(ctx.lib.qms_comm_unique_id(raw, 128))
+            token = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        dist.broadcast(token, src=0)
+        raw = (C.c_ubyte * 128).from_buffer_copy(token.cpu().numpy().tobytes())
+        ctx.call("qms_comm_init", raw, dist.get_rank(), world)
+        received, ms = C.c_int64(), C.c_double()
+        ctx.call("qms_allgather_library", C.byref(received), C.byref(ms))
+        return {"bytes_received": received.value, "ms": ms.value, "how": "one ncclAllGather of fixed-stride records (qms_allgather_library)"}
     ptrs = [C.c_void_p() for _ in range(7)]
     ctx.call("qms_envelope_buffers", *[C.byref(p) for p in ptrs])
     ctx.call("qms_synchronize")
     env_ranges = [shard_range(n_env, r, world) for r in range(world)]
     slot_ranges = [(int(slot_off[b]), int(slot_off[e])) for b, e in env_ranges]
-    # every rank must hold the same layout, or the collectives below would wait for each other forever
-    import torch.distributed as dist
-    digest = torch.tensor([n_e.value, n_s.value, int(np.bitwise_xor.reduce(slot_off * np.arange(1, len(slot_off) + 1)))],
-                          dtype=torch.int64, device="cuda:%d" % ctx.device)
-    lo, hi = digest.clone(), digest.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    if not bool(torch.equal(lo, hi)):
-        raise RuntimeError("ranks disagree on the envelope layout (different molecule lists / parameters per rank?): %s vs %s"
-                           % (lo.tolist(), hi.tolist()))
+    _same_on_all_ranks(digest, device)
     specs = [(ptrs[0], np.float64, n_s.value, slot_ranges), (ptrs[1], np.float64, n_s.value, slot_ranges),
              (ptrs[2], np.int32, n_s.value, slot_ranges), (ptrs[3], np.int32, n_s.value, slot_ranges),
              (ptrs[4], np.uint8, n_s.value, slot_ranges), (ptrs[5], np.int32, n_e.value, env_ranges),
@@ -143,7 +177,7 @@ def allgather_envelopes(ctx, n_env, world):
         if total:
             received += allgather_ranges(_device_tensor(pointer.value, total, dtype, ctx.device), ranges)
     torch.cuda.synchronize(ctx.device)
-    return received
+    return {"bytes_received": received, "ms": None, "how": "seven padded torch all-gathers"}
 
 
 _HIT_FIELDS = (("spec", np.int32, "h"), ("entry", np.int32, "h"), ("score", np.float64, "h"), ("scaling", np.float64, "h"),

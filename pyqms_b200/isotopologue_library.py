@@ -639,11 +639,14 @@ class IsotopologueLibrary(dict):
         from . import distributed as dist_mod
         world = dist_mod.world_size() if distributed is not False else 1
         if distributed is None:
-            distributed = world > 1
+            distributed = dist_mod.shard_build_by_default(self._n_env, world)      # small libraries are faster replicated
+        self._build_stats = {"sharded": bool(distributed and world > 1), "world": world, "envelopes": int(self._n_env)}
         if distributed and world > 1:
             begin, end = dist_mod.shard_range(self._n_env, dist_mod.rank(), world)
             ctx.call("qms_build_envelopes", begin, end)
-            dist_mod.allgather_envelopes(ctx, self._n_env, world)
+            t0 = time.perf_counter()
+            self._build_stats.update(dist_mod.allgather_envelopes(ctx, self._n_env, world))
+            self._build_stats["allgather_wall_s"] = time.perf_counter() - t0
         else:
             ctx.call("qms_build_envelopes", 0, self._n_env)
         # ranks of (label tuple, formula) under Python ordering: tie-break of the index sort (IL:836-867)

@@ -61,6 +61,7 @@ def spectrum_id(native_id, index):
     return int(found.group(1)) if found else index + 1
 
 
+LAST_READ = {"scan_blocks": 0}      # facts about the last native read: blocks the tag scan was split into (0 = sequential)
 _NATIVE = None
 _NATIVE_PATH = Path(__file__).resolve().parent / "libqms_mzml.so"
 
@@ -79,6 +80,7 @@ def _native():
             lib.qms_mzml_last_error.restype = C.c_char_p
             lib.qms_mzml_count.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
             lib.qms_mzml_read.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
+            lib.qms_mzml_scan_blocks.argtypes = [C.c_void_p]
             _NATIVE = lib
     return _NATIVE or None
 
@@ -90,6 +92,7 @@ def _read_native(lib, path, ms_level, sort_peaks, threads):
     if rc != 0:
         raise OSError("%s: %s" % (path, lib.qms_mzml_last_error().decode()))
     try:
+        LAST_READ["scan_blocks"] = lib.qms_mzml_scan_blocks(handle)
         n_spectra, n_peaks = C.c_int64(), C.c_int64()
         level = 0 if ms_level is None else int(ms_level)
         rc = lib.qms_mzml_count(handle, level, C.byref(n_spectra), C.byref(n_peaks))

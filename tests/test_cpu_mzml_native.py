@@ -2,6 +2,7 @@
 (N3), for every encoding the writer produces and for hand-written files with the variations converters produce."""
 import base64
 import ctypes
+import os
 import re
 import struct
 import zlib
@@ -34,7 +35,7 @@ def same_run(a, b):
 def test_native_library_exports_the_declared_symbols():
     header = (ROOT / "include" / "qms_mzml.h").read_text()
     declared = sorted(set(re.findall(r"\b(qms_mzml_[a-z_]+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S))))
-    assert len(declared) == 5
+    assert len(declared) == 6
     lib = ctypes.CDLL(str(ROOT / "pyqms_b200" / "libqms_mzml.so"))
     for name in declared:
         assert hasattr(lib, name), name
@@ -160,19 +161,31 @@ def test_indexed_files_are_scanned_in_parallel_blocks(tmp_path):
         got = read_mzml(path, ms_level=None, native=True, threads=threads)
         assert np.array_equal(got.peaks, want.peaks) and np.array_equal(got.offsets, want.offsets)
         assert got.spec_ids == want.spec_ids and got.rts == want.rts and got.ms_levels == want.ms_levels
+        assert mzml.LAST_READ["scan_blocks"] > 1 or (os.cpu_count() or 1) < 4     # the index WAS used (half the cores, at least 2)
     assert same_run(read_mzml(path, ms_level=1, native=False)._replace(name="x"), read_mzml(path, ms_level=1, native=True)._replace(name="x"))
     # an index whose offsets do not point at <spectrum> tags (file edited after indexing) is not used
     text = path.read_text()
-    shifted = re.sub(r"<offset ([^>]*)>(\\d+)</offset>", lambda m: "<offset %s>%d</offset>" % (m.group(1), int(m.group(2)) + 3), text)
+    shifted = re.sub(r"<offset ([^>]*)>(\d+)</offset>", lambda m: "<offset %s>%d</offset>" % (m.group(1), int(m.group(2)) + 3), text)
+    assert shifted != text
     bad = tmp_path / "bad_index.mzML"
     bad.write_text(shifted)
     got = read_mzml(bad, ms_level=None, native=True)
+    assert mzml.LAST_READ["scan_blocks"] == 0                                      # untrusted index: sequential scan
     assert np.array_equal(got.peaks, want.peaks) and got.spec_ids == want.spec_ids
     # an index that lists fewer spectra than the file holds (count mismatch inside a block) falls back as well
-    fewer = re.sub(r'<offset idRef="[^"]*scan=(?:7|8|9)">\\d+</offset>\\n', "", text)
+    fewer = re.sub(r'<offset idRef="[^"]*scan=(?:7|8|9)">\d+</offset>\n', "", text)
+    assert fewer != text
     short = tmp_path / "short_index.mzML"
     short.write_text(fewer)
     got = read_mzml(short, ms_level=None, native=True)
+    assert mzml.LAST_READ["scan_blocks"] == 0                                      # block counts disagree with the index: sequential scan
+    assert np.array_equal(got.peaks, want.peaks) and got.spec_ids == want.spec_ids
+    # attribute order and quote character of the <index> element are the writer's business
+    quoted = tmp_path / "quoted_index.mzML"
+    assert '<index name="spectrum">' in text
+    quoted.write_text(text.replace('<index name="spectrum">', "<index  name='spectrum' >"))
+    got = read_mzml(quoted, ms_level=None, native=True, threads=4)
+    assert mzml.LAST_READ["scan_blocks"] > 1 or (os.cpu_count() or 1) < 4
     assert np.array_equal(got.peaks, want.peaks) and got.spec_ids == want.spec_ids
 
 
@@ -189,6 +202,13 @@ def test_gzip_compressed_files(tmp_path):
         got = read_mzml(packed, native=native)
         assert np.array_equal(got.peaks, want.peaks) and np.array_equal(got.offsets, want.offsets)
         assert got.spec_ids == want.spec_ids and got.rts == want.rts and got.name == "run.mzML.gz"
+    # several gzip members in one file (bgzip, pigz, cat a.gz b.gz): all of them are read, like gzip.open does
+    raw = plain.read_bytes()
+    members = tmp_path / "members.mzML.gz"
+    members.write_bytes(gzip.compress(raw[:len(raw) // 3]) + gzip.compress(raw[len(raw) // 3:]))
+    for native in (True, False):
+        got = read_mzml(members, native=native)
+        assert np.array_equal(got.peaks, want.peaks) and got.spec_ids == want.spec_ids
     broken = tmp_path / "cut.mzML.gz"
     broken.write_bytes(packed.read_bytes()[:2000])
     with pytest.raises(OSError):

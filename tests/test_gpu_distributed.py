@@ -54,6 +54,34 @@ def _worker(rank, world, port, out_dir):
             assert np.array_equal(merged[name], whole[name][:nh]), name
         assert np.array_equal(merged["win_off"], whole["win_off"][:nh + 1])
         assert np.array_equal(merged["mmz"], whole["mmz"][:nw], equal_nan=True)
+    assert sharded._build_stats["sharded"] and sharded._build_stats["how"].startswith("one ncclAllGather")
+    assert sharded._build_stats["bytes_received"] > 0
+    # the same through the shared-memory arena: the library copies each rank's hits into the rank's page-locked
+    # segment, rank 0 maps the segments of all ranks (no pickling, no collective on the data path)
+    arena = qd.SharedHitArena()
+    sharded.use_hit_arena(arena)
+    for step in range(2):
+        mine = sharded.match_packed(peaks[offsets[begin]:offsets[end]], offsets[begin:end + 1] - offsets[begin])
+        batches = arena.collect(mine, begin)
+        if rank == 0:
+            nh, nw = whole["n_hits"], whole["n_windows"]
+            assert [b["rank"] for b in batches] == list(range(world))
+            assert np.array_equal(np.concatenate([b["spec"] + b["spec_base"] for b in batches]), whole["spec"][:nh])
+            for name in ("entry", "score", "scaling"):
+                assert np.array_equal(np.concatenate([b[name] for b in batches]), whole[name][:nh]), name
+            assert np.array_equal(np.concatenate([b["mmz"] for b in batches]), whole["mmz"][:nw], equal_nan=True)
+            shift = np.cumsum([0] + [b["n_windows"] for b in batches])
+            assert np.array_equal(np.concatenate([b["win_off"][:-1] + shift[k] for k, b in enumerate(batches)]), whole["win_off"][:nh])
+            # a peak row counts from the first row of the rank's shard
+            row_shift = [offsets[qd.shard_range(64, b["rank"], world)[0]] for b in batches]
+            rows = np.concatenate([np.where(b["peak"] >= 0, b["peak"] + row_shift[k], -1) for k, b in enumerate(batches)])
+            assert np.array_equal(rows, whole["peak"][:nw])
+        else:
+            assert batches is None
+        dist.barrier()
+    del batches, mine
+    sharded.use_hit_arena(None)
+    arena.close()
     dist.barrier()
     dist.destroy_process_group()
     Path(out_dir, "ok%d" % rank).write_text("ok")

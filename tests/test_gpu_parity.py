@@ -234,6 +234,25 @@ def test_match_isotopologue(pyqms):
     assert again is not None and abs(again[0] - best[0]) < 1e-12
 
 
+def test_match_isotopologue_of_a_list_spectrum(pyqms):
+    """match_isotopologue(index=, mz_i_list=<list>): +-2 ELEMENTS around the entry's own range (IL:1957-1966, Q12), against
+    vectors of the unmodified reference with crowded first / last windows (tests/golden/make_golden_entry.py)."""
+    from tests.golden.make_golden_entry import LIB
+    cases = json.loads((GOLDEN / "entry_list.json").read_text())["cases"]
+    lib = pyqms.IsotopologueLibrary(verbose=False, **LIB)
+    matched = 0
+    for index, spectrum, want in cases:
+        got = lib.match_isotopologue(index=index, mz_i_list=[tuple(p) for p in spectrum], mz_score_percentile=0.4)
+        if want is None:
+            assert got is None, index
+            continue
+        matched += 1
+        assert got is not None, index
+        assert abs(got[0] - want[0]) < SCORE_TOL and abs(got[1] - want[1]) <= SCORE_TOL * max(1.0, abs(want[1]))
+        assert [(p[0], p[1], p[4]) for p in got[2]] == [(p[0], p[1], p[4]) for p in want[2]], index
+    assert matched > 30
+
+
 def test_edge_cases(pyqms):
     lib = pyqms.IsotopologueLibrary(molecules=["DDSPDLPK", "LVTDLTK"], charges=[1, 2], verbose=False)
     assert len(lib.match_all(mz_i_list=[], file_name="f", spec_id=0, spec_rt=0.0)) == 0

@@ -135,3 +135,18 @@ def test_list_vs_numpy_slicing_quirk():
     a = lib.slice_list(spec, ((443.7, 0), (445.3, 0)))
     b = lib.slice_list(np.array(spec), ((443.7, 0), (445.3, 0)))
     assert len(a) == 9 and len(b) == 7
+
+
+def test_match_isotopologue_of_a_list_spectrum():
+    """IL:1957-1966 + Q12: element-wise slicing around the entry's own range (tests/golden/make_golden_entry.py)."""
+    from tests.golden.make_golden_entry import LIB
+    cases = json.loads((GOLDEN / "entry_list.json").read_text())["cases"]
+    lib = OracleLibrary(**LIB)
+    for index, spectrum, want in cases:
+        got = lib.match_isotopologue_of_spectrum(index, [tuple(p) for p in spectrum], 0.4)
+        if want is None:
+            assert got is None
+            continue
+        assert (float(got[0]), float(got[1])) == (want[0], want[1])
+        assert [[None if a is None else float(a), None if b is None else float(b), float(c), float(d), int(e)]
+                for a, b, c, d, e in got[2]] == want[2]
