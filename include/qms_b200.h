@@ -91,7 +91,7 @@ int qms_device_bytes(qms_ctx* ctx, int64_t* out);    /* device memory currently 
 /* Implementation switches that never change a result, only which kernels produce it (tests run both paths):
  *   "dense_mode"  0 = always the row-streaming matcher, 1 = the spectrum-resident matcher whenever its tables allow it,
  *                 2 = by library density (default; QMS_DENSE_MODE overrides the default)
- *   "dense_ctas"  resident CTAs per SM of the spectrum-resident kernel (default 4; QMS_DENSE_CTAS)
+ *   "dense_ctas"  resident CTAs per SM of the spectrum-resident kernel (default 2 CTAs of 512 threads; QMS_DENSE_CTAS)
  *   "sub_batch_rows"  peak rows per sub-batch when a host-resident run is pipelined (copies of neighbouring sub-batches
  *                 overlap the kernels); 0 = default (16 Mi rows) */
 int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value);

@@ -268,7 +268,7 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     REL(pair_score); REL(pair_scaling); REL(pair_flag); REL(pair_win_off); REL(pair_best);
     REL(blk_hits); REL(blk_wins); REL(live_rows); REL(live_count); REL(live_prefix); REL(need_of_nc); REL(pair_vals); REL(pair_vals_alt);
     REL(pair_nc); REL(scr_first); REL(scr_cur); REL(scr_best); REL(heavy_list); REL(tile_spec);
-    REL(probe2); REL(cell_range); REL(win_lohi); REL(win_entry); REL(zone_tab);
+    REL(probe2); REL(cell_range); REL(win_rec); REL(win_entry); REL(zone_tab);
     REL(st_key); REL(st_key_alt); REL(st_score); REL(st_scaling); REL(st_woff); REL(st_nc); REL(st_rows); REL(st_order); REL(st_order_alt);
     REL(spec_buckets); REL(spec_rows); REL(st_nc_sorted); REL(st_win_off);
     REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak);

@@ -260,10 +260,19 @@ __global__ void cell_range_kernel(int64_t span, const int32_t* __restrict__ cell
     cell_range[c] = make_int2(first < end ? first : end, end);
 }
 
-__global__ void win_lohi_kernel(int64_t n_windows, const int32_t* __restrict__ win_lo, const int32_t* __restrict__ win_hi,
-                                int2* __restrict__ win_lohi) {
+__global__ void win_rec_kernel(int64_t n_windows, const int32_t* __restrict__ win_lo, const int32_t* __restrict__ win_hi,
+                               const int32_t* __restrict__ win_ci, const double* __restrict__ win_cmz,
+                               const double* __restrict__ win_ri, WinRec* __restrict__ win_rec) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < n_windows) win_lohi[w] = make_int2(win_lo[w], win_hi[w]);
+    if (w >= n_windows) return;
+    WinRec r;
+    r.lo = win_lo[w];
+    r.hi = win_hi[w];
+    r.ci = win_ci[w];
+    r.pad = 0;
+    r.cmz = win_cmz[w];
+    r.ri = win_ri[w];
+    win_rec[w] = r;
 }
 
 // flags[0] |= 1 if some entry's windows touch, overlap or descend; flags[0] |= 2 if a window count does not fit 12 bits
@@ -462,7 +471,9 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
             QMS_TRY(qms_reserve(ctx, first_cover.b, (size_t)span + 1));
             QMS_TRY(qms_reserve(ctx, flags.b, 1));
             QMS_TRY(qms_reserve(ctx, ctx->probe2, nw1));
-            QMS_TRY(qms_reserve(ctx, ctx->win_lohi, nw1));
+#if QMS_WINDOW_RECORDS
+            QMS_TRY(qms_reserve(ctx, ctx->win_rec, nw1));
+#endif
             QMS_TRY(qms_reserve(ctx, ctx->cell_range, (size_t)span + 1));
             fill_i32_kernel<<<qms_blocks(span + 1, threads), threads, 0, ctx->stream>>>(span + 1, INT32_MAX, first_cover.b.p);
             QMS_CUDA(ctx, cudaMemsetAsync(flags.b.p, 0, sizeof(int32_t), ctx->stream));
@@ -487,7 +498,10 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
                                                                                   first_cover.b.p);
             cell_range_kernel<<<qms_blocks(span, threads), threads, 0, ctx->stream>>>(span, ctx->cell_start.p, first_cover.b.p,
                                                                                      ctx->cell_range.p);
-            win_lohi_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->win_lo.p, ctx->win_hi.p, ctx->win_lohi.p);
+#if QMS_WINDOW_RECORDS
+            win_rec_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->win_lo.p, ctx->win_hi.p, ctx->win_ci.p,
+                                                                                   ctx->win_cmz.p, ctx->win_ri.p, ctx->win_rec.p);
+#endif
             ctx->cnt.kernel_launches += 7;
             int32_t h_flags = 0;
             QMS_CUDA(ctx, cudaMemcpyAsync(&h_flags, flags.b.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -31,7 +31,9 @@
 
 #include "match_shared.cuh"
 
-#define MS_THREADS 256
+#ifndef MS_THREADS
+#define MS_THREADS 512          // measured (kernel ms, proteome shard): 256 x 4 CTAs 102.6 | 512 x 2 CTAs 94.1 | 1024 x 1 CTA 95.7 | 256 x 3 CTAs (85 registers) 109.7
+#endif
 #define MS_WARPS (MS_THREADS / 32)
 #define MS_CELLS 8192          // direct-address table cells per spectrum (16-bit entries)
 #define MS_BUCKETS 3072        // distinct covered buckets kept in shared memory; larger spectra spill to global scratch
@@ -40,11 +42,23 @@
 #define MS_MAXNC 16            // most windows of an entry that is scored inline
 #define MS_GROUPS 8            // entry groups with zone masks
 #define MS_NONE 0xffffffffu
+// Tuning variants, built side by side with tools/dense_variants.sh and timed with tools/ab_variants.sh (B200, proteome
+// shard, ms of this kernel): both off 102.3 | records 111.2 | prefetch 109.2 | both 119.0 -- the prefetch registers push the
+// 64-register kernel into spills, the 32-byte records quadruple the sectors the gate touches for its (lo, hi) loads.
+#ifndef MS_PREFETCH
+#define MS_PREFETCH 0          // record strips / buckets / zone rows fetched one ahead
+#endif
+#ifndef MS_RECORDS
+#define MS_RECORDS QMS_WINDOW_RECORDS      // window data from 32-byte records instead of the per-field arrays (qms_internal.cuh)
+#endif
+#ifndef MS_MIN_CTAS
+#define MS_MIN_CTAS 2          // resident CTAs per SM the register allocation aims at (64 registers per thread)
+#endif
 
 struct SpectrumView {
     const int4* probe2;
     const int2* cell_range;
-    const int2* win_lohi;
+    const WinRec* win_rec;
     const int32_t* win_entry;
     const int2* zone_tab;
     int zone_groups, zone_band_shift;
@@ -66,17 +80,35 @@ struct SpectrumView {
 
 struct InlineRows {   // rows of one pair with at most one candidate per window
     const MatchView* v;
-    int64_t w0, p_begin;
+    const WinRec* rec;    // the entry's windows
+    int64_t p_begin;
     int nc;
     const uint32_t* rows;
     __device__ int n() const { return nc; }
     __device__ bool matched(int m) const { return rows[m] != MS_NONE; }
     __device__ double mmz(int m) const { return __ldg(&v->peaks[p_begin + rows[m]].x); }
     __device__ double mi(int m) const { return __ldg(&v->peaks[p_begin + rows[m]].y); }
+#if MS_RECORDS
+    __device__ double ri(int m) const { return __ldg(&rec[m].ri); }
+    __device__ double cmz(int m) const { return __ldg(&rec[m].cmz); }
+    __device__ double ci(int m) const { return (double)__ldg(&rec[m].ci); }
+#else
+    int64_t w0;
     __device__ double ri(int m) const { return __ldg(&v->win_ri[w0 + m]); }
     __device__ double cmz(int m) const { return __ldg(&v->win_cmz[w0 + m]); }
     __device__ double ci(int m) const { return (double)__ldg(&v->win_ci[w0 + m]); }
+#endif
 };
+
+#if MS_RECORDS
+__device__ __forceinline__ int2 window_bounds(const MatchView&, const WinRec* rec, int64_t w) {            // (lo, hi): one 8-byte load
+    return __ldg(reinterpret_cast<const int2*>(rec + w));
+}
+#else
+__device__ __forceinline__ int2 window_bounds(const MatchView& v, const WinRec*, int64_t w) {
+    return make_int2(__ldg(&v.win_lo[w]), __ldg(&v.win_hi[w]));
+}
+#endif
 
 // Append the passing lanes' hits to the staging area (all 32 lanes call; rows = the lane's matched rows, n_c of them).
 __device__ __forceinline__ void stage_hits(const SpectrumView& d, unsigned long long* counters, bool pass, unsigned long long key,
@@ -108,7 +140,7 @@ __device__ __forceinline__ void stage_hits(const SpectrumView& d, unsigned long 
     for (int m = 0; m < nc; ++m) d.st_rows[w + m] = rows[m];
 }
 
-__global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView v, SpectrumView d, int64_t p_begin,
+__global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) match_spectrum_kernel(MatchView v, SpectrumView d, int64_t p_begin,
                                                                        unsigned long long* __restrict__ counters) {
     extern __shared__ uint32_t smem[];
     int32_t* s_b = reinterpret_cast<int32_t*>(smem);                                  // MS_BUCKETS + 2
@@ -134,7 +166,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
     unsigned long long* w_mask = s_mask + warp * MS_GROUPS;
     const int sh = d.table_shift;
     if (tid <= MS_MAXNC) s_need[tid] = tid <= d.max_nc ? __ldg(&v.need_of_nc[tid]) : INT32_MAX;
-    unsigned long long st_cov = 0, st_inc = 0, st_pairs = 0, st_combos = 0, st_windows = 0, st_gated = 0;
+    unsigned long long st_cov = 0, st_inc = 0, st_pairs = 0, st_combos = 0, st_windows = 0, st_gated = 0, st_bound = 0;
 
     for (;;) {
         __syncthreads();                                   // the previous spectrum is done before its tables are overwritten
@@ -233,7 +265,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                     for (int m = 0; m < nc; ++m) {
                         rows[m] = MS_NONE;
                         if (zoned && !((fields >> (2 * m)) & 3u)) continue;      // empty zone: the window holds no bucket
-                        const int2 w = __ldg(&d.win_lohi[w0 + m]);
+                        const int2 w = window_bounds(v, d.win_rec, w0 + m);
                         const uint32_t a = m == k ? i : first_at_or_above(w.x);
                         if (B[a] <= w.y) {
                             rows[m] = row_base + R[a];
@@ -250,7 +282,11 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                         d.pair_vals[slot] = ((unsigned long long)(row_base + R[i]) << 16) | (unsigned long long)k;
                     }
                 } else {
-                    const InlineRows r{&v, w0, p_begin, nc, rows};
+                    #if MS_RECORDS
+                    const InlineRows r{&v, d.win_rec + w0, p_begin, nc, rows};
+#else
+                    const InlineRows r{&v, nullptr, p_begin, nc, rows, w0};
+#endif
                     ++st_combos;
                     st_windows += (unsigned long long)nc;
                     pass = n_matched >= v.min_match;                  // IL:1862-1870
@@ -268,7 +304,10 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                                 calculated += r.ci(m) * ri;
                             }
                         }
-                        if (calculated > 0.0 && ri_hit < v.score_thr * ri_all * (1.0 - 1e-9)) pass = false;
+                        if (calculated > 0.0 && ri_hit < v.score_thr * ri_all * (1.0 - 1e-9)) {
+                            pass = false;
+                            ++st_bound;
+                        }
                     }
                     if (pass) {
                         score_rows(r, v.min_rel, v.rel_mz, v.rel_i, v.xi, score, scaling);
@@ -292,34 +331,34 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                 bool own = true;
                 ++st_gated;
                 if (((knc >> 12) & 15u) != 15u) {
-                    // only windows whose zone holds a bucket can hold one: the others are skipped without a load
-                    const uint32_t occupied = (fields | (fields >> 1)) & 0x55555555u;      // bit 2m: zone of window m not empty
-                    uint32_t lower = occupied & ((1u << (2 * k)) - 1u);
-                    while (lower) {                          // a lower window with a bucket owns the pair
-                        const int m = (__ffs(lower) - 1) >> 1;
-                        lower &= lower - 1u;
-                        const int2 w = __ldg(&d.win_lohi[(int64_t)w0u + m]);
-                        if (B[first_at_or_above(w.x)] <= w.y) {
-                            own = false;
-                            break;
+                    // only windows whose zone holds a bucket can hold one: the others are skipped without a load.  The
+                    // occupied windows are visited in ascending order (a bucket in a window below k means that incidence
+                    // owns the pair), the bounds of the next one are fetched while the current one is counted.
+                    uint32_t todo = (fields | (fields >> 1)) & 0x55555555u;              // bit 2m: zone of window m not empty
+                    int m = (__ffs(todo) - 1) >> 1;                                       // never empty: window k holds bucket i
+                    int2 w = window_bounds(v, d.win_rec, (int64_t)w0u + m);
+                    todo &= todo - 1u;
+                    for (;;) {
+                        const int m_next = todo ? (__ffs(todo) - 1) >> 1 : -1;
+                        int2 w_next = make_int2(0, 0);
+                        if (m_next >= 0) w_next = window_bounds(v, d.win_rec, (int64_t)w0u + m_next);
+                        todo &= todo - 1u;
+                        uint32_t a = m == k ? i : first_at_or_above(w.x);
+                        if (m < k) {
+                            if (B[a] <= w.y) {
+                                own = false;
+                                break;
+                            }
+                        } else {
+                            while (B[a] <= w.y) {
+                                ++a;
+                                ++cnt;
+                            }
+                            if (cnt >= need) break;
                         }
-                    }
-                    uint32_t upper = own ? occupied >> (2 * k) : 0u;
-                    while (upper) {
-                        const int m = k + ((__ffs(upper) - 1) >> 1);
-                        upper &= upper - 1u;
-                        uint32_t a = i;
-                        int32_t hi = 0;
-                        {
-                            const int2 w = __ldg(&d.win_lohi[(int64_t)w0u + m]);
-                            hi = w.y;
-                            if (m != k) a = first_at_or_above(w.x);
-                        }
-                        while (B[a] <= hi) {
-                            ++a;
-                            ++cnt;
-                        }
-                        if (cnt >= need) break;
+                        if (m_next < 0) break;
+                        m = m_next;
+                        w = w_next;
                     }
                 } else {
                     bool done = false;
@@ -327,7 +366,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                         int2 w[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            w[u] = m0 + u < nc ? __ldg(&d.win_lohi[(int64_t)w0u + m0 + u]) : make_int2(INT32_MAX, INT32_MAX);
+                            w[u] = m0 + u < nc ? window_bounds(v, d.win_rec, (int64_t)w0u + m0 + u) : make_int2(INT32_MAX, INT32_MAX);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int m = m0 + u;
@@ -365,21 +404,46 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                 __syncwarp();
             }
         };
-        for (;;) {
-            // buckets differ in cost by an order of magnitude (records per cell, survivors): the warps draw them one by one
+        // buckets differ in cost by an order of magnitude (records per cell, survivors): the warps draw them one by one,
+        // one bucket ahead, so that the next bucket's record range is on its way while the current one is worked on
+        auto draw = [&]() -> uint32_t {
             uint32_t i = 0;
             if (lane == 0) i = atomicAdd(&s_next, 1u);
-            i = __shfl_sync(0xffffffffu, i, 0);
+            return __shfl_sync(0xffffffffu, i, 0);
+        };
+#if MS_PREFETCH
+        uint32_t i_next = draw();
+        int2 range_next = make_int2(0, 0);
+        if (i_next < n) range_next = __ldg(&d.cell_range[B[i_next] - v.t_min]);
+#endif
+        for (;;) {
+#if MS_PREFETCH
+            const uint32_t i = i_next;
+            if (i >= n) break;
+            const int2 range = range_next;
+            const int32_t t = B[i];
+            const int32_t t_before = i ? B[i - 1] : INT32_MIN;
+            int4 rec_next = make_int4(0, INT32_MIN, 0, 0);
+            if (range.x + lane < range.y) rec_next = __ldg(&d.probe2[range.x + lane]);      // first strip of records
+            i_next = draw();
+            if (i_next < n) range_next = __ldg(&d.cell_range[B[i_next] - v.t_min]);
+#else
+            const uint32_t i = draw();
             if (i >= n) break;
             const int32_t t = B[i];
             const int32_t t_before = i ? B[i - 1] : INT32_MIN;
+            const int2 range = __ldg(&d.cell_range[t - v.t_min]);
+#endif
             // zone masks of this bucket: per entry group, 2-bit (saturating) bucket counts of the 32 zones in which the
             // other windows of an entry that holds t in one of its windows can lie; lane = zone
             if (d.zone_groups > 0) {
                 int band = (t - v.t_min) >> d.zone_band_shift;
                 band = band < 31 ? band : 31;
+                const int2* zones = d.zone_tab + (band * 16) * 32 + lane;
+                int2 z_next = __ldg(zones);
                 for (int g = 0; g < d.zone_groups; ++g) {
-                    const int2 z = __ldg(&d.zone_tab[(band * 16 + g) * 32 + lane]);
+                    const int2 z = z_next;
+                    if (g + 1 < d.zone_groups) z_next = __ldg(zones + (g + 1) * 32);
                     uint32_t cnt = 0;
                     if (z.x <= z.y) {
                         const int32_t lo = max(t + z.x, v.t_min), hi = min(t + z.y, v.t_max);
@@ -394,11 +458,15 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
                 }
                 __syncwarp();
             }
-            const int2 range = __ldg(&d.cell_range[t - v.t_min]);
             for (int32_t jb = range.x; jb < range.y; jb += 32) {
-                const int32_t j = jb + lane;
+#if MS_PREFETCH
+                int4 rec = rec_next;                                   // lo, hi, first window of the entry, k | group << 12 | n_c << 16
+                rec_next = make_int4(0, INT32_MIN, 0, 0);
+                if (jb + 32 + lane < range.y) rec_next = __ldg(&d.probe2[jb + 32 + lane]);   // the next strip travels meanwhile
+#else
                 int4 rec = make_int4(0, INT32_MIN, 0, 0);
-                if (j < range.y) rec = __ldg(&d.probe2[j]);            // lo, hi, first window of the entry, k | group << 12 | n_c << 16
+                if (jb + lane < range.y) rec = __ldg(&d.probe2[jb + lane]);
+#endif
                 const bool incident = rec.y >= t;
                 bool push = incident && t_before < rec.x;              // the bucket is the first of the window
                 st_inc += incident;
@@ -442,6 +510,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
         st_combos += __shfl_xor_sync(0xffffffffu, st_combos, sft);
         st_windows += __shfl_xor_sync(0xffffffffu, st_windows, sft);
         st_gated += __shfl_xor_sync(0xffffffffu, st_gated, sft);
+        st_bound += __shfl_xor_sync(0xffffffffu, st_bound, sft);
     }
     if (lane == 0) {
         if (st_cov) atomicAdd(&counters[C_LIVE], st_cov);
@@ -450,6 +519,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) match_spectrum_kernel(MatchView
         if (st_combos) atomicAdd(&counters[C_COMBOS], st_combos);
         if (st_windows) atomicAdd(&counters[C_PAIR_WINDOWS], st_windows);
         if (st_gated) atomicAdd(&counters[C_GATED], st_gated);
+        if (st_bound) atomicAdd(&counters[C_BOUND], st_bound);
     }
 }
 
@@ -568,7 +638,7 @@ int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
     SpectrumView d;
     d.probe2 = ctx->probe2.p;
     d.cell_range = ctx->cell_range.p;
-    d.win_lohi = ctx->win_lohi.p;
+    d.win_rec = ctx->win_rec.p;          // empty unless the library was built with QMS_WINDOW_RECORDS
     d.win_entry = ctx->win_entry.p;
     d.zone_tab = ctx->zone_tab.p;
     d.zone_groups = ctx->zone_groups <= MS_GROUPS ? ctx->zone_groups : 0;
@@ -589,7 +659,7 @@ int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
         QMS_CUDA(ctx, cudaFuncSetAttribute(match_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_set = true;
     }
-    const int ctas_per_sm = ctx->dense_ctas > 0 ? ctx->dense_ctas : 4;
+    const int ctas_per_sm = ctx->dense_ctas > 0 ? ctx->dense_ctas : 2;
     int64_t grid = (int64_t)ctx->sm_count * ctas_per_sm;
     if (grid > n_spectra) grid = n_spectra;
     static int heavy_min = -1;
@@ -650,6 +720,7 @@ int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
         n_multi = (int64_t)ctx->h_pinned[C_MULTI];
         const int64_t live = (int64_t)ctx->h_pinned[C_LIVE], inc = (int64_t)ctx->h_pinned[C_INCID], pairs = (int64_t)ctx->h_pinned[C_PAIRS];
         const int64_t gated = (int64_t)ctx->h_pinned[C_GATED];
+        if (getenv("QMS_DEBUG_COUNTERS")) fprintf(stderr, "[qms] pairs %lld, rejected by the score bound %lld, multi %lld\n", (long long)pairs, (long long)ctx->h_pinned[C_BOUND], (long long)n_multi);
         int64_t combos = (int64_t)ctx->h_pinned[C_COMBOS], pair_windows = (int64_t)ctx->h_pinned[C_PAIR_WINDOWS];
         const bool multi_overflow = n_multi > cap_m;
         bool overflow = multi_overflow;

@@ -44,6 +44,17 @@ struct ProbeRec {  // one c-peak window in the lo-sorted probe list (16 B, one L
     int32_t k;  // ordinal of the window inside its entry
 };
 
+#ifndef QMS_WINDOW_RECORDS
+#define QMS_WINDOW_RECORDS 0       // build (and use) the 32-byte window records: measured slower, see match_spectrum.cu
+#endif
+
+struct __align__(32) WinRec {   // one c-peak window of an index entry, everything the matcher needs in one 32-byte sector
+    int32_t lo, hi;             // integer m/z window
+    int32_t ci;                 // integer abundance
+    int32_t pad;
+    double cmz, ri;             // theoretical m/z, relative abundance
+};
+
 struct qms_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -98,7 +109,7 @@ struct qms_ctx {
     // tables of the spectrum-resident matcher (match_spectrum.cu), derived from the ones above
     DBuf<int4> probe2;            // probe record as {lo, hi, first window of the entry, k | group << 12 | n_c << 16}
     DBuf<int2> cell_range;        // per grid cell: [first probe record that covers it, first record with lo > cell)
-    DBuf<int2> win_lohi;          // (lo, hi) of every window, entry-major: one 8-byte load per window
+    DBuf<WinRec> win_rec;         // every window, entry-major, as one 32-byte record
     DBuf<int32_t> win_entry;      // index entry of every window
     DBuf<int2> zone_tab;          // [32 m/z bands][16 groups][32 window-ordinal differences]: where the other windows of an entry lie
     int zone_groups = 0, zone_band_shift = 0;
@@ -126,7 +137,7 @@ struct qms_ctx {
     int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
     int dense_mode = 2;            // spectrum-resident matcher: 0 never, 1 whenever its tables allow it, 2 by library density
     int64_t sub_batch_rows = 0;   // rows per sub-batch of the pipelined run (0: default)
-    int dense_ctas = 4;            // its resident CTAs per SM
+    int dense_ctas = 2;            // its resident CTAs per SM
     bool last_values = true;                   // ... including the matched (m/z, intensity) values
     DBuf<uint8_t> cub_tmp;
     DBuf<unsigned long long> dev_counters;   // see match.cu

@@ -828,11 +828,15 @@ class IsotopologueLibrary(dict):
                                          C.byref(nh), C.byref(nw))
         if rc == QMS_E_CAPACITY:
             del out, hits
-            out, hits = buffers(nh.value + nh.value // 8 + 64, nw.value + nw.value // 8 + 512)
+            cap_h, cap_w = nh.value + nh.value // 8 + 64, nw.value + nw.value // 8 + 512
+            out, hits = buffers(cap_h, cap_w)
             rc = ctx.lib.qms_fetch_hits(ctx.handle, C.byref(hits), C.byref(nh), C.byref(nw))
         ctx.check(rc)
         h, w = nh.value, nw.value
-        self._hit_caps = (max(4096, h + h // 4), max(32768, w + w // 4))     # the next call of a run needs about as much
+        if only_entry is None:
+            # the next call of a run needs about as much: keep the capacities (and with them the pool's size classes)
+            # stable, grow them only when a run comes close to them
+            self._hit_caps = (cap_h if h < 0.95 * cap_h else h + h // 8 + 64, cap_w if w < 0.95 * cap_w else w + w // 8 + 512)
         for k in ("spec", "entry", "score", "scaling"):
             out[k] = out[k][:h]
         out["win_off"] = out["win_off"][:h + 1]
