@@ -88,10 +88,14 @@ int qms_synchronize(qms_ctx* ctx);
 int qms_get_counters(qms_ctx* ctx, qms_counters* out);
 int qms_reset_counters(qms_ctx* ctx);
 int qms_device_bytes(qms_ctx* ctx, int64_t* out);    /* device memory currently owned by the context */
-/* Implementation switches that never change a result, only which kernels produce it (tests run both paths):
+/* Implementation switches that never change a result, only which kernels produce it or when the library gives up
+ * (tests run both matcher paths):
  *   "dense_mode"  0 = always the row-streaming matcher, 1 = the spectrum-resident matcher whenever its tables allow it,
  *                 2 = by library density (default; QMS_DENSE_MODE overrides the default)
  *   "dense_ctas"  resident CTAs per SM of the spectrum-resident kernel (default 2 CTAs of 512 threads; QMS_DENSE_CTAS)
+ *   "combination_limit_log2"  log2 of the candidate combinations (IL:2004-2034) one (spectrum, entry) pair may hold (default 32);
+ *                 a batch with a pair above it fails with QMS_E_LIMIT instead of enumerating for hours like the reference
+ *   "combination_budget_log2"  log2 of the combinations of all many-candidate pairs of one batch (default 35)
  *   "sub_batch_rows"  peak rows per sub-batch when a host-resident run is pipelined (copies of neighbouring sub-batches
  *                 overlap the kernels); 0 = default (16 Mi rows) */
 int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value);

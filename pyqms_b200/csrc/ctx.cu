@@ -242,6 +242,9 @@ int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value) {
     } else if (!strcmp(key, "dense_ctas")) {
         if (value < 1 || value > 32) return qms_fail(ctx, QMS_E_ARG, "dense_ctas must be in [1, 32]");
         ctx->dense_ctas = value;
+    } else if (!strcmp(key, "combination_limit_log2") || !strcmp(key, "combination_budget_log2")) {
+        if (value < 4 || value > 62) return qms_fail(ctx, QMS_E_ARG, "%s must be in [4, 62]", key);
+        (key[12] == 'l' ? ctx->combination_limit : ctx->combination_budget) = 1ull << value;
     } else if (!strcmp(key, "sub_batch_rows")) {
         if (value < 0) return qms_fail(ctx, QMS_E_ARG, "sub_batch_rows must be >= 0");
         ctx->sub_batch_rows = value;
@@ -267,6 +270,7 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     REL(d_peaks); REL(d_offsets); REL(pair_keys); REL(pair_keys_alt); REL(cub_tmp); REL(dev_counters);
     REL(pair_score); REL(pair_scaling); REL(pair_flag); REL(pair_win_off); REL(pair_best);
     REL(blk_hits); REL(blk_wins); REL(live_rows); REL(live_count); REL(live_prefix); REL(need_of_nc); REL(pair_vals); REL(pair_vals_alt);
+    REL(pair_total); REL(item_pair); REL(item_chunk); REL(item_rows); REL(huge_first); REL(huge_items); REL(item_score); REL(item_scaling); REL(item_have);
     REL(pair_nc); REL(scr_first); REL(scr_cur); REL(scr_best); REL(heavy_list); REL(tile_spec);
     REL(probe2); REL(cell_range); REL(win_rec); REL(win_entry); REL(zone_tab);
     REL(st_key); REL(st_key_alt); REL(st_score); REL(st_scaling); REL(st_woff); REL(st_nc); REL(st_rows); REL(st_order); REL(st_order_alt);

@@ -208,65 +208,12 @@ __device__ bool gate_incidence(const MatchView& v, int64_t sb, int64_t se, int64
 #define PROBE_THREADS 256
 #define ROW_CHECK_ONLY 0x80000000u   // row listed only because its bucket is below its predecessor's
 
-// K5a: the streaming half.  Every (m/z, intensity) row is read once with one LDG.128, coalesced (a warp
-// covers 512 contiguous bytes per load, UNROLL independent loads in flight per thread).  A row
-// survives if its bucket is covered by a library window (two-level bitmap, the coarse level is a few KB
-// and stays in L1) or if its bucket descends against the previous row (sortedness is verified by K5b,
-// which knows the spectrum boundaries).  Survivors are appended to the block's own segment of
-// `live_rows` through a shared-memory cursor (warp-aggregated), so the stream issues no global atomics.
-__device__ __forceinline__ double2 load_row_streaming(const double2* p) {
-    // read-once stream: evict-first so the cover bitmaps and the cell table keep their L1/L2 lines
-    double2 r;
-    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
-}
-
-template <int UNROLL, bool STREAMING>
-__global__ void __launch_bounds__(PROBE_THREADS) spectrum_probe_kernel(MatchView v, int64_t p_begin, int64_t p_end,
-                                                                        int64_t seg_cap, uint32_t* __restrict__ live_rows,
-                                                                        uint32_t* __restrict__ live_count) {
-    __shared__ uint32_t s_cursor;
-    if (threadIdx.x == 0) s_cursor = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    uint32_t* segment = live_rows + (int64_t)blockIdx.x * seg_cap;
-    const int64_t tile = (int64_t)PROBE_THREADS * UNROLL;
-    for (int64_t base = p_begin + (int64_t)blockIdx.x * tile; base < p_end; base += (int64_t)gridDim.x * tile) {
-        double2 row[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t i = base + (int64_t)u * PROBE_THREADS + threadIdx.x;
-            row[u] = i < p_end ? (STREAMING ? load_row_streaming(&v.peaks[i]) : __ldg(&v.peaks[i])) : make_double2(0.0, 0.0);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t i = base + (int64_t)u * PROBE_THREADS + threadIdx.x;
-            const bool valid = i < p_end;
-            const int32_t t = qms_tmz(row[u].x, v.precision);
-            int32_t t_prev = __shfl_up_sync(0xffffffffu, t, 1);
-            if (lane == 0) t_prev = (valid && i > p_begin) ? tmz_at(v.peaks, i - 1, v.precision) : t;
-            // branch-free coarse test (the few-KB coarse bitmap is L1-resident; index clamped when out of range),
-            // only the ~3 % of rows that pass it touch the fine bitmap
-            const bool in_range = valid && t >= v.t_min && t <= v.t_max;
-            const uint32_t c = in_range ? (uint32_t)(t - v.t_min) : 0u;
-            bool live = in_range && ((__ldg(&v.cover2[c >> 10]) >> ((c >> 5) & 31)) & 1u);
-            if (live) live = (__ldg(&v.cover[c >> 5]) >> (c & 31)) & 1u;
-            const bool descends = valid && t < t_prev;
-            const bool push = live || descends;
-            const unsigned mask = __ballot_sync(0xffffffffu, push);
-            if (mask) {
-                uint32_t warp_base = 0;
-                if (lane == 0) warp_base = atomicAdd(&s_cursor, (uint32_t)__popc(mask));
-                warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
-                if (push)
-                    segment[warp_base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(i - p_begin) | (live ? 0u : ROW_CHECK_ONLY);
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) live_count[blockIdx.x] = s_cursor;
-}
-
+// K5a: the streaming half.  Every (m/z, intensity) row is read once, coalesced.  A row survives if its bucket is covered
+// by a library window (two-level bitmap, the coarse level is a few KB and stays in L1) or if its bucket descends against
+// the previous row (sortedness is verified by K5b, which knows the spectrum boundaries).  Survivors are appended to the
+// block's own segment of `live_rows` through a shared-memory cursor (warp-aggregated), so the stream issues no global
+// atomics.  Variants measured and dropped in round 1 (evict-first loads 0.75-0.77 of the HBM peak, 8 loads per lane
+// 0.73-0.83, thread-strided rows 0.83, persistent CTAs on a tile ticket 0.72 against 0.90 for this one) are in the history.
 // K5a, warp-contiguous layout: a warp owns 32*UNROLL consecutive rows of the tile, so the predecessor of a
 // lane-0 row is lane 31 of the same warp one load earlier (register shuffle); only the first row of the
 // warp's chunk needs its predecessor from memory and that load is issued together with the row loads, which
@@ -589,13 +536,25 @@ __device__ __forceinline__ int64_t next_bucket(const MatchView& v, int64_t j, in
 
 #define K6_LOCAL 16
 #define K6B_CANDS 8      // most candidate buckets per window a pair may have to be scored by K6b
+#define K6C_MAXNC 64     // K6c: most windows of a pair, ...
+#define K6C_ENTRIES 2048 // ... most candidates over all its windows (table rows in shared memory),
+#define K6C_THREADS 256
+#define K6C_CHUNK (1ull << 20)   // ... combinations per work item
+
+struct PairLists {       // where score_pair sends the pairs it does not enumerate itself
+    int64_t* heavy;              // K6b list (filled from the front), nullptr: every pair is enumerated by its thread
+    int64_t* huge_end;           // K6c list (filled from the end of the same array)
+    unsigned long long* pair_total;   // combinations of a K6c pair
+    int heavy_min;               // combinations from which a pair is handed over
+    unsigned long long limit;    // combinations above which a pair is reported, not enumerated
+};
 
 __device__ void score_pair(const MatchView& v, int64_t p, const unsigned long long* __restrict__ keys,
                            const unsigned long long* __restrict__ vals, int entry_bits, int64_t p_begin, int max_nc,
                            int64_t* __restrict__ scr_first, int64_t* __restrict__ scr_cur, int64_t* __restrict__ scr_best,
                            int64_t* __restrict__ pair_best, double* __restrict__ pair_score, double* __restrict__ pair_scaling,
                            int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters,
-                           int64_t* __restrict__ heavy_list, int heavy_min, unsigned long long& combos_out, int& windows_out) {
+                           const PairLists& lists, unsigned long long& combos_out, int& windows_out) {
     const int64_t s = (int64_t)(keys[p] >> entry_bits);
     const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
     const int64_t row0 = p_begin + (int64_t)(vals[p] >> 16);   // canonical incidence: first bucket of the
@@ -654,23 +613,40 @@ __device__ void score_pair(const MatchView& v, int64_t p, const unsigned long lo
         cur[m] = best[m] = first[m];
         n_matched += first[m] >= 0;
     }
-    // Pairs with many candidate combinations go to the warp-cooperative kernel (K6b): there the 32 lanes score
-    // different combinations of the same pair with identical control flow instead of one lane grinding through
-    // all of them while its neighbours idle.
-    if (heavy_list != nullptr && nc <= K6_LOCAL && n_matched > 0) {
+    // Pairs with many candidate combinations leave this thread: K6b scores the combinations of a pair with the 32 lanes of
+    // a warp (tables in shared memory: <= 16 windows, <= 8 candidates per window, <= 2^18 combinations), K6c spreads the
+    // combinations of larger pairs over CTAs in chunks of 2^20 (<= 64 windows, <= 255 candidates per window).  A pair
+    // above the combination limit is reported instead of enumerated (the reference would enumerate it for hours).
+    if (lists.heavy != nullptr && n_matched > 0) {
+        double total_d = 1.0;
         unsigned long long total = 1;
-        bool fits = true;
-        for (int m = 0; m < nc && fits; ++m) {
+        int widest = 0, entries = 0;
+        for (int m = 0; m < nc; ++m) {
             if (first[m] < 0) continue;
             int count = 1;
             for (int64_t j = next_bucket(v, first[m], cb, __ldg(&whi[m])); j >= 0; j = next_bucket(v, j, cb, __ldg(&whi[m]))) ++count;
-            fits = count <= K6B_CANDS;
-            total *= (unsigned long long)count;
-            if (total > (1ull << 40)) fits = false;
+            widest = count > widest ? count : widest;
+            entries += count;
+            total_d *= (double)count;
+            if (total_d < 1.0e19) total *= (unsigned long long)count;
         }
-        if (fits && total >= (unsigned long long)heavy_min) {
-            heavy_list[atomicAdd(&counters[C_HEAVY], 1ull)] = p;
-            return;
+        if (total_d >= (double)lists.heavy_min) {
+            if (nc <= K6_LOCAL && widest <= K6B_CANDS && total_d <= 262144.0) {
+                lists.heavy[atomicAdd(&counters[C_HEAVY], 1ull)] = p;
+                return;
+            }
+            const bool shaped = nc <= K6C_MAXNC && widest <= 255 && entries <= K6C_ENTRIES;
+            if (total_d > (double)lists.limit || (!shaped && total_d > 1048576.0)) {
+                atomicAdd(&counters[C_TOO_MANY], 1ull);
+                atomicMax(&counters[C_TOO_MANY_KEY], keys[p]);
+                pair_flag[p] = 0;
+                return;
+            }
+            if (shaped) {
+                lists.pair_total[p] = total;
+                lists.huge_end[-1 - (int64_t)atomicAdd(&counters[C_HUGE], 1ull)] = p;
+                return;
+            }
         }
     }
     PairRows rows{&v, w0, nc, cur};
@@ -820,7 +796,7 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
                                                              int64_t* __restrict__ pair_best,
                                                              double* __restrict__ pair_score, double* __restrict__ pair_scaling,
                                                              int32_t* __restrict__ pair_flag, unsigned long long* __restrict__ counters,
-                                                             int64_t* __restrict__ heavy_list, int heavy_min) {
+                                                             PairLists lists) {
     // statistics: one global atomic per warp (one per pair cost more than the scoring itself on the dense libraries;
     // a per-CTA sum needs a barrier, and finished warps parked at it were 23 % of the kernel's stall samples)
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -828,7 +804,7 @@ __global__ void __launch_bounds__(128) assemble_score_kernel(MatchView v, int64_
     int windows = 0;
     if (p < n_pairs && keys[p] != ~0ull)          // n_pairs = list capacity; all-ones = unused slot
         score_pair(v, p, keys, vals, entry_bits, p_begin, max_nc, scr_first, scr_cur, scr_best, pair_best, pair_score, pair_scaling,
-                   pair_flag, counters, heavy_list, heavy_min, combos, windows);
+                   pair_flag, counters, lists, combos, windows);
     unsigned long long w = (unsigned long long)windows;
     for (int sft = 16; sft > 0; sft >>= 1) {
         combos += __shfl_xor_sync(0xffffffffu, combos, sft);
@@ -1048,6 +1024,371 @@ __global__ void __launch_bounds__(32 * K6B_WARPS) score_heavy_kernel(MatchView v
     }
 }
 
+// ---- K6c: pairs whose combinations do not fit one warp ----------------------------------------------------------------
+// Work item = (pair, chunk of K6C_CHUNK combinations).  A CTA draws items from a ticket, builds the pair's candidate tables
+// in shared memory (compact: the candidates of window m are rows off[m] .. off[m] + count[m]), and its threads score the
+// chunk's combinations k, k + 256, ... with the arithmetic of the K6 fast path; the best under the reference's
+// (score, scaling, peaks) order goes to the item's slot.  huge_reduce_kernel then picks the best item of every pair.
+__global__ void huge_items_kernel(int64_t n_huge, const int64_t* __restrict__ huge_end, const unsigned long long* __restrict__ pair_total,
+                                  int64_t item_cap, int64_t* __restrict__ item_pair, int64_t* __restrict__ item_chunk,
+                                  int64_t* __restrict__ huge_first, int64_t* __restrict__ huge_items,
+                                  unsigned long long* __restrict__ counters) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_huge) return;
+    const int64_t p = huge_end[-1 - h];
+    const int64_t n = (int64_t)((pair_total[p] + K6C_CHUNK - 1) / K6C_CHUNK);
+    const int64_t first = (int64_t)atomicAdd(&counters[C_ITEMS], (unsigned long long)n);
+    huge_first[h] = first;
+    huge_items[h] = n;
+    for (int64_t j = 0; j < n && first + j < item_cap; ++j) {
+        item_pair[first + j] = p;
+        item_chunk[first + j] = j;
+    }
+}
+
+struct HugeShared {
+    int64_t row[K6C_ENTRIES];
+    double mmz[K6C_ENTRIES], mi[K6C_ENTRIES], p[K6C_ENTRIES], mz_term[K6C_ENTRIES];
+    double ri[K6C_MAXNC], ci[K6C_MAXNC], span[K6C_MAXNC];
+    int count[K6C_MAXNC], off[K6C_MAXNC];              // count < 0: candidates of a window below the intensity floor (not enumerated)
+    double best_score[K6C_THREADS], best_scaling[K6C_THREADS];
+    unsigned char best_digits[K6C_THREADS][K6C_MAXNC];
+    int have[K6C_THREADS];
+    long long item;
+};
+
+__device__ __forceinline__ bool huge_greater(const HugeShared& S, int nc, double s_a, double f_a, const unsigned char* d_a, double s_b,
+                                             double f_b, const unsigned char* d_b) {
+    if (s_a != s_b) return s_a > s_b;
+    if (f_a != f_b) return f_a > f_b;
+    for (int m = 0; m < nc; ++m) {
+        if (S.count[m] == 0 || d_a[m] == d_b[m]) continue;
+        const int a = S.off[m] + d_a[m], b = S.off[m] + d_b[m];
+        if (S.mmz[a] != S.mmz[b]) return S.mmz[a] > S.mmz[b];
+        if (S.mi[a] != S.mi[b]) return S.mi[a] > S.mi[b];
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(K6C_THREADS) score_huge_kernel(MatchView v, const unsigned long long* __restrict__ keys,
+                                                                 const unsigned long long* __restrict__ vals, int entry_bits,
+                                                                 int64_t p_begin, int max_nc, int64_t n_items,
+                                                                 const int64_t* __restrict__ item_pair, const int64_t* __restrict__ item_chunk,
+                                                                 const unsigned long long* __restrict__ pair_total,
+                                                                 double* __restrict__ item_score, double* __restrict__ item_scaling,
+                                                                 int64_t* __restrict__ item_rows, int32_t* __restrict__ item_have,
+                                                                 unsigned long long* __restrict__ counters) {
+    extern __shared__ unsigned char huge_smem[];
+    HugeShared& S = *reinterpret_cast<HugeShared*>(huge_smem);
+    const int tid = threadIdx.x;
+    const double one_minus_xi = __dsub_rn(1.0, v.xi);
+    const double one_plus_reli = __dadd_rn(1.0, v.rel_i);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) S.item = (long long)atomicAdd(&counters[C_ITEM_TICKET], 1ull);
+        __syncthreads();
+        const int64_t item = S.item;
+        if (item >= n_items) break;
+        const int64_t p = item_pair[item];
+        const int64_t s = (int64_t)(keys[p] >> entry_bits);
+        const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
+        const int64_t row0 = p_begin + (int64_t)(vals[p] >> 16);
+        const int64_t sb = __ldg(&v.offsets[s]), se = __ldg(&v.offsets[s + 1]);
+        int64_t ca, cb;
+        entry_clamp(v, sb, se, x, ca, cb);
+        const int64_t w0 = __ldg(&v.ent_win_off[x]);
+        const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - w0);
+        // candidates of window m (distinct buckets in [lo, hi], first row of each), counted, then written behind off[m]
+        for (int pass = 0; pass < 2; ++pass) {
+            if (tid < nc) {
+                const int m = tid;
+                const int32_t lo = __ldg(&v.win_lo[w0 + m]), hi = __ldg(&v.win_hi[w0 + m]);
+                const double ri = __ldg(&v.win_ri[w0 + m]), cmz = __ldg(&v.win_cmz[w0 + m]);
+                int count = 0;
+                int32_t last = INT32_MIN;
+                for (int64_t j = row0; j < cb; ++j) {
+                    const int32_t tj = tmz_at(v.peaks, j, v.precision);
+                    if (tj > hi) break;
+                    if (tj == last || tj < lo) {
+                        last = tj;
+                        continue;
+                    }
+                    last = tj;
+                    if (pass == 1) {
+                        const int e = S.off[m] + count;
+                        const double2 row = __ldg(&v.peaks[j]);
+                        S.row[e] = j;
+                        S.mmz[e] = row.x;
+                        S.mi[e] = row.y;
+                        S.p[e] = __dmul_rn(row.y, ri);
+                        double term = 0.0;
+                        if (cmz > QMS_DBL_EPS) {
+                            const double err = __ddiv_rn(fabs(__dsub_rn(row.x, cmz)), cmz);
+                            const double local = err > v.rel_mz ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, v.rel_mz));
+                            term = __dmul_rn(local, ri);
+                        }
+                        S.mz_term[e] = term;
+                    }
+                    ++count;
+                }
+                if (pass == 0) {
+                    S.ri[m] = ri;
+                    S.ci[m] = (double)__ldg(&v.win_ci[w0 + m]);
+                    S.span[m] = __dsub_rn(one_plus_reli, ri);
+                    S.count[m] = ri < v.min_rel ? -count : count;
+                }
+            }
+            __syncthreads();
+            if (pass == 0 && tid == 0) {
+                int run = 0;
+                for (int m = 0; m < nc; ++m) {
+                    S.off[m] = run;
+                    run += S.count[m] < 0 ? -S.count[m] : S.count[m];
+                }
+            }
+            __syncthreads();
+        }
+        // combination-independent sums, in window order (every thread redundantly: uniform)
+        double calculated = 0.0, ri_sum = 0.0;
+        unsigned long long total = 1;
+        for (int m = 0; m < nc; ++m) {
+            const int c = S.count[m];
+            if (S.ri[m] < v.min_rel) continue;
+            if (c > 0) {
+                calculated = __dadd_rn(calculated, __dmul_rn(S.ci[m], S.ri[m]));
+                total *= (unsigned long long)c;
+            }
+            ri_sum = __dadd_rn(ri_sum, S.ri[m]);
+        }
+        const unsigned long long begin = (unsigned long long)item_chunk[item] * K6C_CHUNK;
+        unsigned long long end = begin + K6C_CHUNK;
+        if (end > total) end = total;
+        // mixed-radix digits of this thread's first combination (last window fastest) and of the stride
+        unsigned char digits[K6C_MAXNC], stride[K6C_MAXNC], best[K6C_MAXNC];
+        {
+            unsigned long long value = begin + (unsigned long long)tid, step = K6C_THREADS;
+            for (int m = nc - 1; m >= 0; --m) {
+                const int c = S.count[m];
+                digits[m] = stride[m] = best[m] = 0;
+                if (c <= 0) continue;
+                digits[m] = (unsigned char)(value % (unsigned long long)c);
+                value /= (unsigned long long)c;
+                stride[m] = (unsigned char)(step % (unsigned long long)c);
+                step /= (unsigned long long)c;
+            }
+        }
+        double b_score = 0.0, b_scaling = 0.0;
+        bool have = false;
+        for (unsigned long long k = begin + (unsigned long long)tid; k < end; k += K6C_THREADS) {
+            double measured = 0.0;
+            for (int m = 0; m < nc; ++m)
+                if (S.count[m] > 0) measured = __dadd_rn(measured, S.p[S.off[m] + digits[m]]);
+            const double scaling = __ddiv_rn(measured, calculated);
+            double mz_score = 0.0, i_score = 0.0;
+            for (int m = 0; m < nc; ++m) {
+                if (S.count[m] <= 0) continue;
+                const int e = S.off[m] + digits[m];
+                double term = 0.0;
+                const double si = __dmul_rn(S.ci[m], scaling);
+                if (si > QMS_DBL_EPS) {
+                    const double err = __ddiv_rn(fabs(__dsub_rn(S.mi[e], si)), si);
+                    const double span = S.span[m];
+                    const double local = err > span ? 0.0 : __dsub_rn(1.0, __ddiv_rn(err, span));
+                    term = __dmul_rn(local, S.ri[m]);
+                }
+                mz_score = __dadd_rn(mz_score, S.mz_term[e]);
+                i_score = __dadd_rn(i_score, term);
+            }
+            mz_score = __ddiv_rn(mz_score, ri_sum);
+            i_score = __ddiv_rn(i_score, ri_sum);
+            const double score = __dadd_rn(__dmul_rn(mz_score, v.xi), __dmul_rn(i_score, one_minus_xi));
+            if (!have || huge_greater(S, nc, score, scaling, digits, b_score, b_scaling, best)) {
+                have = true;
+                b_score = score;
+                b_scaling = scaling;
+                for (int m = 0; m < nc; ++m) best[m] = digits[m];
+            }
+            int carry = 0;                                   // digits += stride, least significant (last) window first
+            for (int m = nc - 1; m >= 0; --m) {
+                const int c = S.count[m];
+                if (c <= 0) continue;
+                int dgt = (int)digits[m] + (int)stride[m] + carry;
+                carry = dgt >= c;
+                if (carry) dgt -= c;
+                digits[m] = (unsigned char)dgt;
+            }
+        }
+        S.best_score[tid] = b_score;
+        S.best_scaling[tid] = b_scaling;
+        S.have[tid] = have;
+        for (int m = 0; m < nc; ++m) S.best_digits[tid][m] = best[m];
+        __syncthreads();
+        if (tid == 0) {
+            int win = -1;
+            for (int t = 0; t < K6C_THREADS; ++t) {
+                if (!S.have[t]) continue;
+                if (win < 0 || huge_greater(S, nc, S.best_score[t], S.best_scaling[t], S.best_digits[t], S.best_score[win],
+                                            S.best_scaling[win], S.best_digits[win]))
+                    win = t;
+            }
+            item_have[item] = win >= 0;
+            if (win >= 0) {
+                item_score[item] = S.best_score[win];
+                item_scaling[item] = S.best_scaling[win];
+                int64_t* rows = item_rows + item * max_nc;
+                for (int m = 0; m < nc; ++m) {
+                    const int c = S.count[m];
+                    rows[m] = c == 0 ? -1 : S.row[S.off[m] + (c > 0 ? S.best_digits[win][m] : 0)];
+                }
+            }
+        }
+    }
+}
+
+// best item of every K6c pair under (score, scaling, peaks); thresholds of match_all (IL:1860-1870)
+__global__ void huge_reduce_kernel(MatchView v, int64_t n_huge, const int64_t* __restrict__ huge_end, const unsigned long long* __restrict__ keys,
+                                   int entry_bits, int max_nc, const int64_t* __restrict__ huge_first, const int64_t* __restrict__ huge_items,
+                                   const unsigned long long* __restrict__ pair_total, const double* __restrict__ item_score,
+                                   const double* __restrict__ item_scaling, const int64_t* __restrict__ item_rows,
+                                   const int32_t* __restrict__ item_have, int64_t* __restrict__ pair_best, double* __restrict__ pair_score,
+                                   double* __restrict__ pair_scaling, int32_t* __restrict__ pair_flag,
+                                   unsigned long long* __restrict__ counters) {
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_huge) return;
+    const int64_t p = huge_end[-1 - h];
+    const int32_t x = (int32_t)(keys[p] & ((1ull << entry_bits) - 1ull));
+    const int nc = (int)(__ldg(&v.ent_win_off[x + 1]) - __ldg(&v.ent_win_off[x]));
+    int64_t win = -1;
+    for (int64_t it = huge_first[h]; it < huge_first[h] + huge_items[h]; ++it) {
+        if (!item_have[it]) continue;
+        bool better = win < 0;
+        if (!better) {
+            if (item_score[it] != item_score[win])
+                better = item_score[it] > item_score[win];
+            else if (item_scaling[it] != item_scaling[win])
+                better = item_scaling[it] > item_scaling[win];
+            else {
+                const int64_t* a_rows = item_rows + it * max_nc;
+                const int64_t* b_rows = item_rows + win * max_nc;
+                for (int m = 0; m < nc; ++m) {
+                    if (a_rows[m] < 0 || a_rows[m] == b_rows[m]) continue;
+                    const double2 a = __ldg(&v.peaks[a_rows[m]]), b = __ldg(&v.peaks[b_rows[m]]);
+                    if (a.x != b.x) {
+                        better = a.x > b.x;
+                        break;
+                    }
+                    if (a.y != b.y) {
+                        better = a.y > b.y;
+                        break;
+                    }
+                }
+            }
+        }
+        if (better) win = it;
+    }
+    bool pass = win >= 0;
+    int n_matched = 0;
+    if (win >= 0) {
+        const int64_t* rows = item_rows + win * max_nc;
+        int64_t* out = pair_best + p * max_nc;
+        for (int m = 0; m < nc; ++m) {
+            out[m] = rows[m];
+            n_matched += rows[m] >= 0;
+        }
+        pair_score[p] = item_score[win];
+        pair_scaling[p] = item_scaling[win];
+        if (v.only_entry < 0) {
+            if (item_score[win] < v.score_thr) pass = false;
+            if (n_matched < v.min_match) pass = false;
+        }
+    }
+    pair_flag[p] = pass ? nc : 0;
+    atomicAdd(&counters[C_COMBOS], pair_total[p]);
+    atomicAdd(&counters[C_PAIR_WINDOWS], (unsigned long long)nc);
+}
+
+static int score_huge_pairs(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, const unsigned long long* keys, const unsigned long long* vals,
+                            int entry_bits, int64_t p_begin, unsigned long long n_huge_pairs, unsigned long long n_too_many,
+                            unsigned long long too_many_key);
+
+// K6b over the list assemble_score_kernel has filled (reads its count on the device); with `and_huge` the host also looks at
+// the K6c list right away (one extra round trip), otherwise the caller does so when it reads the counters anyway.
+static int score_listed_pairs(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, const unsigned long long* keys, const unsigned long long* vals,
+                              int entry_bits, int64_t p_begin, bool and_huge) {
+    const int max_nc = ctx->max_nc > 0 ? ctx->max_nc : 1;
+    int64_t hblocks = (n_pairs + K6B_WARPS - 1) / K6B_WARPS;
+    const int64_t hmax = (int64_t)ctx->sm_count * 8;
+    if (hblocks > hmax) hblocks = hmax;
+    score_heavy_kernel<<<(unsigned)hblocks, 32 * K6B_WARPS, 0, ctx->stream>>>(
+        v, keys, vals, entry_bits, p_begin, max_nc, ctx->heavy_list.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p,
+        ctx->pair_flag.p, ctx->dev_counters.p);
+    QMS_CUDA(ctx, cudaGetLastError());
+    ctx->cnt.kernel_launches++;
+    if (!and_huge) return QMS_OK;
+    // K6c needs its pair count on the host (item buffers)
+    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 56, ctx->dev_counters.p + C_HUGE, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 57, ctx->dev_counters.p + C_TOO_MANY, 2 * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return score_huge_pairs(ctx, v, n_pairs, keys, vals, entry_bits, p_begin, ctx->h_pinned[56], ctx->h_pinned[57], ctx->h_pinned[58]);
+}
+
+static int score_huge_pairs(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, const unsigned long long* keys, const unsigned long long* vals,
+                            int entry_bits, int64_t p_begin, unsigned long long n_huge_pairs, unsigned long long n_too_many,
+                            unsigned long long too_many_key) {
+    const int max_nc = ctx->max_nc > 0 ? ctx->max_nc : 1;
+    if (n_too_many) {
+        const unsigned long long key = too_many_key;
+        return qms_fail(ctx, QMS_E_LIMIT,
+                        "%llu (spectrum, entry) pair(s) hold more candidate combinations than the limit of %llu (IL:2004-2034 would "
+                        "enumerate them all); e.g. spectrum %llu of the batch, index entry %llu -- narrow REL_MZ_RANGE or raise the "
+                        "limit (qms_set_tuning \"combination_limit_log2\")",
+                        n_too_many, (unsigned long long)ctx->combination_limit,
+                        (unsigned long long)(key >> entry_bits), (unsigned long long)(key & ((1ull << entry_bits) - 1ull)));
+    }
+    const int64_t n_huge = (int64_t)n_huge_pairs;
+    if (n_huge == 0) return QMS_OK;
+    const int64_t item_cap = (int64_t)((ctx->combination_budget + K6C_CHUNK - 1) / K6C_CHUNK) + n_huge;
+    QMS_TRY(qms_reserve(ctx, ctx->item_pair, (size_t)item_cap));
+    QMS_TRY(qms_reserve(ctx, ctx->item_chunk, (size_t)item_cap));
+    QMS_TRY(qms_reserve(ctx, ctx->huge_first, (size_t)n_huge));
+    QMS_TRY(qms_reserve(ctx, ctx->huge_items, (size_t)n_huge));
+    int64_t* huge_end = ctx->heavy_list.p + n_pairs;
+    huge_items_kernel<<<qms_blocks(n_huge, 128), 128, 0, ctx->stream>>>(n_huge, huge_end, ctx->pair_total.p, item_cap, ctx->item_pair.p,
+                                                                       ctx->item_chunk.p, ctx->huge_first.p, ctx->huge_items.p,
+                                                                       ctx->dev_counters.p);
+    QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 56, ctx->dev_counters.p + C_ITEMS, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t n_items = (int64_t)ctx->h_pinned[56];
+    if (n_items > item_cap)
+        return qms_fail(ctx, QMS_E_LIMIT,
+                        "the batch holds more than %llu candidate combinations in pairs of many candidates (%lld chunks of 2^20); "
+                        "narrow REL_MZ_RANGE, send fewer spectra per batch or raise the budget (qms_set_tuning \"combination_budget_log2\")",
+                        (unsigned long long)ctx->combination_budget, (long long)n_items);
+    QMS_TRY(qms_reserve(ctx, ctx->item_score, (size_t)n_items));
+    QMS_TRY(qms_reserve(ctx, ctx->item_scaling, (size_t)n_items));
+    QMS_TRY(qms_reserve(ctx, ctx->item_have, (size_t)n_items));
+    QMS_TRY(qms_reserve(ctx, ctx->item_rows, (size_t)n_items * (size_t)max_nc + 1));
+    static bool attr_set = false;
+    if (!attr_set) {
+        QMS_CUDA(ctx, cudaFuncSetAttribute(score_huge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HugeShared)));
+        attr_set = true;
+    }
+    int64_t blocks = n_items < (int64_t)ctx->sm_count * 2 ? n_items : (int64_t)ctx->sm_count * 2;
+    score_huge_kernel<<<(unsigned)blocks, K6C_THREADS, sizeof(HugeShared), ctx->stream>>>(
+        v, keys, vals, entry_bits, p_begin, max_nc, n_items, ctx->item_pair.p, ctx->item_chunk.p, ctx->pair_total.p, ctx->item_score.p,
+        ctx->item_scaling.p, ctx->item_rows.p, ctx->item_have.p, ctx->dev_counters.p);
+    huge_reduce_kernel<<<qms_blocks(n_huge, 128), 128, 0, ctx->stream>>>(
+        v, n_huge, huge_end, keys, entry_bits, max_nc, ctx->huge_first.p, ctx->huge_items.p, ctx->pair_total.p, ctx->item_score.p,
+        ctx->item_scaling.p, ctx->item_rows.p, ctx->item_have.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p,
+        ctx->pair_flag.p, ctx->dev_counters.p);
+    QMS_CUDA(ctx, cudaGetLastError());
+    ctx->cnt.kernel_launches += 3;
+    return QMS_OK;
+}
+
 // ---- K7: order-preserving warp-ballot compaction -----------------------------------------------------
 #define CMP_THREADS 256
 
@@ -1248,23 +1589,16 @@ int qms_score_pair_list(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, const
     QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)n_pairs));
     QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)n_pairs));
     QMS_TRY(qms_reserve(ctx, ctx->heavy_list, (size_t)n_pairs + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->pair_total, (size_t)n_pairs));
     QMS_CUDA(ctx, cudaMemsetAsync(ctx->pair_flag.p, 0, (size_t)n_pairs * sizeof(int32_t), ctx->stream));
+    const PairLists lists{heavy_min > 0 ? ctx->heavy_list.p : nullptr, ctx->heavy_list.p + n_pairs, ctx->pair_total.p, heavy_min,
+                          ctx->combination_limit};
     assemble_score_kernel<<<qms_blocks(n_pairs, 128), 128, 0, ctx->stream>>>(
         v, n_pairs, keys, vals, entry_bits, p_begin, max_nc, ctx->scr_first.p, ctx->scr_cur.p, ctx->scr_best.p, ctx->pair_best.p,
-        ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p, heavy_min > 0 ? ctx->heavy_list.p : nullptr,
-        heavy_min);
+        ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p, lists);
     QMS_CUDA(ctx, cudaGetLastError());
     ctx->cnt.kernel_launches++;
-    if (heavy_min > 0) {
-        int64_t hblocks = (n_pairs + K6B_WARPS - 1) / K6B_WARPS;
-        const int64_t hmax = (int64_t)ctx->sm_count * 8;
-        if (hblocks > hmax) hblocks = hmax;
-        score_heavy_kernel<<<(unsigned)hblocks, 32 * K6B_WARPS, 0, ctx->stream>>>(
-            v, keys, vals, entry_bits, p_begin, max_nc, ctx->heavy_list.p, ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p,
-            ctx->pair_flag.p, ctx->dev_counters.p);
-        QMS_CUDA(ctx, cudaGetLastError());
-        ctx->cnt.kernel_launches++;
-    }
+    if (heavy_min > 0) QMS_TRY(score_listed_pairs(ctx, v, n_pairs, keys, vals, entry_bits, p_begin, true));
     return QMS_OK;
 }
 
@@ -1582,13 +1916,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     // sentinel key that sorts behind every real (spectrum, entry) key, so the sort, the window scan and the scoring
     // kernels can be launched over the capacity without knowing the pair count (no host round trip after the gate).
     ctx->last_values = true;
-    static int variant = -1;   // QMS_PROBE_VARIANT: tuning switch for profiling runs (default = best measured)
-    if (variant < 0) {
-        const char* e = getenv("QMS_PROBE_VARIANT");
-        variant = e ? atoi(e) : 4;
-    }
-    const int unroll = (variant == 2 || variant == 3 || variant == 5) ? 8 : 4;
-    const int tile_shift = unroll == 8 ? 11 : 10;
+    const int unroll = 4, tile_shift = 10;      // rows per lane and log2(rows per probe tile)
     const int64_t tile = (int64_t)PROBE_THREADS * unroll;
     const int64_t tiles_total = (n_peaks + tile - 1) / tile;
     int64_t blocks = tiles_total;
@@ -1648,6 +1976,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         QMS_TRY(qms_reserve(ctx, ctx->pair_scaling, (size_t)cap));
         QMS_TRY(qms_reserve(ctx, ctx->pair_flag, (size_t)cap));
         QMS_TRY(qms_reserve(ctx, ctx->heavy_list, (size_t)cap + 1));
+        QMS_TRY(qms_reserve(ctx, ctx->pair_total, (size_t)cap));
         cblocks = qms_blocks(cap, CMP_THREADS);
         QMS_TRY(qms_reserve(ctx, ctx->blk_hits, (size_t)cblocks + 1));
         QMS_TRY(qms_reserve(ctx, ctx->blk_wins, (size_t)cblocks + 1));
@@ -1661,14 +1990,8 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         QMS_CUDA(ctx, cudaMemsetAsync(ctx->pair_keys.p, 0xFF, (size_t)cap * sizeof(unsigned long long), ctx->stream));
         QMS_CUDA(ctx, cudaMemsetAsync(ctx->pair_flag.p, 0, (size_t)cap * sizeof(int32_t), ctx->stream));
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-        switch (variant) {
-            case 1: spectrum_probe_kernel<4, true><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
-            case 2: spectrum_probe_kernel<8, false><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
-            case 3: spectrum_probe_kernel<8, true><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
-            case 5: spectrum_probe_warp_kernel<8><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
-            case 0: spectrum_probe_kernel<4, false><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
-            default: spectrum_probe_warp_kernel<4><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p, ctx->live_count.p); break;
-        }
+        spectrum_probe_warp_kernel<4><<<(unsigned)blocks, PROBE_THREADS, 0, ctx->stream>>>(v, p_begin, p_end, seg_cap, ctx->live_rows.p,
+                                                                                       ctx->live_count.p);
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
         tile_spectrum_kernel<<<qms_blocks(tiles_total + 1, 256) + 1, 256, 0, ctx->stream>>>(
@@ -1690,21 +2013,13 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         vals = ctx->pair_vals_alt.p;
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
         // K6 / K6b
+        const PairLists lists{heavy_min > 0 ? ctx->heavy_list.p : nullptr, ctx->heavy_list.p + cap, ctx->pair_total.p, heavy_min,
+                              ctx->combination_limit};
         assemble_score_kernel<<<qms_blocks(cap, 128), 128, 0, ctx->stream>>>(
             v, cap, keys, vals, entry_bits, p_begin, max_nc, ctx->scr_first.p, ctx->scr_cur.p, ctx->scr_best.p,
-            ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p,
-            heavy_min > 0 ? ctx->heavy_list.p : nullptr, heavy_min);
+            ctx->pair_best.p, ctx->pair_score.p, ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p, lists);
         QMS_CUDA(ctx, cudaGetLastError());
-        if (heavy_min > 0) {
-            int64_t hblocks = (cap + K6B_WARPS - 1) / K6B_WARPS;
-            const int64_t hmax = (int64_t)ctx->sm_count * 8;
-            if (hblocks > hmax) hblocks = hmax;
-            score_heavy_kernel<<<(unsigned)hblocks, 32 * K6B_WARPS, 0, ctx->stream>>>(
-                v, keys, vals, entry_bits, p_begin, max_nc, ctx->heavy_list.p, ctx->pair_best.p, ctx->pair_score.p,
-                ctx->pair_scaling.p, ctx->pair_flag.p, ctx->dev_counters.p);
-            ctx->cnt.kernel_launches++;
-        }
-        QMS_CUDA(ctx, cudaGetLastError());
+        if (heavy_min > 0) QMS_TRY(score_listed_pairs(ctx, v, cap, keys, vals, entry_bits, p_begin, false));
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
         // K7a: hit and window counts
         compact_count_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(cap, ctx->pair_flag.p, ctx->blk_hits.p,
@@ -1732,6 +2047,20 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
             return qms_fail(ctx, QMS_E_INPUT, "m/z values are not ascending inside %llu spectrum position(s)",
                             (unsigned long long)ctx->h_pinned[C_UNSORTED]);
         n_pairs = ctx->h_pinned[C_PAIRS];
+        if ((int64_t)n_pairs <= cap && (ctx->h_pinned[C_HUGE] || ctx->h_pinned[C_TOO_MANY])) {
+            // rare: pairs whose combinations are spread over CTAs (K6c) -- scored now, then the hits are counted again and
+            // emitted by the "did not fit" branch below
+            QMS_TRY(score_huge_pairs(ctx, v, cap, keys, vals, entry_bits, p_begin, ctx->h_pinned[C_HUGE], ctx->h_pinned[C_TOO_MANY],
+                                     ctx->h_pinned[C_TOO_MANY_KEY]));
+            compact_count_kernel<<<(unsigned)cblocks, CMP_THREADS, 0, ctx->stream>>>(cap, ctx->pair_flag.p, ctx->blk_hits.p, ctx->blk_wins.p);
+            compact_scan_kernel<<<1, 32, 0, ctx->stream>>>(cblocks, ctx->blk_hits.p, ctx->blk_wins.p, ctx->dev_counters.p + 40);
+            QMS_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->dev_counters.p, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                          ctx->stream));
+            QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->cnt.kernel_launches += 2;
+            target.cap_hits = target.cap_windows = -1;       // whatever was emitted before is stale
+            target.callers = false;
+        }
         int64_t want = ((int64_t)(n_pairs + n_pairs / 4) + 4095) / 4096 * 4096;   // 25 % head room, 4 Ki granules
         if (want < 4096) want = 4096;
         ctx->pair_cap_hint = want;

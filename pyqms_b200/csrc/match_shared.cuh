@@ -8,7 +8,7 @@
 
 // slots of the device counter block (slots 40 / 41: hit and hit-window totals of the compaction scan)
 enum { C_LIVE = 0, C_INCID, C_PAIRS, C_UNSORTED, C_COMBOS, C_HEAVY, C_PAIR_WINDOWS, C_GATE_TICKET, C_SPEC_TICKET, C_MULTI, C_STAGE_HITS,
-       C_STAGE_WINDOWS, C_GATED, C_BOUND, C_N };
+       C_STAGE_WINDOWS, C_GATED, C_BOUND, C_HUGE, C_ITEMS, C_ITEM_TICKET, C_TOO_MANY, C_TOO_MANY_KEY, C_N };
 
 struct MatchView {
     const double2* peaks;

@@ -124,6 +124,12 @@ struct qms_ctx {
     DBuf<int64_t> d_offsets;
     DBuf<unsigned long long> pair_keys, pair_keys_alt, pair_vals, pair_vals_alt;
     DBuf<int64_t> pair_nc, scr_first, scr_cur, scr_best, heavy_list;
+    DBuf<unsigned long long> pair_total;                       // K6c: combinations of a pair
+    DBuf<int64_t> item_pair, item_chunk, item_rows, huge_first, huge_items;
+    DBuf<double> item_score, item_scaling;
+    DBuf<int32_t> item_have;
+    unsigned long long combination_limit = 1ull << 32;         // per (spectrum, entry) pair; above it the batch fails with QMS_E_LIMIT
+    unsigned long long combination_budget = 1ull << 35;        // per batch, over the pairs K6c enumerates
     DBuf<int32_t> tile_spec;
     int32_t max_nc = 0;            // most c-peak windows of any index entry
     DBuf<int32_t> need_of_nc;      // per window count: buckets needed to pass the overlap gates (params x library)

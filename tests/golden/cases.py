@@ -122,4 +122,9 @@ CASES = {
         lib=dict(molecules=BSA_MOLECULES, charges=[1, 2, 3, 4], fixed_labels=CAM_FIXED_LABEL,
                  metabolic_labels={"15N": [round(0.01 * i, 2) for i in range(100)]}),
         run=dict(n_spectra=20, mean_peaks=300, seed=27, elution_sigma=1.0, entry_fraction=0.004), skip_trees=True, heavy=True),
+    # wide windows, ten candidates in every window of a six-window entry: 10^6 candidate combinations for one pair
+    # (IL:2004-2034; the reference enumerates and sorts them all -- minutes and ~1 GB for this one spectrum)
+    "many_candidates": dict(
+        lib=dict(molecules=["LKPDPNTLCDEFK"], charges=[2], params={"REL_MZ_RANGE": 1e-4, "M_SCORE_THRESHOLD": 0.1}),
+        run=dict(n_spectra=1, mean_peaks=40, seed=28, elution_sigma=3.0, entry_fraction=0.0, crowd=10), heavy=True),
 }

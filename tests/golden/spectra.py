@@ -19,6 +19,7 @@ def entry_peaks(lib):
 def draw_case_spectra(lib, run, name):
     run = dict(run)
     dense = run.pop("dense", False)
+    crowd = run.pop("crowd", 0)
     offset_ppm = run.pop("offset_ppm", 0.0)
     mzs, cis = entry_peaks(lib)
     lo = float(lib.params["LOWER_MZ_LIMIT"]) - 30
@@ -44,6 +45,30 @@ def draw_case_spectra(lib, run, name):
         peaks = np.ascontiguousarray(allp[order])
         offsets = np.zeros(len(offsets), dtype=np.int64)
         np.cumsum(np.bincount(spec, minlength=len(offsets) - 1), out=offsets[1:])
+    if crowd:
+        # `crowd` peaks in distinct 1/P-Da buckets inside every window of every entry, in every spectrum: crowd ** n_c
+        # candidate combinations per (spectrum, entry) pair (IL:2004-2034)
+        rng = np.random.default_rng(run["seed"] + 2000)
+        rel = float(lib.params["REL_MZ_RANGE"])
+        precision = float(lib.params["INTERNAL_PRECISION"])
+        n_spec = len(offsets) - 1
+        rows = [[] for _ in range(n_spec)]
+        for mz_list, ci_list in zip(mzs, cis):
+            for mz, ci in zip(mz_list, ci_list):
+                half = int(mz * rel * precision) - 1
+                for s in range(n_spec):
+                    picks = rng.choice(np.arange(-half, half + 1), size=crowd, replace=False)
+                    for b in picks:
+                        rows[s].append(((round(mz * precision) + int(b)) / precision,
+                                        float(ci * 40.0 * rng.uniform(0.5, 1.5))))
+        spec = np.repeat(np.arange(n_spec), np.diff(offsets))
+        extra_spec = np.concatenate([np.full(len(r), s) for s, r in enumerate(rows)])
+        allp = np.concatenate([peaks] + [np.array(r).reshape(-1, 2) for r in rows])
+        spec = np.concatenate([spec, extra_spec])
+        order = np.lexsort((allp[:, 1], allp[:, 0], spec))
+        peaks = np.ascontiguousarray(allp[order])
+        offsets = np.zeros(n_spec + 1, dtype=np.int64)
+        np.cumsum(np.bincount(spec, minlength=n_spec), out=offsets[1:])
     if name == "c1_basic":   # prepend the docs' quick-start spectrum as spectrum 0
         qs = np.array(QUICK_START_PEAKS)
         peaks = np.concatenate([qs, peaks])

@@ -253,6 +253,24 @@ def test_match_isotopologue_of_a_list_spectrum(pyqms):
     assert matched > 30
 
 
+def test_combination_limit_is_reported_not_enumerated(pyqms):
+    """A pair with more candidate combinations than the limit fails the batch (QMS_E_LIMIT) instead of occupying the GPU for
+    as long as the reference's enumeration would take (IL:2004-2034); below the limit the CTA-cooperative kernel handles it."""
+    from pyqms_b200._capi import QmsError
+    blob, peaks, offsets = load_case("many_candidates")
+    lib = pyqms.IsotopologueLibrary(verbose=False, **CASES["many_candidates"]["lib"])
+    for mode in (0, 1):
+        lib._ctx.set_tuning("dense_mode", mode)
+        lib._ctx.set_tuning("combination_limit_log2", 16)
+        with pytest.raises(QmsError) as failure:
+            lib.match_packed(peaks, offsets)
+        assert failure.value.code == -5 and "candidate combinations" in str(failure.value)
+        lib._ctx.set_tuning("combination_limit_log2", 32)
+        before = lib.device_counters()["combinations"]
+        out = lib.match_packed(peaks, offsets)
+        assert out["n_hits"] == 1 and lib.device_counters()["combinations"] - before >= 10 ** 6
+
+
 def test_edge_cases(pyqms):
     lib = pyqms.IsotopologueLibrary(molecules=["DDSPDLPK", "LVTDLTK"], charges=[1, 2], verbose=False)
     assert len(lib.match_all(mz_i_list=[], file_name="f", spec_id=0, spec_rt=0.0)) == 0

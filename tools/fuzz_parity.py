@@ -79,6 +79,8 @@ def check(seed):
         print("seed %d: empty library, skipped" % seed)
         return
     lib = pyqms_b200.IsotopologueLibrary(verbose=False, **kwargs)
+    dense = seed % 2 == 1                                # odd seeds: the spectrum-resident matcher wherever the library allows it
+    lib._ctx.set_tuning("dense_mode", 1 if dense else 0)
     peaks, offsets = synth_run(*entry_peaks(oracle), **run)
     want, got = {}, None
     spectra = [peaks[offsets[s]:offsets[s + 1]] for s in range(len(offsets) - 1)]
@@ -90,8 +92,9 @@ def check(seed):
     tie_prone = any(len(v) > 2 for v in (kwargs["metabolic_labels"] or {}).values()) or len(kwargs["metabolic_labels"] or {}) > 1
     assert_results_equal(results_to_rows(got), results_to_rows(want), score_tol=1e-6, cmz_rel=1e-12, ri_rel=1e-9, key_order=not tie_prone)
     hits = sum(len(v) for v in want.values())
-    print("seed %d: ok  entries %d, %d spectra (%s), %d keys, %d hits, %.1f s" % (
-        seed, len(oracle.formulas_sorted_by_mz), len(spectra), "lists" if as_lists else "numpy", len(want), hits, time.time() - t0), flush=True)
+    print("seed %d: ok  entries %d, %d spectra (%s), %d keys, %d hits, %d spectrum-resident batches, %.1f s" % (
+        seed, len(oracle.formulas_sorted_by_mz), len(spectra), "lists" if as_lists else "numpy", len(want), hits,
+        lib.device_counters()["dense_batches"], time.time() - t0), flush=True)
 
 
 if __name__ == "__main__":
