@@ -416,7 +416,8 @@ def run_ours(args):
     e2e_value = world * n_spec * args.steps / float(t.item())
     h2d = int(peaks.nbytes + offsets.nbytes)
     own = out if world == 1 else gather_stats.get("own", out)
-    d2h = int(sum(np.asarray(own[k]).nbytes for k in ("spec", "entry", "score", "scaling", "win_off", "peak")))
+    d2h = int(sum(dict.__getitem__(own, k).nbytes for k in ("spec", "entry", "score", "scaling", "win_off", "peak", "peak32", "mmz", "mi")
+                  if k in dict.keys(own)))      # the arrays the device copied out (lazily gathered ones do not count)
     e2e_counters = ctx.counters()
 
     # ---- roofline of the kernel that dominates the step (SURVEY.md 8d algorithmic bytes)

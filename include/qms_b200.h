@@ -97,7 +97,8 @@ int qms_device_bytes(qms_ctx* ctx, int64_t* out);    /* device memory currently 
  *                 a batch with a pair above it fails with QMS_E_LIMIT instead of enumerating for hours like the reference
  *   "combination_budget_log2"  log2 of the combinations of all many-candidate pairs of one batch (default 35)
  *   "sub_batch_rows"  peak rows per sub-batch when a host-resident run is pipelined (copies of neighbouring sub-batches
- *                 overlap the kernels); 0 = default (16 Mi rows) */
+ *                 overlap the kernels); 0 = automatic (16 Mi rows, 8 Mi or 4 Mi when the copies of
+ *                 the previous run took more than half / four fifths of the kernels' time, as they do with eight GPUs on one host) */
 int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value);
 
 /* Page-locked host memory for spectrum and hit buffers (cudaHostAlloc, portable): copies to and from such buffers run
@@ -218,7 +219,8 @@ int qms_transform_mz(qms_ctx* ctx, int64_t n, const double* mz, int32_t* lo, int
  * is the size query of that two-call pattern.
  *   hit_spec[h], hit_entry[h], hit_score[h], hit_scaling[h], hit_win_off[h] (cap_hits+1 entries)
  *   per hit window w in [hit_win_off[h], hit_win_off[h+1]): hit_mmz[w], hit_mi[w] (NaN = None,
- *   IL:1994-2000) and hit_peak[w] = row of the matched peak in `peaks` (-1 = None).
+ *   IL:1994-2000) and hit_peak[w] = row of the matched peak in `peaks` (-1 = None); hit_peak32[w] = the same row
+ *   counted from offsets[0], as int32.
  * Any output pointer may be NULL to skip it. */
 typedef struct qms_hits {
     int64_t cap_hits, cap_windows;
@@ -230,6 +232,9 @@ typedef struct qms_hits {
     double* hit_mmz;
     double* hit_mi;
     int64_t* hit_peak;
+    int32_t* hit_peak32;   /* optional narrow form of hit_peak: row of the matched peak counted from the first row of the batch
+                            * (offsets[0]), -1 = None; half the bytes on the way to the host.  Filled if not NULL (hit_peak may
+                            * then be NULL). */
 } qms_hits;
 int qms_match_batch(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra,
                     int32_t input_kind, double mz_score_percentile, qms_hits* out, int64_t* n_hits,

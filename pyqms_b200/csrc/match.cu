@@ -1509,6 +1509,33 @@ static int copy_out(qms_ctx* ctx, T* dst, const T* src, size_t n) {
     return QMS_OK;
 }
 
+__global__ void narrow_peaks_kernel(int64_t n, const int64_t* __restrict__ rows, int64_t base, int32_t* __restrict__ narrow) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) narrow[i] = rows[i] < 0 ? -1 : (int32_t)(rows[i] - base);
+}
+
+// hit_peak32, step 1: rows [w0, w0 + n) of the retained o_peak, counted from `base`, narrowed on `stream` -- into the
+// caller's array if that is device memory, else into o_peak32 (step 2 copies it out)
+static int narrow_peak32(qms_ctx* ctx, cudaStream_t stream, int32_t* dst, int64_t w0, size_t n, int64_t base) {
+    if (!dst || !n) return QMS_OK;
+    int32_t* narrow = dst;
+    if (!qms_is_device_ptr(dst)) {
+        QMS_TRY(qms_reserve(ctx, ctx->o_peak32, ctx->o_peak.cap));      // same shape as o_peak, so offsets agree
+        narrow = ctx->o_peak32.p + w0;
+    }
+    narrow_peaks_kernel<<<qms_blocks((int64_t)n, 256), 256, 0, stream>>>((int64_t)n, ctx->o_peak.p + w0, base, narrow);
+    QMS_CUDA(ctx, cudaGetLastError());
+    ctx->cnt.kernel_launches++;
+    return QMS_OK;
+}
+
+static int copy_out_peak32(qms_ctx* ctx, cudaStream_t stream, int32_t* dst, int64_t w0, size_t n, int64_t base, bool narrowed = false) {
+    if (!dst || !n) return QMS_OK;
+    if (!narrowed) QMS_TRY(narrow_peak32(ctx, stream, dst, w0, n, base));
+    if (!qms_is_device_ptr(dst)) return qms_copy_to_host(ctx, dst, ctx->o_peak32.p + w0, n * sizeof(int32_t), stream);
+    return QMS_OK;
+}
+
 static float elapsed(qms_ctx* ctx, int a, int b) {
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
@@ -1530,7 +1557,7 @@ struct EmitTarget {
 static EmitTarget emit_target(qms_ctx* ctx, const qms_hits* out) {
     EmitTarget t;
     const bool callers = out && out->hit_spec && out->hit_entry && out->hit_score && out->hit_scaling && out->hit_win_off &&
-                         out->hit_mmz && out->hit_mi && out->hit_peak && qms_is_device_ptr(out->hit_spec) &&
+                         out->hit_mmz && out->hit_mi && out->hit_peak && !out->hit_peak32 && qms_is_device_ptr(out->hit_spec) &&
                          qms_is_device_ptr(out->hit_entry) && qms_is_device_ptr(out->hit_score) && qms_is_device_ptr(out->hit_scaling) &&
                          qms_is_device_ptr(out->hit_win_off) && qms_is_device_ptr(out->hit_mmz) && qms_is_device_ptr(out->hit_mi) &&
                          qms_is_device_ptr(out->hit_peak);
@@ -1604,7 +1631,8 @@ int qms_score_pair_list(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, const
 
 // caller buffers the emit kernels can write directly: all in device memory (the matched values are optional)
 static bool callers_on_device(const qms_hits* out) {
-    if (!out || !out->hit_spec || !out->hit_entry || !out->hit_score || !out->hit_scaling || !out->hit_win_off || !out->hit_peak)
+    if (!out || !out->hit_spec || !out->hit_entry || !out->hit_score || !out->hit_scaling || !out->hit_win_off || !out->hit_peak ||
+        out->hit_peak32)
         return false;
     if ((out->hit_mmz == nullptr) != (out->hit_mi == nullptr)) return false;
     for (const void* p : {(const void*)out->hit_spec, (const void*)out->hit_entry, (const void*)out->hit_score, (const void*)out->hit_scaling,
@@ -1717,7 +1745,16 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
     }
     // sub-batches: cut at spectrum boundaries every ~sub_rows rows (host-resident runs only)
     std::vector<int64_t> cuts{0};
-    const int64_t sub_rows = ctx->sub_batch_rows > 0 ? ctx->sub_batch_rows : (int64_t)16 << 20;   // measured: 4 Mi rows 147 ms, 8 Mi 138 ms, 16 Mi 135 ms per 39 M-row shard
+    // Sub-batch size.  With one GPU on the bus the copies are short against the kernels and large sub-batches win (measured
+    // per 39 M-row shard: 4 Mi rows 147 ms, 8 Mi 138 ms, 16 Mi 135 ms).  With eight GPUs sharing the host's memory system the
+    // hits leave at ~13 GB/s per GPU, the copies take as long as the kernels and only the last sub-batch's copy is exposed:
+    // the smaller it is the better.  The size follows the copy / kernel time ratio of the previous run.
+    int64_t sub_rows = (int64_t)16 << 20;
+    if (ctx->copy_kernel_ratio > 0.8)
+        sub_rows = (int64_t)4 << 20;
+    else if (ctx->copy_kernel_ratio > 0.5)
+        sub_rows = (int64_t)8 << 20;
+    if (ctx->sub_batch_rows > 0) sub_rows = ctx->sub_batch_rows;
     if (!peaks_on_device && n_peaks > sub_rows + sub_rows / 2) {
         int64_t next = p_begin + sub_rows;
         for (int64_t s = 1; s < n_spectra; ++s)
@@ -1739,14 +1776,15 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
         cudaEventRecord(e, stream);
         timing.push_back(e);
     };
-    size_t n_in_events = 0;
+    std::vector<char> is_upload;                                  // per pair
+    const double kernel_ms_before = ctx->cnt.ms_gate + ctx->cnt.ms_score + ctx->cnt.ms_compact;
     auto upload = [&](size_t b) -> int {
         if (peaks_on_device) return QMS_OK;
         const int64_t r0 = h_off[cuts[b]], r1 = h_off[cuts[b + 1]];
         stamp(ctx->s_in);
         QMS_TRY(qms_copy_to_device(ctx, ctx->d_peaks.p + 2 * r0, peaks + 2 * r0, (size_t)(r1 - r0) * 2 * sizeof(double), ctx->s_in));
         stamp(ctx->s_in);
-        n_in_events += 2;
+        is_upload.push_back(1);
         QMS_CUDA(ctx, cudaEventRecord(ctx->ev_in[b & 1], ctx->s_in));
         return QMS_OK;
     };
@@ -1760,6 +1798,8 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
             fits = false;                                         // keep counting: the call reports the sizes it needs
             return QMS_OK;
         }
+        // the narrowing kernel shares the SMs with the next sub-batch's matcher: it is launched before the clock of the copies starts
+        QMS_TRY(narrow_peak32(ctx, ctx->s_out, out->hit_peak32 ? out->hit_peak32 + part.w0 : nullptr, part.w0, (size_t)part.nw, p_begin));
         stamp(ctx->s_out);
         QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_spec ? out->hit_spec + part.h0 : nullptr, ctx->o_spec.p + part.h0, (size_t)part.nh));
         QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_entry ? out->hit_entry + part.h0 : nullptr, ctx->o_entry.p + part.h0, (size_t)part.nh));
@@ -1773,9 +1813,12 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
             QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_mi + part.w0, ctx->o_mi.p + part.w0, (size_t)part.nw));
         }
         QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_peak ? out->hit_peak + part.w0 : nullptr, ctx->o_peak.p + part.w0, (size_t)part.nw));
+        QMS_TRY(copy_out_peak32(ctx, ctx->s_out, out->hit_peak32 ? out->hit_peak32 + part.w0 : nullptr, part.w0, (size_t)part.nw, p_begin, true));
         stamp(ctx->s_out);
+        is_upload.push_back(0);
         return QMS_OK;
     };
+    ctx->last_row_base = p_begin;
     if (!direct && ctx->run_hits_hint > 0) QMS_TRY(reserve_run(ctx, ctx->run_hits_hint, ctx->run_windows_hint, want_values));
     int64_t total_h = 0, total_w = 0;
     bool have_pending = false, wrote_callers = false;
@@ -1826,11 +1869,15 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
     if (have_pending) QMS_TRY(download(pending));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    double copy_ms = 0.0;
     for (size_t k = 0; k + 1 < timing.size(); k += 2) {
         float ms = 0;
         cudaEventElapsedTime(&ms, timing[k], timing[k + 1]);
-        (k < n_in_events ? ctx->cnt.ms_h2d : ctx->cnt.ms_d2h) += ms;
+        (is_upload[k / 2] ? ctx->cnt.ms_h2d : ctx->cnt.ms_d2h) += ms;
+        if (!is_upload[k / 2]) copy_ms += ms;
     }
+    const double kernel_ms = ctx->cnt.ms_gate + ctx->cnt.ms_score + ctx->cnt.ms_compact - kernel_ms_before;
+    if (n_sub > 1 && kernel_ms > 0.0) ctx->copy_kernel_ratio = copy_ms / kernel_ms;
     for (cudaEvent_t e : timing) cudaEventDestroy(e);
     ctx->cnt.dense_batches += (int64_t)n_sub;
     ctx->cnt.hits += total_h;
@@ -1910,6 +1957,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     MatchView v;
     QMS_TRY(make_view(ctx, v, d_peaks, d_off, n_spectra, input_kind, only_entry, mz_score_percentile));
+    ctx->last_row_base = p_begin;
 
     // ---- K5a .. K7a are enqueued back to back; the host looks at the counters once, after the hit count ----
     // The pair list has a capacity learned from the previous batch (its pair count + 25 %); unused slots hold an all-ones
@@ -2123,6 +2171,7 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         QMS_TRY(copy_out(ctx, out->hit_mmz, ctx->o_mmz.p, (size_t)nw));
         QMS_TRY(copy_out(ctx, out->hit_mi, ctx->o_mi.p, (size_t)nw));
         QMS_TRY(copy_out(ctx, out->hit_peak, ctx->o_peak.p, (size_t)nw));
+        QMS_TRY(copy_out_peak32(ctx, ctx->stream, out->hit_peak32, 0, (size_t)nw, p_begin));
     }
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2161,6 +2210,7 @@ extern "C" int qms_fetch_hits(qms_ctx* ctx, qms_hits* out, int64_t* n_hits, int6
     QMS_TRY(copy_out(ctx, out->hit_mmz, ctx->o_mmz.p, (size_t)nw));
     QMS_TRY(copy_out(ctx, out->hit_mi, ctx->o_mi.p, (size_t)nw));
     QMS_TRY(copy_out(ctx, out->hit_peak, ctx->o_peak.p, (size_t)nw));
+    QMS_TRY(copy_out_peak32(ctx, ctx->stream, out->hit_peak32, 0, (size_t)nw, ctx->last_row_base));
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->cnt.ms_d2h += elapsed(ctx, 3, 4);

@@ -142,6 +142,7 @@ struct qms_ctx {
     int64_t pair_cap_hint = 0;     // capacity of the pair list, learned from the previous batch (+25 %)
     int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
     int dense_mode = 2;            // spectrum-resident matcher: 0 never, 1 whenever its tables allow it, 2 by library density
+    double copy_kernel_ratio = 0.0;  // hit copies / kernels (device ms) of the last pipelined run: picks the next sub-batch size
     int64_t sub_batch_rows = 0;   // rows per sub-batch of the pipelined run (0: default)
     int dense_ctas = 2;            // its resident CTAs per SM
     bool last_values = true;                   // ... including the matched (m/z, intensity) values
@@ -155,6 +156,8 @@ struct qms_ctx {
     DBuf<int32_t> o_spec, o_entry;
     DBuf<double> o_score, o_scaling, o_mmz, o_mi;
     DBuf<int64_t> o_win_off, o_peak;
+    DBuf<int32_t> o_peak32;        // o_peak narrowed for the trip to the host (hit_peak32)
+    int64_t last_row_base = 0;     // first row of the last batch: what hit_peak32 counts from
     unsigned long long* h_pinned = nullptr;  // small pinned mailbox for counters
     // staging of the spectrum-resident matcher: hits in discovery order, sorted by (spectrum, entry) afterwards
     DBuf<unsigned long long> st_key, st_key_alt;

@@ -181,15 +181,16 @@ def allgather_envelopes(ctx, n_env, world):
 
 
 _HIT_FIELDS = (("spec", np.int32, "h"), ("entry", np.int32, "h"), ("score", np.float64, "h"), ("scaling", np.float64, "h"),
-               ("win_off", np.int64, "h1"), ("peak", np.int64, "w"), ("mmz", np.float64, "w"), ("mi", np.float64, "w"))
+               ("win_off", np.int64, "h1"), ("peak", np.int64, "w"), ("peak32", np.int32, "w"), ("mmz", np.float64, "w"),
+               ("mi", np.float64, "w"))
 
 
 def _segment_layout(cap_h, cap_w, values):
     """Byte offsets of the hit arrays inside a segment with room for cap_h hits and cap_w hit windows."""
     offset, layout = 64, {}
     for name, dtype, kind in _HIT_FIELDS:
-        if name in ("mmz", "mi") and not values:
-            continue
+        if (name in ("mmz", "mi", "peak") and not values) or (name == "peak32" and values):
+            continue                                     # without the values the rows travel as int32 (hit_peak32)
         count = {"h": cap_h, "h1": cap_h + 1, "w": cap_w}[kind]
         layout[name] = (offset, np.dtype(dtype), count)
         offset = (offset + count * np.dtype(dtype).itemsize + 63) // 64 * 64

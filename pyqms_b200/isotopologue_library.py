@@ -189,8 +189,15 @@ class PackedHits(dict):
     def __init__(self, peaks=None):
         super().__init__()
         self._peaks = peaks
+        self._row_base = 0
 
     def __missing__(self, key):
+        if key == "peak" and "peak32" in dict.keys(self):      # the device sent the rows as int32 counted from the batch's first row
+            narrow = dict.__getitem__(self, "peak32")
+            rows = narrow.astype(np.int64)
+            rows[narrow >= 0] += self._row_base
+            self[key] = rows
+            return rows
         if key not in ("mmz", "mi") or self._peaks is None:
             raise KeyError(key)
         row = self["peak"]
@@ -811,12 +818,14 @@ class IsotopologueLibrary(dict):
                 out.update(self._hit_arena.arrays(h, w, values))          # shared segment of this rank (distributed.SharedHitArena)
             else:
                 out.update({"spec": pool.array(np.int32, h), "entry": pool.array(np.int32, h), "score": pool.array(np.float64, h),
-                            "scaling": pool.array(np.float64, h), "win_off": pool.array(np.int64, h + 1),
-                            "peak": pool.array(np.int64, w)})
+                            "scaling": pool.array(np.float64, h), "win_off": pool.array(np.int64, h + 1)})
                 if values:
-                    out["mmz"], out["mi"] = pool.array(np.float64, w), pool.array(np.float64, w)
-            hits = QmsHits(h, w, *[out[k].ctypes.data if k in out else None
-                                   for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
+                    out["mmz"], out["mi"], out["peak"] = pool.array(np.float64, w), pool.array(np.float64, w), pool.array(np.int64, w)
+                else:
+                    out["peak32"] = pool.array(np.int32, w)       # rows counted from offsets[0]: half the bytes across the bus
+            out._row_base = int(offsets[0])
+            hits = QmsHits(h, w, *[out[k].ctypes.data if k in dict.keys(out) else None
+                                   for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak", "peak32")])
             return out, hits
 
         out, hits = buffers(cap_h, cap_w)
@@ -842,8 +851,8 @@ class IsotopologueLibrary(dict):
         out["win_off"] = out["win_off"][:h + 1]
         if h == 0:
             out["win_off"][0] = 0
-        for k in ("peak", "mmz", "mi"):
-            if k in out:
+        for k in ("peak", "peak32", "mmz", "mi"):
+            if k in dict.keys(out):
                 out[k] = out[k][:w]
         out["n_hits"], out["n_windows"] = h, w
         return out
