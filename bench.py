@@ -269,7 +269,7 @@ def device_buffers(torch, QmsHits, cap_h, cap_w):
     return dev, QmsHits(cap_h, cap_w, *[dev[k].data_ptr() for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak")])
 
 
-def sparse_probe_figure(pyqms_b200, torch, local, peak_gbs, n_spectra=10000, steps=10):
+def sparse_probe_figure(pyqms_b200, torch, local, peak_gbs, n_spectra=30000, steps=10):
     """The HBM-bound regime (configs[1], BSA library: 99 % of the peaks are rejected by the cover bitmap): roofline of the
     streaming probe kernel, reported beside the headline as `roofline_sparse`."""
     import ctypes as C
@@ -419,6 +419,9 @@ def run_ours(args):
     d2h = int(sum(dict.__getitem__(own, k).nbytes for k in ("spec", "entry", "score", "scaling", "win_off", "peak", "peak32", "mmz", "mi")
                   if k in dict.keys(own)))      # the arrays the device copied out (lazily gathered ones do not count)
     e2e_counters = ctx.counters()
+    e2e_calls = max(args.steps + max(1, min(args.warmup, 3)), 1)
+    ms_h2d_step = (e2e_counters["ms_h2d"] - counters["ms_h2d"]) / e2e_calls
+    ms_d2h_step = (e2e_counters["ms_d2h"] - counters["ms_d2h"]) / e2e_calls
 
     # ---- roofline of the kernel that dominates the step (SURVEY.md 8d algorithmic bytes)
     peaks_json = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
@@ -485,8 +488,12 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": static_config(args),
             "e2e": {"value": e2e_value, "unit": "spectra/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * float(t.item()) / args.steps, "gather": gather_stats.get("summary"),
-                    "ms_h2d_per_step": (e2e_counters["ms_h2d"] - counters["ms_h2d"]) / max(args.steps + min(args.warmup, 3), 1),
-                    "ms_d2h_per_step": (e2e_counters["ms_d2h"] - counters["ms_d2h"]) / max(args.steps + min(args.warmup, 3), 1)},
+                    "ms_h2d_per_step": ms_h2d_step, "ms_d2h_per_step": ms_d2h_step,
+                    "h2d_gbs_per_gpu": h2d / ms_h2d_step / 1e6 if ms_h2d_step > 0 else None,
+                    "d2h_gbs_per_gpu": d2h / ms_d2h_step / 1e6 if ms_d2h_step > 0 else None,
+                    "sub_batches_per_step": (e2e_counters["dense_batches"] - counters["dense_batches"]) / e2e_calls,
+                    "note": "copies of neighbouring sub-batches overlap the kernels (copy streams); the GB/s are per GPU with all "
+                            "GPUs of the run copying at once: the host's memory system is shared"},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "workload_stats": {"shard": shard, "spectra": n_spec, "peaks": int(len(peaks)), "run_source": run_how, "synth_s": synth_s,
