@@ -87,6 +87,91 @@ def _restore_library(state, formulas):
     return library
 
 
+class _LazyDict(dict):
+    """A dict whose content is produced by ``fill(self)`` on first use: lookups of a large library that the build itself
+    never reads (500 000 ``setdefault`` calls cost more than the device part of the build)."""
+
+    def __init__(self, fill):
+        super().__init__()
+        self._fill = fill
+
+    def _ensure(self):
+        fill, self._fill = self._fill, None
+        if fill is not None:
+            fill(self)
+
+    def __getitem__(self, key):
+        self._ensure()
+        return dict.__getitem__(self, key)
+
+    def __iter__(self):
+        self._ensure()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._ensure()
+        return dict.__len__(self)
+
+    def __contains__(self, key):
+        self._ensure()
+        return dict.__contains__(self, key)
+
+    def __eq__(self, other):
+        self._ensure()
+        if isinstance(other, _LazyDict):
+            other._ensure()
+        return dict.__eq__(self, other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._ensure()
+        return dict.__repr__(self)
+
+    def keys(self):
+        self._ensure()
+        return dict.keys(self)
+
+    def values(self):
+        self._ensure()
+        return dict.values(self)
+
+    def items(self):
+        self._ensure()
+        return dict.items(self)
+
+    def get(self, key, default=None):
+        self._ensure()
+        return dict.get(self, key, default)
+
+    def setdefault(self, key, default=None):
+        self._ensure()
+        return dict.setdefault(self, key, default)
+
+    def pop(self, *args):
+        self._ensure()
+        return dict.pop(self, *args)
+
+    def update(self, *args, **kwargs):
+        self._ensure()
+        return dict.update(self, *args, **kwargs)
+
+    def __setitem__(self, key, value):
+        self._ensure()
+        return dict.__setitem__(self, key, value)
+
+    def copy(self):
+        self._ensure()
+        return dict(self)
+
+    def __reduce__(self):
+        self._ensure()
+        return (dict, (dict(self),))
+
+
 class _FormulaRecord(dict):
     """``lib[formula]``: ``{"env": label tuple -> envelope, "cc": composition}``, both built on first access (a
     library of 10^6 formulas does not create 2*10^6 dictionaries nobody reads)."""
@@ -290,6 +375,7 @@ class IsotopologueLibrary(dict):
                 self._n_bins(), *self.match_set_mz_range))
 
     # ------------------------------------------------------------------ save / load
+    _fixed_label_fast_path = True        # tests switch it off to compare with the general expansion
     _hit_pool = None                     # page-locked result arrays, created with the first match
     _hit_caps = (4096, 32768)            # (hits, hit windows) the next result arrays are sized for
 
@@ -435,6 +521,27 @@ class IsotopologueLibrary(dict):
         letters = "".join(re.escape(k) for k in self.aa_compositions if len(k) == 1)
         not_a_residue = re.compile("[^%s]" % letters) if letters else re.compile(".", re.S)
         labelled_residue = re.compile("|".join(re.escape(k) for k in self.fixed_labels)) if self.fixed_labels else None
+        # Fast path for the usual case -- every labelled residue has exactly one label (carbamidomethyl cysteine) and
+        # nothing is locked: the single combination of IL:1375-1677 puts state 0 behind every labelled residue, which is one
+        # str.replace per molecule (0.3 us instead of 7 us; a 500 000-peptide library spent 2 s here).  Molecules that hold
+        # anything besides residue letters (modifications, add-ons) take the general path below.
+        simple = (self._fixed_label_fast_path and locked is None and labelled_residue is not None and all(len(k) == 1 and len(v) == 1 for k, v in self.fixed_labels.items()))
+        if simple:
+            residue_letters = "".join(k for k in self.aa_compositions if len(k) == 1)
+            states = [(k, k + "0") for k in self.fixed_labels]
+            variations = self.lookup["molecule fixed label variations"]
+            general = []
+            for full_molecule in molecules:
+                if full_molecule.strip(residue_letters):         # something besides residue letters
+                    general.append(full_molecule)
+                    continue
+                labelled = full_molecule
+                for residue, with_state in states:
+                    labelled = labelled.replace(residue, with_state)
+                expanded.add(labelled)
+                if len(labelled) != len(full_molecule):
+                    variations.setdefault(full_molecule, set()).add(labelled)
+            molecules = general
         for full_molecule in molecules:
             stop = not_a_residue.search(full_molecule)      # the sequence ends at the first non-residue character
             cut = stop.start() if stop else len(full_molecule)
@@ -531,9 +638,14 @@ class IsotopologueLibrary(dict):
         counts, seen = np.ascontiguousarray(counts[:, keep]), np.ascontiguousarray(seen[:, keep])
         formulas = planner.hill_formulas(counts, symbols)
         self.lookup["molecule to formula"].update(zip(ordered, formulas))
-        to_molecule = self.lookup["formula to molecule"]
-        for molecule, formula in zip(ordered, formulas):
-            to_molecule.setdefault(formula, []).append(molecule)
+        known_pairs = self.lookup["formula to molecule"]
+
+        def fill_formula_to_molecule(target, earlier=known_pairs, ordered=ordered, formulas=formulas):
+            dict.update(target, earlier)
+            for molecule, formula in zip(ordered, formulas):
+                dict.setdefault(target, formula, []).append(molecule)
+
+        self.lookup["formula to molecule"] = _LazyDict(fill_formula_to_molecule)
         if trivial_names is not None:
             for molecule, formula in zip(ordered, formulas):
                 name = trivial_names.get(molecule, None)

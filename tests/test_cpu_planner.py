@@ -172,3 +172,23 @@ def test_formula_records_behave_like_the_reference_dicts():
         record["nothing"]
     peptide = lib[lib.lookup["molecule to formula"]["PEPTIDEK"]]["cc"]
     assert list(peptide.items()) == list(host_composition("PEPTIDEK").items())
+
+
+def test_fixed_label_fast_path_equals_the_general_expansion():
+    """One label per labelled residue, nothing locked: a str.translate per molecule must give what the site / combination
+    loop of IL:1375-1677 gives (expanded molecule set, variation lookup, formulas)."""
+    import pyqms_b200
+    from pyqms_b200.synthetic import CAM_FIXED_LABEL, random_tryptic_peptides
+    peptides = random_tryptic_peptides(3000, seed=3)
+    molecules = peptides + [p + "#Oxidation:1" for p in peptides[:40]] + ["+C6H12O6", "PEPTIDEC+PO3", "CCCC", "AAAK"]
+    kwargs = dict(molecules=molecules, charges=[2], fixed_labels=dict(CAM_FIXED_LABEL, M=["O(1)"]), verbose=False, _plan_only=True)
+    fast = pyqms_b200.IsotopologueLibrary(**kwargs)
+    pyqms_b200.IsotopologueLibrary._fixed_label_fast_path = False
+    try:
+        slow = pyqms_b200.IsotopologueLibrary(**kwargs)
+    finally:
+        pyqms_b200.IsotopologueLibrary._fixed_label_fast_path = True
+    assert list(fast.keys()) == list(slow.keys())
+    for name in ("molecule to formula", "formula to molecule", "molecule fixed label variations"):
+        assert fast.lookup[name] == slow.lookup[name], name
+    assert len(fast.lookup["molecule fixed label variations"]) > 1000
