@@ -213,3 +213,35 @@ def test_gzip_compressed_files(tmp_path):
     broken.write_bytes(packed.read_bytes()[:2000])
     with pytest.raises(OSError):
         read_mzml(broken, native=True)
+
+
+def _check_against(path, want, native, threads=None):
+    for level in (None, 1, 2):
+        run = read_mzml(path, ms_level=level, native=native, threads=threads)
+        keep = [i for i, l in enumerate(want["levels"]) if level is None or l == level]
+        peaks = np.concatenate([want["peaks"][want["offsets"][i]:want["offsets"][i + 1]] for i in keep])
+        assert np.array_equal(run.peaks, peaks) and run.spec_ids == [int(want["ids"][i]) for i in keep]
+        assert np.array_equal(np.diff(run.offsets), np.diff(want["offsets"])[keep])
+        assert run.rts == [(float(want["rts"][i]), "minute") for i in keep] and run.ms_levels == [int(want["levels"][i]) for i in keep]
+
+
+def test_converter_style_document_not_written_by_our_writer(tmp_path):
+    """An indexedmzML in the layout msconvert writes (cvList, param groups, pretty printing, unit attributes, precursor
+    lists, a chromatogram list and a second index, mixed 32/64-bit and zlib/plain arrays, an empty spectrum), assembled by
+    tests/data/make_pwiz_style.py with struct / zlib / base64 only -- both readers, all MS-level filters."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_pwiz_style", ROOT / "tests" / "data" / "make_pwiz_style.py")
+    maker = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(maker)
+    want = np.load(ROOT / "tests" / "data" / "pwiz_style_small_expected.npz")
+    raw, again = maker.document(9)
+    assert raw == (ROOT / "tests" / "data" / "pwiz_style_small.mzML").read_bytes()      # the committed file is what the script writes
+    for native in (True, False):
+        _check_against(ROOT / "tests" / "data" / "pwiz_style_small.mzML", want, native)
+    # 450 spectra: enough for the native reader to split the tag scan at the file's own spectrum index
+    big, expected = maker.document(450)
+    path = tmp_path / "pwiz_style_big.mzML"
+    path.write_bytes(big)
+    _check_against(path, expected, True, threads=4)
+    assert mzml.LAST_READ["scan_blocks"] > 1 or (os.cpu_count() or 1) < 4
+    _check_against(path, expected, False)
