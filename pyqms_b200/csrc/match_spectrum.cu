@@ -45,6 +45,9 @@
 // Tuning variants, built side by side with tools/dense_variants.sh and timed with tools/ab_variants.sh (B200, proteome
 // shard, ms of this kernel): both off 102.3 | records 111.2 | prefetch 109.2 | both 119.0 -- the prefetch registers push the
 // 64-register kernel into spills, the 32-byte records quadruple the sectors the gate touches for its (lo, hi) loads.
+// Also measured and dropped: enumerating pairs with 2-4 candidate combinations inside this kernel (a third queue, 32 such
+// pairs at a time) instead of handing them to K6 -- it saves the 14 ms combination pass and costs 28 ms here (94 -> 122 ms:
+// two more 16-entry local arrays and 150 bytes of spills in a kernel that lives on 64 registers).
 #ifndef MS_PREFETCH
 #define MS_PREFETCH 0          // record strips / buckets / zone rows fetched one ahead
 #endif
@@ -470,6 +473,10 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MIN_CTAS) match_spectrum_kernel
                 const bool incident = rec.y >= t;
                 bool push = incident && t_before < rec.x;              // the bucket is the first of the window
                 st_inc += incident;
+#ifdef MS_STATS
+                if (jb + lane < range.y) atomicAdd(&counters[30], 1ull);                         // records scanned
+                if (incident && !(t_before < rec.x)) atomicAdd(&counters[31], 1ull);              // not the first bucket of the window
+#endif
                 const int g = (rec.w >> 12) & 15;
                 uint32_t fields = 0;
                 if (push && g < d.zone_groups) {
@@ -720,7 +727,10 @@ int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
         n_multi = (int64_t)ctx->h_pinned[C_MULTI];
         const int64_t live = (int64_t)ctx->h_pinned[C_LIVE], inc = (int64_t)ctx->h_pinned[C_INCID], pairs = (int64_t)ctx->h_pinned[C_PAIRS];
         const int64_t gated = (int64_t)ctx->h_pinned[C_GATED];
-        if (getenv("QMS_DEBUG_COUNTERS")) fprintf(stderr, "[qms] pairs %lld, rejected by the score bound %lld, multi %lld\n", (long long)pairs, (long long)ctx->h_pinned[C_BOUND], (long long)n_multi);
+        if (getenv("QMS_DEBUG_COUNTERS"))      // records scanned / not first in window: only in a -DMS_STATS build (tools/dense_variants.sh)
+            fprintf(stderr, "[qms] incidences %lld, records scanned %lld, not first in window %lld, gated %lld, pairs %lld, rejected by the "
+                            "score bound %lld, multi %lld\n", (long long)inc, (long long)ctx->h_pinned[30], (long long)ctx->h_pinned[31],
+                    (long long)gated, (long long)pairs, (long long)ctx->h_pinned[C_BOUND], (long long)n_multi);
         int64_t combos = (int64_t)ctx->h_pinned[C_COMBOS], pair_windows = (int64_t)ctx->h_pinned[C_PAIR_WINDOWS];
         const bool multi_overflow = n_multi > cap_m;
         bool overflow = multi_overflow;
