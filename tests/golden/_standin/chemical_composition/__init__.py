@@ -11,7 +11,22 @@ from pathlib import Path
 
 _TOKEN = re.compile(r"(?P<iso>\d*)(?P<el>[A-Z][a-z]*)(?:\((?P<n>-?\d+)\)|(?P<c>\d*))")
 _RESIDUE = re.compile(r"([A-Z])(\d*)")
-_DEFAULT_UNIMOD = Path("/root/reference/pyqms/kb/ext/unimod.xml")
+
+
+def _default_unimod():
+    """unimod.xml of the pyqms package that imported this stand-in (the reference source tree in the build container, its
+    copy under baseline/_ref on the GPU box)."""
+    try:
+        import pyqms
+        found = Path(pyqms.__file__).resolve().parent / "kb" / "ext" / "unimod.xml"
+        if found.exists():
+            return found
+    except Exception:
+        pass
+    return Path("/root/reference/pyqms/kb/ext/unimod.xml")
+
+
+_DEFAULT_UNIMOD = _default_unimod()
 _XML_CACHE = {}
 
 
