@@ -97,8 +97,7 @@ int qms_device_bytes(qms_ctx* ctx, int64_t* out);    /* device memory currently 
  *                 a batch with a pair above it fails with QMS_E_LIMIT instead of enumerating for hours like the reference
  *   "combination_budget_log2"  log2 of the combinations of all many-candidate pairs of one batch (default 35)
  *   "sub_batch_rows"  peak rows per sub-batch when a host-resident run is pipelined (copies of neighbouring sub-batches
- *                 overlap the kernels); 0 = automatic (16 Mi rows, 8 Mi or 4 Mi when the copies of
- *                 the previous run took more than half / four fifths of the kernels' time, as they do with eight GPUs on one host) */
+ *                 overlap the kernels); 0 = default (16 Mi rows) */
 int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value);
 
 /* Page-locked host memory for spectrum and hit buffers (cudaHostAlloc, portable): copies to and from such buffers run

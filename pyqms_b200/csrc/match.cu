@@ -1745,16 +1745,12 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
     }
     // sub-batches: cut at spectrum boundaries every ~sub_rows rows (host-resident runs only)
     std::vector<int64_t> cuts{0};
-    // Sub-batch size.  With one GPU on the bus the copies are short against the kernels and large sub-batches win (measured
-    // per 39 M-row shard: 4 Mi rows 147 ms, 8 Mi 138 ms, 16 Mi 135 ms).  With eight GPUs sharing the host's memory system the
-    // hits leave at ~13 GB/s per GPU, the copies take as long as the kernels and only the last sub-batch's copy is exposed:
-    // the smaller it is the better.  The size follows the copy / kernel time ratio of the previous run.
-    int64_t sub_rows = (int64_t)16 << 20;
-    if (ctx->copy_kernel_ratio > 0.8)
-        sub_rows = (int64_t)4 << 20;
-    else if (ctx->copy_kernel_ratio > 0.5)
-        sub_rows = (int64_t)8 << 20;
-    if (ctx->sub_batch_rows > 0) sub_rows = ctx->sub_batch_rows;
+    // Sub-batch size: a sub-batch ends when its slowest CTA does and its sort + emit overlap nothing, so few large sub-batches
+    // win over many small ones.  Measured per 39 M-row shard, end to end: uniform 4 Mi rows 147 ms, 8 Mi 138 ms, 16 Mi 130-135 ms
+    // on one GPU; 16 Mi 188 ms against 216 ms for 4-8 Mi with eight GPUs sharing the host's memory system (hits leave at
+    // 13-16 GB/s per GPU there); a plan with a quarter-size first and last sub-batch (early start, short end of the copy
+    // pipeline) 141 ms on one GPU.
+    const int64_t sub_rows = ctx->sub_batch_rows > 0 ? ctx->sub_batch_rows : (int64_t)16 << 20;
     if (!peaks_on_device && n_peaks > sub_rows + sub_rows / 2) {
         int64_t next = p_begin + sub_rows;
         for (int64_t s = 1; s < n_spectra; ++s)
