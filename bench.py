@@ -388,7 +388,7 @@ def run_ours(args):
     spec_ids = list(range(n_spec))
     gather_stats = {}
     arena = None
-    if world > 1:
+    if world > 1 and not os.environ.get("QMS_BENCH_NO_ARENA"):
         # hits of every rank land, by DMA, in a page-locked shared-memory segment that rank 0 maps (no data-path collective)
         from pyqms_b200.distributed import SharedHitArena, gather_hits_to_rank0
         arena = SharedHitArena()
@@ -398,7 +398,7 @@ def run_ours(args):
         # the call a user makes for a whole run: host (N,2) array in, pyqms Results out (hits stay packed until read)
         res = lib.match_many(h_peaks, file_name="run", spec_ids=spec_ids, spec_rts=spec_ids, offsets=h_offsets)
         out = res.packed_batches()[-1]
-        if world > 1:
+        if arena is not None:
             out = gather_hits_to_rank0(out, spectrum_begin=rank * n_spec, arena=arena, stats=gather_stats)
         return out
 
@@ -406,8 +406,11 @@ def run_ours(args):
         out = e2e_step()
     barrier()
     t0 = time.perf_counter()
+    e2e_each = []
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         out = e2e_step()
+        e2e_each.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -415,7 +418,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n_spec * args.steps / float(t.item())
     h2d = int(peaks.nbytes + offsets.nbytes)
-    own = out if world == 1 else gather_stats.get("own", out)
+    own = out if arena is None else gather_stats.get("own", out)
     d2h = int(sum(dict.__getitem__(own, k).nbytes for k in ("spec", "entry", "score", "scaling", "win_off", "peak", "peak32", "mmz", "mi")
                   if k in dict.keys(own)))      # the arrays the device copied out (lazily gathered ones do not count)
     e2e_counters = ctx.counters()
@@ -492,6 +495,8 @@ def run_ours(args):
                     "h2d_gbs_per_gpu": h2d / ms_h2d_step / 1e6 if ms_h2d_step > 0 else None,
                     "d2h_gbs_per_gpu": d2h / ms_d2h_step / 1e6 if ms_d2h_step > 0 else None,
                     "sub_batches_per_step": (e2e_counters["dense_batches"] - counters["dense_batches"]) / e2e_calls,
+                    "kernel_ms_per_step": sum(e2e_counters[k] - counters[k] for k in ("ms_probe", "ms_gate", "ms_score", "ms_compact")) / e2e_calls,
+                    "ms_per_step_each": [round(1e3 * x, 1) for x in e2e_each], "hits_in_shared_memory": arena is not None,
                     "note": "copies of neighbouring sub-batches overlap the kernels (copy streams); the GB/s are per GPU with all "
                             "GPUs of the run copying at once: the host's memory system is shared"},
             "gpu_launches": int(round(launches_per_step * args.steps)),

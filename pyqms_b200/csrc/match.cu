@@ -1794,8 +1794,6 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
             fits = false;                                         // keep counting: the call reports the sizes it needs
             return QMS_OK;
         }
-        // the narrowing kernel shares the SMs with the next sub-batch's matcher: it is launched before the clock of the copies starts
-        QMS_TRY(narrow_peak32(ctx, ctx->s_out, out->hit_peak32 ? out->hit_peak32 + part.w0 : nullptr, part.w0, (size_t)part.nw, p_begin));
         stamp(ctx->s_out);
         QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_spec ? out->hit_spec + part.h0 : nullptr, ctx->o_spec.p + part.h0, (size_t)part.nh));
         QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_entry ? out->hit_entry + part.h0 : nullptr, ctx->o_entry.p + part.h0, (size_t)part.nh));
@@ -1809,7 +1807,9 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
             QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_mi + part.w0, ctx->o_mi.p + part.w0, (size_t)part.nw));
         }
         QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_peak ? out->hit_peak + part.w0 : nullptr, ctx->o_peak.p + part.w0, (size_t)part.nw));
-        QMS_TRY(copy_out_peak32(ctx, ctx->s_out, out->hit_peak32 ? out->hit_peak32 + part.w0 : nullptr, part.w0, (size_t)part.nw, p_begin, true));
+        // (the int32 rows were written by the emit kernel: a narrowing kernel on this stream would wait for an SM until the
+        // next sub-batch's matcher, which fills the GPU, is done -- and every copy queued behind it with it)
+        QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_peak32 ? out->hit_peak32 + part.w0 : nullptr, ctx->o_peak32.p + part.w0, (size_t)part.nw));
         stamp(ctx->s_out);
         is_upload.push_back(0);
         return QMS_OK;
@@ -1855,8 +1855,13 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
             target.hit_mmz = want_values ? ctx->o_mmz.p + total_w : nullptr;
             target.hit_mi = want_values ? ctx->o_mi.p + total_w : nullptr;
             target.hit_peak = ctx->o_peak.p + total_w;
+            target.hit_peak32 = nullptr;
+            if (out && out->hit_peak32) {
+                QMS_TRY(qms_reserve(ctx, ctx->o_peak32, ctx->o_peak.cap, true));      // same shape as o_peak, so offsets agree
+                target.hit_peak32 = ctx->o_peak32.p + total_w;
+            }
         }
-        QMS_TRY(qms_dense_emit(ctx, vb, r0, entry_bits, spec_bits, nh, cuts[b], total_w, target));
+        QMS_TRY(qms_dense_emit(ctx, vb, r0, entry_bits, spec_bits, nh, cuts[b], total_w, target, p_begin));
         pending = Part{total_h, nh, total_w, nw};
         have_pending = nh > 0;
         total_h += nh;

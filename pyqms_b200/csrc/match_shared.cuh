@@ -89,4 +89,4 @@ bool qms_dense_eligible(qms_ctx* ctx, int input_kind, int only_entry, int64_t lo
 int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p_end, int entry_bits,
                     const std::function<int()>& while_running, int64_t* n_hits, int64_t* n_windows);
 int qms_dense_emit(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int entry_bits, int spec_bits, int64_t nh, int64_t spec_base,
-                   int64_t win_base, const qms_hits& out);
+                   int64_t win_base, const qms_hits& out, int64_t run_begin);

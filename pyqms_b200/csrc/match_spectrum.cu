@@ -587,7 +587,8 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(MatchView v, int64_t n
                                                           int32_t* __restrict__ o_entry, double* __restrict__ o_score,
                                                           double* __restrict__ o_scaling, int64_t* __restrict__ o_win_off,
                                                           double* __restrict__ o_mmz, double* __restrict__ o_mi,
-                                                          int64_t* __restrict__ o_peak, const int64_t* __restrict__ local_win_off,
+                                                          int64_t* __restrict__ o_peak, int32_t* __restrict__ o_peak32,
+                                                          int64_t peak32_base, const int64_t* __restrict__ local_win_off,
                                                           int64_t spec_base, int64_t win_base) {
     // o_* point at this batch's first hit / first window inside the run's arrays; spectra and window offsets are
     // rebased to the run (spec_base = spectra before this batch, win_base = hit windows before it)
@@ -612,6 +613,7 @@ __global__ void __launch_bounds__(256) emit_sorted_kernel(MatchView v, int64_t n
         const uint32_t r = rows[m];
         const bool none = r == MS_NONE;
         o_peak[w + m] = none ? -1 : p_begin + (int64_t)r;
+        if (o_peak32) o_peak32[w + m] = none ? -1 : (int32_t)(peak32_base + (int64_t)r);      // counted from the run's first row
         if (o_mmz) {
             const double2 row = none ? make_double2(nan, nan) : __ldg(&v.peaks[p_begin + (int64_t)r]);
             o_mmz[w + m] = row.x;
@@ -786,9 +788,10 @@ int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
 
 // Stage 2: sort the staged hits by (spectrum, entry) and write them to `out` (device arrays, already pointing at this
 // batch's first hit / first hit window; hit_mmz / hit_mi may be NULL).  Spectrum numbers are rebased by spec_base,
-// window offsets by win_base; out.hit_win_off receives nh + 1 values.  Synchronises the context's stream.
+// window offsets by win_base; out.hit_win_off receives nh + 1 values; out.hit_peak32 (may be NULL) receives the peak rows
+// counted from run_begin as int32.  Synchronises the context's stream.
 int qms_dense_emit(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int entry_bits, int spec_bits, int64_t nh, int64_t spec_base,
-                   int64_t win_base, const qms_hits& out) {
+                   int64_t win_base, const qms_hits& out, int64_t run_begin) {
     if (nh == 0) return QMS_OK;
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
     QMS_TRY(qms_reserve(ctx, ctx->st_key_alt, (size_t)nh + 1));
@@ -810,7 +813,7 @@ int qms_dense_emit(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int entry_
     emit_sorted_kernel<<<qms_blocks(nh + 1, 256), 256, 0, ctx->stream>>>(
         v, nh, entry_bits, p_begin, ctx->st_key_alt.p, ctx->st_order_alt.p, ctx->st_score.p, ctx->st_scaling.p, ctx->st_woff.p,
         ctx->st_rows.p, out.hit_spec, out.hit_entry, out.hit_score, out.hit_scaling, out.hit_win_off, out.hit_mmz, out.hit_mi,
-        out.hit_peak, ctx->st_win_off.p, spec_base, win_base);
+        out.hit_peak, out.hit_peak32, p_begin - run_begin, ctx->st_win_off.p, spec_base, win_base);
     QMS_CUDA(ctx, cudaGetLastError());
     ctx->cnt.kernel_launches += 3 + 2 + (key_bits + 7) / 8 + 2;
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
