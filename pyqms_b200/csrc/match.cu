@@ -1745,18 +1745,24 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
     }
     // sub-batches: cut at spectrum boundaries every ~sub_rows rows (host-resident runs only)
     std::vector<int64_t> cuts{0};
-    // Sub-batch size: a sub-batch ends when its slowest CTA does and its sort + emit overlap nothing, so few large sub-batches
-    // win over many small ones.  Measured per 39 M-row shard, end to end: uniform 4 Mi rows 147 ms, 8 Mi 138 ms, 16 Mi 130-135 ms
-    // on one GPU; 16 Mi 188 ms against 216 ms for 4-8 Mi with eight GPUs sharing the host's memory system (hits leave at
-    // 13-16 GB/s per GPU there); a plan with a quarter-size first and last sub-batch (early start, short end of the copy
-    // pipeline) 141 ms on one GPU.
+    // Sub-batch plan: [small | big ... big | small].  A sub-batch ends when its slowest CTA does and its sort + emit overlap
+    // nothing, so few large sub-batches keep the matcher efficient -- but the hits of a sub-batch can only start to leave when it
+    // is done, and the last sub-batch's copy overlaps nothing.  With eight GPUs sharing the host's memory system the hits leave
+    // at ~15 GB/s per GPU and the copies take as long as the kernels: the copy pipeline has to start early and end short, so the
+    // first and the last sub-batch are a quarter of the others (16 Mi rows).
     const int64_t sub_rows = ctx->sub_batch_rows > 0 ? ctx->sub_batch_rows : (int64_t)16 << 20;
     if (!peaks_on_device && n_peaks > sub_rows + sub_rows / 2) {
-        int64_t next = p_begin + sub_rows;
+        const int64_t edge = sub_rows / 4;
+        const int64_t middle = n_peaks - 2 * edge;
+        const int64_t parts = (middle + sub_rows - 1) / sub_rows;
+        const int64_t step = (middle + parts - 1) / parts;
+        int64_t next = p_begin + edge;
         for (int64_t s = 1; s < n_spectra; ++s)
-            if (h_off[s] >= next && p_end - h_off[s] > sub_rows / 4) {
+            if (h_off[s] >= next && p_end - h_off[s] > edge / 4) {
                 cuts.push_back(s);
-                next = h_off[s] + sub_rows;
+                const bool last_edge = p_end - h_off[s] <= edge + step / 8;
+                next = last_edge ? p_end + 1 : std::min(h_off[s] + step, p_end - edge);
+                if (next <= h_off[s]) next = p_end + 1;
             }
     }
     cuts.push_back(n_spectra);
