@@ -389,10 +389,22 @@ def run_ours(args):
     gather_stats = {}
     arena = None
     if world > 1 and not os.environ.get("QMS_BENCH_NO_ARENA"):
-        # hits of every rank land, by DMA, in a page-locked shared-memory segment that rank 0 maps (no data-path collective)
+        # hits of every rank land, by DMA, in a page-locked shared-memory segment that rank 0 maps (no data-path collective);
+        # the ranks agree first that /dev/shm has room for all segments (a container may come with 64 MB of it)
         from pyqms_b200.distributed import SharedHitArena, gather_hits_to_rank0
-        arena = SharedHitArena()
-        lib.use_hit_arena(arena)
+        need = world * (80 * max(device_hits, 1) + (64 << 20))            # ~58 bytes per hit of this workload + growth head room
+        try:
+            room = os.statvfs("/dev/shm")
+            enough = room.f_bavail * room.f_frsize > need
+        except OSError:
+            enough = False
+        agreed = torch.tensor([1 if enough else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        if int(agreed.item()):
+            arena = SharedHitArena()
+            lib.use_hit_arena(arena)
+        else:
+            gather_stats["summary"] = {"unavailable": "/dev/shm has no room for %d bytes of hit segments; every rank keeps its hits" % need}
 
     def e2e_step():
         # the call a user makes for a whole run: host (N,2) array in, pyqms Results out (hits stay packed until read)

@@ -255,6 +255,10 @@ class SharedHitArena:
                 cap_h, cap_w = max(cap_h, own[3]), max(cap_w, own[4])
             cap_h, cap_w = cap_h + cap_h // 4 + 64, cap_w + cap_w // 4 + 512
             layout, nbytes = _segment_layout(cap_h, cap_w, values)
+            room = os.statvfs("/dev/shm")
+            if room.f_bavail * room.f_frsize < nbytes + (16 << 20):
+                raise OSError("/dev/shm has %d bytes free, the hit segment of rank %d needs %d (use the page-locked pool instead: "
+                              "lib.use_hit_arena(None))" % (room.f_bavail * room.f_frsize, self.rank, nbytes))
             self.generation += 1
             name = self._name(self.rank, self.generation)
             fd = os.open("/dev/shm/" + name, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
