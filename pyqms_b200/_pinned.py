@@ -10,7 +10,7 @@ import numpy as np
 from . import _capi
 
 _LOCK_LATER_BYTES = 32 << 20     # arrays from this size on are page-locked from their second use
-_LIMIT_BYTES = 24 << 30          # blocks kept for reuse; beyond it freed blocks are released to the OS
+_LIMIT_BYTES = 12 << 30          # blocks kept for reuse; beyond it freed blocks are released to the OS
 
 
 class _Block:

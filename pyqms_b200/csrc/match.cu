@@ -1371,10 +1371,9 @@ static int score_huge_pairs(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, c
     QMS_TRY(qms_reserve(ctx, ctx->item_scaling, (size_t)n_items));
     QMS_TRY(qms_reserve(ctx, ctx->item_have, (size_t)n_items));
     QMS_TRY(qms_reserve(ctx, ctx->item_rows, (size_t)n_items * (size_t)max_nc + 1));
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->huge_attr_set) {                             // per context: function attributes belong to the device
         QMS_CUDA(ctx, cudaFuncSetAttribute(score_huge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HugeShared)));
-        attr_set = true;
+        ctx->huge_attr_set = true;
     }
     int64_t blocks = n_items < (int64_t)ctx->sm_count * 2 ? n_items : (int64_t)ctx->sm_count * 2;
     score_huge_kernel<<<(unsigned)blocks, K6C_THREADS, sizeof(HugeShared), ctx->stream>>>(
@@ -1771,7 +1770,11 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
     const bool direct = n_sub == 1 && callers_on_device(out);     // one batch straight into the caller's device arrays
     MatchView v;
     QMS_TRY(make_view(ctx, v, d_peaks, d_off, n_spectra, 0, -1, xi));
-    std::vector<cudaEvent_t> timing;                              // (start, stop) pairs on the copy streams
+    struct EventList : std::vector<cudaEvent_t> {                 // destroyed on every way out of this function
+        ~EventList() {
+            for (cudaEvent_t e : *this) cudaEventDestroy(e);
+        }
+    } timing;                                                     // (start, stop) pairs on the copy streams
     auto stamp = [&](cudaStream_t stream) {
         cudaEvent_t e = nullptr;
         cudaEventCreate(&e);
@@ -1885,7 +1888,6 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
     }
     const double kernel_ms = ctx->cnt.ms_gate + ctx->cnt.ms_score + ctx->cnt.ms_compact - kernel_ms_before;
     if (n_sub > 1 && kernel_ms > 0.0) ctx->copy_kernel_ratio = copy_ms / kernel_ms;
-    for (cudaEvent_t e : timing) cudaEventDestroy(e);
     ctx->cnt.dense_batches += (int64_t)n_sub;
     ctx->cnt.hits += total_h;
     ctx->cnt.hit_windows += total_w;

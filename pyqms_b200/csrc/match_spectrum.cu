@@ -664,10 +664,9 @@ int qms_dense_stage(qms_ctx* ctx, const MatchView& v, int64_t p_begin, int64_t p
     const size_t smem_bytes = ((size_t)(MS_BUCKETS + 2) + (size_t)MS_WARPS * 8 * MS_QUEUE) * sizeof(uint32_t) +
                               (size_t)MS_WARPS * MS_GROUPS * sizeof(unsigned long long) +
                               ((size_t)(MS_CELLS + 2) + (size_t)(MS_BUCKETS + 2)) * sizeof(uint16_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->dense_attr_set) {                            // per context: function attributes belong to the device
         QMS_CUDA(ctx, cudaFuncSetAttribute(match_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        attr_set = true;
+        ctx->dense_attr_set = true;
     }
     const int ctas_per_sm = ctx->dense_ctas > 0 ? ctx->dense_ctas : 2;
     int64_t grid = (int64_t)ctx->sm_count * ctas_per_sm;

@@ -145,6 +145,7 @@ struct qms_ctx {
     double copy_kernel_ratio = 0.0;  // hit copies / kernels (device ms) of the last pipelined run (reported by the bench)
     int64_t sub_batch_rows = 0;   // rows per sub-batch of the pipelined run (0: default)
     int dense_ctas = 2;            // its resident CTAs per SM
+    bool dense_attr_set = false, huge_attr_set = false;   // dynamic shared-memory sizes of the large kernels set on this device
     bool last_values = true;                   // ... including the matched (m/z, intensity) values
     DBuf<uint8_t> cub_tmp;
     DBuf<unsigned long long> dev_counters;   // see match.cu

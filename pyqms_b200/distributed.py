@@ -366,16 +366,18 @@ def gather_hits_to_rank0(out, spectrum_begin, arena, stats=None):
     return batches if batches is not None else out
 
 
-def gather_packed_hits(out, spectrum_begin, world):
+def gather_packed_hits(out, spectrum_begin, world, row_begin=0):
     """Gather per-rank packed hit dicts on rank 0 in rank (= spectrum) order; other ranks get None.
 
     ``out`` is the dict of ``IsotopologueLibrary.match_packed`` for this rank's spectrum shard whose first
-    spectrum has global index ``spectrum_begin``.  Works with any backend (object gather of numpy arrays)."""
+    spectrum has global index ``spectrum_begin`` and whose first peak row has global index ``row_begin``.  Works with any
+    backend (object gather of numpy arrays: fine for small results and CPU tests; ``SharedHitArena`` is the way for runs)."""
     d = _dist()
     nh, nw = out["n_hits"], out["n_windows"]
+    rows = np.asarray(out["peak"][:nw], dtype=np.int64)
     local = {"spec": out["spec"][:nh] + np.int32(spectrum_begin), "entry": out["entry"][:nh], "score": out["score"][:nh],
              "scaling": out["scaling"][:nh], "win_len": np.diff(out["win_off"][:nh + 1]), "mmz": out["mmz"][:nw],
-             "mi": out["mi"][:nw]}
+             "mi": out["mi"][:nw], "peak": np.where(rows >= 0, rows + np.int64(row_begin), -1)}
     if d is None or world == 1:
         parts = [local]
     else:

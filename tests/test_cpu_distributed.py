@@ -46,13 +46,16 @@ def _worker(rank, world, port, out_dir):
     nh = 2 * (end - begin)
     local = {"spec": np.repeat(np.arange(end - begin, dtype=np.int32), 2), "entry": np.tile(np.array([3, 7], dtype=np.int32), end - begin),
              "score": np.linspace(0.5, 0.9, nh), "scaling": np.ones(nh), "win_off": np.arange(0, 3 * nh + 1, 3, dtype=np.int64),
-             "mmz": np.arange(3 * nh, dtype=np.float64) + 1000 * rank, "mi": np.ones(3 * nh), "n_hits": nh, "n_windows": 3 * nh}
-    merged = qd.gather_packed_hits(local, begin, world)
+             "mmz": np.arange(3 * nh, dtype=np.float64) + 1000 * rank, "mi": np.ones(3 * nh), "n_hits": nh, "n_windows": 3 * nh,
+             "peak": np.where(np.arange(3 * nh) % 3 == 2, -1, np.arange(3 * nh)).astype(np.int64)}
+    merged = qd.gather_packed_hits(local, begin, world, row_begin=500 * rank)
     if rank == 0:
         assert merged["n_hits"] == 2 * n_spec and merged["n_windows"] == 6 * n_spec
         assert list(merged["spec"]) == [s for s in range(n_spec) for _ in range(2)]
         assert list(merged["win_off"]) == list(range(0, 6 * n_spec + 1, 3))
-        assert merged["mmz"][6 * (qd.shard_range(n_spec, 1, world)[0])] == 1000.0
+        first_of_rank_1 = 6 * (qd.shard_range(n_spec, 1, world)[0])
+        assert merged["mmz"][first_of_rank_1] == 1000.0
+        assert merged["peak"][first_of_rank_1] == 500 and merged["peak"][first_of_rank_1 + 2] == -1 and merged["peak"][1] == 1
     else:
         assert merged is None
     # --- the same through the shared-memory arena: every rank's hits land in its own segment, rank 0 maps them all
