@@ -75,7 +75,7 @@ def _restore_library(state, formulas):
     library = IsotopologueLibrary.__new__(IsotopologueLibrary)
     dict.__init__(library)
     library.__dict__.update(state)
-    dict.update(library, ((formula, _FormulaRecord(library, k, formula)) for k, formula in enumerate(formulas)))
+    dict.update(library, dict.fromkeys(formulas))           # records are made on first access
     library._ctx = Context(_restore_device.get())      # raises without the CUDA library / a GPU: no fallback
     library._views = {}
     library._push_params()
@@ -385,6 +385,51 @@ class IsotopologueLibrary(dict):
         """Let the hits of batched matching land in ``arena`` (``distributed.SharedHitArena``; None = back to the pool)."""
         self._hit_arena = arena
 
+    # ---- lib[formula] records: made on first access (a placeholder per formula until then) -------------------------
+    def __getitem__(self, formula):
+        record = dict.__getitem__(self, formula)
+        if record is None:
+            record = _FormulaRecord(self, self._formula_index[formula], formula)
+            dict.__setitem__(self, formula, record)
+        return record
+
+    def get(self, formula, default=None):
+        return self[formula] if dict.__contains__(self, formula) else default
+
+    def _all_records(self):
+        for formula, record in list(dict.items(self)):
+            if record is None:
+                self[formula]
+        return self
+
+    def values(self):
+        return dict.values(self._all_records())
+
+    def items(self):
+        return dict.items(self._all_records())
+
+    def pop(self, formula, *default):
+        if dict.__contains__(self, formula):
+            self[formula]
+        return dict.pop(self, formula, *default)
+
+    def popitem(self):
+        return dict.popitem(self._all_records())
+
+    def setdefault(self, formula, default=None):
+        return self[formula] if dict.__contains__(self, formula) else dict.setdefault(self, formula, default)
+
+    def copy(self):
+        return dict(self._all_records())
+
+    def __eq__(self, other):
+        return dict.__eq__(self._all_records(), other._all_records() if isinstance(other, IsotopologueLibrary) else other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
     _DEVICE_STATE = ("_hit_pool", "_hit_arena", "_ctx", "_views", "_entry_static", "_ent_env", "_ent_z", "_ent_lower", "_ent_upper", "_ent_win_off",
                      "_win_lo", "_win_hi", "_win_cmz", "_win_ri", "_win_ci")
 
@@ -637,7 +682,13 @@ class IsotopologueLibrary(dict):
         symbols = [symbols[k] for k in keep]
         counts, seen = np.ascontiguousarray(counts[:, keep]), np.ascontiguousarray(seen[:, keep])
         formulas = planner.hill_formulas(counts, symbols)
-        self.lookup["molecule to formula"].update(zip(ordered, formulas))
+        known_formulas = self.lookup["molecule to formula"]
+
+        def fill_molecule_to_formula(target, earlier=known_formulas, ordered=ordered, formulas=formulas):
+            dict.update(target, earlier)
+            dict.update(target, zip(ordered, formulas))
+
+        self.lookup["molecule to formula"] = _LazyDict(fill_molecule_to_formula)
         known_pairs = self.lookup["formula to molecule"]
 
         def fill_formula_to_molecule(target, earlier=known_pairs, ordered=ordered, formulas=formulas):
@@ -653,14 +704,18 @@ class IsotopologueLibrary(dict):
                     self.lookup["formula to trivial name"].setdefault(formula, []).append(name)
                 else:
                     print("No trivial name for molecule", molecule)
-        # one record per formula, taken from the first molecule (in sorted order) that has it
+        # one record per formula, taken from the first molecule (in sorted order) that has it.  The records themselves are made
+        # when somebody asks for them (``lib[formula]``): the dict holds a placeholder per formula until then.
         first_molecule = dict(zip(reversed(formulas), range(len(formulas) - 1, -1, -1)))
-        new = sorted((i, formula) for formula, i in first_molecule.items() if formula not in self)
-        rows = np.array([i for i, _ in new], dtype=np.int64)
+        if dict.__len__(self):
+            for formula in [f for f in first_molecule if dict.__contains__(self, f)]:
+                del first_molecule[formula]
+        rows = np.fromiter(first_molecule.values(), dtype=np.int64, count=len(first_molecule))
+        rows.sort()
         self._symbols = symbols
         self._cc_counts = np.ascontiguousarray(counts[rows]) if len(rows) else np.zeros((0, len(symbols)), dtype=np.int32)
         self._cc_seen = np.ascontiguousarray(seen[rows]) if len(rows) else np.zeros((0, len(symbols)), dtype=np.int16)
-        dict.update(self, ((formula, _FormulaRecord(self, k, formula)) for k, (_, formula) in enumerate(new)))
+        dict.update(self, dict.fromkeys([formulas[i] for i in rows.tolist()]))
         # highest atom count per element (insertion order = first molecule, then position inside it) and the count range
         # of the elements with two-isotope tables (IL:438-466)
         present = seen >= 0
