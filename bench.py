@@ -471,6 +471,18 @@ def run_ours(args):
         except Exception:
             pass
 
+    # ---- N > 1: the same library once more with the envelope build sharded over the ranks and assembled by one
+    # ncclAllGather (qms_allgather_library) -- not the default for a library of this size, reported for comparison
+    sharded_variant = None
+    if world > 1 and not args.no_extras:
+        del out
+        t0 = time.perf_counter()
+        sharded = pyqms_b200.IsotopologueLibrary(verbose=False, device=local, distributed=True, **library_kwargs(args))
+        sharded_variant = dict(sharded._build_stats, seconds_wall=time.perf_counter() - t0,
+                               ms_envelopes_this_rank=sharded.device_counters()["ms_envelopes"],
+                               identical_index=bool(sharded._n_entries == lib._n_entries and sharded._n_windows == lib._n_windows))
+        del sharded
+
     line = None
     if rank == 0:
         extras = {}
@@ -522,7 +534,7 @@ def run_ours(args):
                               "envelopes_per_s_device": (build_counters["envelopes"] / (build_counters["ms_envelopes"] * 1e-3)
                                                          if build_counters["ms_envelopes"] > 0 else None),
                               "envelopes_per_s_wall": build_counters["envelopes"] / build_s,
-                              "distributed": getattr(lib, "_build_stats", None)},
+                              "distributed": getattr(lib, "_build_stats", None), "sharded_variant": sharded_variant},
             "counters_per_step": {k: per_step[k] for k in ("peaks", "live_peaks", "incidences", "candidates", "candidate_windows",
                                                             "combinations", "hits", "hit_windows")},
         }

@@ -463,46 +463,18 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
         QMS_CUDA(ctx, cudaGetLastError());
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->window_density = ctx->h_pinned[0] ? (double)width_sum / (double)ctx->h_pinned[0] : 0.0;
-        // tables of the spectrum-resident matcher
-        ctx->dense_tables = false;
+        // the spectrum-resident matcher: whether its tables can be built for this library is decided here (cheap), the tables
+        // themselves are built when it first runs (qms_build_dense_tables): a library that is only built, or only matched by
+        // the row-streaming kernels, does not pay for them (60 M grid cells for a 60 kDa m/z range)
+        ctx->dense_tables = ctx->dense_tables_built = false;
         ctx->windows_disjoint = false;
         if (n_win < 0x7fffffffll) {
-            TmpBuf<int32_t> first_cover(ctx), flags(ctx);
-            QMS_TRY(qms_reserve(ctx, first_cover.b, (size_t)span + 1));
+            TmpBuf<int32_t> flags(ctx);
             QMS_TRY(qms_reserve(ctx, flags.b, 1));
-            QMS_TRY(qms_reserve(ctx, ctx->probe2, nw1));
-#if QMS_WINDOW_RECORDS
-            QMS_TRY(qms_reserve(ctx, ctx->win_rec, nw1));
-#endif
-            QMS_TRY(qms_reserve(ctx, ctx->cell_range, (size_t)span + 1));
-            fill_i32_kernel<<<qms_blocks(span + 1, threads), threads, 0, ctx->stream>>>(span + 1, INT32_MAX, first_cover.b.p);
             QMS_CUDA(ctx, cudaMemsetAsync(flags.b.p, 0, sizeof(int32_t), ctx->stream));
             window_shape_kernel<<<qms_blocks(n_entries, threads), threads, 0, ctx->stream>>>(n_entries, ctx->ent_win_off.p, ctx->win_lo.p,
                                                                                            ctx->win_hi.p, flags.b.p);
-            // zone table: groups = charge indices (entries of one charge share the isotope spacing)
-            ctx->zone_groups = n_charges <= 8 ? n_charges : 0;
-            ctx->zone_band_shift = 0;
-            while ((span >> ctx->zone_band_shift) >= ZONE_BANDS) ++ctx->zone_band_shift;
-            const int zone_cells = ZONE_BANDS * ZONE_GROUPS * ZONE_OFFSETS;
-            QMS_TRY(qms_reserve(ctx, ctx->zone_tab, (size_t)zone_cells));
-            zone_init_kernel<<<qms_blocks(zone_cells, threads), threads, 0, ctx->stream>>>(zone_cells, ctx->zone_tab.p);
-            if (ctx->zone_groups > 0) {
-                const size_t zone_smem = (size_t)2 * ZONE_BANDS * ctx->zone_groups * ZONE_OFFSETS * sizeof(int);
-                QMS_CUDA(ctx, cudaFuncSetAttribute(zone_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zone_smem));
-                zone_table_kernel<<<ctx->sm_count * 2, threads, zone_smem, ctx->stream>>>(
-                    n_entries, ctx->ent_win_off.p, ctx->ent_z.p, ctx->win_lo.p, ctx->win_hi.p, ctx->t_min, ctx->zone_band_shift,
-                    ctx->zone_groups, ctx->zone_tab.p);
-            }
-            probe2_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->probe.p, ctx->ent_win_off.p, ctx->ent_z.p,
-                                                                                  ctx->zone_groups, ctx->probe2.p, ctx->t_min,
-                                                                                  first_cover.b.p);
-            cell_range_kernel<<<qms_blocks(span, threads), threads, 0, ctx->stream>>>(span, ctx->cell_start.p, first_cover.b.p,
-                                                                                     ctx->cell_range.p);
-#if QMS_WINDOW_RECORDS
-            win_rec_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->win_lo.p, ctx->win_hi.p, ctx->win_ci.p,
-                                                                                   ctx->win_cmz.p, ctx->win_ri.p, ctx->win_rec.p);
-#endif
-            ctx->cnt.kernel_launches += 7;
+            ctx->cnt.kernel_launches++;
             int32_t h_flags = 0;
             QMS_CUDA(ctx, cudaMemcpyAsync(&h_flags, flags.b.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
             QMS_CUDA(ctx, cudaGetLastError());
@@ -519,6 +491,55 @@ extern "C" int qms_finalize_index(qms_ctx* ctx, int32_t n_charges, const int32_t
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     ctx->cnt.ms_index += ms;
     ctx->have_index = true;
+    return QMS_OK;
+}
+
+// Tables of the spectrum-resident matcher (match_spectrum.cu), built once per index when that matcher first runs.
+int qms_build_dense_tables(qms_ctx* ctx) {
+    if (ctx->dense_tables_built) return QMS_OK;
+    if (!ctx->have_index || !ctx->dense_tables) return qms_fail(ctx, QMS_E_ARG, "no index the spectrum-resident matcher can use");
+    const int threads = 256;
+    const int64_t n_win = ctx->n_windows, n_entries = ctx->n_entries;
+    const int64_t span = (int64_t)ctx->t_max - ctx->t_min + 1;
+    const size_t nw1 = (size_t)n_win + 1;
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    TmpBuf<int32_t> first_cover(ctx);
+    QMS_TRY(qms_reserve(ctx, first_cover.b, (size_t)span + 1));
+    QMS_TRY(qms_reserve(ctx, ctx->probe2, nw1));
+#if QMS_WINDOW_RECORDS
+    QMS_TRY(qms_reserve(ctx, ctx->win_rec, nw1));
+#endif
+    QMS_TRY(qms_reserve(ctx, ctx->cell_range, (size_t)span + 1));
+    fill_i32_kernel<<<qms_blocks(span + 1, threads), threads, 0, ctx->stream>>>(span + 1, INT32_MAX, first_cover.b.p);
+    // zone table: groups = charge indices (entries of one charge share the isotope spacing)
+    ctx->zone_groups = ctx->n_charges <= 8 ? ctx->n_charges : 0;
+    ctx->zone_band_shift = 0;
+    while ((span >> ctx->zone_band_shift) >= ZONE_BANDS) ++ctx->zone_band_shift;
+    const int zone_cells = ZONE_BANDS * ZONE_GROUPS * ZONE_OFFSETS;
+    QMS_TRY(qms_reserve(ctx, ctx->zone_tab, (size_t)zone_cells));
+    zone_init_kernel<<<qms_blocks(zone_cells, threads), threads, 0, ctx->stream>>>(zone_cells, ctx->zone_tab.p);
+    if (ctx->zone_groups > 0) {
+        const size_t zone_smem = (size_t)2 * ZONE_BANDS * ctx->zone_groups * ZONE_OFFSETS * sizeof(int);
+        QMS_CUDA(ctx, cudaFuncSetAttribute(zone_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zone_smem));
+        zone_table_kernel<<<ctx->sm_count * 2, threads, zone_smem, ctx->stream>>>(
+            n_entries, ctx->ent_win_off.p, ctx->ent_z.p, ctx->win_lo.p, ctx->win_hi.p, ctx->t_min, ctx->zone_band_shift, ctx->zone_groups,
+            ctx->zone_tab.p);
+    }
+    probe2_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->probe.p, ctx->ent_win_off.p, ctx->ent_z.p,
+                                                                          ctx->zone_groups, ctx->probe2.p, ctx->t_min, first_cover.b.p);
+    cell_range_kernel<<<qms_blocks(span, threads), threads, 0, ctx->stream>>>(span, ctx->cell_start.p, first_cover.b.p, ctx->cell_range.p);
+#if QMS_WINDOW_RECORDS
+    win_rec_kernel<<<qms_blocks(n_win, threads), threads, 0, ctx->stream>>>(n_win, ctx->win_lo.p, ctx->win_hi.p, ctx->win_ci.p,
+                                                                           ctx->win_cmz.p, ctx->win_ri.p, ctx->win_rec.p);
+#endif
+    ctx->cnt.kernel_launches += 6;
+    QMS_CUDA(ctx, cudaGetLastError());
+    QMS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->cnt.ms_index += ms;
+    ctx->dense_tables_built = true;
     return QMS_OK;
 }
 

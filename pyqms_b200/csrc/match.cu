@@ -1730,6 +1730,7 @@ static int reserve_run(qms_ctx* ctx, int64_t hits, int64_t windows, bool values)
 static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, const int64_t* d_off, int64_t n_spectra,
                      double xi, int entry_bits, qms_hits* out, int64_t* n_hits, int64_t* n_hit_windows) {
     const int64_t p_begin = h_off[0], p_end = h_off[n_spectra], n_peaks = p_end - p_begin;
+    QMS_TRY(qms_build_dense_tables(ctx));                       // once per index
     const bool peaks_on_device = qms_is_device_ptr(peaks);
     const double2* d_peaks = reinterpret_cast<const double2*>(peaks);
     if (!peaks_on_device) {

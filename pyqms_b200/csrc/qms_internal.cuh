@@ -113,7 +113,8 @@ struct qms_ctx {
     DBuf<int32_t> win_entry;      // index entry of every window
     DBuf<int2> zone_tab;          // [32 m/z bands][16 groups][32 window-ordinal differences]: where the other windows of an entry lie
     int zone_groups = 0, zone_band_shift = 0;
-    bool dense_tables = false;    // the four tables exist (window ids fit 31 bits, k and n_c fit 16)
+    bool dense_tables = false;    // the tables can be built (window ids fit 31 bits, k and n_c fit 12) ...
+    bool dense_tables_built = false;   // ... and have been (qms_build_dense_tables, on the first spectrum-resident match)
     bool windows_disjoint = false;   // every entry's windows ascend without touching (lo[m+1] > hi[m])
     int32_t t_min = 0, t_max = -1, max_width = 0;
     double mz_min = 0, mz_max = 0;
@@ -216,6 +217,7 @@ inline int qms_download(qms_ctx* ctx, T* host, const T* dev, size_t n) {
     return QMS_OK;
 }
 bool qms_is_device_ptr(const void* p);
+int qms_build_dense_tables(qms_ctx* ctx);
 extern "C" int qms_comm_destroy(qms_ctx* ctx);
 
 
