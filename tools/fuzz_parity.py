@@ -2,6 +2,7 @@
 """Randomised differential run: CUDA path vs the CPU oracle over random libraries, params and spectra (both input kinds).
 
     python tools/fuzz_parity.py [n_configs] [first_seed] [seconds_per_config=20]
+    python tools/fuzz_parity.py --matchers [n_configs] [first_seed]      # the two matchers of the library against each other
 
 Prints one line per configuration and exits non-zero at the first mismatch.  (Test infrastructure: imports oracle/.)
 The oracle enumerates candidate combinations like the reference and can take minutes on a dense spectrum with wide
@@ -97,5 +98,56 @@ def check(seed):
         lib.device_counters()["dense_batches"], time.time() - t0), flush=True)
 
 
+def check_matchers(seed):
+    """Row-streaming against spectrum-resident matcher on a random dense library (no oracle: hundreds to thousands of
+    peptides, label sets, window widths, crowded spectra, sub-batched host runs): packed hits must agree bit for bit."""
+    rng = random.Random(seed)
+    molecules = random_tryptic_peptides(rng.randint(300, 6000), seed=seed)
+    charges = sorted(rng.sample([1, 2, 3, 4, 5], rng.randint(2, 5)))
+    labels = rng.choice([None, None, {"15N": [0, 0.99]}, {"15N": [0, 0.2, 0.5, 0.8, 0.99]}])
+    fixed = rng.choice([None, {"C": ["C(2)H(3)14N(1)O(1)"]}])
+    params = {"M_SCORE_THRESHOLD": rng.choice([0.2, 0.5, 0.7]), "REL_MZ_RANGE": rng.choice([5e-6, 1e-5, 3e-5]),
+              "MINIMUM_NUMBER_OF_MATCHED_ISOTOPOLOGUES": rng.choice([1, 2, 3]), "REQUIRED_PERCENTILE_PEAK_OVERLAP": rng.choice([0.2, 0.5, 0.8]),
+              "MZ_SCORE_PERCENTILE": rng.choice([0.0, 0.4, 1.0]), "INTERNAL_PRECISION": rng.choice([1000, 1000, 10000]),
+              "MIN_REL_PEAK_INTENSITY_FOR_MATCHING": rng.choice([0.01, 0.05])}
+    lib = pyqms_b200.IsotopologueLibrary(molecules=molecules, charges=charges, metabolic_labels=labels, fixed_labels=fixed,
+                                         params=params, verbose=False)
+    mz, ci = lib.entry_peaks()
+    peaks, offsets = synth_run(mz, ci, n_spectra=rng.randint(20, 300), seed=seed + 1, mean_peaks=rng.choice([300, 1500, 5000]),
+                               max_peaks=rng.choice([5000, 20000]), elution_sigma=rng.choice([1.0, 4.0]),
+                               entry_fraction=rng.choice([0.01, 0.1, 0.5]), ppm_sd=rng.choice([1.0, 3.0]), dropout=rng.choice([0.0, 0.3]))
+    from pyqms_b200._capi import QmsError
+    outs, refused = [], 0
+    for mode, sub_rows in ((0, 0), (1, 0), (1, rng.choice([20000, 100000]))):
+        lib._ctx.set_tuning("dense_mode", mode)
+        lib._ctx.set_tuning("sub_batch_rows", sub_rows)
+        before = lib.device_counters()["dense_batches"]
+        try:
+            outs.append(lib.match_packed(peaks, offsets))
+        except QmsError as error:                       # wide label grids x crowded spectra: 2^32 combinations in one pair
+            assert error.code == -5 and "candidate combinations" in str(error), error
+            refused += 1
+        used = lib.device_counters()["dense_batches"] - before
+    if refused:
+        assert refused == 3, "the matchers disagree on the combination limit"
+        print("seed %d: both matchers refuse the batch (a pair above the combination limit)" % seed, flush=True)
+        return
+    a = outs[0]
+    for b in outs[1:]:
+        assert a["n_hits"] == b["n_hits"] and a["n_windows"] == b["n_windows"], (seed, a["n_hits"], b["n_hits"])
+        for k in ("spec", "entry", "win_off", "peak"):
+            assert np.array_equal(a[k], b[k]), (seed, k)
+        for k in ("score", "scaling", "mmz", "mi"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), (seed, k)
+    print("seed %d: ok  entries %d, windows %d, %d spectra, %d peaks, %d hits, %d spectrum-resident sub-batches in the last run" % (
+        seed, lib._n_entries, lib._n_windows, len(offsets) - 1, len(peaks), a["n_hits"], used), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--matchers":
+        count = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+        start = int(sys.argv[3]) if len(sys.argv) > 3 else 5000
+        for config_seed in range(start, start + count):
+            check_matchers(config_seed)
+    else:
+        main()
