@@ -141,6 +141,59 @@ def test_spectrum_resident_matcher_equals_row_streaming_matcher():
         lib._ctx.set_tuning("sub_batch_rows", 0)
 
 
+def test_proteome_at_its_named_size():
+    """configs[3] at full size: the 500 000-peptide library against shard 0 of the 200 000-spectrum run (25 000 spectra,
+    39.4 M peaks; the spectra come from the committed planted-peak table, like in bench.py).  Size-independent properties:
+    hits strictly ordered by (spectrum, entry), every score above the threshold, idempotence, batch-split invariance
+    (device-resident single batch = pipelined host run = two halves), and exact agreement with the CPU oracle for a
+    300-peptide sub-library on 40 spectra (matching an entry does not depend on the other entries, numpy input)."""
+    import sys
+    from pathlib import Path
+    import pyqms_b200
+    from oracle.qms_oracle import OracleLibrary
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root))
+    import bench
+    table = np.load(bench.FIXTURE)
+    planted = {"n_entries": int(table["n_entries"]), "lens": table["lens"].astype(np.int64), "mz": table["mz"], "ci": table["ci"].astype(np.float64)}
+    peaks, offsets = synth_run(None, None, n_spectra=25000, seed=20260104, entry_fraction=0.02, planted=planted)
+    assert len(peaks) == 39371082
+    peptides = random_tryptic_peptides(500000, seed=20260104)
+    lib = pyqms_b200.IsotopologueLibrary(molecules=peptides, charges=[1, 2, 3, 4, 5], fixed_labels=CAM_FIXED_LABEL, verbose=False)
+    assert lib._n_entries == planted["n_entries"] == 1585058
+    whole = lib.match_packed(peaks, offsets)                                  # pipelined host run (sub-batches)
+    assert lib.device_counters()["dense_batches"] >= 3
+    nh = whole["n_hits"]
+    assert nh == 25096897
+    key = whole["spec"].astype(np.int64) << 32 | whole["entry"]
+    assert np.all(key[1:] > key[:-1])
+    assert np.all(whole["score"] >= lib.params["M_SCORE_THRESHOLD"])
+    assert np.all(np.diff(whole["win_off"]) >= 2) and whole["win_off"][-1] == whole["n_windows"]
+    rows = whole["peak"][whole["peak"] >= 0]
+    assert np.array_equal(peaks[rows, 0], whole["mmz"][whole["peak"] >= 0])   # matched values = the caller's rows
+    cut = 11003                                                               # two halves = the whole
+    first = lib.match_packed(peaks[:offsets[cut]], offsets[:cut + 1])
+    second = lib.match_packed(peaks[offsets[cut]:], offsets[cut:] - offsets[cut])
+    assert first["n_hits"] + second["n_hits"] == nh
+    for k in ("entry", "score", "scaling"):
+        assert np.array_equal(np.concatenate([first[k], second[k]]), whole[k]), k
+    assert np.array_equal(np.concatenate([first["spec"], second["spec"] + cut]), whole["spec"])
+    del first, second
+    # oracle on a sub-library: same hits for its formulas
+    sample = list(range(0, 25000, 625))
+    subset = peptides[::1667][:300]
+    ora = OracleLibrary(molecules=subset, charges=[1, 2, 3, 4, 5], fixed_labels=CAM_FIXED_LABEL)
+    want = {}
+    for s in sample:
+        ora.match_all(peaks[offsets[s]:offsets[s + 1]], "run", s, float(s), want)
+    got = lib.match_many([peaks[offsets[s]:offsets[s + 1]] for s in sample], file_name="run", spec_ids=sample,
+                         spec_rts=[float(s) for s in sample])
+    formulas = set(ora.keys())
+    got_rows = [r for r in results_to_rows(got) if r[0][1] in formulas]
+    assert_results_equal(got_rows, results_to_rows(want), score_tol=1e-6, cmz_rel=1e-12, ri_rel=1e-9, key_order=False)
+    assert sum(len(v) for v in want.values()) > 5
+
+
 def test_envelope_sweep_against_oracle():
     """configs[4] shape, bounded: averagine formulas 100 Da - 12 kDa, FP64 abundance parity 1e-9 vs the oracle."""
     sys.setrecursionlimit(20000)
