@@ -141,6 +141,36 @@ def test_spectrum_resident_matcher_equals_row_streaming_matcher():
         lib._ctx.set_tuning("sub_batch_rows", 0)
 
 
+def test_bsa_percentile_grid_run_properties():
+    """configs[2] at its named library size (19 BSA molecules x 100 label percentiles, 7 600 entries whose windows pile up
+    on the same m/z: the combination-heavy regime) against 6 000 spectra of the run: both matchers agree bit for bit, hits
+    are ordered, a split run equals the whole."""
+    import pyqms_b200
+    lib = pyqms_b200.IsotopologueLibrary(molecules=BSA_MOLECULES, charges=[1, 2, 3, 4], fixed_labels=CAM_FIXED_LABEL,
+                                         metabolic_labels={"15N": [round(0.01 * i, 2) for i in range(100)]}, verbose=False)
+    assert lib._n_entries == 7600
+    mz, ci = lib.entry_peaks()
+    peaks, offsets = synth_run(mz, ci, n_spectra=6000, seed=20260101)
+    outs = {}
+    for mode in (0, 1):
+        lib._ctx.set_tuning("dense_mode", mode)
+        outs[mode] = lib.match_packed(peaks, offsets)
+    lib._ctx.set_tuning("dense_mode", 2)
+    a, b = outs[0], outs[1]
+    assert a["n_hits"] == b["n_hits"] > 100000
+    for k in ("spec", "entry", "win_off", "peak"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("score", "scaling", "mmz", "mi"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    key = a["spec"].astype(np.int64) << 32 | a["entry"]
+    assert np.all(key[1:] > key[:-1])
+    cut = 2517
+    first = lib.match_packed(peaks[:offsets[cut]], offsets[:cut + 1])
+    second = lib.match_packed(peaks[offsets[cut]:], offsets[cut:] - offsets[cut])
+    assert np.array_equal(np.concatenate([first["score"], second["score"]]), a["score"])
+    assert np.array_equal(np.concatenate([first["entry"], second["entry"]]), a["entry"])
+
+
 def test_proteome_at_its_named_size():
     """configs[3] at full size: the 500 000-peptide library against shard 0 of the 200 000-spectrum run (25 000 spectra,
     39.4 M peaks; the spectra come from the committed planted-peak table, like in bench.py).  Size-independent properties:
