@@ -10,19 +10,26 @@
 //            of every bucket, Q9) plus a direct-address table over the m/z grid (coarse cell -> first bucket at or
 //            above it), so "how many spectrum buckets lie in [lo, hi]" costs one table read and one or two bucket
 //            reads, with no search and no divergent walk.
-//   phase B  the warps take the buckets in turn, read each bucket's probe records coalesced, queue the incident ones
-//            in shared memory and gate 32 queued incidences at a time, one per lane: the entry passes when the bucket
-//            counts of its windows add up to the overlap need; the incidence owns the (spectrum, entry) pair when no
-//            lower window holds a bucket and its own bucket is the first of its window (the entry's windows are
-//            disjoint and ascending, checked at index build, so the count over the union is the sum over the windows).
-//            Survivors are queued again and scored 32 at a time: pairs whose windows hold at most one bucket each
-//            (one candidate combination) are scored inline with the reference's operation order; pairs with several
-//            candidates in a window go to the pair list and through K6 / K6b of match.cu.
+//   phase B  the warps draw the buckets one by one.  Per bucket and entry group (= charge) the 32 lanes count the spectrum
+//            buckets inside the 32 "zones" in which the other windows of an entry holding this bucket can lie (zone table
+//            of the index: extremes over all entries, so the containment holds for any library) -> a 64-bit zone mask per
+//            group.  The bucket's probe records are read coalesced; for an incident record (window k of an entry with n_c
+//            windows) the mask, shifted by k, bounds the buckets in the entry's windows from above: below the overlap need
+//            the incidence is dropped with a shift, two popcounts and a compare.  Survivors are queued in shared memory and
+//            gated 32 at a time, one per lane, looking only at windows whose zone is occupied: the entry passes when the
+//            bucket counts of its windows add up to the overlap need (IL:1968-1976); the incidence owns the (spectrum,
+//            entry) pair when no lower window holds a bucket and its own bucket is the first of its window (the entry's
+//            windows are disjoint and ascending, checked at index build, so the count over the union is the sum over the
+//            windows).  Passing pairs are queued again and scored 32 at a time: pairs whose windows hold at most one bucket
+//            each (one candidate combination) inline with the reference's operation order -- after an exact-safe bound
+//            (score <= sum of matched ri / sum of ri) that spares a quarter of them the divisions --, pairs with several
+//            candidates in a window go to the pair list and through K6 / K6b / K6c of match.cu.
 //   hits are appended to a staging area in discovery order, then sorted by (spectrum, entry) and emitted -- only the
 //   hits (13 % of the candidate pairs on the proteome workload) are ever sorted or written.
 //
-// Used when the library is dense (window_density >= 4), the input has numpy semantics and all entries have disjoint
-// ascending windows; everything else runs through match.cu.
+// Used when the library is dense (window_density >= 4), the input has numpy semantics, no spectrum has more than 65 534
+// rows and all entries have disjoint ascending windows; everything else runs through match.cu.  Both matchers give the
+// same hits bit for bit (tests/test_gpu_scale.py, tools/fuzz_parity.py --matchers).
 #include <stdlib.h>
 
 #include <algorithm>
