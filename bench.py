@@ -431,8 +431,11 @@ def run_ours(args):
     e2e_value = world * n_spec * args.steps / float(t.item())
     h2d = int(peaks.nbytes + offsets.nbytes)
     own = out if arena is None else gather_stats.get("own", out)
-    d2h = int(sum(dict.__getitem__(own, k).nbytes for k in ("spec", "entry", "score", "scaling", "win_off", "peak", "peak32", "mmz", "mi")
-                  if k in dict.keys(own)))      # the arrays the device copied out (lazily gathered ones do not count)
+    have = dict.keys(own)                         # the arrays the device copied out (columns widened on the host do not count)
+    shipped = ("entry", "score", "scaling", "peak16", "spec_off") if "peak16" in have else \
+        ("spec", "entry", "score", "scaling", "win_off", "peak32") if "peak32" in have else \
+        ("spec", "entry", "score", "scaling", "win_off", "peak", "mmz", "mi")
+    d2h = int(sum(dict.__getitem__(own, k).nbytes for k in shipped))
     e2e_counters = ctx.counters()
     e2e_calls = max(args.steps + max(1, min(args.warmup, 3)), 1)
     ms_h2d_step = (e2e_counters["ms_h2d"] - counters["ms_h2d"]) / e2e_calls

@@ -234,6 +234,15 @@ typedef struct qms_hits {
     int32_t* hit_peak32;   /* optional narrow form of hit_peak: row of the matched peak counted from the first row of the batch
                             * (offsets[0]), -1 = None; half the bytes on the way to the host.  Filled if not NULL (hit_peak may
                             * then be NULL). */
+    /* Optional compact forms (each filled if not NULL; the wide array it stands for may then be NULL): with them a hit costs
+     * 21 bytes + 2 per window on the way to the host instead of 32 + 8.
+     *   hit_nc8[h]       windows of hit h = hit_win_off[h+1] - hit_win_off[h]   (QMS_E_LIMIT if an entry has > 255 windows)
+     *   hit_peak16[w]    row of the matched peak counted from the first row of the hit's spectrum, 0xFFFF = None
+     *                    (QMS_E_LIMIT if a spectrum of the batch has more than 65 534 rows)
+     *   spec_hit_off[s]  n_spectra + 1 values: the hits of spectrum s are [spec_hit_off[s], spec_hit_off[s+1])           */
+    uint8_t* hit_nc8;
+    uint16_t* hit_peak16;
+    int64_t* spec_hit_off;
 } qms_hits;
 int qms_match_batch(qms_ctx* ctx, const double* peaks, const int64_t* offsets, int64_t n_spectra,
                     int32_t input_kind, double mz_score_percentile, qms_hits* out, int64_t* n_hits,

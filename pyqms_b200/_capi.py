@@ -45,7 +45,8 @@ class QmsIndexInfo(C.Structure):
 class QmsHits(C.Structure):
     _fields_ = [("cap_hits", C.c_int64), ("cap_windows", C.c_int64), ("hit_spec", C.c_void_p), ("hit_entry", C.c_void_p),
                 ("hit_score", C.c_void_p), ("hit_scaling", C.c_void_p), ("hit_win_off", C.c_void_p), ("hit_mmz", C.c_void_p),
-                ("hit_mi", C.c_void_p), ("hit_peak", C.c_void_p), ("hit_peak32", C.c_void_p)]
+                ("hit_mi", C.c_void_p), ("hit_peak", C.c_void_p), ("hit_peak32", C.c_void_p), ("hit_nc8", C.c_void_p),
+                ("hit_peak16", C.c_void_p), ("spec_hit_off", C.c_void_p)]
 
 
 EXPORTS = {  # name -> (restype, argtypes); must list every symbol of include/qms_b200.h

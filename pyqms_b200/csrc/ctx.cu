@@ -275,7 +275,7 @@ void qms_ctx_destroy(qms_ctx* ctx) {
     REL(probe2); REL(cell_range); REL(win_rec); REL(win_entry); REL(zone_tab);
     REL(st_key); REL(st_key_alt); REL(st_score); REL(st_scaling); REL(st_woff); REL(st_nc); REL(st_rows); REL(st_order); REL(st_order_alt);
     REL(spec_buckets); REL(spec_rows); REL(st_nc_sorted); REL(st_win_off);
-    REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak); REL(o_peak32);
+    REL(o_spec); REL(o_entry); REL(o_score); REL(o_scaling); REL(o_mmz); REL(o_mi); REL(o_win_off); REL(o_peak); REL(o_peak32); REL(o_nc8); REL(o_peak16); REL(o_spec_off);
 #undef REL
     for (int i = 0; i < 12; ++i) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

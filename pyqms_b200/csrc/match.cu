@@ -1535,6 +1535,78 @@ static int copy_out_peak32(qms_ctx* ctx, cudaStream_t stream, int32_t* dst, int6
     return QMS_OK;
 }
 
+// ---- compact forms of the retained hits (qms_hits: hit_nc8, hit_peak16, spec_hit_off) ----
+__global__ void compact_hits_kernel(int64_t nh, const int64_t* __restrict__ win_off, const int32_t* __restrict__ spec,
+                                    const int64_t* __restrict__ peak, const int64_t* __restrict__ offsets, uint8_t* __restrict__ nc8,
+                                    uint16_t* __restrict__ peak16) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nh) return;
+    const int64_t w0 = win_off[q], w1 = win_off[q + 1];
+    if (nc8) nc8[q] = (uint8_t)(w1 - w0);
+    if (!peak16) return;
+    const int64_t first_row = offsets[spec[q]];
+    for (int64_t w = w0; w < w1; ++w) {
+        const int64_t row = peak[w];
+        peak16[w] = row < 0 ? (uint16_t)0xFFFF : (uint16_t)(row - first_row);
+    }
+}
+
+// spec_hit_off of the spectra [s_begin, s_end] from the (sorted) spectrum column of hits [h0, h0 + nh): thread q writes
+// the offset of every spectrum between the one of hit q-1 (exclusive) and the one of hit q (inclusive); thread nh closes
+// the range, so spectra without hits and the element behind the last spectrum get their value too
+__global__ void spec_hit_off_kernel(int64_t nh, int64_t h0, const int32_t* __restrict__ spec, int64_t s_begin, int64_t s_end,
+                                    int64_t* __restrict__ off) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > nh) return;
+    const int64_t prev = q == 0 ? s_begin - 1 : (int64_t)spec[h0 + q - 1];
+    const int64_t cur = q == nh ? s_end : (int64_t)spec[h0 + q];
+    for (int64_t s = prev + 1; s <= cur; ++s) off[s] = h0 + q;
+}
+
+static bool wants_compact(const qms_hits* out) { return out && (out->hit_nc8 || out->hit_peak16 || out->spec_hit_off); }
+
+static int compact_limits(qms_ctx* ctx, const qms_hits* out, int64_t longest_spectrum) {
+    if (out && out->hit_nc8 && ctx->max_nc > 255)
+        return qms_fail(ctx, QMS_E_LIMIT, "hit_nc8: an entry of this library has %d windows (more than 255)", ctx->max_nc);
+    if (out && out->hit_peak16 && longest_spectrum > 65534)
+        return qms_fail(ctx, QMS_E_LIMIT, "hit_peak16: a spectrum of the batch has %lld rows (more than 65534)", (long long)longest_spectrum);
+    return QMS_OK;
+}
+
+// the compact forms of hits [h0, h0 + nh) / hit windows from w0 / spectra [s_begin, s_end) of the retained arrays, on `stream`
+static int fill_compact(qms_ctx* ctx, cudaStream_t stream, const qms_hits* out, int64_t h0, int64_t nh, int64_t s_begin, int64_t s_end) {
+    if (!wants_compact(out)) return QMS_OK;
+    if (out->hit_nc8) QMS_TRY(qms_reserve(ctx, ctx->o_nc8, ctx->o_spec.cap, true));
+    if (out->hit_peak16) QMS_TRY(qms_reserve(ctx, ctx->o_peak16, ctx->o_peak.cap, true));
+    if (out->spec_hit_off) QMS_TRY(qms_reserve(ctx, ctx->o_spec_off, (size_t)ctx->last_n_spectra + 1, true));
+    if (nh > 0 && (out->hit_nc8 || out->hit_peak16)) {
+        compact_hits_kernel<<<qms_blocks(nh, 256), 256, 0, stream>>>(nh, ctx->o_win_off.p + h0, ctx->o_spec.p + h0, ctx->o_peak.p,
+                                                                     ctx->d_offsets.p, out->hit_nc8 ? ctx->o_nc8.p + h0 : nullptr,
+                                                                     out->hit_peak16 ? ctx->o_peak16.p : nullptr);
+        QMS_CUDA(ctx, cudaGetLastError());
+        ctx->cnt.kernel_launches++;
+    }
+    if (out->spec_hit_off) {
+        spec_hit_off_kernel<<<qms_blocks(nh + 1, 256), 256, 0, stream>>>(nh, h0, ctx->o_spec.p, s_begin, s_end, ctx->o_spec_off.p);
+        QMS_CUDA(ctx, cudaGetLastError());
+        ctx->cnt.kernel_launches++;
+    }
+    return QMS_OK;
+}
+
+template <class T>
+static int copy_out_on(qms_ctx* ctx, cudaStream_t stream, T* dst, const T* src, size_t n);
+
+static int copy_compact(qms_ctx* ctx, cudaStream_t stream, const qms_hits* out, int64_t h0, int64_t nh, int64_t w0, int64_t nw, int64_t s_begin,
+                        int64_t s_end) {
+    if (!wants_compact(out)) return QMS_OK;
+    if (out->hit_nc8) QMS_TRY(copy_out_on(ctx, stream, out->hit_nc8 + h0, ctx->o_nc8.p + h0, (size_t)nh));
+    if (out->hit_peak16) QMS_TRY(copy_out_on(ctx, stream, out->hit_peak16 + w0, ctx->o_peak16.p + w0, (size_t)nw));
+    if (out->spec_hit_off)
+        QMS_TRY(copy_out_on(ctx, stream, out->spec_hit_off + s_begin, ctx->o_spec_off.p + s_begin, (size_t)(s_end - s_begin) + 1));
+    return QMS_OK;
+}
+
 static float elapsed(qms_ctx* ctx, int a, int b) {
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
@@ -1556,7 +1628,8 @@ struct EmitTarget {
 static EmitTarget emit_target(qms_ctx* ctx, const qms_hits* out) {
     EmitTarget t;
     const bool callers = out && out->hit_spec && out->hit_entry && out->hit_score && out->hit_scaling && out->hit_win_off &&
-                         out->hit_mmz && out->hit_mi && out->hit_peak && !out->hit_peak32 && qms_is_device_ptr(out->hit_spec) &&
+                         out->hit_mmz && out->hit_mi && out->hit_peak && !out->hit_peak32 && !wants_compact(out) &&
+                         qms_is_device_ptr(out->hit_spec) &&
                          qms_is_device_ptr(out->hit_entry) && qms_is_device_ptr(out->hit_score) && qms_is_device_ptr(out->hit_scaling) &&
                          qms_is_device_ptr(out->hit_win_off) && qms_is_device_ptr(out->hit_mmz) && qms_is_device_ptr(out->hit_mi) &&
                          qms_is_device_ptr(out->hit_peak);
@@ -1631,7 +1704,7 @@ int qms_score_pair_list(qms_ctx* ctx, const MatchView& v, int64_t n_pairs, const
 // caller buffers the emit kernels can write directly: all in device memory (the matched values are optional)
 static bool callers_on_device(const qms_hits* out) {
     if (!out || !out->hit_spec || !out->hit_entry || !out->hit_score || !out->hit_scaling || !out->hit_win_off || !out->hit_peak ||
-        out->hit_peak32)
+        out->hit_peak32 || wants_compact(out))
         return false;
     if ((out->hit_mmz == nullptr) != (out->hit_mi == nullptr)) return false;
     for (const void* p : {(const void*)out->hit_spec, (const void*)out->hit_entry, (const void*)out->hit_score, (const void*)out->hit_scaling,
@@ -1688,6 +1761,11 @@ static int write_empty_result(qms_ctx* ctx, qms_hits* out) {
         const int64_t zero = 0;
         QMS_CUDA(ctx, cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t),
                                  qms_is_device_ptr(out->hit_win_off) ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
+    }
+    if (out && out->spec_hit_off) {                                // no hits: every spectrum's range is [0, 0)
+        const size_t bytes = ((size_t)ctx->last_n_spectra + 1) * sizeof(int64_t);
+        if (qms_is_device_ptr(out->spec_hit_off)) QMS_CUDA(ctx, cudaMemset(out->spec_hit_off, 0, bytes));
+        else memset(out->spec_hit_off, 0, bytes);
     }
     return QMS_OK;
 }
@@ -1795,7 +1873,7 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
         return QMS_OK;
     };
     struct Part {
-        int64_t h0, nh, w0, nw;
+        int64_t h0, nh, w0, nw, s0, s1;                           // hits, hit windows and spectra of a sub-batch
     };
     bool fits = out != nullptr;
     auto download = [&](const Part& part) -> int {                // hits of one sub-batch -> the caller's arrays
@@ -1820,6 +1898,7 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
         // (the int32 rows were written by the emit kernel: a narrowing kernel on this stream would wait for an SM until the
         // next sub-batch's matcher, which fills the GPU, is done -- and every copy queued behind it with it)
         QMS_TRY(copy_out_on(ctx, ctx->s_out, out->hit_peak32 ? out->hit_peak32 + part.w0 : nullptr, ctx->o_peak32.p + part.w0, (size_t)part.nw));
+        QMS_TRY(copy_compact(ctx, ctx->s_out, out, part.h0, part.nh, part.w0, part.nw, part.s0, part.s1));
         stamp(ctx->s_out);
         is_upload.push_back(0);
         return QMS_OK;
@@ -1828,7 +1907,7 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
     if (!direct && ctx->run_hits_hint > 0) QMS_TRY(reserve_run(ctx, ctx->run_hits_hint, ctx->run_windows_hint, want_values));
     int64_t total_h = 0, total_w = 0;
     bool have_pending = false, wrote_callers = false;
-    Part pending{0, 0, 0, 0};
+    Part pending{0, 0, 0, 0, 0, 0};
     QMS_TRY(upload(0));
     for (size_t b = 0; b < n_sub; ++b) {
         const int64_t r0 = h_off[cuts[b]], r1 = h_off[cuts[b + 1]];
@@ -1846,7 +1925,7 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
         QMS_TRY(qms_dense_stage(ctx, vb, r0, r1, entry_bits, overlap, &nh, &nw));
         int spec_bits = 1;
         while ((1ll << spec_bits) < vb.n_spectra) ++spec_bits;
-        qms_hits target;
+        qms_hits target{};
         if (direct && nh <= out->cap_hits && nw <= out->cap_windows) {
             target = *out;
             wrote_callers = true;
@@ -1872,8 +1951,12 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
             }
         }
         QMS_TRY(qms_dense_emit(ctx, vb, r0, entry_bits, spec_bits, nh, cuts[b], total_w, target, p_begin));
-        pending = Part{total_h, nh, total_w, nw};
-        have_pending = nh > 0;
+        if (!wrote_callers && wants_compact(out)) {               // on the compute stream, before the next sub-batch fills the GPU
+            QMS_TRY(fill_compact(ctx, ctx->stream, out, total_h, nh, cuts[b], cuts[b + 1]));
+            QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        pending = Part{total_h, nh, total_w, nw, cuts[b], cuts[b + 1]};
+        have_pending = nh > 0 || (out && out->spec_hit_off);
         total_h += nh;
         total_w += nw;
     }
@@ -1931,6 +2014,10 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
                                       ctx->stream));
         QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         h_off = ctx->h_offsets.data();
+        // the compact hit forms read the offsets again, possibly as late as qms_fetch_hits: keep a copy
+        QMS_TRY(qms_reserve(ctx, ctx->d_offsets, (size_t)n_spectra + 1));
+        QMS_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets.p, offsets, ((size_t)n_spectra + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
     } else {
         QMS_TRY(qms_upload(ctx, ctx->d_offsets, offsets, (size_t)n_spectra + 1));
         d_off = ctx->d_offsets.p;
@@ -1945,6 +2032,9 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
     const int64_t n_peaks = p_end - p_begin;
     if (n_peaks > 0 && !peaks) return qms_fail(ctx, QMS_E_ARG, "peaks is NULL");
     if (n_peaks >= 0x7fffffffll) return qms_fail(ctx, QMS_E_LIMIT, "at most 2^31-2 peaks per batch (split the run)");
+    ctx->last_n_spectra = n_spectra;
+    ctx->last_longest = longest;
+    QMS_TRY(compact_limits(ctx, out, longest));
     ctx->cnt.spectra += n_spectra;
     ctx->cnt.peaks += n_peaks;
     if (n_peaks == 0 || n_spectra == 0 || ctx->n_windows == 0) {
@@ -2182,6 +2272,8 @@ static int match_impl(qms_ctx* ctx, const double* peaks, const int64_t* offsets,
         QMS_TRY(copy_out(ctx, out->hit_mi, ctx->o_mi.p, (size_t)nw));
         QMS_TRY(copy_out(ctx, out->hit_peak, ctx->o_peak.p, (size_t)nw));
         QMS_TRY(copy_out_peak32(ctx, ctx->stream, out->hit_peak32, 0, (size_t)nw, p_begin));
+        QMS_TRY(fill_compact(ctx, ctx->stream, out, 0, nh, 0, n_spectra));
+        QMS_TRY(copy_compact(ctx, ctx->stream, out, 0, nh, 0, nw, 0, n_spectra));
     }
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2204,13 +2296,12 @@ extern "C" int qms_fetch_hits(qms_ctx* ctx, qms_hits* out, int64_t* n_hits, int6
         return qms_fail(ctx, QMS_E_CAPACITY, "hit buffers too small: need %lld hits / %lld windows", (long long)nh, (long long)nw);
     if ((out->hit_mmz || out->hit_mi) && !ctx->last_values && nw > 0)
         return qms_fail(ctx, QMS_E_ARG, "the last match was asked not to keep the matched values (hit_mmz / hit_mi were NULL)");
+    QMS_TRY(compact_limits(ctx, out, ctx->last_longest));
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     if (nh == 0) {
         const int64_t zero = 0;
-        if (out->hit_win_off)
-            QMS_CUDA(ctx, cudaMemcpy(out->hit_win_off, &zero, sizeof(int64_t),
-                                     qms_is_device_ptr(out->hit_win_off) ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost));
-        return QMS_OK;
+        (void)zero;
+        return write_empty_result(ctx, out);
     }
     QMS_TRY(copy_out(ctx, out->hit_spec, ctx->o_spec.p, (size_t)nh));
     QMS_TRY(copy_out(ctx, out->hit_entry, ctx->o_entry.p, (size_t)nh));
@@ -2221,6 +2312,8 @@ extern "C" int qms_fetch_hits(qms_ctx* ctx, qms_hits* out, int64_t* n_hits, int6
     QMS_TRY(copy_out(ctx, out->hit_mi, ctx->o_mi.p, (size_t)nw));
     QMS_TRY(copy_out(ctx, out->hit_peak, ctx->o_peak.p, (size_t)nw));
     QMS_TRY(copy_out_peak32(ctx, ctx->stream, out->hit_peak32, 0, (size_t)nw, ctx->last_row_base));
+    QMS_TRY(fill_compact(ctx, ctx->stream, out, 0, nh, 0, ctx->last_n_spectra));
+    QMS_TRY(copy_compact(ctx, ctx->stream, out, 0, nh, 0, nw, 0, ctx->last_n_spectra));
     QMS_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     QMS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->cnt.ms_d2h += elapsed(ctx, 3, 4);

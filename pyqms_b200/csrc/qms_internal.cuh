@@ -159,6 +159,10 @@ struct qms_ctx {
     DBuf<double> o_score, o_scaling, o_mmz, o_mi;
     DBuf<int64_t> o_win_off, o_peak;
     DBuf<int32_t> o_peak32;        // o_peak narrowed for the trip to the host (hit_peak32)
+    DBuf<uint8_t> o_nc8;           // compact forms of the retained hits (hit_nc8, hit_peak16, spec_hit_off)
+    DBuf<uint16_t> o_peak16;
+    DBuf<int64_t> o_spec_off;
+    int64_t last_n_spectra = 0, last_longest = 0;   // shape of the last batch (its row offsets stay in d_offsets)
     int64_t last_row_base = 0;     // first row of the last batch: what hit_peak32 counts from
     unsigned long long* h_pinned = nullptr;  // small pinned mailbox for counters
     // staging of the spectrum-resident matcher: hits in discovery order, sorted by (spectrum, entry) afterwards

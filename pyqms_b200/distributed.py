@@ -181,17 +181,28 @@ def allgather_envelopes(ctx, n_env, world):
 
 
 _HIT_FIELDS = (("spec", np.int32, "h"), ("entry", np.int32, "h"), ("score", np.float64, "h"), ("scaling", np.float64, "h"),
-               ("win_off", np.int64, "h1"), ("peak", np.int64, "w"), ("peak32", np.int32, "w"), ("mmz", np.float64, "w"),
-               ("mi", np.float64, "w"))
+               ("win_off", np.int64, "h1"), ("peak", np.int64, "w"), ("peak32", np.int32, "w"), ("peak16", np.uint16, "w"),
+               ("mmz", np.float64, "w"), ("mi", np.float64, "w"), ("spec_off", np.int64, "s1"), ("row_off", np.int64, "s1"))
+# what a segment holds, by what the matching pass brings back from the device (IsotopologueLibrary._run_matcher):
+# the matched values, or the int32 peak rows, or the compact columns (+ the shard's row offsets, which widen them)
+_MODE_FIELDS = {"values": ("spec", "entry", "score", "scaling", "win_off", "peak", "mmz", "mi"),
+                "rows32": ("spec", "entry", "score", "scaling", "win_off", "peak32"),
+                "compact": ("entry", "score", "scaling", "peak16", "spec_off", "row_off")}
+_MODES = ("rows32", "values", "compact")
 
 
-def _segment_layout(cap_h, cap_w, values):
-    """Byte offsets of the hit arrays inside a segment with room for cap_h hits and cap_w hit windows."""
+def _mode_name(values):
+    return values if isinstance(values, str) else ("values" if values else "rows32")
+
+
+def _segment_layout(cap_h, cap_w, values, cap_s=0):
+    """Byte offsets of the hit arrays inside a segment with room for cap_h hits, cap_w hit windows and cap_s spectra."""
     offset, layout = 64, {}
+    wanted = _MODE_FIELDS[_mode_name(values)]
     for name, dtype, kind in _HIT_FIELDS:
-        if (name in ("mmz", "mi", "peak") and not values) or (name == "peak32" and values):
-            continue                                     # without the values the rows travel as int32 (hit_peak32)
-        count = {"h": cap_h, "h1": cap_h + 1, "w": cap_w}[kind]
+        if name not in wanted:
+            continue
+        count = {"h": cap_h, "h1": cap_h + 1, "w": cap_w, "s1": cap_s + 1}[kind]
         layout[name] = (offset, np.dtype(dtype), count)
         offset = (offset + count * np.dtype(dtype).itemsize + 63) // 64 * 64
     return layout, offset
@@ -217,7 +228,8 @@ class SharedHitArena:
         self.tag = tag or "qms_%d_%s" % (os.getppid(), os.environ.get("MASTER_PORT", "0"))
         self.register = register
         self.generation = 0
-        self._own = None           # (name, mmap, bytes, cap_h, cap_w, values)
+        self._own = None           # (name, mmap, bytes, cap_h, cap_w, mode, cap_s)
+        self.entry_windows = None  # windows per index entry (IsotopologueLibrary.use_hit_arena): widens compact columns
         self._peers = {}           # rank 0: (rank, generation) -> mmap
         self.stats = {}
 
@@ -244,17 +256,19 @@ class SharedHitArena:
             pass
         self._own = None
 
-    def arrays(self, cap_h, cap_w, values):
-        """numpy views (capacity cap_h hits / cap_w windows) inside this rank's segment, growing it when needed."""
+    def arrays(self, cap_h, cap_w, values, cap_s=0):
+        """numpy views (capacity cap_h hits / cap_w windows / cap_s spectra) inside this rank's segment, growing it when
+        needed.  ``values``: True (with the matched values), False (int32 peak rows) or "compact" (see _MODE_FIELDS)."""
         import mmap
         import os
         own = self._own
-        if own is None or own[3] < cap_h or own[4] < cap_w or own[5] != values:
+        values = _mode_name(values)
+        if own is None or own[3] < cap_h or own[4] < cap_w or own[5] != values or own[6] < cap_s:
             self._drop_own()
             if own is not None:
-                cap_h, cap_w = max(cap_h, own[3]), max(cap_w, own[4])
+                cap_h, cap_w, cap_s = max(cap_h, own[3]), max(cap_w, own[4]), max(cap_s, own[6])
             cap_h, cap_w = cap_h + cap_h // 4 + 64, cap_w + cap_w // 4 + 512
-            layout, nbytes = _segment_layout(cap_h, cap_w, values)
+            layout, nbytes = _segment_layout(cap_h, cap_w, values, cap_s)
             room = os.statvfs("/dev/shm")
             if room.f_bavail * room.f_frsize < nbytes + (16 << 20):
                 raise OSError("/dev/shm has %d bytes free, the hit segment of rank %d needs %d (use the page-locked pool instead: "
@@ -274,10 +288,11 @@ class SharedHitArena:
                 rc = lib.qms_host_register(address, nbytes)
                 if rc != _capi.QMS_OK:
                     raise _capi.QmsError(rc, (lib.qms_last_error(None) or b"").decode())
-            self._own = (name, mapping, nbytes, cap_h, cap_w, values)
-        name, mapping, nbytes, cap_h, cap_w, values = self._own
-        layout, _ = _segment_layout(cap_h, cap_w, values)
-        return {field: np.frombuffer(mapping, dtype=dtype, count=count, offset=offset) for field, (offset, dtype, count) in layout.items()}
+            self._own = (name, mapping, nbytes, cap_h, cap_w, values, cap_s)
+        name, mapping, nbytes, cap_h, cap_w, values, cap_s = self._own
+        layout, _ = _segment_layout(cap_h, cap_w, values, cap_s)
+        return {field: np.frombuffer(mapping, dtype=dtype, count=count, offset=offset) for field, (offset, dtype, count) in layout.items()
+                if field != "row_off"}
 
     # ---- rank 0: the hits of all ranks ---------------------------------------------------------------------------
     def collect(self, out, spectrum_begin=0):
@@ -290,15 +305,24 @@ class SharedHitArena:
         from .isotopologue_library import PackedHits
         t0 = time.perf_counter()
         own = self._own
-        in_segment = own is not None and out["n_hits"] > 0 and out["spec"].ctypes.data >= C.addressof(C.c_char.from_buffer(own[1])) and \
-            out["spec"].ctypes.data < C.addressof(C.c_char.from_buffer(own[1])) + own[2]
+        have = dict.keys(out)
+        mode = "values" if "mmz" in have else ("compact" if "peak16" in have else "rows32")
+        n_spec = len(out["spec_off"]) - 1 if mode == "compact" else 0
+        probe = dict.__getitem__(out, "entry")
+        in_segment = own is not None and own[5] == mode and out["n_hits"] > 0 and \
+            C.addressof(C.c_char.from_buffer(own[1])) <= probe.ctypes.data < C.addressof(C.c_char.from_buffer(own[1])) + own[2]
         if own is None or not in_segment:                    # matched before the arena was attached, or nothing to show
-            fresh = self.arrays(max(1, out["n_hits"]), max(1, out["n_windows"]), "mmz" in dict.keys(out))
+            fresh = self.arrays(max(1, out["n_hits"]), max(1, out["n_windows"]), mode, n_spec)
             for field, array in fresh.items():
                 source = out[field]
                 array[:len(source)] = source
             own = self._own
-        meta = [out["n_hits"], out["n_windows"], own[3], own[4], self.generation, int(own[5]), int(spectrum_begin)]
+        if mode == "compact":                                # the shard's row offsets, counted from its first row
+            layout, _ = _segment_layout(own[3], own[4], mode, own[6])
+            offset, dtype, count = layout["row_off"]
+            rows = np.frombuffer(own[1], dtype=dtype, count=n_spec + 1, offset=offset)
+            rows[:] = np.asarray(out._offsets[:n_spec + 1], dtype=np.int64) - int(out._offsets[0])
+        meta = [out["n_hits"], out["n_windows"], own[3], own[4], self.generation, _MODES.index(own[5]), int(spectrum_begin), n_spec, own[6]]
         d = _dist()
         if d is None or self.world == 1:
             gathered = [meta]
@@ -307,12 +331,12 @@ class SharedHitArena:
             on_gpu = d.get_backend() == "nccl"
             mine = torch.tensor(meta, dtype=torch.int64, device="cuda" if on_gpu else "cpu")
             pieces = [torch.empty_like(mine) for _ in range(self.world)]
-            d.all_gather(pieces, mine)                       # 56 bytes per rank: the only collective of the matching path
+            d.all_gather(pieces, mine)                       # 72 bytes per rank: the only collective of the matching path
             gathered = [piece.tolist() for piece in pieces]
         if self.rank != 0:
             return None
         batches = []
-        for r, (n_hits, n_windows, cap_h, cap_w, generation, values, begin) in enumerate(gathered):
+        for r, (n_hits, n_windows, cap_h, cap_w, generation, mode, begin, n_spec, cap_s) in enumerate(gathered):
             if r == self.rank:
                 mapping = own[1]
             else:
@@ -329,15 +353,18 @@ class SharedHitArena:
                     finally:
                         os.close(fd)
                     self._peers[(r, generation)] = mapping
-            layout, _ = _segment_layout(cap_h, cap_w, bool(values))
-            batch = PackedHits()
+            layout, _ = _segment_layout(cap_h, cap_w, _MODES[mode], cap_s)
+            views = {}
             for field, (offset, dtype, count) in layout.items():
-                used = {"spec": n_hits, "entry": n_hits, "score": n_hits, "scaling": n_hits, "win_off": n_hits + 1}.get(field, n_windows)
-                batch[field] = np.frombuffer(mapping, dtype=dtype, count=used, offset=offset)
+                used = {"spec": n_hits, "entry": n_hits, "score": n_hits, "scaling": n_hits, "win_off": n_hits + 1,
+                        "spec_off": n_spec + 1, "row_off": n_spec + 1}.get(field, n_windows)
+                views[field] = np.frombuffer(mapping, dtype=dtype, count=used, offset=offset)
+            batch = PackedHits(None, views.pop("row_off", None), self.entry_windows)
+            batch.update(views)
             batch["n_hits"], batch["n_windows"], batch["spec_base"], batch["rank"] = n_hits, n_windows, begin, r
             batches.append(batch)
         self.stats = {"collect_ms": 1e3 * (time.perf_counter() - t0), "hits": [int(g[0]) for g in gathered],
-                      "bytes_per_rank": [int(g[0]) * 32 + int(g[1]) * (24 if g[5] else 8) for g in gathered]}
+                      "bytes_per_rank": [int(g[0]) * (20 if g[5] == 2 else 32) + int(g[1]) * (4, 24, 2)[g[5]] for g in gathered]}
         return batches
 
     def close(self):

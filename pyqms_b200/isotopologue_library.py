@@ -269,27 +269,46 @@ class PackedHits(dict):
     """Packed hit arrays of one device pass: spec, entry, score, scaling (per hit), win_off (n_hits + 1), peak (row of the
     matched peak per hit window, -1 = None), n_hits, n_windows -- and ``mmz`` / ``mi``, the matched (m/z, intensity)
     values (NaN = None).  When the pass did not bring the values back from the device they are gathered from the
-    spectra by ``peak`` row on first access (the spectra array is kept alive for that; do not overwrite it)."""
+    spectra by ``peak`` row on first access (the spectra array is kept alive for that; do not overwrite it).
 
-    def __init__(self, peaks=None):
+    A pass without the values also leaves the wide index columns on the device and brings their compact forms
+    (``qms_hits``: hit_peak16, spec_hit_off): ``spec`` is then expanded from ``spec_off``, ``win_off`` summed from the
+    window counts of the hits' entries and ``peak`` widened from ``peak16`` + the first row of the hit's spectrum, each
+    on first access."""
+
+    def __init__(self, peaks=None, offsets=None, entry_windows=None):
         super().__init__()
         self._peaks = peaks
+        self._offsets = offsets                  # first row of every spectrum (n_spectra + 1), as handed to the matcher
+        self._entry_windows = entry_windows      # windows of every index entry
         self._row_base = 0
 
     def __missing__(self, key):
-        if key == "peak" and "peak32" in dict.keys(self):      # the device sent the rows as int32 counted from the batch's first row
+        have = dict.keys(self)
+        if key == "spec" and "spec_off" in have:
+            spec_off = dict.__getitem__(self, "spec_off")
+            value = np.repeat(np.arange(len(spec_off) - 1, dtype=np.int32), np.diff(spec_off))
+        elif key == "win_off" and "entry" in have and self._entry_windows is not None:
+            value = np.zeros(len(self["entry"]) + 1, dtype=np.int64)
+            np.cumsum(self._entry_windows[self["entry"]], out=value[1:])
+        elif key == "peak" and "peak32" in have:      # the device sent the rows as int32 counted from the batch's first row
             narrow = dict.__getitem__(self, "peak32")
-            rows = narrow.astype(np.int64)
-            rows[narrow >= 0] += self._row_base
-            self[key] = rows
-            return rows
-        if key not in ("mmz", "mi") or self._peaks is None:
+            value = narrow.astype(np.int64)
+            value[narrow >= 0] += self._row_base
+        elif key == "peak" and "peak16" in have:      # ... or as uint16 counted from the first row of the hit's spectrum
+            narrow = dict.__getitem__(self, "peak16")
+            first_row = np.asarray(self._offsets, dtype=np.int64)[self["spec"]]
+            value = np.repeat(first_row, np.diff(self["win_off"]))
+            value += narrow
+            value[narrow == 0xFFFF] = -1
+        elif key in ("mmz", "mi") and self._peaks is not None:
+            row = self["peak"]
+            value = self._peaks[np.maximum(row, 0), 0 if key == "mmz" else 1]
+            value[row < 0] = _NAN
+        else:
             raise KeyError(key)
-        row = self["peak"]
-        values = self._peaks[np.maximum(row, 0), 0 if key == "mmz" else 1]
-        values[row < 0] = _NAN
-        self[key] = values
-        return values
+        self[key] = value
+        return value
 
     def get(self, key, default=None):
         try:
@@ -380,10 +399,20 @@ class IsotopologueLibrary(dict):
     _hit_caps = (4096, 32768)            # (hits, hit windows) the next result arrays are sized for
 
     _hit_arena = None                    # distributed.SharedHitArena: result arrays in shared memory instead of the pool
+    _compact_hits = True                 # deferred batches fetch the compact hit columns (PackedHits widens them on access)
+    _ent_windows = None
 
     def use_hit_arena(self, arena):
         """Let the hits of batched matching land in ``arena`` (``distributed.SharedHitArena``; None = back to the pool)."""
         self._hit_arena = arena
+        if arena is not None:
+            arena.entry_windows = self._entry_windows()       # rank 0 widens the compact columns of every rank with it
+
+    def _entry_windows(self):
+        """Windows of every index entry = windows of each of its hits."""
+        if self._ent_windows is None or len(self._ent_windows) != self._n_entries:
+            self._ent_windows = np.diff(self._ent_win_off)
+        return self._ent_windows
 
     # ---- lib[formula] records: made on first access (a placeholder per formula until then) -------------------------
     def __getitem__(self, formula):
@@ -431,7 +460,7 @@ class IsotopologueLibrary(dict):
     __hash__ = None
 
     _DEVICE_STATE = ("_hit_pool", "_hit_arena", "_ctx", "_views", "_entry_static", "_ent_env", "_ent_z", "_ent_lower", "_ent_upper", "_ent_win_off",
-                     "_win_lo", "_win_hi", "_win_cmz", "_win_ri", "_win_ci")
+                     "_ent_windows", "_win_lo", "_win_hi", "_win_cmz", "_win_ri", "_win_ci")
 
     def __reduce__(self):
         """Pickling keeps the host plan (knowledge base, lookups, isotope pools, envelope terms) and drops everything
@@ -855,6 +884,7 @@ class IsotopologueLibrary(dict):
         ctx.call("qms_export_windows", ptr(self._win_lo), ptr(self._win_hi), ptr(self._win_cmz), ptr(self._win_ri),
                  ptr(self._win_ci))
         self._entry_static = {}
+        self._ent_windows = None
         if self.verbose:
             print("\n> Execution time {0:.2f} seconds".format(time.time() - self.break_points["Building isotopologues"]))
 
@@ -979,10 +1009,18 @@ class IsotopologueLibrary(dict):
             pool = self._hit_pool = PinnedPool()
         cap_h, cap_w = self._hit_caps
 
+        # without the values the index columns travel in their compact forms (qms_hits: hit_peak16, spec_hit_off; the
+        # window offsets follow from the entries): 20 bytes + 2 per window instead of 32 + 4
+        compact = (not values and only_entry is None and self._compact_hits and n_spec > 0
+                   and int(np.max(np.diff(offsets))) <= 65534)
+
         def buffers(h, w):
-            out = PackedHits(peaks if not values else None)
+            out = PackedHits(peaks if not values else None, offsets, self._entry_windows())
             if self._hit_arena is not None and only_entry is None:
-                out.update(self._hit_arena.arrays(h, w, values))          # shared segment of this rank (distributed.SharedHitArena)
+                out.update(self._hit_arena.arrays(h, w, "compact" if compact else values, n_spec))    # shared segment of this rank
+            elif compact:
+                out.update({"entry": pool.array(np.int32, h), "score": pool.array(np.float64, h), "scaling": pool.array(np.float64, h),
+                            "peak16": pool.array(np.uint16, w), "spec_off": pool.array(np.int64, n_spec + 1)})
             else:
                 out.update({"spec": pool.array(np.int32, h), "entry": pool.array(np.int32, h), "score": pool.array(np.float64, h),
                             "scaling": pool.array(np.float64, h), "win_off": pool.array(np.int64, h + 1)})
@@ -991,8 +1029,10 @@ class IsotopologueLibrary(dict):
                 else:
                     out["peak32"] = pool.array(np.int32, w)       # rows counted from offsets[0]: half the bytes across the bus
             out._row_base = int(offsets[0])
-            hits = QmsHits(h, w, *[out[k].ctypes.data if k in dict.keys(out) else None
-                                   for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak", "peak32")])
+            have = dict.keys(out)
+            hits = QmsHits(h, w, *[out[k].ctypes.data if k in have else None
+                                   for k in ("spec", "entry", "score", "scaling", "win_off", "mmz", "mi", "peak", "peak32", "nc8", "peak16",
+                                             "spec_off")])
             return out, hits
 
         out, hits = buffers(cap_h, cap_w)
@@ -1013,14 +1053,19 @@ class IsotopologueLibrary(dict):
             # the next call of a run needs about as much: keep the capacities (and with them the pool's size classes)
             # stable, grow them only when a run comes close to them
             self._hit_caps = (cap_h if h < 0.95 * cap_h else h + h // 8 + 64, cap_w if w < 0.95 * cap_w else w + w // 8 + 512)
-        for k in ("spec", "entry", "score", "scaling"):
+        have = set(dict.keys(out))
+        for k in have & {"spec", "entry", "score", "scaling"}:
             out[k] = out[k][:h]
-        out["win_off"] = out["win_off"][:h + 1]
-        if h == 0:
-            out["win_off"][0] = 0
-        for k in ("peak", "peak32", "mmz", "mi"):
-            if k in dict.keys(out):
-                out[k] = out[k][:w]
+        if "win_off" in have:
+            out["win_off"] = out["win_off"][:h + 1]
+            if h == 0:
+                out["win_off"][0] = 0
+        if "spec_off" in have:
+            out["spec_off"] = out["spec_off"][:n_spec + 1]
+            if h == 0:
+                out["spec_off"][:] = 0
+        for k in have & {"peak", "peak32", "peak16", "mmz", "mi"}:
+            out[k] = out[k][:w]
         out["n_hits"], out["n_windows"] = h, w
         return out
 

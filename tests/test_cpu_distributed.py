@@ -82,6 +82,33 @@ def _worker(rank, world, port, out_dir):
         else:
             assert batches is None
         dist.barrier()                                  # rank 0 has read the segments before anybody writes them again
+    # --- a step in the compact form (what a deferred match_many fetches): entry / score / scaling per hit, uint16 rows per
+    # window, hit offsets per spectrum; rank 0 widens spec / win_off / peak of every rank from them
+    n_local = end - begin
+    row_off = 100 * rank + 40 * np.arange(n_local + 1, dtype=np.int64)            # first row of every spectrum of the shard
+    entry_windows = np.full(16, 3, dtype=np.int64)
+    arena.entry_windows = entry_windows
+    target = arena.arrays(nh, 3 * nh, "compact", n_local)
+    assert set(target) == {"entry", "score", "scaling", "peak16", "spec_off"}
+    out = PackedHits(None, row_off, entry_windows)
+    for field in ("entry", "score", "scaling"):
+        target[field][:nh] = local[field]
+        out[field] = target[field][:nh]
+    target["peak16"][:3 * nh] = np.where(np.arange(3 * nh) % 3 == 2, 0xFFFF, np.arange(3 * nh) % 7)
+    target["spec_off"][:n_local + 1] = 2 * np.arange(n_local + 1)
+    out["peak16"], out["spec_off"] = target["peak16"][:3 * nh], target["spec_off"][:n_local + 1]
+    out["n_hits"], out["n_windows"] = nh, 3 * nh
+    assert list(out["spec"]) == list(local["spec"]) and list(out["win_off"]) == list(local["win_off"])
+    assert out["peak"][2] == -1 and out["peak"][4] == row_off[0] + 4 and out["peak"][6] == row_off[1] + 6
+    batches = arena.collect(out, begin)
+    if rank == 0:
+        assert all("spec" not in dict.keys(b) and "win_off" not in dict.keys(b) for b in batches)      # widened on access, not shipped
+        spectra = np.concatenate([b["spec"] + b["spec_base"] for b in batches])
+        assert list(spectra) == [s for s in range(n_spec) for _ in range(2)]
+        for b in batches:
+            assert list(b["win_off"]) == list(range(0, 3 * b["n_hits"] + 1, 3))
+            assert b["peak"][2] == -1 and b["peak"][6] == 40 + 6          # rows counted from the first row of the rank's shard
+    dist.barrier()
     del batches, out, target
     arena.close()
     dist.barrier()

@@ -134,10 +134,42 @@ def test_spectrum_resident_matcher_equals_row_streaming_matcher():
         res = lib.match_many(peaks, file_name="run", spec_ids=list(range(n)), spec_rts=list(range(n)), offsets=offsets)
         lazy = res.packed_batches()[-1]
         assert "mmz" not in dict.keys(lazy)                  # the values did not cross the bus ...
+        assert "peak16" in dict.keys(lazy) and "spec" not in dict.keys(lazy)      # ... and the index columns came in their compact forms
         for k in ("spec", "entry", "win_off", "peak", "score", "scaling"):
             assert np.array_equal(b[k], lazy[k]), k
         assert np.array_equal(b["mmz"], lazy["mmz"], equal_nan=True) and np.array_equal(b["mi"], lazy["mi"], equal_nan=True)   # ... and are gathered on demand
+        # the compact columns on every way out of the device: fetched after a capacity miss, from the row-streaming matcher,
+        # and -- switched off -- the int32 rows instead
+        for variant in ("fetch", "row-streaming", "rows32"):
+            if variant == "fetch":
+                lib._hit_caps = (64, 512)
+            lib._ctx.set_tuning("dense_mode", 0 if variant == "row-streaming" else 2)
+            lib._compact_hits = variant != "rows32"
+            got = lib._run_matcher(peaks, offsets, 0, lib.params["MZ_SCORE_PERCENTILE"], values=False)
+            assert ("peak16" in dict.keys(got)) == (variant != "rows32") and ("peak32" in dict.keys(got)) == (variant == "rows32")
+            for k in ("spec", "entry", "win_off", "peak", "score", "scaling"):
+                assert np.array_equal(b[k], got[k]), (variant, k)
+            assert np.array_equal(b["mmz"], got["mmz"], equal_nan=True), variant
+            if variant != "rows32":
+                compact_rows = dict.__getitem__(got, "peak16").copy()
+        # hit_nc8 through the C-ABI, and the limits of the compact forms
+        import ctypes as C
+        from pyqms_b200._capi import QMS_E_LIMIT, QmsHits
+        nh, nw = b["n_hits"], b["n_windows"]
+        nc8, peak16, spec_off = np.zeros(nh, np.uint8), np.zeros(nw, np.uint16), np.full(n + 1, -1, np.int64)
+        hits = QmsHits(nh, nw, None, None, None, None, None, None, None, None, None, nc8.ctypes.data, peak16.ctypes.data, spec_off.ctypes.data)
+        got_h, got_w = C.c_int64(), C.c_int64()
+        lib._ctx.check(lib._ctx.lib.qms_fetch_hits(lib._ctx.handle, C.byref(hits), C.byref(got_h), C.byref(got_w)))
+        assert got_h.value == nh and np.array_equal(nc8, np.diff(b["win_off"])) and np.array_equal(peak16, compact_rows)
+        assert np.array_equal(spec_off, np.searchsorted(b["spec"], np.arange(n + 1)))
+        long_off = np.array([0, len(peaks)], dtype=np.int64)                      # one spectrum of > 65 534 rows
+        order = np.argsort(peaks[:, 0], kind="stable")
+        rc = lib._ctx.lib.qms_match_batch(lib._ctx.handle, np.ascontiguousarray(peaks[order]).ctypes.data, long_off.ctypes.data, 1, 0,
+                                          C.c_double(lib.params["MZ_SCORE_PERCENTILE"]), C.byref(hits), C.byref(got_h), C.byref(got_w))
+        assert len(peaks) > 65534 and rc == QMS_E_LIMIT
     finally:
+        lib._compact_hits = True
+        lib._ctx.set_tuning("dense_mode", 2)
         lib._ctx.set_tuning("sub_batch_rows", 0)
 
 
