@@ -97,7 +97,11 @@ int qms_device_bytes(qms_ctx* ctx, int64_t* out);    /* device memory currently 
  *                 a batch with a pair above it fails with QMS_E_LIMIT instead of enumerating for hours like the reference
  *   "combination_budget_log2"  log2 of the combinations of all many-candidate pairs of one batch (default 35)
  *   "sub_batch_rows"  peak rows per sub-batch when a host-resident run is pipelined (copies of neighbouring sub-batches
- *                 overlap the kernels); 0 = default (16 Mi rows) */
+ *                 overlap the kernels); 0 = default (16 Mi rows)
+ *   "taper"       1 (default) = the last sub-batches of a pipelined run shrink step by step by the ratio (hit copy time) /
+ *                 (kernel time) measured on the previous run, so the copies still in flight when the last kernel ends are
+ *                 short even when several GPUs share the host's memory bandwidth; 0 = [small | big ... big | small] always
+ *                 (QMS_TAPER overrides the default) */
 int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value);
 
 /* Page-locked host memory for spectrum and hit buffers (cudaHostAlloc, portable): copies to and from such buffers run

@@ -196,6 +196,7 @@ int qms_ctx_create(int device, qms_ctx** out) {
     if (const char* e = getenv("QMS_DENSE_MODE")) ctx->dense_mode = atoi(e);
     if (const char* e = getenv("QMS_DENSE_CTAS")) ctx->dense_ctas = atoi(e);
     if (const char* e = getenv("QMS_SUB_BATCH_ROWS")) ctx->sub_batch_rows = atoll(e);
+    if (const char* e = getenv("QMS_TAPER")) ctx->taper = atoi(e) != 0;
     *out = ctx;
     return QMS_OK;
 }
@@ -245,6 +246,8 @@ int qms_set_tuning(qms_ctx* ctx, const char* key, int32_t value) {
     } else if (!strcmp(key, "combination_limit_log2") || !strcmp(key, "combination_budget_log2")) {
         if (value < 4 || value > 62) return qms_fail(ctx, QMS_E_ARG, "%s must be in [4, 62]", key);
         (key[12] == 'l' ? ctx->combination_limit : ctx->combination_budget) = 1ull << value;
+    } else if (!strcmp(key, "taper")) {
+        ctx->taper = value != 0;
     } else if (!strcmp(key, "sub_batch_rows")) {
         if (value < 0) return qms_fail(ctx, QMS_E_ARG, "sub_batch_rows must be >= 0");
         ctx->sub_batch_rows = value;

@@ -1823,24 +1823,35 @@ static int dense_run(qms_ctx* ctx, const double* peaks, const int64_t* h_off, co
     }
     // sub-batches: cut at spectrum boundaries every ~sub_rows rows (host-resident runs only)
     std::vector<int64_t> cuts{0};
-    // Sub-batch plan: [small | big ... big | small].  A sub-batch ends when its slowest CTA does and its sort + emit overlap
-    // nothing, so few large sub-batches keep the matcher efficient -- but the hits of a sub-batch can only start to leave when it
-    // is done, and the last sub-batch's copy overlaps nothing.  With eight GPUs sharing the host's memory system the hits leave
-    // at ~15 GB/s per GPU and the copies take as long as the kernels: the copy pipeline has to start early and end short, so the
-    // first and the last sub-batch are a quarter of the others (16 Mi rows).
+    // Sub-batch plan: [small | big ... big | tapering to small].  A sub-batch ends when its slowest CTA does and its sort + emit
+    // overlap nothing, so few large sub-batches keep the matcher efficient -- but the hits of a sub-batch can only start to leave
+    // when it is done: the copy of sub-batch b runs under the kernels of b+1, and whatever of it (and of the last sub-batch) does
+    // not fit there is the tail of the run.  With rho = (hit copy time) / (kernel time) per row, the copies keep up when every
+    // sub-batch is at least rho times its predecessor, and the tail is rho times the last one.  One GPU on its own PCIe link has
+    // rho ~ 0.17: [4 | 16 ... 16 | 4] Mi rows.  Eight GPUs sharing the host's memory system have rho ~ 0.6 (the hits leave at
+    // ~13 GB/s per GPU): the back of the plan shrinks step by step by that ratio, measured on the previous pipelined run.
     const int64_t sub_rows = ctx->sub_batch_rows > 0 ? ctx->sub_batch_rows : (int64_t)16 << 20;
     if (!peaks_on_device && n_peaks > sub_rows + sub_rows / 2) {
-        const int64_t edge = sub_rows / 4;
-        const int64_t middle = n_peaks - 2 * edge;
-        const int64_t parts = (middle + sub_rows - 1) / sub_rows;
-        const int64_t step = (middle + parts - 1) / parts;
-        int64_t next = p_begin + edge;
-        for (int64_t s = 1; s < n_spectra; ++s)
-            if (h_off[s] >= next && p_end - h_off[s] > edge / 4) {
+        const double rho = ctx->taper ? std::min(0.8, std::max(0.25, ctx->copy_kernel_ratio * 1.15)) : 0.25;
+        const int64_t first = sub_rows / 4;
+        double size = rho > 0.4 ? (double)(sub_rows * 5 / 32) : (double)(sub_rows / 4);
+        std::vector<int64_t> sizes;                               // back to front
+        for (int64_t left = n_peaks - first; left > 0;) {
+            int64_t rows = std::min(std::max((int64_t)size, (int64_t)1), left);
+            if (left - rows < first / 2) rows = left;             // no crumb at the front
+            sizes.push_back(rows);
+            left -= rows;
+            size = std::min((double)sub_rows, size / rho);
+        }
+        sizes.push_back(first);
+        int64_t next = p_begin;
+        size_t k = sizes.size();
+        next += sizes[--k];
+        for (int64_t s = 1; s < n_spectra && k > 0; ++s)
+            if (h_off[s] >= next) {
                 cuts.push_back(s);
-                const bool last_edge = p_end - h_off[s] <= edge + step / 8;
-                next = last_edge ? p_end + 1 : std::min(h_off[s] + step, p_end - edge);
-                if (next <= h_off[s]) next = p_end + 1;
+                while (k > 0 && next <= h_off[s]) next += sizes[--k];
+                if (next <= h_off[s]) break;                      // the rest is one sub-batch
             }
     }
     cuts.push_back(n_spectra);

@@ -143,6 +143,7 @@ struct qms_ctx {
     int64_t pair_cap_hint = 0;     // capacity of the pair list, learned from the previous batch (+25 %)
     int64_t last_hits = 0, last_windows = 0;   // hits of the last match, retained in o_* for qms_fetch_hits
     int dense_mode = 2;            // spectrum-resident matcher: 0 never, 1 whenever its tables allow it, 2 by library density
+    int taper = 1;                   // shrink the last sub-batches by the measured copy/kernel ratio (tuning key "taper")
     double copy_kernel_ratio = 0.0;  // hit copies / kernels (device ms) of the last pipelined run (reported by the bench)
     int64_t sub_batch_rows = 0;   // rows per sub-batch of the pipelined run (0: default)
     int dense_ctas = 2;            // its resident CTAs per SM
