@@ -115,6 +115,16 @@ int qms_parse_molecules(const char* text, const int64_t* str_off, int64_t n, int
         return QMS_E_ARG;
     const SymbolTable symbols(n_symbols, symbols_blob, symbol_off);
     const SymbolTable residues(n_residues, residue_blob, residue_off);     // "A", "C", "C0", "K1", ...
+    // letter (+ one index digit) -> residue without a string or a hash per residue; longer names go through the table above
+    int16_t quick[26][11];
+    for (auto& letter : quick)
+        for (auto& slot : letter) slot = -1;
+    for (int32_t r = 0; r < n_residues && r < 32767; ++r) {
+        const char* name = residue_blob + residue_off[r];
+        const int32_t len = residue_off[r + 1] - residue_off[r];
+        if (len >= 1 && len <= 2 && is_upper(name[0]) && (len == 1 || is_digit(name[1])))
+            quick[name[0] - 'A'][len == 1 ? 0 : 1 + (name[1] - '0')] = (int16_t)r;
+    }
     const int h = symbols.find("H", "H" + 1), o = symbols.find("O", "O" + 1);
     for (int64_t m = 0; m < n; ++m) {
         const char* p = text + str_off[m];
@@ -139,7 +149,7 @@ int qms_parse_molecules(const char* text, const int64_t* str_off, int64_t n, int
                 }
                 ++q;
                 while (q < seq_end && is_digit(*q)) ++q;
-                const int r = residues.find(name, q);
+                const int r = q - name <= 2 ? quick[name[0] - 'A'][q - name == 1 ? 0 : 1 + (name[1] - '0')] : residues.find(name, q);
                 if (r < 0) {
                     ok = false;
                     break;
@@ -191,11 +201,21 @@ int qms_hill_formulas(const int32_t* counts, int64_t n, int32_t n_symbols, const
         for (int s : order) {
             const int32_t c = counts[m * n_symbols + s];
             if (c == 0) continue;
-            const int digits = snprintf(number, sizeof(number), "(%d)", c);
+            // "(<c>)" written back to front (a printf call per count was most of the time of a 500 000-formula library)
+            char* tail = number + sizeof(number);
+            *--tail = ')';
+            uint32_t magnitude = c < 0 ? 0u - (uint32_t)c : (uint32_t)c;
+            do {
+                *--tail = (char)('0' + magnitude % 10u);
+                magnitude /= 10u;
+            } while (magnitude);
+            if (c < 0) *--tail = '-';
+            *--tail = '(';
+            const int digits = (int)(number + sizeof(number) - tail);
             const int64_t len = (int64_t)names[s].size() + digits;
             if (out && used + len <= out_cap) {
                 memcpy(out + used, names[s].data(), names[s].size());
-                memcpy(out + used + names[s].size(), number, (size_t)digits);
+                memcpy(out + used + names[s].size(), tail, (size_t)digits);
             }
             used += len;
         }

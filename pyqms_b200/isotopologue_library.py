@@ -603,9 +603,15 @@ class IsotopologueLibrary(dict):
         if simple:
             residue_letters = "".join(k for k in self.aa_compositions if len(k) == 1)
             states = [(k, k + "0") for k in self.fixed_labels]
+            molecule_list = molecules if isinstance(molecules, list) else list(molecules)
+            labelled_list = self._label_all_at_once(molecule_list, residue_letters, states)
+            if labelled_list is not None:                        # nothing but residue letters anywhere: no Python loop at all
+                expanded.update(labelled_list)
+                self._note_label_variations(molecule_list, labelled_list)
+                return expanded
             variations = self.lookup["molecule fixed label variations"]
             general = []
-            for full_molecule in molecules:
+            for full_molecule in molecule_list:
                 if full_molecule.strip(residue_letters):         # something besides residue letters
                     general.append(full_molecule)
                     continue
@@ -646,6 +652,36 @@ class IsotopologueLibrary(dict):
                     self.lookup["molecule fixed label variations"].setdefault(full_molecule, set()).add(labelled + addon)
         return expanded
 
+    @staticmethod
+    def _label_all_at_once(molecule_list, residue_letters, states):
+        """The single-label fast path over the whole list in three C-level passes: join, ``str.replace`` per labelled
+        residue, split.  None when a molecule holds anything besides residue letters (or the separator)."""
+        if not molecule_list or not residue_letters.isascii():
+            return None
+        joined = "\n".join(molecule_list)
+        if not joined.isascii():
+            return None
+        rest = joined.encode("ascii").translate(None, residue_letters.encode("ascii"))
+        if len(rest) != len(molecule_list) - 1 or rest.count(b"\n") != len(rest):
+            return None                                          # other characters, or a separator inside a molecule
+        for residue, with_state in states:
+            joined = joined.replace(residue, with_state)
+        labelled_list = joined.split("\n")
+        return labelled_list if len(labelled_list) == len(molecule_list) else None
+
+    def _note_label_variations(self, molecule_list, labelled_list):
+        """``lookup["molecule fixed label variations"]`` of the fast path (molecule -> {labelled molecule}), filled when
+        somebody reads it."""
+        earlier = self.lookup["molecule fixed label variations"]
+
+        def fill(target, earlier=earlier, molecule_list=molecule_list, labelled_list=labelled_list):
+            dict.update(target, earlier)
+            for molecule, labelled in zip(molecule_list, labelled_list):
+                if len(labelled) != len(molecule):
+                    dict.setdefault(target, molecule, set()).add(labelled)
+
+        self.lookup["molecule fixed label variations"] = _LazyDict(fill)
+
     # ------------------------------------------------------------------ molecules -> formulas (IL:312-497)
     def _register_molecules(self, molecules, trivial_names, add_default_files):
         """Molecule strings -> formulas, lookups, per-formula count rows.  Plain formulas and unmodified peptides are
@@ -663,7 +699,7 @@ class IsotopologueLibrary(dict):
         ordered = sorted(set(molecules))
         symbols = list(known)
         if self._native_planner:
-            counts, seen, status = planner.parse_molecules(ordered, symbols, self.aa_compositions)
+            counts, seen, status, symbols = planner.parse_molecules(ordered, symbols, self.aa_compositions, compact=True)
         else:                                              # unit tests: every molecule through the host parser
             counts = np.zeros((len(ordered), len(symbols)), dtype=np.int32)
             seen = np.full((len(ordered), len(symbols)), planner.ABSENT, dtype=np.int16)
@@ -692,14 +728,19 @@ class IsotopologueLibrary(dict):
                           "element {0}{1}, enrichment levels set to {2}".format(enriched, template, target))
                 known[element] = {self.zero_labeled_percentile: self._recalc_isotopic_distribution(
                     element=template, target_percentile=target, enriched_isotope=enriched)}
-        # columns for symbols the host parser introduced and for the bare elements fixed-label isotopes fold into
-        for symbol in list(known) + [level_symbol[-1] for level_symbol in levels]:
-            if symbol not in symbols and symbol in known:
-                symbols.append(symbol)
-        if len(symbols) > counts.shape[1]:
-            grow = len(symbols) - counts.shape[1]
-            counts = np.hstack([counts, np.zeros((len(ordered), grow), dtype=np.int32)])
-            seen = np.hstack([seen, np.full((len(ordered), grow), planner.ABSENT, dtype=np.int16)])
+        # columns for symbols the host parser introduced and for the bare elements fixed-label isotopes fold into, in the
+        # order of the knowledge base (the native parser may have come back with the few columns peptides need)
+        needed = set(symbols) | {level_symbol[-1] for level_symbol in levels}
+        for composition in parsed_on_host.values():
+            needed.update(composition)
+        wider = [symbol for symbol in known if symbol in needed]
+        if wider != symbols:
+            place = [wider.index(symbol) for symbol in symbols]
+            wide_counts = np.zeros((len(ordered), len(wider)), dtype=np.int32)
+            wide_seen = np.full((len(ordered), len(wider)), planner.ABSENT, dtype=np.int16)
+            wide_counts[:, place] = counts
+            wide_seen[:, place] = seen
+            counts, seen, symbols = wide_counts, wide_seen, wider
         column = {symbol: k for k, symbol in enumerate(symbols)}
         for i, composition in parsed_on_host.items():
             for position, (element, count) in enumerate(composition.items()):

@@ -35,25 +35,48 @@ def _symbol_table(symbols):
     return blob, offsets
 
 
-def parse_molecules(molecules, symbols, aa_compositions):
+_PEPTIDE_BYTES = np.zeros(256, dtype=bool)
+_PEPTIDE_BYTES[[ord(c) for c in "ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"]] = True
+
+
+def parse_molecules(molecules, symbols, aa_compositions, compact=False):
     """(counts[n,S] int32, first_seen[n,S] int16, status[n] uint8) of ``molecules`` over the element ``symbols``.
     ``first_seen``: rank at which a symbol entered the molecule's composition (ABSENT if not part of it);
-    status 1 = left to the host parser (the row is empty)."""
+    status 1 = left to the host parser (the row is empty).
+
+    ``compact=True`` returns a fourth value, the symbols the columns stand for: when the text holds nothing but residue
+    letters and label indices, only the symbols some residue is made of (a knowledge base lists ~100 symbols, peptides
+    use 5: the full-width matrices of a 500 000-peptide library were 300 MB of zeros), else ``symbols`` unchanged."""
     n, n_symbols = len(molecules), len(symbols)
+    usable = not (n == 0 or n_symbols == 0 or n_symbols > 127 or not all(s.isascii() for s in symbols))
+    names, rows = [], []
+    if usable:
+        known = set(symbols)
+        for name, value in aa_compositions.items():          # "A", "C", and the fixed-label variants "C0", "K1", ...
+            if not _RESIDUE_NAME.match(name):
+                continue
+            items = parse_formula(value) if isinstance(value, str) else dict(value)
+            if all(symbol in known for symbol in items):
+                names.append(name)
+                rows.append(items)
+        text, str_off = _pack(molecules)
+        if compact:
+            held = np.bincount(np.frombuffer(text, dtype=np.uint8), minlength=256) > 0
+            if not held[~_PEPTIDE_BYTES].any():              # peptides only: the symbols of the residues that occur, + water
+                wanted = {"H", "O"}
+                for name, items in zip(names, rows):
+                    if held[ord(name[0])]:
+                        wanted.update(items)
+                symbols = [s for s in symbols if s in wanted]
+                n_symbols = len(symbols)
+                kept = [k for k, items in enumerate(rows) if all(symbol in wanted for symbol in items)]
+                names, rows = [names[k] for k in kept], [rows[k] for k in kept]
     counts = np.zeros((n, n_symbols), dtype=np.int32)
     first_seen = np.full((n, n_symbols), ABSENT, dtype=np.int16)
     status = np.ones(n, dtype=np.uint8)
-    if n == 0 or n_symbols == 0 or n_symbols > 127 or not all(s.isascii() for s in symbols):
-        return counts, first_seen, status
+    if not usable or n_symbols == 0:
+        return (counts, first_seen, status, symbols) if compact else (counts, first_seen, status)
     column = {s: i for i, s in enumerate(symbols)}
-    names, rows = [], []
-    for name, value in aa_compositions.items():          # "A", "C", and the fixed-label variants "C0", "K1", ...
-        if not _RESIDUE_NAME.match(name):
-            continue
-        items = parse_formula(value) if isinstance(value, str) else dict(value)
-        if all(symbol in column for symbol in items):
-            names.append(name)
-            rows.append(items)
     residue_counts = np.zeros((len(names), n_symbols), dtype=np.int32)
     residue_order = np.full((len(names), n_symbols), ABSENT, dtype=np.int8)
     for r, items in enumerate(rows):
@@ -61,14 +84,13 @@ def parse_molecules(molecules, symbols, aa_compositions):
             residue_counts[r, column[symbol]] = count
             residue_order[r, k] = column[symbol]
     residue_blob, residue_off = _symbol_table(names)
-    text, str_off = _pack(molecules)
     symbols_blob, symbol_off = _symbol_table(symbols)
     rc = _capi.load().qms_parse_molecules(text, _capi.ptr(str_off), n, n_symbols, symbols_blob, _capi.ptr(symbol_off),
                                           len(names), residue_blob, _capi.ptr(residue_off), _capi.ptr(residue_counts),
                                           _capi.ptr(residue_order), _capi.ptr(counts), _capi.ptr(first_seen), _capi.ptr(status))
     if rc != _capi.QMS_OK:
         raise _capi.QmsError(rc, "qms_parse_molecules: bad argument")
-    return counts, first_seen, status
+    return (counts, first_seen, status, symbols) if compact else (counts, first_seen, status)
 
 
 def hill_formulas(counts, symbols):
@@ -81,14 +103,14 @@ def hill_formulas(counts, symbols):
     symbols_blob, symbol_off = _symbol_table(symbols)
     offsets = np.zeros(n + 1, dtype=np.int64)
     needed = C.c_int64()
-    lib.qms_hill_formulas(_capi.ptr(counts), n, len(symbols), symbols_blob, _capi.ptr(symbol_off), None, 0, _capi.ptr(offsets),
-                          C.byref(needed))
-    out = C.create_string_buffer(max(1, needed.value))
-    rc = lib.qms_hill_formulas(_capi.ptr(counts), n, len(symbols), symbols_blob, _capi.ptr(symbol_off), out, needed.value,
+    # one pass into a buffer that is large enough for any counts: "(-2147483648)" is 13 characters
+    room = n * (len(symbols_blob) + 13 * len(symbols))
+    out = C.create_string_buffer(max(1, room))
+    rc = lib.qms_hill_formulas(_capi.ptr(counts), n, len(symbols), symbols_blob, _capi.ptr(symbol_off), out, room,
                                _capi.ptr(offsets), C.byref(needed))
     if rc != _capi.QMS_OK:
         raise _capi.QmsError(rc, "qms_hill_formulas failed")
-    text = out.raw[:needed.value].decode("ascii")
+    text = C.string_at(out, needed.value).decode("ascii")
     bounds = offsets.tolist()
     return [text[a:b] for a, b in zip(bounds[:-1], bounds[1:])]
 

@@ -192,3 +192,52 @@ def test_fixed_label_fast_path_equals_the_general_expansion():
     for name in ("molecule to formula", "formula to molecule", "molecule fixed label variations"):
         assert fast.lookup[name] == slow.lookup[name], name
     assert len(fast.lookup["molecule fixed label variations"]) > 1000
+
+
+def test_fixed_label_fast_path_over_the_whole_list_at_once():
+    """A list of nothing but residue letters is labelled by join / replace / split; the result, the lazily filled
+    variation lookup and the compact element columns of the native parser must equal the general expansion."""
+    import pyqms_b200
+    from pyqms_b200.isotopologue_library import _LazyDict
+    from pyqms_b200.synthetic import CAM_FIXED_LABEL, random_tryptic_peptides
+    peptides = random_tryptic_peptides(3000, seed=5) + ["CCCC", "AAAK", "C", "MCMK"]
+    kwargs = dict(molecules=peptides, charges=[2], fixed_labels=dict(CAM_FIXED_LABEL, M=["O(1)"]), verbose=False, _plan_only=True)
+    fast = pyqms_b200.IsotopologueLibrary(**kwargs)
+    assert isinstance(fast.lookup["molecule fixed label variations"], _LazyDict)          # the whole-list path ran
+    assert len(fast._symbols) <= 6                                                      # C H N O S, not the knowledge base
+    pyqms_b200.IsotopologueLibrary._fixed_label_fast_path = False
+    try:
+        slow = pyqms_b200.IsotopologueLibrary(**kwargs)
+    finally:
+        pyqms_b200.IsotopologueLibrary._fixed_label_fast_path = True
+    assert list(fast.keys()) == list(slow.keys()) and fast._symbols == slow._symbols
+    assert np.array_equal(fast._cc_counts, slow._cc_counts) and np.array_equal(fast._cc_seen, slow._cc_seen)
+    for name in ("molecule to formula", "formula to molecule", "molecule fixed label variations"):
+        assert fast.lookup[name] == slow.lookup[name], name
+    assert fast.lookup["molecule fixed label variations"]["MCMK"] == {"M0C0M0K"}
+    for a, b in zip(fast._terms + fast._pool_tables, slow._terms + slow._pool_tables):
+        assert np.array_equal(a, b, equal_nan=np.asarray(a).dtype.kind == "f")
+    # one molecule with anything else (or a line break) sends the list to the per-molecule paths
+    label = pyqms_b200.IsotopologueLibrary._label_all_at_once
+    assert label(["ACK", "CC"], "ACK", [("C", "C0")]) == ["AC0K", "C0C0"]
+    assert label(["ACK", "CC+PO3"], "ACK", [("C", "C0")]) is None and label(["ACK", "C\nC"], "ACK", [("C", "C0")]) is None
+    assert label([], "ACK", [("C", "C0")]) is None and label([""], "ACK", [("C", "C0")]) == [""]
+
+
+def test_compact_symbol_columns_of_the_native_parser():
+    symbols = list(knowledge_base.isotopic_distributions)
+    residues = dict(knowledge_base.aa_compositions, U="C3H5NOSe")          # a residue that brings its own element
+    peptides = random_tryptic_peptides(500, seed=9) + ["UK", "PEPTIDEK", "BK"]     # "B": no such residue, left to the host
+    wide = planner.parse_molecules(peptides, symbols, residues)
+    counts, seen, status, used = planner.parse_molecules(peptides, symbols, residues, compact=True)
+    assert len(used) < 10 and "Se" in used and used == [s for s in symbols if s in used]
+    columns = [symbols.index(s) for s in used]
+    assert np.array_equal(wide[0][:, columns], counts) and np.array_equal(wide[1][:, columns], seen) and np.array_equal(wide[2], status)
+    assert not np.delete(wide[0], columns, axis=1).any() and status[-1] == 1 and status[:-1].sum() == 0
+    # anything that is not a residue letter or an index keeps the full table
+    assert planner.parse_molecules(peptides + ["+C6H12O6"], symbols, residues, compact=True)[3] == symbols
+
+
+def test_hill_formulas_write_any_count():
+    counts = np.array([[1, 0, -6, 2147483647], [12, 1, 0, -2147483648], [0, 0, 0, 0]], dtype=np.int32)
+    assert planner.hill_formulas(counts, ["H", "13C", "C", "N"]) == ["C(-6)H(1)N(2147483647)", "H(12)13C(1)N(-2147483648)", ""]
