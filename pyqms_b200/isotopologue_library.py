@@ -917,17 +917,26 @@ class IsotopologueLibrary(dict):
         self._ent_win_off = np.zeros(n + 1, dtype=np.int64)
         ctx.call("qms_export_index", ptr(self._ent_env), ptr(self._ent_z), ptr(self._ent_lower), ptr(self._ent_upper),
                  ptr(self._ent_win_off))
-        self._win_lo = np.empty(w, dtype=np.int32)
-        self._win_hi = np.empty(w, dtype=np.int32)
-        self._win_cmz = np.empty(w, dtype=np.float64)
-        self._win_ri = np.empty(w, dtype=np.float64)
-        self._win_ci = np.empty(w, dtype=np.int32)
-        ctx.call("qms_export_windows", ptr(self._win_lo), ptr(self._win_hi), ptr(self._win_cmz), ptr(self._win_ri),
-                 ptr(self._win_ci))
+        for name in self._WINDOW_VIEWS:                  # exported when somebody reads them (__getattr__): 28 bytes per window
+            self.__dict__.pop(name, None)
         self._entry_static = {}
         self._ent_windows = None
         if self.verbose:
             print("\n> Execution time {0:.2f} seconds".format(time.time() - self.break_points["Building isotopologues"]))
+
+    _WINDOW_VIEWS = ("_win_lo", "_win_hi", "_win_cmz", "_win_ri", "_win_ci")
+
+    def __getattr__(self, name):
+        """The entry-major window arrays of the index (grid bounds, centre m/z, relative intensity, isotopologue ordinal)
+        come to the host on first use: labelling hits needs them, building and matching do not."""
+        if name in IsotopologueLibrary._WINDOW_VIEWS and "_ctx" in self.__dict__ and "_n_windows" in self.__dict__:
+            w = self._n_windows
+            views = {"_win_lo": np.empty(w, dtype=np.int32), "_win_hi": np.empty(w, dtype=np.int32), "_win_cmz": np.empty(w, dtype=np.float64),
+                     "_win_ri": np.empty(w, dtype=np.float64), "_win_ci": np.empty(w, dtype=np.int32)}
+            self._ctx.call("qms_export_windows", *[ptr(views[k]) for k in IsotopologueLibrary._WINDOW_VIEWS])
+            self.__dict__.update(views)
+            return views[name]
+        raise AttributeError(name)
 
     # ------------------------------------------------------------------ lazy host views
     def _n_bins(self):
