@@ -212,3 +212,41 @@ def test_c_abi_links_from_plain_c(tmp_path):
     if not torch.cuda.is_available():
         done = subprocess.run([str(exe)], capture_output=True, text=True)
         assert done.returncode == 2 and "no CPU fallback" in done.stderr
+
+
+def test_packed_hits_widen_the_compact_columns():
+    """What a deferred pass brings back (entry / score / scaling per hit, uint16 rows per hit window, hit offsets per
+    spectrum) widens on the host to the columns every consumer reads: spec, win_off, peak -- and mmz / mi by row."""
+    from pyqms_b200.isotopologue_library import PackedHits
+    rng = np.random.default_rng(11)
+    n_spec, n_entries = 40, 25
+    lengths = rng.integers(0, 300, size=n_spec)
+    lengths[[3, 17]] = 0                                               # empty spectra
+    offsets = 1000 + np.concatenate([[0], np.cumsum(lengths)])         # a batch that starts at row 1000 of the array
+    peaks = rng.uniform(100.0, 2000.0, size=(int(offsets[-1]), 2))
+    entry_windows = rng.integers(1, 12, size=n_entries)
+    hits_per_spectrum = np.where(lengths > 0, rng.integers(0, 5, size=n_spec), 0)
+    spec = np.repeat(np.arange(n_spec, dtype=np.int32), hits_per_spectrum)
+    entry = rng.integers(0, n_entries, size=len(spec)).astype(np.int32)
+    win_off = np.concatenate([[0], np.cumsum(entry_windows[entry])]).astype(np.int64)
+    first_row = np.repeat(offsets[spec], entry_windows[entry])
+    span = np.repeat(lengths[spec], entry_windows[entry])
+    local = (rng.uniform(size=win_off[-1]) * span).astype(np.int64)
+    missing = rng.uniform(size=win_off[-1]) < 0.2
+    peak = np.where(missing, -1, first_row + local)
+    out = PackedHits(peaks, offsets, entry_windows)
+    out.update({"entry": entry, "score": rng.uniform(size=len(spec)), "scaling": rng.uniform(size=len(spec)),
+                "peak16": np.where(missing, 0xFFFF, local).astype(np.uint16),
+                "spec_off": np.concatenate([[0], np.cumsum(hits_per_spectrum)]).astype(np.int64), "n_hits": len(spec), "n_windows": int(win_off[-1])})
+    assert "spec" not in dict.keys(out) and out.get("nothing", 7) == 7
+    assert np.array_equal(out["spec"], spec) and out["spec"].dtype == np.int32
+    assert np.array_equal(out["win_off"], win_off) and out["win_off"].dtype == np.int64
+    assert np.array_equal(out["peak"], peak) and out["peak"].dtype == np.int64
+    expected = np.where(missing, np.nan, peaks[np.maximum(peak, 0), 0])
+    assert np.array_equal(out["mmz"], expected, equal_nan=True)
+    assert np.array_equal(np.isnan(out["mi"]), missing)
+    assert "spec" in dict.keys(out)                                    # widened once, then kept
+    # no hits at all
+    empty = PackedHits(peaks, offsets, entry_windows)
+    empty.update({"entry": entry[:0], "peak16": np.zeros(0, np.uint16), "spec_off": np.zeros(n_spec + 1, np.int64)})
+    assert len(empty["spec"]) == 0 and list(empty["win_off"]) == [0] and len(empty["peak"]) == 0 and len(empty["mmz"]) == 0
