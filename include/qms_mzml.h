@@ -4,11 +4,12 @@
  * pymzml.run.Reader -> spectrum.centroidedPeaks -> match_all) by one pass that goes from the file to the packed
  * layout qms_match_batch consumes: an (N, 2) float64 array of (m/z, intensity) rows + row offsets.  Host-only
  * code (no CUDA): the file is memory-mapped and indexed by a tag scanner, the binary arrays (base64, optional
- * zlib, 32/64-bit floats; mzML 1.1 accessions MS:1000514/515/521/523/574/576) are decoded by a pool of threads
- * straight into their slots of the packed array.
+ * zlib; 32/64-bit floats, 32/64-bit integers, MS-Numpress linear / positive-integer / short-logged-float, alone or followed
+ * by zlib; mzML accessions MS:1000514/515/519/521/522/523/574/576, MS:1002312-1002314, MS:1002746-1002748) are decoded by a
+ * pool of threads straight into their slots of the packed array.
  *
  * Every call returns 0 or a negative code; qms_mzml_last_error() gives the message of the calling thread.
- * QMS_MZML_E_UNSUPPORTED (numpress / integer arrays / external data) tells the caller to use another reader. */
+ * QMS_MZML_E_UNSUPPORTED (the truncation codecs MS:1003088-1003090) tells the caller that no reader here decodes the file. */
 #ifndef QMS_MZML_H
 #define QMS_MZML_H
 
@@ -45,6 +46,11 @@ int qms_mzml_count(qms_mzml* file, int32_t ms_level, int64_t* n_spectra, int64_t
  * sort_peaks != 0: spectra whose m/z are not ascending are stably reordered by m/z. */
 int qms_mzml_read(qms_mzml* file, int32_t ms_level, int32_t sort_peaks, int32_t n_threads, double* peaks, int64_t* offsets,
                   int64_t* ids, double* rt, uint8_t* rt_unit, int32_t* levels);
+
+/* One MS-Numpress stream (after base64 and zlib) -> doubles.  kind: 0 linear prediction, 1 positive integer, 2 short logged
+ * float.  *count receives the number of values; out == NULL only counts.  What pymzml's decoder does for the reference's
+ * scripts; exported for the ElementTree reader of pyqms_b200/mzml.py and for the tests. */
+int qms_numpress_decode(int32_t kind, const unsigned char* data, int64_t size, double* out, int64_t capacity, int64_t* count);
 
 #ifdef __cplusplus
 }

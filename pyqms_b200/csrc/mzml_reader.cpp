@@ -8,6 +8,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <math.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -46,9 +47,12 @@ struct Span {
     std::string str() const { return std::string(a, b); }
 };
 
+enum Packing { PACK_FLOAT, PACK_INT32, PACK_INT64, PACK_NUMPRESS_LINEAR, PACK_NUMPRESS_PIC, PACK_NUMPRESS_SLOF };
+
 struct ArrayInfo {
     Span text;            // base64 payload
     bool present = false, f32 = false, zlib = false;
+    Packing packing = PACK_FLOAT;     // a numpress / integer accession wins over the float width, wherever it stands
     int64_t length = -1;  // arrayLength attribute, if given
 };
 
@@ -147,10 +151,17 @@ void apply_param(const Param& p, SpectrumInfo& s, ArrayInfo* array, ArrayKind* k
         else if (acc.equals("MS:1000523")) array->f32 = false;
         else if (acc.equals("MS:1000574")) array->zlib = true;
         else if (acc.equals("MS:1000576")) array->zlib = false;
-        else if (acc.equals("MS:1000519") || acc.equals("MS:1000522") ||                              // integer arrays
-                 acc.equals("MS:1002312") || acc.equals("MS:1002313") || acc.equals("MS:1002314") ||  // numpress
-                 acc.equals("MS:1002746") || acc.equals("MS:1002747") || acc.equals("MS:1002748"))
+        else if (acc.equals("MS:1000519")) array->packing = PACK_INT32;
+        else if (acc.equals("MS:1000522")) array->packing = PACK_INT64;
+        else if (acc.equals("MS:1002312")) array->packing = PACK_NUMPRESS_LINEAR;
+        else if (acc.equals("MS:1002313")) array->packing = PACK_NUMPRESS_PIC;
+        else if (acc.equals("MS:1002314")) array->packing = PACK_NUMPRESS_SLOF;
+        else if (acc.equals("MS:1002746") || acc.equals("MS:1002747") || acc.equals("MS:1002748")) {     // numpress, then zlib
+            array->packing = acc.equals("MS:1002746") ? PACK_NUMPRESS_LINEAR : acc.equals("MS:1002747") ? PACK_NUMPRESS_PIC : PACK_NUMPRESS_SLOF;
+            array->zlib = true;
+        } else if (acc.equals("MS:1003088") || acc.equals("MS:1003089") || acc.equals("MS:1003090")) {   // truncation codecs
             s.unsupported = true;
+        }
     }
 }
 
@@ -449,6 +460,91 @@ struct Scratch {
     std::vector<int64_t> order;
 };
 
+// ---- MS-Numpress (Teleman et al. 2014; the rules are spelled out in pyqms_b200/numpress.py) ----
+struct HalfBytes {
+    const unsigned char* data;
+    size_t size, at;
+    bool low = false;
+    bool at_end() const { return at >= size || (at == size - 1 && low && (data[at] & 0xF) == 0); }
+    bool next(unsigned& out) {
+        if (at >= size) return false;
+        if (low) {
+            out = data[at++] & 0xFu;
+            low = false;
+        } else {
+            out = data[at] >> 4;
+            low = true;
+        }
+        return true;
+    }
+    // one integer: a head half byte (<= 8: that many leading zero half bytes, else head - 8 leading 0xF ones), then the rest,
+    // least significant first
+    bool integer(int32_t& out) {
+        unsigned head;
+        if (!next(head)) return false;
+        unsigned lead = head <= 8 ? head : head - 8;
+        uint32_t value = 0;
+        if (head > 8)
+            for (unsigned i = 0; i < lead; ++i) value |= 0xF0000000u >> (4 * i);
+        for (unsigned i = 0; i + lead < 8; ++i) {
+            unsigned hb;
+            if (!next(hb)) return false;
+            value |= (uint32_t)hb << (4 * i);
+        }
+        out = (int32_t)value;
+        return true;
+    }
+};
+
+bool numpress_fixed_point(const unsigned char* data, size_t size, double& out) {
+    if (size < 8) return false;
+    unsigned char raw[8];
+    for (int i = 0; i < 8; ++i) raw[i] = data[7 - i];          // stored most significant byte first
+    memcpy(&out, raw, 8);
+    return true;
+}
+
+uint32_t le32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+bool numpress_decode(Packing kind, const unsigned char* data, size_t size, std::vector<double>& out) {
+    out.clear();
+    if (kind == PACK_NUMPRESS_PIC) {
+        HalfBytes h{data, size, 0};
+        while (!h.at_end()) {
+            int32_t v;
+            if (!h.integer(v)) return false;
+            out.push_back((double)(uint32_t)v);
+        }
+        return true;
+    }
+    double fixed_point;
+    if (!numpress_fixed_point(data, size, fixed_point)) return false;
+    if (kind == PACK_NUMPRESS_SLOF) {
+        if ((size - 8) % 2) return false;
+        out.reserve((size - 8) / 2);
+        for (size_t i = 8; i + 1 < size; i += 2) out.push_back(exp((double)((unsigned)data[i] | ((unsigned)data[i + 1] << 8)) / fixed_point) - 1.0);
+        return true;
+    }
+    if (size == 8) return true;                                // linear prediction
+    if (size < 12) return false;
+    int64_t before = (int64_t)le32(data + 8);
+    out.push_back((double)before / fixed_point);
+    if (size == 12) return true;
+    if (size < 16) return false;
+    int64_t last = (int64_t)le32(data + 12);
+    out.push_back((double)last / fixed_point);
+    HalfBytes h{data, size, 16};
+    while (!h.at_end()) {
+        int32_t residual;
+        if (!h.integer(residual)) return false;
+        const int64_t value = last + (last - before) + (int64_t)residual;
+        out.push_back((double)value / fixed_point);
+        before = last;
+        last = value;
+    }
+    return true;
+}
+
 // one binary array -> doubles; false on a broken payload
 bool decode_array(const ArrayInfo& a, int64_t expected, Scratch& s, std::vector<double>& out) {
     out.clear();
@@ -459,6 +555,23 @@ bool decode_array(const ArrayInfo& a, int64_t expected, Scratch& s, std::vector<
         const size_t guess = expected > 0 ? (size_t)expected * (a.f32 ? 4 : 8) : 0;
         if (!s.inflater.run(s.raw, s.plain, guess)) return false;
         bytes = &s.plain;
+    }
+    if (a.packing >= PACK_NUMPRESS_LINEAR) return numpress_decode(a.packing, bytes->data(), bytes->size(), out);
+    if (a.packing == PACK_INT32 || a.packing == PACK_INT64) {
+        const size_t wide = a.packing == PACK_INT32 ? 4 : 8;
+        out.resize(bytes->size() / wide);
+        for (size_t i = 0; i < out.size(); ++i) {
+            if (wide == 4) {
+                int32_t v;
+                memcpy(&v, bytes->data() + 4 * i, 4);
+                out[i] = (double)v;
+            } else {
+                int64_t v;
+                memcpy(&v, bytes->data() + 8 * i, 8);
+                out[i] = (double)v;
+            }
+        }
+        return true;
     }
     const size_t width = a.f32 ? 4 : 8;
     const size_t n = bytes->size() / width;
@@ -480,10 +593,11 @@ int64_t expected_length(const SpectrumInfo& s, const ArrayInfo& a) { return a.le
 // rows of a spectrum before decoding: exact for uncompressed arrays, the declared length for compressed ones
 int64_t planned_rows(const SpectrumInfo& s) {
     if (!s.mz.present) return 0;
-    if (!s.mz.zlib) {
+    if (!s.mz.zlib && s.mz.packing < PACK_NUMPRESS_LINEAR) {
         size_t symbols = 0;
         for (const char* p = s.mz.text.a; p < s.mz.text.b; ++p) symbols += g_base64.value[(unsigned char)*p] >= 0;
-        return (int64_t)(symbols * 6 / 8 / (s.mz.f32 ? 4 : 8));
+        const size_t width = s.mz.packing == PACK_INT32 ? 4 : s.mz.packing == PACK_INT64 ? 8 : s.mz.f32 ? 4 : 8;
+        return (int64_t)(symbols * 6 / 8 / width);
     }
     const int64_t n = expected_length(s, s.mz);
     return n < 0 ? 0 : n;
@@ -597,6 +711,18 @@ void qms_mzml_close(qms_mzml* f) {
 }
 
 int qms_mzml_scan_blocks(qms_mzml* file) { return file ? file->scan_blocks : 0; }
+
+int qms_numpress_decode(int32_t kind, const unsigned char* data, int64_t size, double* out, int64_t capacity, int64_t* count) {
+    if (kind < 0 || kind > 2 || size < 0 || (size > 0 && !data) || !count) return fail(QMS_MZML_E_ARG, "qms_numpress_decode: bad argument");
+    static thread_local std::vector<double> values;
+    if (!numpress_decode((Packing)(PACK_NUMPRESS_LINEAR + kind), data, (size_t)size, values))
+        return fail(QMS_MZML_E_FORMAT, "numpress stream is cut short");
+    *count = (int64_t)values.size();
+    if (!out || capacity < *count) return out ? fail(QMS_MZML_E_ARG, "qms_numpress_decode: room for %lld values, the stream holds %lld",
+                                                     (long long)capacity, (long long)*count) : QMS_MZML_OK;
+    if (!values.empty()) memcpy(out, values.data(), values.size() * sizeof(double));
+    return QMS_MZML_OK;
+}
 
 int qms_mzml_count(qms_mzml* f, int32_t ms_level, int64_t* n_spectra, int64_t* n_peaks) {
     if (!f || !n_spectra || !n_peaks) return fail(QMS_MZML_E_ARG, "qms_mzml_count: NULL argument");

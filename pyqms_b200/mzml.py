@@ -4,7 +4,8 @@ The reference's scripts loop ``pymzml.run.Reader`` and hand every MS1 spectrum's
 ``match_all`` (example_scripts/quantify_mzml.py:59-73).  This reader goes from the file straight to the packed
 layout the batched matcher consumes -- one (N, 2) float64 array of (m/z, intensity) rows plus row offsets --
 without a Python object per peak (plain or gzip-compressed files): binary arrays are base64/zlib-decoded into numpy buffers (mzML 1.1: MS:1000514
-m/z array, MS:1000515 intensity array, MS:1000521/523 32/64-bit float, MS:1000574 zlib, MS:1000576 none).
+m/z array, MS:1000515 intensity array, MS:1000521/523 32/64-bit float, MS:1000519/522 32/64-bit integer, MS:1000574 zlib,
+MS:1000576 none, MS:1002312-1002314 / MS:1002746-1002748 MS-Numpress alone / followed by zlib -- ``numpress.py``).
 
     run = read_mzml("BSA1.mzML", ms_level=1)
     results = lib.match_many(run.peaks, file_name=run.name, spec_ids=run.spec_ids, spec_rts=run.rts, offsets=run.offsets)
@@ -21,10 +22,14 @@ import xml.etree.ElementTree as ET
 
 import numpy as np
 
+from . import numpress
+
 Run = namedtuple("Run", ["name", "peaks", "offsets", "spec_ids", "rts", "ms_levels"])
 
 _MZ, _INTENSITY = "MS:1000514", "MS:1000515"
 _F32, _F64, _ZLIB = "MS:1000521", "MS:1000523", "MS:1000574"
+_I32, _I64 = "MS:1000519", "MS:1000522"
+_TRUNCATION_CODECS = ("MS:1003088", "MS:1003089", "MS:1003090")
 _MS_LEVEL, _SCAN_START = "MS:1000511", "MS:1000016"
 _ID_NUMBER = re.compile(r"(?:scan|index|spectrum)=(\d+)")
 
@@ -34,7 +39,7 @@ def _local(tag):
 
 
 def _decode(array_element):
-    kind, dtype, compressed, text = None, np.float64, False, ""
+    kind, dtype, compressed, packed, text = None, np.float64, False, None, ""
     for child in array_element:
         name = _local(child.tag)
         if name == "cvParam":
@@ -47,12 +52,38 @@ def _decode(array_element):
                 dtype = np.float64
             elif accession == _ZLIB:
                 compressed = True
+            elif accession in (_I32, _I64):
+                packed = np.int32 if accession == _I32 else np.int64
+            elif accession in numpress.KIND_OF_ACCESSION:
+                packed, then_zlib = numpress.KIND_OF_ACCESSION[accession]
+                compressed = compressed or then_zlib
+            elif accession in _TRUNCATION_CODECS:
+                raise ValueError("binary array encoding %s (%s) is not decoded by this reader" % (accession, child.get("name")))
         elif name == "binary":
             text = child.text or ""
     raw = base64.b64decode(text) if text.strip() else b""
     if compressed and raw:
         raw = zlib.decompress(raw)
+    if isinstance(packed, str):
+        return kind, _numpress_values(packed, raw)
+    if packed is not None:
+        dtype = packed
     return kind, np.frombuffer(raw, dtype=np.dtype(dtype).newbyteorder("<")).astype(np.float64)
+
+
+def _numpress_values(kind, raw):
+    """One numpress stream -> float64 values: through libqms_mzml.so when it is built, else the plain Python decoder."""
+    lib = _native()
+    if lib is None:
+        return numpress.DECODERS[kind](raw)
+    count = C.c_int64()
+    code = ("linear", "pic", "slof").index(kind)
+    if lib.qms_numpress_decode(code, raw, len(raw), None, 0, C.byref(count)) != 0:
+        raise numpress.NumpressError(lib.qms_mzml_last_error().decode())
+    values = np.empty(count.value, dtype=np.float64)
+    if lib.qms_numpress_decode(code, raw, len(raw), values.ctypes.data, len(values), C.byref(count)) != 0:
+        raise numpress.NumpressError(lib.qms_mzml_last_error().decode())
+    return values
 
 
 def spectrum_id(native_id, index):
@@ -81,6 +112,7 @@ def _native():
             lib.qms_mzml_count.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
             lib.qms_mzml_read.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
             lib.qms_mzml_scan_blocks.argtypes = [C.c_void_p]
+            lib.qms_numpress_decode.argtypes = [C.c_int32, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
             _NATIVE = lib
     return _NATIVE or None
 
@@ -123,8 +155,8 @@ def read_mzml(path, ms_level=1, sort_peaks=True, native=None, threads=None):
     what ``Results``/``calc_amounts`` understand (results.py:1240-1246).
 
     ``native``: None (default) uses libqms_mzml.so when it is built -- the file is memory-mapped, indexed by a tag
-    scanner and decoded by ``threads`` threads -- and falls back to the ElementTree reader below for encodings it
-    does not decode (numpress, integer arrays); True insists on the native reader, False on the ElementTree one."""
+    scanner and decoded by ``threads`` threads; True insists on the native reader, False on the ElementTree one below (same
+    encodings: floats, integers, MS-Numpress, zlib; neither decodes the truncation codecs MS:1003088-1003090)."""
     if native is not False:
         lib = _native()
         if lib is None and native:
@@ -183,21 +215,35 @@ def read_mzml(path, ms_level=1, sort_peaks=True, native=None, threads=None):
     return Run(os.path.basename(str(path)), peaks, offsets, ids, rts, levels)
 
 
-def write_mzml(path, spectra, rts_minutes=None, ms_levels=None, precision=64, compress=True, indexed=False):
+def write_mzml(path, spectra, rts_minutes=None, ms_levels=None, precision=64, compress=True, indexed=False, mz_packing=None,
+               intensity_packing=None):
     """Minimal mzML 1.1 writer (test fixtures and synthetic runs): ``spectra`` = list of (n, 2) arrays.
-    ``indexed``: wrap the document in ``<indexedmzML>`` with the byte offset of every spectrum, as converters do."""
+    ``indexed``: wrap the document in ``<indexedmzML>`` with the byte offset of every spectrum, as converters do.
+    ``mz_packing`` / ``intensity_packing``: None (floats of ``precision`` bits), "int32", "int64", or an MS-Numpress codec
+    "linear", "pic", "slof" (with ``compress`` the combined numpress-then-zlib accession is written, as ProteoWizard does)."""
     dtype = np.dtype("<f8" if precision == 64 else "<f4")
+    numpress_accession = {("linear", False): numpress.LINEAR, ("pic", False): numpress.PIC, ("slof", False): numpress.SLOF,
+                          ("linear", True): numpress.LINEAR_ZLIB, ("pic", True): numpress.PIC_ZLIB, ("slof", True): numpress.SLOF_ZLIB}
 
-    def binary(values, accession, name):
-        raw = np.ascontiguousarray(values, dtype=dtype).tobytes()
+    def binary(values, accession, name, packing):
+        params = [(_F64 if precision == 64 else _F32, "%d-bit float" % precision)]
+        if packing in ("int32", "int64"):
+            raw = np.ascontiguousarray(np.rint(values), dtype="<i4" if packing == "int32" else "<i8").tobytes()
+            params = [(_I32 if packing == "int32" else _I64, "%s-bit integer" % packing[3:])]
+        elif packing in numpress.ENCODERS:
+            raw = numpress.ENCODERS[packing](values)
+            params.append((numpress_accession[(packing, bool(compress))], "MS-Numpress %s%s" % (packing, " followed by zlib" if compress else "")))
+        elif packing is None:
+            raw = np.ascontiguousarray(values, dtype=dtype).tobytes()
+        else:
+            raise ValueError("unknown packing %r" % (packing,))
         if compress:
             raw = zlib.compress(raw)
+        if packing not in numpress.ENCODERS:
+            params.append((_ZLIB, "zlib compression") if compress else ("MS:1000576", "no compression"))
         text = base64.b64encode(raw).decode()
-        return ('<binaryDataArray encodedLength="%d"><cvParam cvRef="MS" accession="%s" name="%d-bit float"/>'
-                '<cvParam cvRef="MS" accession="%s" name="%s"/><cvParam cvRef="MS" accession="%s" name="%s"/>'
-                "<binary>%s</binary></binaryDataArray>") % (
-                    len(text), _F64 if precision == 64 else _F32, precision, _ZLIB if compress else "MS:1000576",
-                    "zlib compression" if compress else "no compression", accession, name, text)
+        return '<binaryDataArray encodedLength="%d">%s<cvParam cvRef="MS" accession="%s" name="%s"/><binary>%s</binary></binaryDataArray>' % (
+            len(text), "".join('<cvParam cvRef="MS" accession="%s" name="%s"/>' % p for p in params), accession, name, text)
 
     with open(path, "w", newline="") as out:
         written, offsets = 0, []
@@ -221,8 +267,8 @@ def write_mzml(path, spectra, rts_minutes=None, ms_levels=None, precision=64, co
                  '<scanList count="1"><scan><cvParam cvRef="MS" accession="MS:1000016" name="scan start time" '
                  'value="%r" unitName="minute"/></scan></scanList><binaryDataArrayList count="2">%s%s'
                  "</binaryDataArrayList></spectrum>\n" % (
-                     n, n + 1, len(spectrum), level, rt, binary(spectrum[:, 0], _MZ, "m/z array"),
-                     binary(spectrum[:, 1], _INTENSITY, "intensity array")))
+                     n, n + 1, len(spectrum), level, rt, binary(spectrum[:, 0], _MZ, "m/z array", mz_packing),
+                     binary(spectrum[:, 1], _INTENSITY, "intensity array", intensity_packing)))
         emit("</spectrumList></run></mzML>\n")
         if indexed:
             list_at = written

@@ -34,8 +34,8 @@ def same_run(a, b):
 
 def test_native_library_exports_the_declared_symbols():
     header = (ROOT / "include" / "qms_mzml.h").read_text()
-    declared = sorted(set(re.findall(r"\b(qms_mzml_[a-z_]+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S))))
-    assert len(declared) == 6
+    declared = sorted(set(re.findall(r"\b(qms_(?:mzml|numpress)_[a-z_]+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S))))
+    assert len(declared) == 7
     lib = ctypes.CDLL(str(ROOT / "pyqms_b200" / "libqms_mzml.so"))
     for name in declared:
         assert hasattr(lib, name), name
@@ -123,14 +123,15 @@ def test_converter_style_variations(tmp_path):
 
 def test_unsupported_encodings_fall_back_and_broken_files_raise(tmp_path):
     level1 = '<cvParam cvRef="MS" accession="MS:1000511" name="ms level" value="1"/>'
-    numpress = _spectrum(0, "scan=1", level1, "", [100.0, 200.0], [1.0, 2.0]).replace(
-        '<cvParam cvRef="MS" accession="MS:1000514"', '<cvParam cvRef="MS" accession="MS:1002312" name="numpress"/><cvParam cvRef="MS" accession="MS:1000514"')
-    path = tmp_path / "numpress.mzML"
-    path.write_text("<mzML><run><spectrumList>%s</spectrumList></run></mzML>" % numpress)
+    truncated = _spectrum(0, "scan=1", level1, "", [100.0, 200.0], [1.0, 2.0]).replace(
+        '<cvParam cvRef="MS" accession="MS:1000514"', '<cvParam cvRef="MS" accession="MS:1003089" name="truncation and zlib compression"/><cvParam cvRef="MS" accession="MS:1000514"')
+    path = tmp_path / "truncation.mzML"
+    path.write_text("<mzML><run><spectrumList>%s</spectrumList></run></mzML>" % truncated)
     with pytest.raises(ValueError, match="does not decode"):
         read_mzml(path, native=True)
-    fallback = read_mzml(path)                                   # default: quietly handled by the ElementTree reader
-    assert fallback.offsets.tolist() == [0, 2]
+    for native in (None, False):                                 # no reader here decodes it: an error, never made-up numbers
+        with pytest.raises(ValueError, match="not decoded"):
+            read_mzml(path, native=native)
     broken = _spectrum(0, "scan=1", level1, "", [100.0, 200.0, 300.0], [1.0, 2.0, 3.0], compressed=True)
     payload = re.search(r"<binary>([^<]+)</binary>", broken).group(1)
     path = tmp_path / "broken.mzML"
@@ -245,3 +246,95 @@ def test_converter_style_document_not_written_by_our_writer(tmp_path):
     _check_against(path, expected, True, threads=4)
     assert mzml.LAST_READ["scan_blocks"] > 1 or (os.cpu_count() or 1) < 4
     _check_against(path, expected, False)
+
+
+# ---- MS-Numpress and integer arrays ---------------------------------------------------------------------------------
+def _native_numpress(kind, data):
+    lib = mzml._native()
+    count = ctypes.c_int64()
+    code = ("linear", "pic", "slof").index(kind)
+    if lib.qms_numpress_decode(code, data, len(data), None, 0, ctypes.byref(count)) != 0:
+        raise ValueError(lib.qms_mzml_last_error().decode())
+    out = np.empty(count.value)
+    assert lib.qms_numpress_decode(code, data, len(data), out.ctypes.data, len(out), ctypes.byref(count)) == 0
+    return out
+
+
+def test_numpress_half_byte_code_and_hand_derived_stream():
+    """The half-byte integer code on hand-derived cases, and one linear stream worked out by hand:
+    [100, 200, 300.00005, 400.0001] at fixed point 1e5 -> integers 1e7, 2e7, 30000005, 40000010; residuals against the
+    linear extrapolation: 5 -> half bytes (7 leading zeros, 5), 0 -> (8); packed 0x75, 0x80 (padded)."""
+    from pyqms_b200 import numpress
+    cases = {0: [8], 5: [7, 5], 16: [6, 0, 1], -1: [15, 15], -2: [15, 14], -17: [14, 15, 14],
+             0x12345678: [0, 8, 7, 6, 5, 4, 3, 2, 1], -0x12345678: [0, 8, 8, 9, 10, 11, 12, 13, 14], 0x0FFFFFFF: [1, 15, 15, 15, 15, 15, 15, 15]}
+    for value, expected in cases.items():
+        half_bytes = []
+        numpress._int_to_half_bytes(value, half_bytes)
+        assert half_bytes == expected, value
+        reader = numpress._HalfByteReader(numpress._pack_half_bytes(half_bytes), 0)
+        assert reader.integer() == value and reader.at_end()
+    stream = numpress.encode_linear([100.0, 200.0, 300.00005, 400.0001], 100000.0)
+    assert stream == struct.pack(">d", 100000.0) + struct.pack("<II", 10000000, 20000000) + bytes([0x75, 0x80])
+    for decode in (numpress.decode_linear, lambda data: _native_numpress("linear", data)):
+        assert np.allclose(decode(stream), [100.0, 200.0, 300.00005, 400.0001], rtol=0, atol=1e-9)
+        assert len(decode(stream[:8])) == 0 and decode(stream[:12]).tolist() == [100.0] and decode(stream[:16]).tolist() == [100.0, 200.0]
+        with pytest.raises(ValueError):
+            decode(stream[:10])
+        with pytest.raises(ValueError):
+            decode(stream[:5])
+    assert numpress.decode_slof(struct.pack(">d", 1000.0) + struct.pack("<HH", 0, 6908)).tolist() == [0.0, np.exp(6.908) - 1.0]
+    assert numpress.decode_pic(bytes([0x88, 0x80])).tolist() == [0.0, 0.0, 0.0] and numpress.decode_pic(bytes([0x88])).tolist() == [0.0, 0.0]
+
+
+def test_native_numpress_decoder_equals_the_python_one():
+    from pyqms_b200 import numpress
+    rng = np.random.default_rng(21)
+    for trial in range(60):
+        n = int(rng.integers(0, 400))
+        mz = np.sort(rng.uniform(100.0, 2500.0, n))
+        if trial % 3 == 0:                                        # profile-like: jumps make large and negative residuals
+            mz = np.cumsum(rng.choice([0.001, 0.5, 40.0], size=n)) + 100.0
+        intensity = np.floor(10.0 ** rng.uniform(0.0, 9.0, n)) * (rng.uniform(size=n) > 0.1)
+        fixed = None if trial % 2 else float(rng.choice([1e3, 1e5, 1234567.0]))
+        for kind, data in (("linear", numpress.encode_linear(mz, fixed)), ("pic", numpress.encode_pic(intensity)),
+                           ("slof", numpress.encode_slof(intensity))):
+            slow, fast = numpress.DECODERS[kind](data), _native_numpress(kind, data)
+            assert np.array_equal(slow, fast), (trial, kind)
+            assert len(slow) == n
+        if n:
+            assert np.abs(numpress.decode_linear(numpress.encode_linear(mz)) - mz).max() < 5e-6 * max(1.0, 1.0)
+            assert np.array_equal(numpress.decode_pic(numpress.encode_pic(intensity)), intensity)
+            back = numpress.decode_slof(numpress.encode_slof(intensity))
+            assert np.all(np.abs(back - intensity) <= 5e-4 * (intensity + 1.0))
+    # a residual that needs all eight half bytes, and values beyond 32 bits once the extrapolation has run
+    wild = np.array([1.0, 2.0, 30000.0, 5.0, 4.0e6, 4.0e6 + 1.0])
+    data = numpress.encode_linear(wild, 500.0)
+    assert np.array_equal(numpress.decode_linear(data), _native_numpress("linear", data)) and np.allclose(numpress.decode_linear(data), wild)
+
+
+@pytest.mark.parametrize("mz_packing,intensity_packing,compress", [("linear", "slof", True), ("linear", "pic", False), ("linear", "slof", False),
+                                                                  (None, "int32", True), ("linear", "int64", False), (None, "pic", True)])
+def test_numpress_and_integer_arrays_through_both_readers(tmp_path, mz_packing, intensity_packing, compress):
+    rng = np.random.default_rng(5)
+    spectra = []
+    for n in range(30):
+        k = int(rng.integers(0, 300)) if n not in (3, 4, 5) else n - 3          # empty, one and two rows too
+        spectra.append(np.column_stack([np.sort(rng.uniform(150.0, 2000.0, k)), np.floor(10.0 ** rng.uniform(2.0, 7.0, k))]))
+    path = tmp_path / "packed.mzML"
+    write_mzml(path, spectra, mz_packing=mz_packing, intensity_packing=intensity_packing, compress=compress, indexed=True)
+    text = path.read_text()
+    assert ("MS:100274" in text) == (compress and "linear" == mz_packing or compress and intensity_packing in ("pic", "slof"))
+    fast, slow = read_mzml(path, native=True), read_mzml(path, native=False)
+    assert same_run(fast, slow) and fast.offsets.tolist() == np.concatenate([[0], np.cumsum([len(s) for s in spectra])]).tolist()
+    expected = np.concatenate(spectra)
+    assert np.abs(fast.peaks[:, 0] - expected[:, 0]).max() < (1e-6 if mz_packing else 1e-12)
+    if intensity_packing == "slof":
+        assert np.all(np.abs(fast.peaks[:, 1] - expected[:, 1]) <= 5e-4 * expected[:, 1])
+    else:
+        assert np.array_equal(fast.peaks[:, 1], expected[:, 1])
+    # without the native library the ElementTree reader decodes with numpress.py: same numbers
+    saved, mzml._NATIVE = mzml._NATIVE, False
+    try:
+        assert same_run(read_mzml(path), slow)
+    finally:
+        mzml._NATIVE = saved
