@@ -309,8 +309,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    from pyqms_b200.distributed import bind_to_gpu_numa_node
+    from pyqms_b200.distributed import bind_to_gpu_numa_node, numa_report
     numa_node = bind_to_gpu_numa_node(local)               # before any pinned allocation
+    numa_facts = numa_report(local)
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
@@ -531,7 +532,7 @@ def run_ours(args):
             "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "workload_stats": {"shard": shard, "spectra": n_spec, "peaks": int(len(peaks)), "run_source": run_how, "synth_s": synth_s,
                                "library_entries": int(lib._n_entries), "library_windows": int(lib._n_windows),
-                               "hits_per_step": device_hits, "numa_node_rank0": numa_node, "matcher": "spectrum-resident" if dense else "row-streaming"},
+                               "hits_per_step": device_hits, "numa_node_rank0": numa_node, "numa_rank0": numa_facts, "matcher": "spectrum-resident" if dense else "row-streaming"},
             "library_build": {"seconds_wall": build_s, "envelopes": int(build_counters["envelopes"]),
                               "ms_trees": build_counters["ms_trees"], "ms_envelopes": build_counters["ms_envelopes"],
                               "ms_index": build_counters["ms_index"],

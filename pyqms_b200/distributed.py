@@ -58,6 +58,29 @@ def bind_to_gpu_numa_node(device):
     return None
 
 
+def numa_report(device):
+    """What the box says about the GPU's place in the host: the sysfs NUMA node of its PCIe function (-1 = the platform
+    does not say, the usual answer of a single-socket VM), the NUMA nodes that are online and the CPUs this process may run
+    on.  Never raises; ``bench.py`` prints it next to the copy rates."""
+    import os
+    report = {"gpu_node": None, "nodes_online": None, "cpus_allowed": None}
+    try:
+        report["cpus_allowed"] = len(os.sched_getaffinity(0))
+        with open("/sys/devices/system/node/online") as fh:
+            report["nodes_online"] = fh.read().strip()
+    except Exception:
+        pass
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            report["gpu_node"] = int(fh.read().strip())
+    except Exception:
+        pass
+    return report
+
+
 def shard_range(n, r, world):
     """Contiguous block partition of range(n): rank r gets [begin, end); sizes differ by at most 1."""
     base, extra = divmod(int(n), int(world))
