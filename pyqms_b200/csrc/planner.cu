@@ -26,10 +26,22 @@ namespace {
 
 struct SymbolTable {
     std::unordered_map<std::string, int> index;
+    int16_t plain[26][27];          // "C", "Cl": capital (+ one small letter) -> symbol, without a string or a hash
     explicit SymbolTable(int32_t n, const char* blob, const int32_t* off) {
-        for (int32_t s = 0; s < n; ++s) index.emplace(std::string(blob + off[s], blob + off[s + 1]), s);
+        for (auto& row : plain)
+            for (auto& slot : row) slot = -1;
+        for (int32_t s = 0; s < n; ++s) {
+            const char* name = blob + off[s];
+            const int32_t len = off[s + 1] - off[s];
+            index.emplace(std::string(name, name + len), s);
+            if (s < 32767 && len >= 1 && len <= 2 && name[0] >= 'A' && name[0] <= 'Z' && (len == 1 || (name[1] >= 'a' && name[1] <= 'z')))
+                plain[name[0] - 'A'][len == 1 ? 0 : 1 + (name[1] - 'a')] = (int16_t)s;
+        }
     }
     int find(const char* a, const char* b) const {
+        const size_t len = (size_t)(b - a);
+        if (len >= 1 && len <= 2 && a[0] >= 'A' && a[0] <= 'Z' && (len == 1 || (a[1] >= 'a' && a[1] <= 'z')))
+            return plain[a[0] - 'A'][len == 1 ? 0 : 1 + (a[1] - 'a')];
         auto it = index.find(std::string(a, b));
         return it == index.end() ? -1 : it->second;
     }

@@ -44,9 +44,9 @@ def parse_molecules(molecules, symbols, aa_compositions, compact=False):
     ``first_seen``: rank at which a symbol entered the molecule's composition (ABSENT if not part of it);
     status 1 = left to the host parser (the row is empty).
 
-    ``compact=True`` returns a fourth value, the symbols the columns stand for: when the text holds nothing but residue
-    letters and label indices, only the symbols some residue is made of (a knowledge base lists ~100 symbols, peptides
-    use 5: the full-width matrices of a 500 000-peptide library were 300 MB of zeros), else ``symbols`` unchanged."""
+    ``compact=True`` returns a fourth value, the symbols the columns stand for: only those the text can hold -- spelled with
+    characters that occur in it, or part of a residue whose letter occurs (a knowledge base lists ~100 symbols, peptides
+    and CHNOS formulas use 5-15: the full-width matrices of a 500 000-peptide library were 300 MB of zeros)."""
     n, n_symbols = len(molecules), len(symbols)
     usable = not (n == 0 or n_symbols == 0 or n_symbols > 127 or not all(s.isascii() for s in symbols))
     names, rows = [], []
@@ -61,12 +61,14 @@ def parse_molecules(molecules, symbols, aa_compositions, compact=False):
                 rows.append(items)
         text, str_off = _pack(molecules)
         if compact:
+            # the symbols the text can possibly hold: those spelled with characters that occur in it, those of the residues
+            # whose letter occurs, and water (a peptide's H2O)
             held = np.bincount(np.frombuffer(text, dtype=np.uint8), minlength=256) > 0
-            if not held[~_PEPTIDE_BYTES].any():              # peptides only: the symbols of the residues that occur, + water
-                wanted = {"H", "O"}
-                for name, items in zip(names, rows):
-                    if held[ord(name[0])]:
-                        wanted.update(items)
+            wanted = {"H", "O"} | {s for s in symbols if all(held[ord(c)] for c in s)}
+            for name, items in zip(names, rows):
+                if held[ord(name[0])]:
+                    wanted.update(items)
+            if len(wanted) < n_symbols:
                 symbols = [s for s in symbols if s in wanted]
                 n_symbols = len(symbols)
                 kept = [k for k, items in enumerate(rows) if all(symbol in wanted for symbol in items)]

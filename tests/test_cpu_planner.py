@@ -230,12 +230,18 @@ def test_compact_symbol_columns_of_the_native_parser():
     peptides = random_tryptic_peptides(500, seed=9) + ["UK", "PEPTIDEK", "BK"]     # "B": no such residue, left to the host
     wide = planner.parse_molecules(peptides, symbols, residues)
     counts, seen, status, used = planner.parse_molecules(peptides, symbols, residues, compact=True)
-    assert len(used) < 10 and "Se" in used and used == [s for s in symbols if s in used]
+    assert len(used) < 20 and "Se" in used and used == [s for s in symbols if s in used]
     columns = [symbols.index(s) for s in used]
     assert np.array_equal(wide[0][:, columns], counts) and np.array_equal(wide[1][:, columns], seen) and np.array_equal(wide[2], status)
     assert not np.delete(wide[0], columns, axis=1).any() and status[-1] == 1 and status[:-1].sum() == 0
-    # anything that is not a residue letter or an index keeps the full table
-    assert planner.parse_molecules(peptides + ["+C6H12O6"], symbols, residues, compact=True)[3] == symbols
+    # formulas: the symbols spelled with the characters of the text (isotope-prefixed ones included), never fewer than used
+    mixed = peptides + ["+C6H12O6", "+C(-6)13C(6)", "+Fe2O3Na1"]
+    wide = planner.parse_molecules(mixed, symbols, residues)
+    counts, seen, status, used = planner.parse_molecules(mixed, symbols, residues, compact=True)
+    assert {"Fe", "Na", "Se"} <= set(used) and len(used) < len(symbols)
+    columns = [symbols.index(s) for s in used]
+    assert np.array_equal(wide[0][:, columns], counts) and np.array_equal(wide[1][:, columns], seen) and np.array_equal(wide[2], status)
+    assert not np.delete(wide[0], columns, axis=1).any() and status[-4:].tolist() == [1, 0, 1, 0]       # 13C is not a symbol of the bare knowledge base: host parser
 
 
 def test_hill_formulas_write_any_count():
